@@ -1,0 +1,156 @@
+/* =============================================================================
+ * smartcore_kmeans_cuda.h -- C ABI of libsmartcore_kmeans_cuda.so
+ *
+ * B200 (sm_100a) implementation of smartcore v0.4.0's k-means hot path.  This is
+ * the drop-in boundary: plain pointers and sizes, opaque handles, int status
+ * codes.  It is what a Rust `src/gpu/ffi.rs` (cargo feature `cuda`) binds; see
+ * INTEGRATION.md for the binding and the edit to src/cluster/kmeans.rs.
+ *
+ * Reference interfaces replaced (paths relative to the smartcore source tree):
+ *   KMeans::fit              src/cluster/kmeans.rs:254-323
+ *   KMeans::predict          src/cluster/kmeans.rs:327-352
+ *   KMeans::kmeans_plus_plus src/cluster/kmeans.rs:354-413
+ *   BBDTree::clustering      src/algorithm/neighbour/bbd_tree.rs:62-163
+ *   Euclidian::squared_distance  src/metrics/distance/euclidian.rs:51-66
+ *
+ * Conventions
+ *   * Every function returns SCKM_OK (0) or an error code; the message is kept
+ *     per context (sckm_last_error).  No C++ exception crosses this boundary.
+ *   * The caller owns every host buffer for the duration of the call only; the
+ *     library keeps no host pointer after return.  Device memory lives behind
+ *     the opaque handles and is released by the matching *_destroy.
+ *   * A context is bound to ONE CUDA device and is not thread-safe; multi-GPU is
+ *     one context per device (one per process under torchrun, or one per host
+ *     thread) joined by sckm_comm_init_rank.  Rows are sharded across ranks; the
+ *     only per-iteration exchange is one all-reduce of [k*d sums | k counts |
+ *     inertia] (f64).
+ *   * The RNG stays on the host (kmeans.rs:355, src/rand_custom.rs:8-33): the
+ *     caller draws `first_index = rng.gen_range(0..n)` and the k-1 uniforms
+ *     `rng.gen::<f64>()` (they do not depend on the data) and passes them in.
+ *   * There is no CPU fallback: every compute entry point fails with
+ *     SCKM_ERR_CUDA when no sm_100 device is usable.
+ * ============================================================================= */
+#ifndef SMARTCORE_KMEANS_CUDA_H
+#define SMARTCORE_KMEANS_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SCKM_ABI_VERSION 1
+
+typedef struct sckm_ctx sckm_ctx;         /* device + stream + workspaces (+ NCCL communicator) */
+typedef struct sckm_dataset sckm_dataset; /* this rank's rows of X, labels y and D^2 array, on device */
+
+enum { SCKM_F32 = 0, SCKM_F64 = 1 };      /* element type TX of X */
+
+enum {
+    SCKM_OK = 0,
+    SCKM_ERR_INVALID = 1, /* bad argument (null pointer, k > n, d mismatch, ...) */
+    SCKM_ERR_CUDA = 2,    /* CUDA runtime / driver error, or no usable device */
+    SCKM_ERR_NCCL = 3,    /* NCCL not loadable or collective failed */
+    SCKM_ERR_STATE = 4    /* call sequence error (e.g. lloyd before labels exist) */
+};
+
+/* Which Lloyd assignment kernel to run.  AUTO picks by shape. */
+enum {
+    SCKM_ASSIGN_AUTO = 0,
+    SCKM_ASSIGN_DIRECT = 1, /* direct-difference form, bit-exact distances (euclidian.rs:56-63) */
+    SCKM_ASSIGN_DMMA = 2,   /* ||x||^2 - 2 X.C^T + ||c||^2 on FP64 DMMA tiles + exact near-tie refine */
+    SCKM_ASSIGN_STREAM = 3  /* small k*d: rows in registers, DFMA scores, HBM-bound */
+};
+
+int sckm_abi_version(void);
+
+/* ---- context ------------------------------------------------------------- */
+int  sckm_ctx_create(int device, sckm_ctx** out);
+void sckm_ctx_destroy(sckm_ctx* ctx);
+/* Last error text of this context (or of the failed sckm_ctx_create when ctx == NULL). */
+const char* sckm_last_error(const sckm_ctx* ctx);
+/* Force an assignment kernel (SCKM_ASSIGN_*); default AUTO. */
+int  sckm_ctx_set_assign_kernel(sckm_ctx* ctx, int which);
+/* Kernels launched by this context since creation (for bench.py's gpu_launches). */
+uint64_t sckm_ctx_launch_count(const sckm_ctx* ctx);
+
+/* ---- multi-GPU (NCCL, loaded with dlopen; one rank per context) ------------ */
+/* Fill a 128-byte ncclUniqueId on rank 0; ship it to the other ranks by any means. */
+int sckm_comm_unique_id(sckm_ctx* ctx, void* id128);
+int sckm_comm_init_rank(sckm_ctx* ctx, int nranks, int rank, const void* id128);
+
+/* ---- dataset: rows [row_offset, row_offset + n_local) of a global n_global x d matrix -- */
+/* Replaces the container reads of DenseMatrix (src/linalg/basic/matrix.rs:367-381,
+ * 391-404): `column_major` != 0 means host[c * n_local + r], else host[r * d + c].
+ * Device storage is always row-major. */
+int sckm_dataset_upload(sckm_ctx* ctx, const void* host, uint64_t n_local, uint64_t d, int dtype,
+                        int column_major, uint64_t row_offset, uint64_t n_global, sckm_dataset** out);
+/* Synthetic Gaussian blobs generated on device (recipe of make_blobs,
+ * src/dataset/generator.rs:10-48, with a counter-based RNG so that any row can be
+ * regenerated on the host bit-for-bit: sckm_blobs_fill_host). */
+int sckm_dataset_generate_blobs(sckm_ctx* ctx, uint64_t n_local, uint64_t d, uint64_t n_centers,
+                                uint64_t seed, int dtype, uint64_t row_offset, uint64_t n_global,
+                                sckm_dataset** out);
+/* Host twin of the generator (pure CPU, no device needed): rows [row0, row0+nrows) row-major. */
+int sckm_blobs_fill_host(void* out, int dtype, uint64_t row0, uint64_t nrows, uint64_t d,
+                         uint64_t n_centers, uint64_t seed);
+int sckm_dataset_download_rows(sckm_dataset* ds, uint64_t local_row0, uint64_t nrows, void* host_out);
+void sckm_dataset_destroy(sckm_dataset* ds);
+
+/* ---- kmeans++ labels (kmeans.rs:354-413) ----------------------------------- */
+/* first_index: global row drawn by rng.gen_range(0..n); uniforms[k-1]: the gen::<f64>() draws.
+ * inject_rows (nullable, k entries): bypass the D^2 sampling and use these global rows as seeds
+ * (parity harness).  On return the dataset holds the labels y (nearest chosen seed) and
+ * seed_rows_out (nullable) the k chosen global rows. */
+int sckm_kmeanspp(sckm_dataset* ds, uint64_t k, uint64_t first_index, const double* uniforms,
+                  const int64_t* inject_rows, int64_t* seed_rows_out);
+
+/* ---- initial centroids = per-label means (kmeans.rs:275-292) ---------------- */
+int sckm_init_centroids(sckm_dataset* ds, uint64_t k, double* centroids_out, int64_t* size_out);
+
+/* ---- one Lloyd step == BBDTree::clustering (bbd_tree.rs:62-87) --------------- */
+/* in: centroids[k*d]; out: sums[k*d], counts[k], *inertia (w.r.t. the INPUT centroids); the
+ * dataset's labels are overwritten.  All-reduced over ranks when a communicator is set. */
+int sckm_lloyd_step(sckm_dataset* ds, const double* centroids, uint64_t k, double* sums_out,
+                    int64_t* counts_out, double* inertia_out);
+
+/* ---- the loop of KMeans::fit (kmeans.rs:294-310) with the reference stop rule ---- */
+/* centroids_inout: initial centroids in, final out.  size_out[k], *distortion_out,
+ * *iters_out = number of clustering steps executed. */
+int sckm_lloyd_fit(sckm_dataset* ds, uint64_t k, uint64_t max_iter, double* centroids_inout,
+                   int64_t* size_out, double* distortion_out, int64_t* iters_out);
+/* Same loop with the stop rule disabled (exactly n_iters steps) and device timing:
+ * ms_per_iter_out[n_iters] (nullable) are CUDA-event times on the context's stream.
+ * inertia_out (nullable) gets n_iters values. */
+int sckm_lloyd_iterate(sckm_dataset* ds, uint64_t k, uint64_t n_iters, double* centroids_inout,
+                       int64_t* size_out, double* inertia_out, float* ms_per_iter_out);
+
+/* Labels of this rank's rows; width = 4 (uint32_t) or 8 (uint64_t, Rust usize). */
+int sckm_labels_download(sckm_dataset* ds, void* out, int width);
+/* The D^2 array of kmeans++ / the per-point min distance of the last Lloyd step. */
+int sckm_mindist_download(sckm_dataset* ds, double* out);
+
+/* ---- predict (kmeans.rs:327-352): direct form in f64, strict <, lowest index wins ---- */
+int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int dtype,
+                 int column_major, const double* centroids, uint64_t k, void* labels_out, int width);
+
+/* ---- whole KMeans::fit from host buffers (what the Rust fit() calls) ----------- */
+/* Validation (k >= 2, max_iter >= 1) stays with the caller so the reference's messages are
+ * produced before any device work.  labels_out: n x width bytes. */
+int sckm_kmeans_fit(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int dtype,
+                    int column_major, uint64_t k, uint64_t max_iter, uint64_t first_index,
+                    const double* uniforms, void* labels_out, int width, int64_t* size_out,
+                    double* centroids_out, double* distortion_out, int64_t* iters_out);
+
+/* ---- measurement helpers ------------------------------------------------------- */
+/* out[0] = HBM copy GB/s (read+write), out[1] = FP64 DFMA TFLOP/s, out[2] = FP64 DMMA TFLOP/s,
+ * measured now on the context's device with CUDA events (micro-kernels, ~100 ms). */
+int sckm_device_peaks(sckm_ctx* ctx, double* out3);
+/* Write > L2-size bytes so the next timed launch starts with a cold L2. */
+int sckm_flush_l2(sckm_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMARTCORE_KMEANS_CUDA_H */

@@ -1,0 +1,467 @@
+// =============================================================================
+// oracle/kmeans_oracle.cpp -- TEST INFRASTRUCTURE ONLY. NOT PRODUCT CODE.
+//
+// CPU restatement of smartcore v0.4.0's k-means hot path, used ONLY as the
+// checker by tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+// --impl reference legs.  Nothing under smartcore_b200/ may import, link or call
+// this file; the product path fails loudly when its CUDA library is missing.
+//
+// What is restated (all paths relative to /root/reference):
+//   * src/cluster/kmeans.rs:254-323   KMeans::fit          -> orc_fit
+//   * src/cluster/kmeans.rs:327-352   KMeans::predict      -> orc_predict
+//   * src/cluster/kmeans.rs:354-413   kmeans_plus_plus     -> kmeanspp<T>
+//   * src/algorithm/neighbour/bbd_tree.rs:42-311  BBDTree  -> struct BBDTree
+//   * src/metrics/distance/euclidian.rs:51-66 squared_distance -> sqdist<T>
+//   * src/rand_custom.rs:8-33 get_rng_impl (default features: SmallRng)
+//
+// Third-party arithmetic that is NOT in /root/reference: crate `rand` 0.8.5
+// (Cargo.toml:28; Cargo.lock is git-ignored), i.e. SmallRng = xoshiro256++,
+// SeedableRng::seed_from_u64, Standard f64 sampling and UniformInt::<usize>
+// sample_single.  Restated here from the published algorithm.  The generator
+// core is checked against the upstream xoshiro256++ test vector
+// (tests/test_oracle.py); the seed_from_u64 expansion has two plausible forms
+// (rand_core 0.6 default PCG32 fill = mode 0, the default; SplitMix64 = mode 1).
+//
+// PARITY PIN STATUS: the Lloyd step (BBDTree::clustering) is pinned to the
+// reference's own golden test bbd_tree.rs:349-363, squared_distance to
+// euclidian.rs:84-91, fit/predict to the self-consistency test
+// kmeans.rs:473-505 and the error strings to kmeans.rs:426-443.  The reference
+// has no test that pins fit()'s labels/centroids or any RNG output, and rustc is
+// not available to run the reference itself, so for the RNG seeding path this
+// oracle is "PARITY UNPINNED"; every parity test can inject the seed-row
+// sequence so Lloyd parity never depends on RNG fidelity.
+//
+// Build: g++ -O2 -ffp-contract=off -fno-fast-math (see oracle/Makefile). Rust
+// never contracts a*b+c into an FMA, so contraction must stay off.
+// =============================================================================
+#include <cstdint>
+#include <cstddef>
+#include <cstring>
+#include <cfloat>
+#include <vector>
+#include <utility>
+#include <chrono>
+
+namespace {
+
+// ---------------------------------------------------------------------------
+// rand 0.8.5 restatement
+// ---------------------------------------------------------------------------
+struct Xoshiro256pp {
+    uint64_t s[4];
+};
+
+inline uint64_t rotl64(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+
+// rand_xoshiro / rand 0.8.5 src/rngs/xoshiro256plusplus.rs next_u64
+inline uint64_t xo_next(Xoshiro256pp& r) {
+    uint64_t result = rotl64(r.s[0] + r.s[3], 23) + r.s[0];
+    uint64_t t = r.s[1] << 17;
+    r.s[2] ^= r.s[0];
+    r.s[3] ^= r.s[1];
+    r.s[1] ^= r.s[2];
+    r.s[0] ^= r.s[3];
+    r.s[2] ^= t;
+    r.s[3] = rotl64(r.s[3], 45);
+    return result;
+}
+
+// Xoshiro256PlusPlus::seed_from_u64 (SplitMix64 fill) -- candidate B
+inline void xo_seed_splitmix(Xoshiro256pp& r, uint64_t state) {
+    for (int i = 0; i < 4; i++) {
+        state += 0x9e3779b97f4a7c15ULL;
+        uint64_t z = state;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ULL;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebULL;
+        z = z ^ (z >> 31);
+        r.s[i] = z;
+    }
+}
+
+// rand_core 0.6 SeedableRng::seed_from_u64 default (PCG32 fill of the 32-byte
+// seed) followed by Xoshiro256PlusPlus::from_seed (4 x LE u64; an all-zero seed
+// falls back to seed_from_u64(0) of the xoshiro impl) -- candidate A (default)
+inline void xo_seed_pcg(Xoshiro256pp& r, uint64_t state) {
+    const uint64_t MUL = 6364136223846793005ULL;
+    const uint64_t INC = 11634580027462260723ULL;
+    uint8_t seed[32];
+    for (int c = 0; c < 8; c++) {
+        state = state * MUL + INC;
+        uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
+        uint32_t rot = (uint32_t)(state >> 59);
+        uint32_t x = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
+        seed[4 * c + 0] = (uint8_t)(x);
+        seed[4 * c + 1] = (uint8_t)(x >> 8);
+        seed[4 * c + 2] = (uint8_t)(x >> 16);
+        seed[4 * c + 3] = (uint8_t)(x >> 24);
+    }
+    bool all_zero = true;
+    for (int i = 0; i < 32; i++) all_zero = all_zero && seed[i] == 0;
+    if (all_zero) { xo_seed_splitmix(r, 0); return; }
+    for (int i = 0; i < 4; i++) {
+        uint64_t v = 0;
+        for (int b = 7; b >= 0; b--) v = (v << 8) | seed[8 * i + b];
+        r.s[i] = v;
+    }
+}
+
+inline void xo_seed(Xoshiro256pp& r, uint64_t seed, int mode) {
+    if (mode == 1) xo_seed_splitmix(r, seed); else xo_seed_pcg(r, seed);
+}
+
+// rand 0.8.5 Standard f64: (next_u64 >> 11) * 2^-53
+inline double xo_gen_f64(Xoshiro256pp& r) {
+    return (double)(xo_next(r) >> 11) * (1.0 / 9007199254740992.0);
+}
+
+// rand 0.8.5 UniformInt<usize>::sample_single(0, n) (64-bit usize)
+inline uint64_t xo_gen_range(Xoshiro256pp& r, uint64_t range) {
+    if (range == 0) return xo_next(r);
+    int lz = __builtin_clzll(range);
+    uint64_t zone = (range << lz) - 1;
+    for (;;) {
+        uint64_t v = xo_next(r);
+        unsigned __int128 m = (unsigned __int128)v * (unsigned __int128)range;
+        uint64_t hi = (uint64_t)(m >> 64), lo = (uint64_t)m;
+        if (lo <= zone) return hi;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// euclidian.rs:51-66 -- diff and square in T, widen, sequential f64 sum
+// ---------------------------------------------------------------------------
+template <typename T>
+inline double sqdist(const T* a, const T* b, size_t d) {
+    double sum = 0.0;
+    for (size_t i = 0; i < d; i++) {
+        T r = a[i] - b[i];
+        T rr = r * r;
+        sum += (double)rr;
+    }
+    return sum;
+}
+
+// ---------------------------------------------------------------------------
+// bbd_tree.rs -- faithful restatement (f64 view of the data, row-major here;
+// the reference reads through data.get((i,j)).to_f64(), layout-agnostic)
+// ---------------------------------------------------------------------------
+struct Node {
+    int64_t count = 0, index = 0;
+    std::vector<double> center, radius, sum;
+    double cost = 0.0;
+    int64_t lower = -1, upper = -1;
+};
+
+struct BBDTree {
+    std::vector<Node> nodes;
+    std::vector<int64_t> index;
+    int64_t root = 0;
+    size_t n = 0, d = 0;
+    const double* x = nullptr;  // borrowed, row-major n x d
+
+    double at(int64_t i, size_t j) const { return x[(size_t)i * d + j]; }
+
+    static double node_cost(const Node& node, const double* center, size_t d) {  // :297-305
+        double scatter = 0.0;
+        for (size_t i = 0; i < d; i++) {
+            double v = (node.sum[i] / (double)node.count) - center[i];
+            scatter += v * v;
+        }
+        return node.cost + (double)node.count * scatter;
+    }
+
+    int64_t build_node(int64_t begin, int64_t end) {  // :195-295
+        Node node;
+        node.center.assign(d, 0.0); node.radius.assign(d, 0.0); node.sum.assign(d, 0.0);
+        node.count = end - begin;
+        node.index = begin;
+        std::vector<double> lo(d), hi(d);
+        for (size_t j = 0; j < d; j++) { lo[j] = at(index[begin], j); hi[j] = lo[j]; }
+        for (int64_t i = begin; i < end; i++)
+            for (size_t j = 0; j < d; j++) {
+                double c = at(index[i], j);
+                if (lo[j] > c) lo[j] = c;
+                if (hi[j] < c) hi[j] = c;
+            }
+        double max_radius = -1.0;
+        size_t split_index = 0;
+        for (size_t j = 0; j < d; j++) {
+            node.center[j] = (lo[j] + hi[j]) / 2.0;
+            node.radius[j] = (hi[j] - lo[j]) / 2.0;
+            if (node.radius[j] > max_radius) { max_radius = node.radius[j]; split_index = j; }
+        }
+        if (max_radius < 1E-10) {  // :234-250 leaf
+            for (size_t j = 0; j < d; j++) node.sum[j] = at(index[begin], j);
+            if (end > begin + 1) {
+                int64_t len = end - begin;
+                for (size_t j = 0; j < d; j++) node.sum[j] *= (double)len;
+            }
+            node.cost = 0.0;
+            nodes.push_back(std::move(node));
+            return (int64_t)nodes.size() - 1;
+        }
+        double split_cutoff = node.center[split_index];
+        int64_t i1 = begin, i2 = end - 1, size = 0;
+        while (i1 <= i2) {  // :252-276
+            bool i1_good = at(index[i1], split_index) < split_cutoff;
+            bool i2_good = at(index[i2], split_index) >= split_cutoff;
+            if (!i1_good && !i2_good) {
+                std::swap(index[i1], index[i2]);
+                i1_good = true; i2_good = true;
+            }
+            if (i1_good) { i1++; size++; }
+            if (i2_good) { i2--; }
+        }
+        int64_t lower = build_node(begin, begin + size);
+        int64_t upper = build_node(begin + size, end);
+        node.lower = lower; node.upper = upper;
+        for (size_t j = 0; j < d; j++) node.sum[j] = nodes[lower].sum[j] + nodes[upper].sum[j];
+        std::vector<double> mean(d);
+        for (size_t j = 0; j < d; j++) mean[j] = node.sum[j] / (double)node.count;
+        node.cost = node_cost(nodes[lower], mean.data(), d) + node_cost(nodes[upper], mean.data(), d);
+        nodes.push_back(std::move(node));
+        return (int64_t)nodes.size() - 1;
+    }
+
+    static bool prune(const double* center, const double* radius, const double* centroids,
+                      size_t d, int64_t best_index, int64_t test_index) {  // :165-193
+        if (best_index == test_index) return false;
+        const double* best = centroids + (size_t)best_index * d;
+        const double* test = centroids + (size_t)test_index * d;
+        double lhs = 0.0, rhs = 0.0;
+        for (size_t i = 0; i < d; i++) {
+            double diff = test[i] - best[i];
+            lhs += diff * diff;
+            if (diff > 0.0) rhs += (center[i] + radius[i] - best[i]) * diff;
+            else            rhs += (center[i] - radius[i] - best[i]) * diff;
+        }
+        return lhs >= 2.0 * rhs;
+    }
+
+    double filter(int64_t ni, const double* centroids, const int64_t* candidates, int64_t k,
+                  double* sums, int64_t* counts, int64_t* membership) const {  // :89-163
+        const Node& node = nodes[ni];
+        double min_dist = sqdist<double>(node.center.data(), centroids + (size_t)candidates[0] * d, d);
+        int64_t closest = candidates[0];
+        for (int64_t i = 1; i < k; i++) {
+            double dist = sqdist<double>(node.center.data(), centroids + (size_t)candidates[i] * d, d);
+            if (dist < min_dist) { min_dist = dist; closest = candidates[i]; }
+        }
+        if (node.lower >= 0) {
+            std::vector<int64_t> new_candidates((size_t)k, 0);
+            int64_t newk = 0;
+            for (int64_t c = 0; c < k; c++)
+                if (!prune(node.center.data(), node.radius.data(), centroids, d, closest, candidates[c]))
+                    new_candidates[(size_t)newk++] = candidates[c];
+            if (newk > 1) {
+                double a = filter(node.lower, centroids, new_candidates.data(), newk, sums, counts, membership);
+                double b = filter(node.upper, centroids, new_candidates.data(), newk, sums, counts, membership);
+                return a + b;
+            }
+        }
+        for (size_t i = 0; i < d; i++) sums[(size_t)closest * d + i] += node.sum[i];
+        counts[closest] += node.count;
+        int64_t last = node.index + node.count;
+        for (int64_t i = node.index; i < last; i++) membership[index[(size_t)i]] = closest;
+        return node_cost(node, centroids + (size_t)closest * d, d);
+    }
+
+    double clustering(const double* centroids, int64_t k, double* sums, int64_t* counts,
+                      int64_t* membership) const {  // :62-87
+        std::vector<int64_t> candidates((size_t)k);
+        for (int64_t i = 0; i < k; i++) {
+            counts[i] = 0;
+            candidates[(size_t)i] = i;
+            for (size_t j = 0; j < d; j++) sums[(size_t)i * d + j] = 0.0;
+        }
+        return filter(root, centroids, candidates.data(), k, sums, counts, membership);
+    }
+};
+
+BBDTree* bbd_new(const double* x, size_t n, size_t d) {  // :42-60
+    BBDTree* t = new BBDTree();
+    t->x = x; t->n = n; t->d = d;
+    t->index.resize(n);
+    for (size_t i = 0; i < n; i++) t->index[i] = (int64_t)i;
+    t->nodes.reserve(2 * n);
+    t->root = t->build_node(0, (int64_t)n);
+    return t;
+}
+
+// Dense restatement of what one BBDTree::clustering call computes:
+// argmin (strict <, lowest index wins), sums of points, counts, inertia as the
+// plain sum of min distances.  gap_out[i] = (second - best) / best (relative gap
+// used by the label-tolerance rule of BASELINE.json.north_star); +inf if k == 1.
+double brute_clustering(const double* x, size_t n, size_t d, const double* centroids, int64_t k,
+                        double* sums, int64_t* counts, int64_t* membership, double* gap_out) {
+    for (int64_t c = 0; c < k; c++) { counts[c] = 0; for (size_t j = 0; j < d; j++) sums[(size_t)c * d + j] = 0.0; }
+    double total = 0.0;
+    for (size_t i = 0; i < n; i++) {
+        double best = DBL_MAX, second = DBL_MAX; int64_t bi = 0;
+        for (int64_t c = 0; c < k; c++) {
+            double dist = sqdist<double>(x + i * d, centroids + (size_t)c * d, d);
+            if (dist < best) { second = best; best = dist; bi = c; }
+            else if (dist < second) second = dist;
+        }
+        membership[i] = bi; counts[bi]++;
+        for (size_t j = 0; j < d; j++) sums[(size_t)bi * d + j] += x[i * d + j];
+        total += best;
+        if (gap_out) gap_out[i] = (second - best) / (best > 0.0 ? best : DBL_MIN);
+    }
+    return total;
+}
+
+// kmeans.rs:354-413.  inject != nullptr: use inject[0..k) as the chosen seed rows
+// (RNG bypass); otherwise draw with the rand restatement.  seed_idx_out gets the k
+// chosen rows, dist_out (nullable) the final D^2 array.
+template <typename T>
+void kmeanspp(const T* x, size_t n, size_t d, size_t k, uint64_t seed, int seed_mode,
+              const int64_t* inject, int64_t* y, int64_t* seed_idx_out, double* dist_out) {
+    Xoshiro256pp rng; xo_seed(rng, seed, seed_mode);
+    for (size_t i = 0; i < n; i++) y[i] = 0;
+    int64_t first = inject ? inject[0] : (int64_t)xo_gen_range(rng, (uint64_t)n);
+    if (seed_idx_out) seed_idx_out[0] = first;
+    std::vector<T> centroid(x + (size_t)first * d, x + (size_t)first * d + d);
+    std::vector<double> dd(n, DBL_MAX);
+    for (size_t j = 1; j < k; j++) {
+        for (size_t i = 0; i < n; i++) {
+            double dist = sqdist<T>(x + i * d, centroid.data(), d);
+            if (dist < dd[i]) { dd[i] = dist; y[i] = (int64_t)(j - 1); }
+        }
+        double sum = 0.0;
+        for (size_t i = 0; i < n; i++) sum += dd[i];
+        size_t index = 0;
+        if (inject) {
+            index = (size_t)inject[j];
+        } else {
+            double cutoff = xo_gen_f64(rng) * sum;
+            double cost = 0.0;
+            while (index < n) {
+                cost += dd[index];
+                if (cost >= cutoff) break;
+                index++;
+            }
+            if (index >= n) index = n - 1;  // the reference would panic here (kmeans.rs:396)
+        }
+        if (seed_idx_out) seed_idx_out[j] = (int64_t)index;
+        centroid.assign(x + index * d, x + index * d + d);
+    }
+    for (size_t i = 0; i < n; i++) {
+        double dist = sqdist<T>(x + i * d, centroid.data(), d);
+        if (dist < dd[i]) { dd[i] = dist; y[i] = (int64_t)(k - 1); }
+    }
+    if (dist_out) for (size_t i = 0; i < n; i++) dist_out[i] = dd[i];
+}
+
+double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+}  // namespace
+
+extern "C" {
+
+// ---- RNG -------------------------------------------------------------------
+void orc_rng_seed(uint64_t seed, int mode, uint64_t* state) {
+    Xoshiro256pp r; xo_seed(r, seed, mode); std::memcpy(state, r.s, 32);
+}
+uint64_t orc_rng_next_u64(uint64_t* state) {
+    Xoshiro256pp r; std::memcpy(r.s, state, 32); uint64_t v = xo_next(r); std::memcpy(state, r.s, 32); return v;
+}
+double orc_rng_gen_f64(uint64_t* state) {
+    Xoshiro256pp r; std::memcpy(r.s, state, 32); double v = xo_gen_f64(r); std::memcpy(state, r.s, 32); return v;
+}
+uint64_t orc_rng_gen_range(uint64_t* state, uint64_t n) {
+    Xoshiro256pp r; std::memcpy(r.s, state, 32); uint64_t v = xo_gen_range(r, n); std::memcpy(state, r.s, 32); return v;
+}
+
+// ---- distance --------------------------------------------------------------
+double orc_squared_distance_f64(const double* a, const double* b, size_t d) { return sqdist<double>(a, b, d); }
+double orc_squared_distance_f32(const float* a, const float* b, size_t d) { return sqdist<float>(a, b, d); }
+double orc_squared_distance_i32(const int32_t* a, const int32_t* b, size_t d) { return sqdist<int32_t>(a, b, d); }
+
+// ---- BBD tree --------------------------------------------------------------
+void* orc_bbd_new(const double* x_rowmajor, size_t n, size_t d) { return bbd_new(x_rowmajor, n, d); }
+void orc_bbd_free(void* t) { delete (BBDTree*)t; }
+size_t orc_bbd_num_nodes(void* t) { return ((BBDTree*)t)->nodes.size(); }
+double orc_bbd_clustering(void* t, const double* centroids, int64_t k, double* sums, int64_t* counts,
+                          int64_t* membership) {
+    return ((BBDTree*)t)->clustering(centroids, k, sums, counts, membership);
+}
+double orc_brute_clustering(const double* x, size_t n, size_t d, const double* centroids, int64_t k,
+                            double* sums, int64_t* counts, int64_t* membership, double* gap_out) {
+    return brute_clustering(x, n, d, centroids, k, sums, counts, membership, gap_out);
+}
+
+// ---- kmeans++ (dtype: 0 = f32, 1 = f64) ------------------------------------
+void orc_kmeanspp(const void* x, int dtype, size_t n, size_t d, size_t k, uint64_t seed, int seed_mode,
+                  const int64_t* inject, int64_t* y, int64_t* seed_idx_out, double* dist_out) {
+    if (dtype == 0) kmeanspp<float>((const float*)x, n, d, k, seed, seed_mode, inject, y, seed_idx_out, dist_out);
+    else            kmeanspp<double>((const double*)x, n, d, k, seed, seed_mode, inject, y, seed_idx_out, dist_out);
+}
+
+// ---- KMeans::fit (kmeans.rs:254-323) ---------------------------------------
+// x row-major n x d of dtype; use_tree = 1 follows the reference (BBD tree filter),
+// 0 = dense brute-force step with the same driver.  Outputs: y[n], size[k],
+// centroids[k*d], *distortion, *iters (number of clustering calls executed),
+// seed_idx[k] (nullable), times[3] (nullable) = {tree build s, kmeans++ s, Lloyd loop s}.
+// Returns 0, or 1 = invalid k, 2 = invalid max_iter (messages formatted by callers).
+int orc_fit(const void* x, int dtype, size_t n, size_t d, size_t k, size_t max_iter, uint64_t seed,
+            int seed_mode, const int64_t* inject, int use_tree, int64_t* y, int64_t* size,
+            double* centroids, double* distortion_out, int64_t* iters_out, int64_t* seed_idx,
+            double* times) {
+    std::vector<double> xd((size_t)n * d);
+    if (dtype == 0) { const float* xf = (const float*)x; for (size_t i = 0; i < n * d; i++) xd[i] = (double)xf[i]; }
+    else std::memcpy(xd.data(), x, n * d * sizeof(double));
+    double t0 = now_s();
+    BBDTree* bbd = use_tree ? bbd_new(xd.data(), n, d) : nullptr;  // built before validation (:255)
+    double t1 = now_s();
+    if (k < 2) { delete bbd; return 1; }
+    if (max_iter == 0) { delete bbd; return 2; }
+    double distortion = DBL_MAX;
+    orc_kmeanspp(x, dtype, n, d, k, seed, seed_mode, inject, y, seed_idx, nullptr);
+    double t2 = now_s();
+    for (size_t c = 0; c < k; c++) size[c] = 0;
+    for (size_t i = 0; i < k * d; i++) centroids[i] = 0.0;
+    for (size_t i = 0; i < n; i++) size[y[i]] += 1;
+    for (size_t i = 0; i < n; i++)
+        for (size_t j = 0; j < d; j++) centroids[(size_t)y[i] * d + j] += xd[i * d + j];
+    for (size_t c = 0; c < k; c++)
+        for (size_t j = 0; j < d; j++) centroids[c * d + j] /= (double)size[c];
+    std::vector<double> sums(k * d, 0.0);
+    int64_t iters = 0;
+    for (size_t it = 1; it <= max_iter; it++) {
+        double dist = use_tree
+            ? bbd->clustering(centroids, (int64_t)k, sums.data(), size, y)
+            : brute_clustering(xd.data(), n, d, centroids, (int64_t)k, sums.data(), size, y, nullptr);
+        iters++;
+        for (size_t c = 0; c < k; c++)
+            if (size[c] > 0)
+                for (size_t j = 0; j < d; j++) centroids[c * d + j] = sums[c * d + j] / (double)size[c];
+        if (distortion <= dist) break; else distortion = dist;
+    }
+    double t3 = now_s();
+    delete bbd;
+    *distortion_out = distortion;
+    if (iters_out) *iters_out = iters;
+    if (times) { times[0] = t1 - t0; times[1] = t2 - t1; times[2] = t3 - t2; }
+    return 0;
+}
+
+// ---- KMeans::predict (kmeans.rs:327-352): rows widened to f64, direct form ---
+void orc_predict(const void* x, int dtype, size_t n, size_t d, const double* centroids, size_t k,
+                 int64_t* out) {
+    std::vector<double> row(d);
+    for (size_t i = 0; i < n; i++) {
+        double min_dist = DBL_MAX; int64_t best = 0;
+        for (size_t j = 0; j < d; j++)
+            row[j] = dtype == 0 ? (double)((const float*)x)[i * d + j] : ((const double*)x)[i * d + j];
+        for (size_t c = 0; c < k; c++) {
+            double dist = sqdist<double>(row.data(), centroids + c * d, d);
+            if (dist < min_dist) { min_dist = dist; best = (int64_t)c; }
+        }
+        out[i] = best;
+    }
+}
+
+}  // extern "C"

@@ -1,0 +1,465 @@
+// sckm_api.cu -- C-ABI entry points (include/smartcore_kmeans_cuda.h) and host orchestration.
+//
+// The driver logic mirrors KMeans::fit (src/cluster/kmeans.rs:254-323): kmeans++ labels ->
+// per-label means -> loop { clustering step; centroid update; stop rule }.  Everything below runs
+// on the context's own CUDA stream; the only host round trip per Lloyd iteration is the 8-byte
+// inertia needed by the stop rule `if distortion <= dist { break }` (kmeans.rs:305).
+#include "sckm_common.cuh"
+#include "sckm_blobs.cuh"
+#include <cfloat>
+#include <algorithm>
+
+namespace sckm {
+const char* create_error_text();
+int launch_assign_dmma(sckm_dataset* ds, uint64_t k);         // sckm_dmma.cu
+bool dmma_supported(const sckm_dataset* ds, uint64_t k);      // sckm_dmma.cu
+}
+using namespace sckm;
+
+extern "C" {
+
+int sckm_abi_version(void) { return SCKM_ABI_VERSION; }
+
+int sckm_ctx_create(int device, sckm_ctx** out) {
+    if (!out) return fail(nullptr, SCKM_ERR_INVALID, "sckm_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(nullptr, SCKM_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                    e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0 || device >= count) return fail(nullptr, SCKM_ERR_INVALID, "device %d out of range (0..%d)", device, count - 1);
+    cudaDeviceProp prop;
+    if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+        return fail(nullptr, SCKM_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, SCKM_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                    device, prop.major, prop.minor);
+    sckm_ctx* ctx = new sckm_ctx();
+    ctx->device = device;
+    ctx->num_sms = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+#define CREATE_CUDA(call)                                                                         \
+    do { cudaError_t _e = (call); if (_e != cudaSuccess) {                                        \
+        int rc = fail(nullptr, SCKM_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(_e));           \
+        sckm_ctx_destroy(ctx); return rc; } } while (0)
+    CREATE_CUDA(cudaSetDevice(device));
+    CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CREATE_CUDA(cudaEventCreate(&ctx->ev0));
+    CREATE_CUDA(cudaEventCreate(&ctx->ev1));
+    CREATE_CUDA(cudaMalloc((void**)&ctx->d_flags, 64));
+    CREATE_CUDA(cudaMemset(ctx->d_flags, 0, 64));
+    CREATE_CUDA(cudaMalloc((void**)&ctx->d_totals, sizeof(double)));
+    CREATE_CUDA(cudaMemset(ctx->d_totals, 0, sizeof(double)));
+    CREATE_CUDA(cudaMallocHost((void**)&ctx->h_pinned, 256 * sizeof(double)));
+#undef CREATE_CUDA
+    *out = ctx;
+    return SCKM_OK;
+}
+
+void sckm_ctx_destroy(sckm_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    nccl_destroy(ctx);
+    cudaFree(ctx->d_centroids); cudaFree(ctx->d_cnorm); cudaFree(ctx->d_packed); cudaFree(ctx->d_partials);
+    cudaFree(ctx->d_size); cudaFree(ctx->d_blocksum); cudaFree(ctx->d_totals); cudaFree(ctx->d_seedrow);
+    cudaFree(ctx->d_seeds); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush);
+    if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+const char* sckm_last_error(const sckm_ctx* ctx) { return ctx ? ctx->err.c_str() : create_error_text(); }
+
+int sckm_ctx_set_assign_kernel(sckm_ctx* ctx, int which) {
+    if (!ctx) return SCKM_ERR_INVALID;
+    if (which < SCKM_ASSIGN_AUTO || which > SCKM_ASSIGN_STREAM) return fail(ctx, SCKM_ERR_INVALID, "unknown assign kernel %d", which);
+    ctx->assign_kernel = which;
+    return SCKM_OK;
+}
+
+uint64_t sckm_ctx_launch_count(const sckm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int sckm_comm_unique_id(sckm_ctx* ctx, void* id128) {
+    if (!ctx || !id128) return SCKM_ERR_INVALID;
+    return nccl_unique_id(ctx, id128);
+}
+int sckm_comm_init_rank(sckm_ctx* ctx, int nranks, int rank, const void* id128) {
+    if (!ctx || (nranks > 1 && !id128)) return SCKM_ERR_INVALID;
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return nccl_init_rank(ctx, nranks, rank, id128);
+}
+
+// ---- dataset ------------------------------------------------------------------------------
+static int dataset_alloc(sckm_ctx* ctx, uint64_t n, uint64_t d, int dtype, uint64_t row_offset, uint64_t n_global,
+                         sckm_dataset** out) {
+    if (!ctx || !out) return SCKM_ERR_INVALID;
+    *out = nullptr;
+    if (dtype != SCKM_F32 && dtype != SCKM_F64) return fail(ctx, SCKM_ERR_INVALID, "dtype must be SCKM_F32 or SCKM_F64");
+    if (d == 0 || d > (1u << 20)) return fail(ctx, SCKM_ERR_INVALID, "d=%llu out of range", (unsigned long long)d);
+    if (n > 0xFFFFFFFFull * 16) return fail(ctx, SCKM_ERR_INVALID, "n too large");
+    if (n_global == 0) n_global = n;
+    if (row_offset + n > n_global) return fail(ctx, SCKM_ERR_INVALID, "rows [%llu,%llu) exceed n_global=%llu",
+        (unsigned long long)row_offset, (unsigned long long)(row_offset + n), (unsigned long long)n_global);
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    sckm_dataset* ds = new sckm_dataset();
+    ds->ctx = ctx; ds->n = n; ds->d = d; ds->dtype = dtype; ds->row_offset = row_offset; ds->n_global = n_global;
+    const size_t nn = std::max<uint64_t>(n, 1);
+    cudaError_t e;
+    if ((e = cudaMalloc(&ds->x, nn * d * ds->elem())) != cudaSuccess ||
+        (e = cudaMalloc((void**)&ds->labels, nn * sizeof(uint32_t))) != cudaSuccess ||
+        (e = cudaMalloc((void**)&ds->mind, nn * sizeof(double))) != cudaSuccess) {
+        sckm_dataset_destroy(ds);
+        return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc for %llu x %llu dataset failed: %s", (unsigned long long)n,
+                    (unsigned long long)d, cudaGetErrorString(e));
+    }
+    *out = ds;
+    return SCKM_OK;
+}
+
+int sckm_dataset_upload(sckm_ctx* ctx, const void* host, uint64_t n_local, uint64_t d, int dtype,
+                        int column_major, uint64_t row_offset, uint64_t n_global, sckm_dataset** out) {
+    if (!ctx) return SCKM_ERR_INVALID;
+    if (!host && n_local) return fail(ctx, SCKM_ERR_INVALID, "host pointer is NULL");
+    sckm_dataset* ds = nullptr;
+    SCKM_TRY(dataset_alloc(ctx, n_local, d, dtype, row_offset, n_global, &ds));
+    const size_t bytes = (size_t)n_local * d * ds->elem();
+    int rc = SCKM_OK;
+    if (bytes) {
+        if (!column_major) {
+            cudaError_t e = cudaMemcpyAsync(ds->x, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+            if (e != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+        } else {
+            void* tmp = nullptr;
+            cudaError_t e = cudaMalloc(&tmp, bytes);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
+            if (e != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "H2D staging failed: %s", cudaGetErrorString(e));
+            if (rc == SCKM_OK) rc = launch_transpose(ctx, tmp, ds->x, n_local, d, dtype);
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(tmp);
+        }
+    }
+    if (rc != SCKM_OK) { sckm_dataset_destroy(ds); return rc; }
+    *out = ds;
+    return SCKM_OK;
+}
+
+int sckm_dataset_generate_blobs(sckm_ctx* ctx, uint64_t n_local, uint64_t d, uint64_t n_centers,
+                                uint64_t seed, int dtype, uint64_t row_offset, uint64_t n_global,
+                                sckm_dataset** out) {
+    if (!ctx) return SCKM_ERR_INVALID;
+    if (n_centers == 0) return fail(ctx, SCKM_ERR_INVALID, "n_centers must be >= 1");
+    sckm_dataset* ds = nullptr;
+    SCKM_TRY(dataset_alloc(ctx, n_local, d, dtype, row_offset, n_global, &ds));
+    int rc = n_local ? launch_blobs(ctx, ds->x, dtype, row_offset, n_local, d, n_centers, seed) : SCKM_OK;
+    if (rc == SCKM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "blob generation failed");
+    if (rc != SCKM_OK) { sckm_dataset_destroy(ds); return rc; }
+    *out = ds;
+    return SCKM_OK;
+}
+
+int sckm_blobs_fill_host(void* out, int dtype, uint64_t row0, uint64_t nrows, uint64_t d,
+                         uint64_t n_centers, uint64_t seed) {
+    if (!out || n_centers == 0 || (dtype != SCKM_F32 && dtype != SCKM_F64)) return SCKM_ERR_INVALID;
+    for (uint64_t r = 0; r < nrows; r++)
+        for (uint64_t c = 0; c < d; c++) {
+            double v = blob_value(seed, n_centers, row0 + r, c);
+            if (dtype == SCKM_F32) ((float*)out)[r * d + c] = (float)v; else ((double*)out)[r * d + c] = v;
+        }
+    return SCKM_OK;
+}
+
+int sckm_dataset_download_rows(sckm_dataset* ds, uint64_t local_row0, uint64_t nrows, void* host_out) {
+    if (!ds || !host_out) return SCKM_ERR_INVALID;
+    sckm_ctx* ctx = ds->ctx;
+    if (local_row0 + nrows > ds->n) return fail(ctx, SCKM_ERR_INVALID, "row range out of bounds");
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    SCKM_CUDA(ctx, cudaMemcpyAsync(host_out, (const char*)ds->x + local_row0 * ds->d * ds->elem(),
+                                   nrows * ds->d * ds->elem(), cudaMemcpyDeviceToHost, ctx->stream));
+    SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCKM_OK;
+}
+
+void sckm_dataset_destroy(sckm_dataset* ds) {
+    if (!ds) return;
+    if (ds->ctx) { cudaSetDevice(ds->ctx->device); cudaStreamSynchronize(ds->ctx->stream); }
+    cudaFree(ds->x); cudaFree(ds->labels); cudaFree(ds->mind);
+    delete ds;
+}
+
+// ---- kmeans++ -----------------------------------------------------------------------------
+static int ensure_kpp(sckm_dataset* ds, uint64_t k) {
+    sckm_ctx* ctx = ds->ctx;
+    SCKM_TRY(ensure_workspace(ctx, k, ds->d, 0));
+    const size_t nb = (ds->n + kKppBlockRows - 1) / kKppBlockRows + 1;
+    if (nb > ctx->cap_blocks) {
+        if (ctx->d_blocksum) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_blocksum); ctx->d_blocksum = nullptr; }
+        SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_blocksum, nb * sizeof(double)));
+        ctx->cap_blocks = nb;
+    }
+    const size_t seed_bytes = ((size_t)ds->d * ds->elem() + 7) / 8 * 8 + 8;
+    if (seed_bytes > ctx->cap_seedrow) {
+        if (ctx->d_seedrow) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_seedrow); ctx->d_seedrow = nullptr; }
+        SCKM_CUDA(ctx, cudaMalloc(&ctx->d_seedrow, seed_bytes));
+        ctx->cap_seedrow = seed_bytes;
+    } else if (seed_bytes < ctx->cap_seedrow) {
+        // the select kernel derives the index slot from the buffer size: keep it exact
+        SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_seedrow); ctx->d_seedrow = nullptr;
+        SCKM_CUDA(ctx, cudaMalloc(&ctx->d_seedrow, seed_bytes));
+        ctx->cap_seedrow = seed_bytes;
+    }
+    return SCKM_OK;
+}
+
+int sckm_kmeanspp(sckm_dataset* ds, uint64_t k, uint64_t first_index, const double* uniforms,
+                  const int64_t* inject_rows, int64_t* seed_rows_out) {
+    if (!ds) return SCKM_ERR_INVALID;
+    sckm_ctx* ctx = ds->ctx;
+    if (k < 1) return fail(ctx, SCKM_ERR_INVALID, "k must be >= 1");
+    if (ds->n_global == 0) return fail(ctx, SCKM_ERR_INVALID, "empty dataset");
+    if (!inject_rows && k > 1 && !uniforms) return fail(ctx, SCKM_ERR_INVALID, "uniforms is NULL");
+    if (!inject_rows && first_index >= ds->n_global) return fail(ctx, SCKM_ERR_INVALID, "first_index out of range");
+    if (inject_rows)
+        for (uint64_t j = 0; j < k; j++)
+            if (inject_rows[j] < 0 || (uint64_t)inject_rows[j] >= ds->n_global)
+                return fail(ctx, SCKM_ERR_INVALID, "inject_rows[%llu] out of range", (unsigned long long)j);
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    SCKM_TRY(ensure_kpp(ds, k));
+    const size_t seed_words = ctx->cap_seedrow / 8;
+    // seed 0: the row drawn by gen_range (kmeans.rs:358-362)
+    SCKM_TRY(launch_kpp_select(ds, 0.0, inject_rows ? inject_rows[0] : (int64_t)first_index, 0));
+    SCKM_TRY(nccl_allreduce_u64(ctx, (unsigned long long*)ctx->d_seedrow, seed_words));
+    for (uint64_t j = 1; j < k; j++) {
+        SCKM_TRY(launch_kpp_refresh(ds, (uint32_t)(j - 1), j == 1));
+        if (ctx->nranks > 1) SCKM_TRY(nccl_allgather_f64(ctx, ctx->d_totals + ctx->rank, ctx->d_totals));
+        SCKM_TRY(launch_kpp_select(ds, inject_rows ? 0.0 : uniforms[j - 1], inject_rows ? inject_rows[j] : -1, (uint32_t)j));
+        SCKM_TRY(nccl_allreduce_u64(ctx, (unsigned long long*)ctx->d_seedrow, seed_words));
+    }
+    SCKM_TRY(launch_kpp_refresh(ds, (uint32_t)(k - 1), k == 1));  // final pass, label k-1 (kmeans.rs:399-410)
+    if (seed_rows_out) {
+        if (ctx->nranks > 1) SCKM_TRY(nccl_allreduce_u64(ctx, (unsigned long long*)ctx->d_seeds, k));
+        SCKM_CUDA(ctx, cudaMemcpyAsync(seed_rows_out, ctx->d_seeds, k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ds->have_labels = true;
+    return SCKM_OK;
+}
+
+// ---- shared pieces of the Lloyd driver -------------------------------------------------------
+static int pick_assign(const sckm_dataset* ds, uint64_t k) {
+    const sckm_ctx* ctx = ds->ctx;
+    int which = ctx->assign_kernel;
+    if (which == SCKM_ASSIGN_AUTO) which = dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA : SCKM_ASSIGN_DIRECT;
+    if (which == SCKM_ASSIGN_DMMA && !dmma_supported(ds, k)) which = SCKM_ASSIGN_DIRECT;
+    if (which == SCKM_ASSIGN_STREAM) which = SCKM_ASSIGN_DIRECT;  // streaming kernel: see sckm_dmma.cu notes
+    return which;
+}
+
+// one clustering step on the device: labels, packed = all-reduced [sums | counts | inertia]
+static int clustering_step(sckm_dataset* ds, uint64_t k) {
+    sckm_ctx* ctx = ds->ctx;
+    const int which = pick_assign(ds, k);
+    if (which == SCKM_ASSIGN_DMMA) SCKM_TRY(launch_assign_dmma(ds, k));
+    else SCKM_TRY(launch_assign_direct(ds, k));
+    SCKM_TRY(launch_update(ds, k, true));
+    SCKM_TRY(nccl_allreduce_f64(ctx, ctx->d_packed, (size_t)k * ds->d + k + 1));
+    ds->have_labels = true;
+    return SCKM_OK;
+}
+
+static int check_k(sckm_dataset* ds, uint64_t k) {
+    if (k < 1 || k > 0x7FFFFFFFull) return fail(ds->ctx, SCKM_ERR_INVALID, "k=%llu out of range", (unsigned long long)k);
+    return SCKM_OK;
+}
+
+int sckm_init_centroids(sckm_dataset* ds, uint64_t k, double* centroids_out, int64_t* size_out) {
+    if (!ds) return SCKM_ERR_INVALID;
+    sckm_ctx* ctx = ds->ctx;
+    SCKM_TRY(check_k(ds, k));
+    if (!ds->have_labels) return fail(ctx, SCKM_ERR_STATE, "no labels on the dataset: run sckm_kmeanspp first");
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    SCKM_TRY(launch_update(ds, k, false));
+    SCKM_TRY(nccl_allreduce_f64(ctx, ctx->d_packed, (size_t)k * ds->d + k + 1));
+    SCKM_TRY(launch_finalize(ctx, k, ds->d, /*guarded=*/false));
+    if (centroids_out) SCKM_CUDA(ctx, cudaMemcpyAsync(centroids_out, ctx->d_centroids, k * ds->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (size_out) SCKM_CUDA(ctx, cudaMemcpyAsync(size_out, ctx->d_size, k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCKM_OK;
+}
+
+int sckm_lloyd_step(sckm_dataset* ds, const double* centroids, uint64_t k, double* sums_out,
+                    int64_t* counts_out, double* inertia_out) {
+    if (!ds || !centroids) return SCKM_ERR_INVALID;
+    sckm_ctx* ctx = ds->ctx;
+    SCKM_TRY(check_k(ds, k));
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    SCKM_TRY(ensure_workspace(ctx, k, ds->d, 0));
+    const size_t kd = (size_t)k * ds->d;
+    SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->d_centroids, centroids, kd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    SCKM_TRY(clustering_step(ds, k));
+    std::vector<double> packed(kd + k + 1);
+    SCKM_CUDA(ctx, cudaMemcpyAsync(packed.data(), ctx->d_packed, packed.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (sums_out) memcpy(sums_out, packed.data(), kd * sizeof(double));
+    if (counts_out) for (uint64_t c = 0; c < k; c++) counts_out[c] = (int64_t)packed[kd + c];
+    if (inertia_out) *inertia_out = packed[kd + k];
+    return SCKM_OK;
+}
+
+static int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop, double* centroids_inout,
+                      int64_t* size_out, double* distortion_out, int64_t* iters_out, double* inertia_trace,
+                      float* ms_trace) {
+    sckm_ctx* ctx = ds->ctx;
+    SCKM_TRY(check_k(ds, k));
+    if (max_iter == 0) return fail(ctx, SCKM_ERR_INVALID, "max_iter must be >= 1");
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    SCKM_TRY(ensure_workspace(ctx, k, ds->d, 0));
+    const size_t kd = (size_t)k * ds->d;
+    if (centroids_inout)
+        SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->d_centroids, centroids_inout, kd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    double distortion = DBL_MAX;
+    int64_t iters = 0;
+    std::vector<cudaEvent_t> evs;
+    if (ms_trace) {
+        evs.resize(max_iter + 1);
+        for (auto& e : evs) SCKM_CUDA(ctx, cudaEventCreate(&e));
+        SCKM_CUDA(ctx, cudaEventRecord(evs[0], ctx->stream));
+    }
+    for (uint64_t it = 1; it <= max_iter; it++) {
+        SCKM_TRY(clustering_step(ds, k));                         // bbd.clustering(...)        kmeans.rs:296
+        SCKM_TRY(launch_finalize(ctx, k, ds->d, /*guarded=*/true));  // centroids = sums / size   kmeans.rs:297-303
+        iters++;
+        if (ms_trace) SCKM_CUDA(ctx, cudaEventRecord(evs[it], ctx->stream));
+        if (honor_stop || inertia_trace) {
+            SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_packed + kd + k, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+            if (honor_stop || it == max_iter || true) SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            const double dist = ctx->h_pinned[0];
+            if (inertia_trace) inertia_trace[it - 1] = dist;
+            if (honor_stop) {
+                if (distortion <= dist) break;                    // kmeans.rs:305-309
+                distortion = dist;
+            }
+        }
+    }
+    if (centroids_inout)
+        SCKM_CUDA(ctx, cudaMemcpyAsync(centroids_inout, ctx->d_centroids, kd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (size_out) SCKM_CUDA(ctx, cudaMemcpyAsync(size_out, ctx->d_size, k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    if (ms_trace) {
+        for (int64_t i = 0; i < iters; i++) SCKM_CUDA(ctx, cudaEventElapsedTime(&ms_trace[i], evs[i], evs[i + 1]));
+        for (auto& e : evs) cudaEventDestroy(e);
+    }
+    if (distortion_out) *distortion_out = distortion;
+    if (iters_out) *iters_out = iters;
+    return SCKM_OK;
+}
+
+int sckm_lloyd_fit(sckm_dataset* ds, uint64_t k, uint64_t max_iter, double* centroids_inout,
+                   int64_t* size_out, double* distortion_out, int64_t* iters_out) {
+    if (!ds || !centroids_inout) return SCKM_ERR_INVALID;
+    return lloyd_loop(ds, k, max_iter, true, centroids_inout, size_out, distortion_out, iters_out, nullptr, nullptr);
+}
+
+int sckm_lloyd_iterate(sckm_dataset* ds, uint64_t k, uint64_t n_iters, double* centroids_inout,
+                       int64_t* size_out, double* inertia_out, float* ms_per_iter_out) {
+    if (!ds || !centroids_inout) return SCKM_ERR_INVALID;
+    return lloyd_loop(ds, k, n_iters, false, centroids_inout, size_out, nullptr, nullptr, inertia_out, ms_per_iter_out);
+}
+
+static int download_labels(sckm_ctx* ctx, const uint32_t* d_labels, uint64_t n, void* out, int width) {
+    if (width == 4) {
+        SCKM_CUDA(ctx, cudaMemcpyAsync(out, d_labels, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        return SCKM_OK;
+    }
+    if (width != 8) return fail(ctx, SCKM_ERR_INVALID, "label width must be 4 or 8");
+    uint64_t* tmp = nullptr;
+    SCKM_CUDA(ctx, cudaMalloc((void**)&tmp, std::max<uint64_t>(n, 1) * 8));
+    int rc = launch_labels_widen(ctx, d_labels, tmp, n);
+    cudaError_t e = cudaSuccess;
+    if (rc == SCKM_OK) e = cudaMemcpyAsync(out, tmp, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    cudaFree(tmp);
+    if (rc == SCKM_OK && e != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "label download failed: %s", cudaGetErrorString(e));
+    return rc;
+}
+
+int sckm_labels_download(sckm_dataset* ds, void* out, int width) {
+    if (!ds || !out) return SCKM_ERR_INVALID;
+    if (!ds->have_labels) return fail(ds->ctx, SCKM_ERR_STATE, "no labels on the dataset yet");
+    SCKM_CUDA(ds->ctx, cudaSetDevice(ds->ctx->device));
+    return download_labels(ds->ctx, ds->labels, ds->n, out, width);
+}
+
+int sckm_mindist_download(sckm_dataset* ds, double* out) {
+    if (!ds || !out) return SCKM_ERR_INVALID;
+    sckm_ctx* ctx = ds->ctx;
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    SCKM_CUDA(ctx, cudaMemcpyAsync(out, ds->mind, ds->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCKM_OK;
+}
+
+// ---- predict --------------------------------------------------------------------------------
+int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int dtype,
+                 int column_major, const double* centroids, uint64_t k, void* labels_out, int width) {
+    if (!ctx) return SCKM_ERR_INVALID;
+    if ((!x_host || !labels_out) && n) return fail(ctx, SCKM_ERR_INVALID, "NULL buffer");
+    if (!centroids || k < 1) return fail(ctx, SCKM_ERR_INVALID, "no centroids");
+    if (width != 4 && width != 8) return fail(ctx, SCKM_ERR_INVALID, "label width must be 4 or 8");
+    if (n == 0) return SCKM_OK;
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    sckm_dataset* ds = nullptr;
+    SCKM_TRY(sckm_dataset_upload(ctx, x_host, n, d, dtype, column_major, 0, n, &ds));
+    int rc = ensure_workspace(ctx, k, d, 0);
+    if (rc == SCKM_OK && cudaMemcpyAsync(ctx->d_centroids, centroids, k * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
+        rc = fail(ctx, SCKM_ERR_CUDA, "centroid upload failed");
+    if (rc == SCKM_OK) rc = launch_assign_direct_raw(ctx, ds->x, dtype, n, d, k, ds->labels, nullptr);
+    if (rc == SCKM_OK) rc = download_labels(ctx, ds->labels, n, labels_out, width);
+    sckm_dataset_destroy(ds);
+    return rc;
+}
+
+// ---- whole fit from host buffers ----------------------------------------------------------------
+int sckm_kmeans_fit(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int dtype,
+                    int column_major, uint64_t k, uint64_t max_iter, uint64_t first_index,
+                    const double* uniforms, void* labels_out, int width, int64_t* size_out,
+                    double* centroids_out, double* distortion_out, int64_t* iters_out) {
+    if (!ctx) return SCKM_ERR_INVALID;
+    if (!centroids_out) return fail(ctx, SCKM_ERR_INVALID, "centroids_out is NULL");
+    if (n == 0) return fail(ctx, SCKM_ERR_INVALID, "empty input");
+    sckm_dataset* ds = nullptr;
+    SCKM_TRY(sckm_dataset_upload(ctx, x_host, n, d, dtype, column_major, 0, n, &ds));
+    int rc = sckm_kmeanspp(ds, k, first_index, uniforms, nullptr, nullptr);
+    if (rc == SCKM_OK) rc = sckm_init_centroids(ds, k, centroids_out, nullptr);
+    if (rc == SCKM_OK) rc = lloyd_loop(ds, k, max_iter, true, nullptr, size_out, distortion_out, iters_out, nullptr, nullptr);
+    if (rc == SCKM_OK && cudaMemcpy(centroids_out, ctx->d_centroids, k * d * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail(ctx, SCKM_ERR_CUDA, "centroid download failed");
+    if (rc == SCKM_OK && labels_out) rc = download_labels(ctx, ds->labels, n, labels_out, width);
+    sckm_dataset_destroy(ds);
+    return rc;
+}
+
+// ---- measurement --------------------------------------------------------------------------------
+int sckm_device_peaks(sckm_ctx* ctx, double* out3) {
+    if (!ctx || !out3) return SCKM_ERR_INVALID;
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    return measure_peaks(ctx, out3);
+}
+
+int sckm_flush_l2(sckm_ctx* ctx) {
+    if (!ctx) return SCKM_ERR_INVALID;
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->d_flush) {
+        ctx->flush_bytes = (size_t)256 << 20;  // > 126 MB L2
+        SCKM_CUDA(ctx, cudaMalloc(&ctx->d_flush, ctx->flush_bytes));
+    }
+    SCKM_CUDA(ctx, cudaMemsetAsync(ctx->d_flush, 0, ctx->flush_bytes, ctx->stream));
+    return SCKM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// sckm_common.cuh -- shared declarations of libsmartcore_kmeans_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstddef>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/smartcore_kmeans_cuda.h"
+
+namespace sckm {
+
+constexpr int kNumSMsB200 = 148;
+constexpr int kKppBlockRows = 1024;   // fixed summation unit of the kmeans++ D^2 array
+constexpr int kWarpRows = 32;         // rows staged per warp slab in the direct kernels
+
+struct NcclApi;  // dlopen'd entry points (sckm_nccl.cu)
+
+}  // namespace sckm
+
+struct sckm_ctx {
+    int device = 0;
+    int num_sms = 0;
+    int smem_optin = 0;          // max dynamic shared memory per CTA
+    cudaStream_t stream = nullptr;
+    std::string err;
+    int assign_kernel = SCKM_ASSIGN_AUTO;
+    uint64_t launches = 0;
+    // communicator (nullptr/1 rank when single GPU)
+    void* nccl_comm = nullptr;
+    int nranks = 1, rank = 0;
+    // workspaces, grown on demand
+    double* d_centroids = nullptr;   // [k*d] current centroids
+    double* d_cnorm = nullptr;       // [k] ||c||^2 (GEMM-form kernels)
+    double* d_packed = nullptr;      // [k*d sums | k counts | inertia]
+    double* d_partials = nullptr;    // [P][k*d + k + 1] per-CTA/warp partial sums (deterministic)
+    size_t cap_centroids = 0, cap_packed = 0, cap_cnorm = 0, cap_size = 0, cap_seeds = 0, cap_partials = 0;
+    int64_t* d_size = nullptr;       // [k]
+    double* d_blocksum = nullptr;    // kmeans++: per-1024-row-block sums of D^2
+    size_t cap_blocks = 0;
+    double* d_totals = nullptr;      // [nranks] rank totals of D^2
+    void* d_seedrow = nullptr;       // [d elements of TX, padded] + global index (8 B)
+    size_t cap_seedrow = 0;
+    int64_t* d_seeds = nullptr;      // [k] chosen global rows
+    unsigned long long* d_flags = nullptr;  // [8] misc device counters (near-tie count, ...)
+    void* d_flush = nullptr;         // L2 flush buffer
+    size_t flush_bytes = 0;
+    double* h_pinned = nullptr;      // small pinned scratch (>= 64 doubles)
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct sckm_dataset {
+    sckm_ctx* ctx = nullptr;
+    void* x = nullptr;               // row-major [n][d] of dtype
+    uint64_t n = 0, d = 0;
+    int dtype = SCKM_F64;
+    uint64_t row_offset = 0, n_global = 0;
+    uint32_t* labels = nullptr;      // [n]
+    double* mind = nullptr;          // [n] kmeans++ D^2 / per-point min distance
+    bool have_labels = false;
+    size_t elem() const { return dtype == SCKM_F32 ? 4 : 8; }
+};
+
+namespace sckm {
+
+int fail(sckm_ctx* ctx, int code, const char* fmt, ...);
+
+#define SCKM_CUDA(ctx, call)                                                               \
+    do {                                                                                   \
+        cudaError_t _e = (call);                                                           \
+        if (_e != cudaSuccess)                                                             \
+            return sckm::fail((ctx), SCKM_ERR_CUDA, "%s failed: %s (%s:%d)", #call,        \
+                              cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+#define SCKM_TRY(expr)                   \
+    do {                                 \
+        int _rc = (expr);                \
+        if (_rc != SCKM_OK) return _rc;  \
+    } while (0)
+
+// ---- NCCL (sckm_nccl.cu) ----
+int nccl_unique_id(sckm_ctx* ctx, void* id128);
+int nccl_init_rank(sckm_ctx* ctx, int nranks, int rank, const void* id128);
+void nccl_destroy(sckm_ctx* ctx);
+int nccl_allreduce_f64(sckm_ctx* ctx, double* buf, size_t count);
+int nccl_allreduce_u64(sckm_ctx* ctx, unsigned long long* buf, size_t count);
+int nccl_allgather_f64(sckm_ctx* ctx, const double* send1, double* recv);  // 1 double per rank
+
+// ---- kernel launchers (sckm_kernels.cu) ----
+int launch_transpose(sckm_ctx* ctx, const void* src_colmajor, void* dst_rowmajor, uint64_t n, uint64_t d, int dtype);
+int launch_blobs(sckm_ctx* ctx, void* x, int dtype, uint64_t row0, uint64_t nrows, uint64_t d,
+                 uint64_t n_centers, uint64_t seed);
+// kmeans++ pass: D^2 refresh against the seed row in ctx->d_seedrow, label = `label` where improved;
+// writes per-1024-row block sums to ctx->d_blocksum and the rank total to ctx->d_totals[rank].
+int launch_kpp_refresh(sckm_dataset* ds, uint32_t label, bool first_pass);
+// pick the next seed: cutoff = u * sum(totals); the owning rank locates the row and publishes it
+// (row + global index) in ctx->d_seedrow; other ranks publish zeros (all-reduced by the caller).
+// inject_row >= 0 bypasses sampling.  Stores the global row in ctx->d_seeds[slot] (owner only; zero elsewhere).
+int launch_kpp_select(sckm_dataset* ds, double u, int64_t inject_row, uint32_t slot);
+// direct-form assignment against ctx->d_centroids (labels + mind)
+int launch_assign_direct(sckm_dataset* ds, uint64_t k);
+int launch_assign_direct_raw(sckm_ctx* ctx, const void* x, int dtype, uint64_t n, uint64_t d, uint64_t k,
+                             uint32_t* labels, double* mind);
+// deterministic per-label sums/counts/inertia of the local rows into ctx->d_packed
+int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia);
+// centroids = sums / counts (guarded: keep old when count == 0; unguarded for the initial means)
+int launch_finalize(sckm_ctx* ctx, uint64_t k, uint64_t d, bool guarded);
+int launch_labels_widen(sckm_ctx* ctx, const uint32_t* in, uint64_t* out, uint64_t n);
+int measure_peaks(sckm_ctx* ctx, double* out3);
+
+int ensure_workspace(sckm_ctx* ctx, uint64_t k, uint64_t d, size_t partial_slots);
+
+}  // namespace sckm

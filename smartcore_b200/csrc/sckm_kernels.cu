@@ -1,0 +1,683 @@
+// sckm_kernels.cu -- hand-written sm_100a kernels of the k-means hot path (first generation:
+// exact direct-form kernels + deterministic update; the DMMA tile kernel lives in sckm_dmma.cu).
+//
+// Reference arithmetic being reproduced (paths relative to the smartcore tree):
+//   Euclidian::squared_distance  src/metrics/distance/euclidian.rs:51-66
+//       diff and square in TX, widened per element to f64, sequential f64 sum, never fused.
+//   kmeans_plus_plus             src/cluster/kmeans.rs:354-413
+//   predict                      src/cluster/kmeans.rs:327-352
+//   BBDTree::clustering          src/algorithm/neighbour/bbd_tree.rs:62-163 (dense equivalent)
+#include "sckm_common.cuh"
+#include "sckm_blobs.cuh"
+#include <cfloat>
+#include <cstdarg>
+
+namespace sckm {
+
+// ------------------------------------------------------------------------------------------
+// small device helpers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// (a-b)^2 with the reference's rounding: subtract and multiply in TX, widen to f64 (no FMA)
+__device__ __forceinline__ double sqdiff(double a, double b) {
+    double r = __dsub_rn(a, b);
+    return __dmul_rn(r, r);
+}
+__device__ __forceinline__ double sqdiff(float a, float b) {
+    float r = __fsub_rn(a, b);
+    return (double)__fmul_rn(r, r);
+}
+
+template <typename T> struct Vec16;  // 16-byte vector of T
+template <> struct Vec16<double> { using type = double2; static constexpr int N = 2; };
+template <> struct Vec16<float>  { using type = float4;  static constexpr int N = 4; };
+
+// pitch (in 16-byte units) of a staged row: odd, so that 8 lanes reading 16 B at consecutive rows
+// hit 8 distinct 16-byte bank groups (conflict-free LDS.128)
+__host__ __device__ inline uint32_t slab_pitch16(uint32_t row_bytes) { return (row_bytes / 16) | 1; }
+
+// ------------------------------------------------------------------------------------------
+// warp-level staging: 32 consecutive rows (a contiguous block in HBM) -> per-warp smem slab
+// with padded pitch, using 16-byte cp.async (coalesced: consecutive lanes, consecutive 16 B).
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void stage_rows_vec(const T* __restrict__ x, uint64_t row0, uint32_t nrows,
+                                               uint32_t d, unsigned char* slab, uint32_t pitch16, int lane) {
+    const uint32_t chunks_per_row = d * sizeof(T) / 16;
+    const uint32_t total = nrows * chunks_per_row;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(x + row0 * d);
+    for (uint32_t c = lane; c < total; c += 32) {
+        uint32_t r = c / chunks_per_row, q = c - r * chunks_per_row;
+        cp_async16(slab + ((size_t)r * pitch16 + q) * 16, src + (size_t)c * 16);
+    }
+    cp_async_wait_all();
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------------------------------
+// K5: kmeans++ D^2 refresh (kmeans.rs:368-379 / 399-410) + per-1024-row block sums (kmeans.rs:381-384)
+// One CTA per 1024-row block, 4 warps, each warp stages 32 rows at a time; one lane = one row.
+// TX arithmetic for diff/square, f64 sequential accumulation over the features: bit-identical D^2.
+// ------------------------------------------------------------------------------------------
+constexpr int KPP_WARPS = 4;
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(KPP_WARPS * 32)
+kpp_refresh_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __restrict__ seedrow,
+                   double* __restrict__ mind, uint32_t* __restrict__ labels, uint32_t label, int first_pass,
+                   double* __restrict__ blocksum, uint32_t pitch16) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    T* cent = reinterpret_cast<T*>(smem);                       // [d] (padded to 16 B)
+    const uint32_t cent_bytes = (d * sizeof(T) + 15) / 16 * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* slab = smem + cent_bytes + (size_t)warp * 32 * pitch16 * 16;
+    __shared__ double warp_part[KPP_WARPS];
+
+    for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) cent[j] = seedrow[j];
+    __syncthreads();
+
+    const uint64_t block_row0 = (uint64_t)blockIdx.x * kKppBlockRows;
+    double acc_rows = 0.0;  // this lane's rows of the block, in ascending row order
+    for (int t = 0; t < kKppBlockRows / (KPP_WARPS * 32); t++) {
+        const uint64_t row0 = block_row0 + (uint64_t)(t * KPP_WARPS + warp) * 32;
+        if (row0 >= n) break;
+        const uint32_t nrows = (uint32_t)min((uint64_t)32, n - row0);
+        double dist = 0.0;
+        if (VEC) {
+            stage_rows_vec<T>(x, row0, nrows, d, slab, pitch16, lane);
+            if (lane < nrows) {
+                using V = typename Vec16<T>::type;
+                const V* xr = reinterpret_cast<const V*>(slab + (size_t)lane * pitch16 * 16);
+                const V* cr = reinterpret_cast<const V*>(cent);
+                const uint32_t nv = d / Vec16<T>::N;
+                for (uint32_t q = 0; q < nv; q++) {
+                    V xv = xr[q], cv = cr[q];
+                    const T* xe = reinterpret_cast<const T*>(&xv);
+                    const T* ce = reinterpret_cast<const T*>(&cv);
+#pragma unroll
+                    for (int e = 0; e < Vec16<T>::N; e++) dist = __dadd_rn(dist, sqdiff(xe[e], ce[e]));
+                }
+            }
+            __syncwarp();
+        } else {
+            if (lane < nrows) {
+                const T* xr = x + (row0 + lane) * d;
+                for (uint32_t j = 0; j < d; j++) dist = __dadd_rn(dist, sqdiff(xr[j], cent[j]));
+            }
+        }
+        if (lane < nrows) {
+            const uint64_t r = row0 + lane;
+            double old = first_pass ? DBL_MAX : mind[r];
+            if (first_pass) labels[r] = 0;
+            if (dist < old) { old = dist; mind[r] = dist; labels[r] = label; }
+            else if (first_pass) mind[r] = old;
+            acc_rows = __dadd_rn(acc_rows, old);
+        }
+    }
+    // fixed-order block reduction: lanes (xor tree), then warps 0..3 sequentially
+    double v = acc_rows;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) warp_part[warp] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < KPP_WARPS; w++) s = __dadd_rn(s, warp_part[w]);
+        blocksum[blockIdx.x] = s;
+    }
+}
+
+// rank total = fixed-order reduction of the block sums (one CTA)
+__global__ void __launch_bounds__(1024) kpp_total_kernel(const double* __restrict__ blocksum, uint32_t nb,
+                                                         double* __restrict__ totals, int rank) {
+    __shared__ double sh[1024];
+    const uint32_t per = (nb + 1023) / 1024;
+    const uint32_t b0 = threadIdx.x * per, b1 = min(nb, b0 + per);
+    double s = 0.0;
+    for (uint32_t b = b0; b < b1; b++) s = __dadd_rn(s, blocksum[b]);
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {  // 32 lanes x 32 chunk sums sequentially, then lane 0 sequentially
+        double t = 0.0;
+        for (int i = 0; i < 32; i++) t = __dadd_rn(t, sh[threadIdx.x * 32 + i]);
+        sh[threadIdx.x * 32] = t;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (int i = 0; i < 32; i++) t = __dadd_rn(t, sh[i * 32]);
+        totals[rank] = t;
+    }
+}
+
+// Select the next seed row (kmeans.rs:385-396).  Every rank runs it with the same (all-gathered)
+// totals; only the owner walks its D^2 array: thread-chunk sums -> block -> row, always as a running
+// `cost += ...; if cost >= cutoff break` like the reference, at three granularities.
+// Publishes [row elements | global index] into seedbuf on the owner and zeros elsewhere.
+template <typename T>
+__global__ void __launch_bounds__(1024)
+kpp_select_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, uint64_t row_offset, uint64_t n_global,
+                  const double* __restrict__ mind, const double* __restrict__ blocksum, uint32_t nb,
+                  const double* __restrict__ totals, int nranks, int rank, double u, long long inject_row,
+                  unsigned char* __restrict__ seedbuf, uint32_t seed_words, long long* __restrict__ seeds,
+                  uint32_t slot) {
+    __shared__ double sh[1024];
+    __shared__ long long s_local;  // local row chosen on this rank, or -1
+    unsigned long long* out = reinterpret_cast<unsigned long long*>(seedbuf);
+    for (uint32_t w = threadIdx.x; w < seed_words; w += blockDim.x) out[w] = 0ull;
+    if (threadIdx.x == 0) s_local = -1;
+    __syncthreads();
+
+    if (inject_row >= 0) {
+        if (threadIdx.x == 0 && (uint64_t)inject_row >= row_offset && (uint64_t)inject_row < row_offset + n)
+            s_local = inject_row - (long long)row_offset;
+    } else {
+        // global total and owner, sequential over ranks (same on every rank)
+        double total = 0.0;
+        for (int r = 0; r < nranks; r++) total = __dadd_rn(total, totals[r]);
+        const double cutoff = __dmul_rn(u, total);
+        double run = 0.0; int owner = -1;
+        for (int r = 0; r < nranks; r++) {
+            double nxt = __dadd_rn(run, totals[r]);
+            if (nxt >= cutoff) { owner = r; break; }
+            run = nxt;
+        }
+        if (owner < 0) {  // rounding left the running cost below the cutoff: clamp to the last row
+            owner = nranks - 1;
+            // the last rank with any rows owns the clamp
+        }
+        if (owner == rank && n > 0) {
+            const uint32_t per = (nb + 1023) / 1024;
+            const uint32_t b0 = min(nb, threadIdx.x * per), b1 = min(nb, b0 + per);
+            double s = 0.0;
+            for (uint32_t b = b0; b < b1; b++) s = __dadd_rn(s, blocksum[b]);
+            sh[threadIdx.x] = s;
+            __syncthreads();
+            __shared__ uint32_t s_block;
+            __shared__ double s_cost;
+            if (threadIdx.x == 0) {
+                double cost = run; uint32_t chunk = 1024;
+                for (uint32_t c = 0; c < 1024; c++) {
+                    double nxt = __dadd_rn(cost, sh[c]);
+                    if (nxt >= cutoff && min(nb, c * per) < nb) { chunk = c; break; }
+                    cost = nxt;
+                }
+                uint32_t blk = nb;  // not found -> clamp
+                if (chunk < 1024) {
+                    const uint32_t cb0 = chunk * per, cb1 = min(nb, cb0 + per);
+                    blk = cb1 - 1;
+                    for (uint32_t b = cb0; b < cb1; b++) {
+                        double nxt = __dadd_rn(cost, blocksum[b]);
+                        if (nxt >= cutoff) { blk = b; break; }
+                        cost = nxt;
+                    }
+                }
+                s_block = blk; s_cost = cost;
+            }
+            __syncthreads();
+            const uint32_t blk = s_block;
+            if (blk >= nb) {
+                if (threadIdx.x == 0) s_local = (long long)n - 1;
+            } else {
+                const uint64_t r0 = (uint64_t)blk * kKppBlockRows;
+                const uint32_t cnt = (uint32_t)min((uint64_t)kKppBlockRows, n - r0);
+                __syncthreads();
+                if (threadIdx.x < cnt) sh[threadIdx.x] = mind[r0 + threadIdx.x];
+                __syncthreads();
+                if (threadIdx.x == 0) {
+                    double cost = s_cost; long long pick = (long long)(r0 + cnt - 1);
+                    for (uint32_t i = 0; i < cnt; i++) {
+                        cost = __dadd_rn(cost, sh[i]);
+                        if (cost >= cutoff) { pick = (long long)(r0 + i); break; }
+                    }
+                    s_local = pick;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const long long loc = s_local;
+    if (loc >= 0) {
+        T* orow = reinterpret_cast<T*>(seedbuf);
+        for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) orow[j] = x[(uint64_t)loc * d + j];
+        if (threadIdx.x == 0) out[seed_words - 1] = (unsigned long long)(loc + (long long)row_offset);
+    }
+    if (threadIdx.x == 0) seeds[slot] = loc >= 0 ? loc + (long long)row_offset : 0;
+    (void)n_global;
+}
+
+// ------------------------------------------------------------------------------------------
+// K7 / direct Lloyd assignment: argmin_j squared_distance(row widened to f64, centroid_j), strict <,
+// lowest index wins (kmeans.rs:334-347).  One lane = one row, rows staged per warp; centroids are
+// streamed through shared memory in chunks and read as broadcasts.
+// ------------------------------------------------------------------------------------------
+constexpr int ASG_WARPS = 4;
+
+template <typename T, bool VEC>
+__global__ void __launch_bounds__(ASG_WARPS * 32)
+assign_direct_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
+                     uint32_t k, uint32_t kc, uint32_t* __restrict__ labels, double* __restrict__ mind,
+                     uint32_t pitch16) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    double* cbuf = reinterpret_cast<double*>(smem);                       // [kc][d]
+    const size_t cbuf_bytes = ((size_t)kc * d * sizeof(double) + 15) / 16 * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* slab = smem + cbuf_bytes + (size_t)warp * 32 * pitch16 * 16;
+
+    const uint64_t tile_rows = ASG_WARPS * 32;
+    const uint64_t ntiles = (n + tile_rows - 1) / tile_rows;
+    for (uint64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const uint64_t row0 = tile * tile_rows + (uint64_t)warp * 32;
+        const uint32_t nrows = row0 < n ? (uint32_t)min((uint64_t)32, n - row0) : 0u;
+        if (VEC && nrows) stage_rows_vec<T>(x, row0, nrows, d, slab, pitch16, lane);
+        double best = DBL_MAX; uint32_t bi = 0;
+        for (uint32_t c0 = 0; c0 < k; c0 += kc) {
+            const uint32_t cn = min(kc, k - c0);
+            __syncthreads();  // previous chunk fully consumed
+            for (uint32_t e = threadIdx.x; e < cn * d; e += blockDim.x) cbuf[e] = centroids[(size_t)c0 * d + e];
+            __syncthreads();
+            if (lane < nrows) {
+                for (uint32_t c = 0; c < cn; c++) {
+                    const double* cr = cbuf + (size_t)c * d;
+                    double dist = 0.0;
+                    if (VEC) {
+                        using V = typename Vec16<T>::type;
+                        const V* xr = reinterpret_cast<const V*>(slab + (size_t)lane * pitch16 * 16);
+                        const uint32_t nv = d / Vec16<T>::N;
+                        for (uint32_t q = 0; q < nv; q++) {
+                            V xv = xr[q];
+                            const T* xe = reinterpret_cast<const T*>(&xv);
+#pragma unroll
+                            for (int e = 0; e < Vec16<T>::N; e++)
+                                dist = __dadd_rn(dist, sqdiff((double)xe[e], cr[q * Vec16<T>::N + e]));
+                        }
+                    } else {
+                        const T* xr = x + (row0 + lane) * d;
+                        for (uint32_t j = 0; j < d; j++) dist = __dadd_rn(dist, sqdiff((double)xr[j], cr[j]));
+                    }
+                    if (dist < best) { best = dist; bi = c0 + c; }
+                }
+            }
+        }
+        if (lane < nrows) {
+            labels[row0 + lane] = bi;
+            if (mind) mind[row0 + lane] = best;
+        }
+        __syncwarp();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: deterministic per-label sums / counts / inertia.  CTA p owns a contiguous run of rows and a
+// private partial [k*d | k | 1] in global memory (L2 resident); thread j owns feature j (j+blockDim, ...)
+// and walks the rows in ascending order, so the summation order is fixed by (n, grid) alone.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void update_partial_kernel(const T* __restrict__ x, uint64_t n, uint32_t d,
+                                      const uint32_t* __restrict__ labels, const double* __restrict__ mind,
+                                      uint32_t k, uint64_t rows_per_cta, double* __restrict__ partials) {
+    const size_t pk = (size_t)k * d + k + 1;
+    double* part = partials + (size_t)blockIdx.x * pk;
+    const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_cta;
+    const uint64_t r1 = min(n, r0 + rows_per_cta);
+    double inertia = 0.0;
+    for (uint64_t r = r0; r < r1; r++) {
+        const uint32_t lbl = labels[r];
+        double* prow = part + (size_t)lbl * d;
+        const T* xr = x + r * d;
+        for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) prow[j] = __dadd_rn(prow[j], (double)xr[j]);
+        if (threadIdx.x == 0) {
+            double* pc = part + (size_t)k * d + lbl;
+            *pc = *pc + 1.0;
+            if (mind) inertia = __dadd_rn(inertia, mind[r]);
+        }
+    }
+    if (threadIdx.x == 0) part[pk - 1] = inertia;
+}
+
+// packed[e] = sum over partial slots in slot order; the slots are zeroed for the next step.
+__global__ void reduce_partials_kernel(double* __restrict__ partials, uint32_t nslots, size_t pk,
+                                       double* __restrict__ packed) {
+    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= pk) return;
+    double s = 0.0;
+    for (uint32_t p = 0; p < nslots; p++) {
+        double* q = partials + (size_t)p * pk + e;
+        s = __dadd_rn(s, *q);
+        *q = 0.0;
+    }
+    packed[e] = s;
+}
+
+// K6: centroids = sums / counts (kmeans.rs:288-292 unguarded, :297-303 guarded), sizes, ||c||^2
+__global__ void finalize_kernel(const double* __restrict__ packed, uint32_t k, uint32_t d, int guarded,
+                                double* __restrict__ centroids, double* __restrict__ cnorm,
+                                long long* __restrict__ size) {
+    const uint32_t c = blockIdx.x;
+    const double cnt = packed[(size_t)k * d + c];
+    if (threadIdx.x == 0) size[c] = (long long)cnt;
+    if (!guarded || cnt > 0.0)
+        for (uint32_t j = threadIdx.x; j < d; j += blockDim.x)
+            centroids[(size_t)c * d + j] = __ddiv_rn(packed[(size_t)c * d + j], cnt);
+    __syncthreads();
+    if (threadIdx.x == 0 && cnorm) {
+        double s = 0.0;
+        for (uint32_t j = 0; j < d; j++) { double v = centroids[(size_t)c * d + j]; s = fma(v, v, s); }
+        cnorm[c] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// layout / generation / misc
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void transpose_kernel(const T* __restrict__ src, T* __restrict__ dst, uint64_t n, uint64_t d) {
+    // src: column-major (d columns of n), dst: row-major n x d; 32x32 tiles through shared memory
+    __shared__ T tile[32][33];
+    const uint64_t r0 = (uint64_t)blockIdx.x * 32, c0 = (uint64_t)blockIdx.y * 32;
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        uint64_t c = c0 + i, r = r0 + threadIdx.x;
+        if (c < d && r < n) tile[i][threadIdx.x] = src[c * n + r];
+    }
+    __syncthreads();
+    for (int i = threadIdx.y; i < 32; i += blockDim.y) {
+        uint64_t r = r0 + i, c = c0 + threadIdx.x;
+        if (r < n && c < d) dst[r * d + c] = tile[threadIdx.x][i];
+    }
+}
+
+template <typename T>
+__global__ void blobs_kernel(T* __restrict__ x, uint64_t row0, uint64_t nrows, uint64_t d, uint64_t n_centers,
+                             uint64_t seed) {
+    const uint64_t total = nrows * d;
+    for (uint64_t e = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (uint64_t)gridDim.x * blockDim.x) {
+        const uint64_t r = e / d, c = e - r * d;
+        x[e] = (T)blob_value(seed, n_centers, row0 + r, c);
+    }
+}
+
+__global__ void widen_labels_kernel(const uint32_t* __restrict__ in, unsigned long long* __restrict__ out, uint64_t n) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x)
+        out[i] = in[i];
+}
+
+// ------------------------------------------------------------------------------------------
+// peak micro-kernels (roofline denominators measured on this very device)
+// ------------------------------------------------------------------------------------------
+__global__ void copy_kernel(const double2* __restrict__ a, double2* __restrict__ b, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) b[i] = a[i];
+}
+__global__ void __launch_bounds__(256) dfma_peak_kernel(double* out, int iters) {
+    double a[8];
+    const double m = 1.0000001, c = 1e-9 * threadIdx.x;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a[i] = threadIdx.x * 1e-3 + i;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++) a[i] = fma(a[i], m, c);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += a[i];
+    if (s == 12345.678) out[0] = s;
+}
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters) {
+    double a = threadIdx.x * 1e-3, b = threadIdx.x * 2e-3;
+    double c[8][2];
+#pragma unroll
+    for (int i = 0; i < 8; i++) { c[i][0] = i; c[i][1] = -i; }
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 8; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                         : "+d"(c[i][0]), "+d"(c[i][1]) : "d"(a), "d"(b));
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) s += c[i][0] + c[i][1];
+    if (s == 12345.678) out[0] = s;
+}
+
+// ------------------------------------------------------------------------------------------
+// host side: error text, workspaces, launchers
+// ------------------------------------------------------------------------------------------
+static thread_local std::string g_create_err;
+const char* create_error_text() { return g_create_err.c_str(); }
+
+int fail(sckm_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[1024];
+    va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+    if (ctx) ctx->err = buf; else g_create_err = buf;
+    return code;
+}
+
+#define LAUNCH_CHECK(ctx)                                                                          \
+    do {                                                                                           \
+        (ctx)->launches++;                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess)                                                                     \
+            return fail((ctx), SCKM_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+template <typename P> static int regrow(sckm_ctx* ctx, P** p, size_t* cap, size_t need_elems, size_t elem) {
+    if (need_elems <= *cap && *p) return SCKM_OK;
+    if (*p) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); SCKM_CUDA(ctx, cudaFree(*p)); *p = nullptr; }
+    SCKM_CUDA(ctx, cudaMalloc((void**)p, need_elems * elem));
+    SCKM_CUDA(ctx, cudaMemsetAsync(*p, 0, need_elems * elem, ctx->stream));
+    *cap = need_elems;
+    return SCKM_OK;
+}
+
+int ensure_workspace(sckm_ctx* ctx, uint64_t k, uint64_t d, size_t partial_slots) {
+    const size_t kd = (size_t)k * d, pk = kd + k + 1;
+    SCKM_TRY(regrow(ctx, &ctx->d_centroids, &ctx->cap_centroids, kd, sizeof(double)));
+    SCKM_TRY(regrow(ctx, &ctx->d_packed, &ctx->cap_packed, pk, sizeof(double)));
+    SCKM_TRY(regrow(ctx, &ctx->d_cnorm, &ctx->cap_cnorm, k, sizeof(double)));
+    SCKM_TRY(regrow(ctx, &ctx->d_size, &ctx->cap_size, k, sizeof(int64_t)));
+    SCKM_TRY(regrow(ctx, &ctx->d_seeds, &ctx->cap_seeds, k, sizeof(int64_t)));
+    if (partial_slots)
+        SCKM_TRY(regrow(ctx, &ctx->d_partials, &ctx->cap_partials, partial_slots * pk, sizeof(double)));
+    return SCKM_OK;
+}
+
+static bool vec_ok(uint64_t d, int dtype) { return (d * (dtype == SCKM_F32 ? 4 : 8)) % 16 == 0; }
+
+int launch_transpose(sckm_ctx* ctx, const void* src, void* dst, uint64_t n, uint64_t d, int dtype) {
+    dim3 grid((unsigned)((n + 31) / 32), (unsigned)((d + 31) / 32)), block(32, 8);
+    if (dtype == SCKM_F32) transpose_kernel<float><<<grid, block, 0, ctx->stream>>>((const float*)src, (float*)dst, n, d);
+    else transpose_kernel<double><<<grid, block, 0, ctx->stream>>>((const double*)src, (double*)dst, n, d);
+    LAUNCH_CHECK(ctx);
+    return SCKM_OK;
+}
+
+int launch_blobs(sckm_ctx* ctx, void* x, int dtype, uint64_t row0, uint64_t nrows, uint64_t d,
+                 uint64_t n_centers, uint64_t seed) {
+    const int grid = ctx->num_sms * 8;
+    if (dtype == SCKM_F32) blobs_kernel<float><<<grid, 256, 0, ctx->stream>>>((float*)x, row0, nrows, d, n_centers, seed);
+    else blobs_kernel<double><<<grid, 256, 0, ctx->stream>>>((double*)x, row0, nrows, d, n_centers, seed);
+    LAUNCH_CHECK(ctx);
+    return SCKM_OK;
+}
+
+template <typename K> static int set_smem(sckm_ctx* ctx, K kernel, size_t bytes) {
+    if (bytes > 48 * 1024) SCKM_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return SCKM_OK;
+}
+
+template <typename T>
+static int kpp_refresh_t(sckm_dataset* ds, uint32_t label, bool first_pass) {
+    sckm_ctx* ctx = ds->ctx;
+    const uint32_t d = (uint32_t)ds->d;
+    const uint32_t nb = (uint32_t)((ds->n + kKppBlockRows - 1) / kKppBlockRows);
+    const uint32_t row_bytes = d * sizeof(T), pitch16 = slab_pitch16(row_bytes);
+    const size_t cent_bytes = ((size_t)row_bytes + 15) / 16 * 16;
+    const size_t smem_vec = cent_bytes + (size_t)KPP_WARPS * 32 * pitch16 * 16;
+    const bool vec = vec_ok(d, ds->dtype) && smem_vec <= (size_t)ctx->smem_optin;
+    if (nb) {
+        if (vec) {
+            SCKM_TRY(set_smem(ctx, kpp_refresh_kernel<T, true>, smem_vec));
+            kpp_refresh_kernel<T, true><<<nb, KPP_WARPS * 32, smem_vec, ctx->stream>>>(
+                (const T*)ds->x, ds->n, d, (const T*)ctx->d_seedrow, ds->mind, ds->labels, label, first_pass ? 1 : 0,
+                ctx->d_blocksum, pitch16);
+        } else {
+            if (cent_bytes > (size_t)ctx->smem_optin) return fail(ctx, SCKM_ERR_INVALID, "d=%u too large", d);
+            SCKM_TRY(set_smem(ctx, kpp_refresh_kernel<T, false>, cent_bytes));
+            kpp_refresh_kernel<T, false><<<nb, KPP_WARPS * 32, cent_bytes, ctx->stream>>>(
+                (const T*)ds->x, ds->n, d, (const T*)ctx->d_seedrow, ds->mind, ds->labels, label, first_pass ? 1 : 0,
+                ctx->d_blocksum, pitch16);
+        }
+        LAUNCH_CHECK(ctx);
+    }
+    kpp_total_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_blocksum, nb, ctx->d_totals, ctx->rank);
+    LAUNCH_CHECK(ctx);
+    return SCKM_OK;
+}
+
+int launch_kpp_refresh(sckm_dataset* ds, uint32_t label, bool first_pass) {
+    return ds->dtype == SCKM_F32 ? kpp_refresh_t<float>(ds, label, first_pass) : kpp_refresh_t<double>(ds, label, first_pass);
+}
+
+int launch_kpp_select(sckm_dataset* ds, double u, int64_t inject_row, uint32_t slot) {
+    sckm_ctx* ctx = ds->ctx;
+    const uint32_t nb = (uint32_t)((ds->n + kKppBlockRows - 1) / kKppBlockRows);
+    const uint32_t seed_words = (uint32_t)(ctx->cap_seedrow / 8);
+    if (ds->dtype == SCKM_F32)
+        kpp_select_kernel<float><<<1, 1024, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d, ds->row_offset,
+            ds->n_global, ds->mind, ctx->d_blocksum, nb, ctx->d_totals, ctx->nranks, ctx->rank, u, (long long)inject_row,
+            (unsigned char*)ctx->d_seedrow, seed_words, (long long*)ctx->d_seeds, slot);
+    else
+        kpp_select_kernel<double><<<1, 1024, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d, ds->row_offset,
+            ds->n_global, ds->mind, ctx->d_blocksum, nb, ctx->d_totals, ctx->nranks, ctx->rank, u, (long long)inject_row,
+            (unsigned char*)ctx->d_seedrow, seed_words, (long long*)ctx->d_seeds, slot);
+    LAUNCH_CHECK(ctx);
+    return SCKM_OK;
+}
+
+template <typename T>
+static int assign_direct_t(sckm_ctx* ctx, const void* x, int dtype, uint64_t n, uint64_t d64, uint64_t k64,
+                           uint32_t* labels, double* mind) {
+    if (n == 0) return SCKM_OK;
+    const uint32_t d = (uint32_t)d64, k = (uint32_t)k64;
+    const uint32_t row_bytes = d * sizeof(T), pitch16 = slab_pitch16(row_bytes);
+    // centroid chunk streamed through shared memory: <= 16 KB, at least one centroid
+    const uint32_t kc = (uint32_t)std::max<uint64_t>(1, std::min<uint64_t>(k, (16 * 1024) / ((uint64_t)d * sizeof(double))));
+    const size_t cbuf_bytes = ((size_t)kc * d * sizeof(double) + 15) / 16 * 16;
+    const size_t smem_vec = cbuf_bytes + (size_t)ASG_WARPS * 32 * pitch16 * 16;
+    const bool vec = vec_ok(d, dtype) && smem_vec <= (size_t)ctx->smem_optin;
+    const uint64_t ntiles = (n + ASG_WARPS * 32 - 1) / (ASG_WARPS * 32);
+    const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)ctx->num_sms * 16);
+    if (vec) {
+        SCKM_TRY(set_smem(ctx, assign_direct_kernel<T, true>, smem_vec));
+        assign_direct_kernel<T, true><<<grid, ASG_WARPS * 32, smem_vec, ctx->stream>>>(
+            (const T*)x, n, d, ctx->d_centroids, k, kc, labels, mind, pitch16);
+    } else {
+        if (cbuf_bytes > (size_t)ctx->smem_optin) return fail(ctx, SCKM_ERR_INVALID, "d=%u too large", d);
+        SCKM_TRY(set_smem(ctx, assign_direct_kernel<T, false>, cbuf_bytes));
+        assign_direct_kernel<T, false><<<grid, ASG_WARPS * 32, cbuf_bytes, ctx->stream>>>(
+            (const T*)x, n, d, ctx->d_centroids, k, kc, labels, mind, pitch16);
+    }
+    LAUNCH_CHECK(ctx);
+    return SCKM_OK;
+}
+
+int launch_assign_direct_raw(sckm_ctx* ctx, const void* x, int dtype, uint64_t n, uint64_t d, uint64_t k,
+                             uint32_t* labels, double* mind) {
+    return dtype == SCKM_F32 ? assign_direct_t<float>(ctx, x, dtype, n, d, k, labels, mind)
+                             : assign_direct_t<double>(ctx, x, dtype, n, d, k, labels, mind);
+}
+
+int launch_assign_direct(sckm_dataset* ds, uint64_t k) {
+    return launch_assign_direct_raw(ds->ctx, ds->x, ds->dtype, ds->n, ds->d, k, ds->labels, ds->mind);
+}
+
+static uint32_t update_slots(const sckm_ctx* ctx, uint64_t n) {
+    uint64_t p = (n + 63) / 64;
+    uint64_t cap = (uint64_t)ctx->num_sms * 16;
+    return (uint32_t)std::max<uint64_t>(1, std::min(p, cap));
+}
+
+int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia) {
+    sckm_ctx* ctx = ds->ctx;
+    const uint32_t slots = update_slots(ctx, ds->n);
+    SCKM_TRY(ensure_workspace(ctx, k, ds->d, slots));
+    const size_t pk = (size_t)k * ds->d + k + 1;
+    const uint64_t rows_per_cta = (ds->n + slots - 1) / slots;
+    const unsigned threads = (unsigned)std::min<uint64_t>(256, (ds->d + 31) / 32 * 32);
+    if (ds->n) {
+        if (ds->dtype == SCKM_F32)
+            update_partial_kernel<float><<<slots, threads, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d,
+                ds->labels, with_inertia ? ds->mind : nullptr, (uint32_t)k, rows_per_cta, ctx->d_partials);
+        else
+            update_partial_kernel<double><<<slots, threads, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d,
+                ds->labels, with_inertia ? ds->mind : nullptr, (uint32_t)k, rows_per_cta, ctx->d_partials);
+        LAUNCH_CHECK(ctx);
+    }
+    reduce_partials_kernel<<<(unsigned)((pk + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_partials, slots, pk, ctx->d_packed);
+    LAUNCH_CHECK(ctx);
+    return SCKM_OK;
+}
+
+int launch_finalize(sckm_ctx* ctx, uint64_t k, uint64_t d, bool guarded) {
+    const unsigned threads = (unsigned)std::min<uint64_t>(256, (d + 31) / 32 * 32);
+    finalize_kernel<<<(unsigned)k, threads, 0, ctx->stream>>>(ctx->d_packed, (uint32_t)k, (uint32_t)d, guarded ? 1 : 0,
+                                                            ctx->d_centroids, ctx->d_cnorm, (long long*)ctx->d_size);
+    LAUNCH_CHECK(ctx);
+    return SCKM_OK;
+}
+
+int launch_labels_widen(sckm_ctx* ctx, const uint32_t* in, uint64_t* out, uint64_t n) {
+    if (!n) return SCKM_OK;
+    widen_labels_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(in, (unsigned long long*)out, n);
+    LAUNCH_CHECK(ctx);
+    return SCKM_OK;
+}
+
+int measure_peaks(sckm_ctx* ctx, double* out3) {
+    float ms = 0;
+    // HBM copy: 1 GiB read + 1 GiB write, best of 5
+    const size_t bytes = (size_t)1 << 30;
+    void *a = nullptr, *b = nullptr;
+    SCKM_CUDA(ctx, cudaMalloc(&a, bytes)); SCKM_CUDA(ctx, cudaMalloc(&b, bytes));
+    SCKM_CUDA(ctx, cudaMemsetAsync(a, 1, bytes, ctx->stream));
+    double best = 0;
+    for (int it = 0; it < 6; it++) {
+        SCKM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        copy_kernel<<<ctx->num_sms * 16, 512, 0, ctx->stream>>>((const double2*)a, (double2*)b, bytes / 16);
+        ctx->launches++;
+        SCKM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        SCKM_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+        SCKM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (it) best = std::max(best, 2.0 * bytes / (ms * 1e-3) / 1e9);
+    }
+    out3[0] = best;
+    cudaFree(a); cudaFree(b);
+    const int iters = 4096;
+    for (int which = 0; which < 2; which++) {
+        best = 0;
+        for (int it = 0; it < 4; it++) {
+            SCKM_CUDA(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+            if (which == 0) dfma_peak_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>((double*)ctx->d_flags, iters);
+            else dmma_peak_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>((double*)ctx->d_flags, iters);
+            ctx->launches++;
+            SCKM_CUDA(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+            SCKM_CUDA(ctx, cudaEventSynchronize(ctx->ev1));
+            SCKM_CUDA(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            const double threads = (double)ctx->num_sms * 8 * 256;
+            const double flops = which == 0 ? threads * iters * 8 * 2.0            // 8 DFMA / thread / iter
+                                            : (threads / 32) * iters * 8 * 512.0;  // 8 m8n8k4 / warp / iter
+            if (it) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+        }
+        out3[1 + which] = best;
+    }
+    return SCKM_OK;
+}
+
+}  // namespace sckm

@@ -1,0 +1,142 @@
+// smartcore_host_shim.cpp -- flat C entry points over the C++ host mirror (smartcore_kmeans.hpp) so
+// that Python (tests/, bench.py, smartcore_b200/cluster.py) can drive KMeans::fit / predict exactly as
+// a Rust caller would.  No arithmetic here: validation + RNG draws live in the header, the compute in
+// libsmartcore_kmeans_cuda.so.
+#include "smartcore_kmeans.hpp"
+#include <cstring>
+
+using namespace smartcore;
+using smartcore::cluster::kmeans::KMeansParameters;
+using smartcore::cluster::kmeans::KMeansSearchParameters;
+using smartcore::linalg::basic::matrix::DenseMatrix;
+
+namespace {
+enum { SCH_F32 = 0, SCH_F64 = 1, SCH_I32 = 2, SCH_I64 = 3 };
+
+struct Model {  // type-erased KMeans<TX, usize>
+    int dtype;
+    cluster::kmeans::KMeans<float, size_t> f32;
+    cluster::kmeans::KMeans<double, size_t> f64;
+    cluster::kmeans::KMeans<int32_t, size_t> i32;
+    cluster::kmeans::KMeans<int64_t, size_t> i64;
+};
+
+void set_err(char* buf, size_t len, const std::string& s) {
+    if (!buf || !len) return;
+    size_t m = s.size() < len - 1 ? s.size() : len - 1;
+    memcpy(buf, s.data(), m); buf[m] = 0;
+}
+
+template <typename T> DenseMatrix<T> wrap(const void* values, size_t nrows, size_t ncols, int column_major) {
+    const T* v = (const T*)values;
+    return DenseMatrix<T>::new_(nrows, ncols, std::vector<T>(v, v + nrows * ncols), column_major != 0).unwrap();
+}
+
+template <typename T, typename M>
+int do_fit(M& slot, const void* values, size_t nrows, size_t ncols, int column_major, const KMeansParameters& p,
+           char* err, size_t errlen) {
+    auto x = wrap<T>(values, nrows, ncols, column_major);
+    auto r = cluster::kmeans::KMeans<T, size_t>::fit(x, p);
+    if (r.is_err()) { set_err(err, errlen, r.unwrap_err().to_string()); return 1; }
+    slot = std::move(r.unwrap());
+    return 0;
+}
+
+template <typename T, typename M>
+int do_predict(const M& m, const void* values, size_t nrows, size_t ncols, int column_major, int64_t* out,
+               char* err, size_t errlen) {
+    auto x = wrap<T>(values, nrows, ncols, column_major);
+    auto r = m.predict(x);
+    if (r.is_err()) { set_err(err, errlen, r.unwrap_err().to_string()); return 1; }
+    for (size_t i = 0; i < nrows; i++) out[i] = (int64_t)r.unwrap()[i];
+    return 0;
+}
+}  // namespace
+
+extern "C" {
+
+// KMeans::fit(&DenseMatrix::new(nrows, ncols, values, column_major), KMeansParameters{k, max_iter, seed})
+int sch_kmeans_fit(int dtype, const void* values, size_t nrows, size_t ncols, int column_major, size_t k,
+                   size_t max_iter, int has_seed, uint64_t seed, void** model_out, char* err, size_t errlen) {
+    KMeansParameters p; p.k = k; p.max_iter = max_iter;
+    if (has_seed) p.seed = seed;
+    Model* m = new Model(); m->dtype = dtype;
+    int rc = 2;
+    switch (dtype) {
+        case SCH_F32: rc = do_fit<float>(m->f32, values, nrows, ncols, column_major, p, err, errlen); break;
+        case SCH_F64: rc = do_fit<double>(m->f64, values, nrows, ncols, column_major, p, err, errlen); break;
+        case SCH_I32: rc = do_fit<int32_t>(m->i32, values, nrows, ncols, column_major, p, err, errlen); break;
+        case SCH_I64: rc = do_fit<int64_t>(m->i64, values, nrows, ncols, column_major, p, err, errlen); break;
+        default: set_err(err, errlen, "unsupported dtype");
+    }
+    if (rc) { delete m; return rc; }
+    *model_out = m;
+    return 0;
+}
+
+int sch_kmeans_predict(void* model, const void* values, size_t nrows, size_t ncols, int column_major, int64_t* out,
+                       char* err, size_t errlen) {
+    Model* m = (Model*)model;
+    switch (m->dtype) {
+        case SCH_F32: return do_predict<float>(m->f32, values, nrows, ncols, column_major, out, err, errlen);
+        case SCH_F64: return do_predict<double>(m->f64, values, nrows, ncols, column_major, out, err, errlen);
+        case SCH_I32: return do_predict<int32_t>(m->i32, values, nrows, ncols, column_major, out, err, errlen);
+        case SCH_I64: return do_predict<int64_t>(m->i64, values, nrows, ncols, column_major, out, err, errlen);
+    }
+    return 2;
+}
+
+#define WITH_MODEL(m, expr)                                   \
+    switch (((Model*)m)->dtype) {                             \
+        case SCH_F32: { auto& M = ((Model*)m)->f32; expr; } break; \
+        case SCH_F64: { auto& M = ((Model*)m)->f64; expr; } break; \
+        case SCH_I32: { auto& M = ((Model*)m)->i32; expr; } break; \
+        default:      { auto& M = ((Model*)m)->i64; expr; } break; \
+    }
+
+// field access (the reference's fields are private; in-crate tests read kmeans._y -- kmeans.rs:503)
+void sch_kmeans_dims(void* model, size_t* k, size_t* n, size_t* d) {
+    WITH_MODEL(model, { *k = M.k; *n = M._y.size(); *d = M.centroids.empty() ? 0 : M.centroids[0].size(); })
+}
+void sch_kmeans_get(void* model, int64_t* y, int64_t* size, double* centroids, double* distortion, int64_t* iters) {
+    WITH_MODEL(model, {
+        if (y) for (size_t i = 0; i < M._y.size(); i++) y[i] = (int64_t)M._y[i];
+        if (size) for (size_t i = 0; i < M.size.size(); i++) size[i] = (int64_t)M.size[i];
+        if (centroids) { size_t o = 0; for (auto& row : M.centroids) for (double v : row) centroids[o++] = v; }
+        if (distortion) *distortion = M._distortion;
+        if (iters) *iters = M._iterations;
+    })
+}
+void sch_kmeans_free(void* model) { delete (Model*)model; }
+
+// KMeansSearchParameters{k, max_iter, seed}.into_iter() flattened; returns the number of items written
+size_t sch_search_parameters(const size_t* k, size_t nk, const size_t* max_iter, size_t nm, const uint64_t* seed,
+                             const int* has_seed, size_t ns, size_t* out_k, size_t* out_max_iter, uint64_t* out_seed,
+                             int* out_has_seed, size_t cap) {
+    KMeansSearchParameters sp;
+    sp.k.assign(k, k + nk); sp.max_iter.assign(max_iter, max_iter + nm); sp.seed.clear();
+    for (size_t i = 0; i < ns; i++) sp.seed.push_back(has_seed[i] ? std::optional<uint64_t>(seed[i]) : std::nullopt);
+    auto it = sp.into_iter();
+    size_t n = 0;
+    while (auto p = it.next()) {
+        if (n >= cap) break;
+        out_k[n] = p->k; out_max_iter[n] = p->max_iter; out_has_seed[n] = p->seed.has_value(); out_seed[n] = p->seed.value_or(0);
+        n++;
+    }
+    return n;
+}
+
+// the host RNG draw sequence of kmeans_plus_plus for (seed, n, k): first index + k-1 uniforms
+void sch_kmeanspp_draws(int has_seed, uint64_t seed, uint64_t n, size_t k, uint64_t* first, double* uniforms) {
+    auto rng = rand_custom::get_rng_impl(has_seed ? std::optional<uint64_t>(seed) : std::nullopt);
+    *first = rng.gen_range(n);
+    for (size_t j = 0; j + 1 < k; j++) uniforms[j] = rng.gen_f64();
+}
+
+// DenseMatrix::get over both layouts (matrix.rs:367-381), f64 only; for layout tests
+double sch_dense_get_f64(const double* values, size_t nrows, size_t ncols, int column_major, size_t r, size_t c) {
+    DenseMatrix<double> m; m.nrows = nrows; m.ncols = ncols; m.column_major = column_major != 0;
+    return column_major ? values[c * nrows + r] : values[c + ncols * r];
+}
+
+}  // extern "C"

@@ -1,0 +1,111 @@
+"""CPU: host-side mirror of the reference API (validation, RNG draws, grid iterator, layouts), the
+C-ABI library's exported symbols, and loud failure without a GPU.  No device compute here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import smartcore_b200 as sc
+from smartcore_b200 import cabi, cluster, dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "smartcore_kmeans_cuda.h")).read()
+    declared = sorted(set(re.findall(r"\b(sckm_[a-z0-9_]+)\s*\(", header)))
+    assert declared, "no declarations found"
+    lib = ctypes.CDLL(cabi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), "libsmartcore_kmeans_cuda.so does not export %s" % name
+    assert sorted(cabi.SYMBOLS) == declared
+    assert lib.sckm_abi_version() == 1
+
+
+def test_no_cpu_fallback_when_device_missing():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    with pytest.raises(sc.SckmError) as e:
+        sc.Context(0)
+    assert "no CPU fallback" in str(e.value)
+    with pytest.raises(sc.Failed) as e2:
+        sc.KMeans.fit(sc.DenseMatrix.from_2d_array([[1.0, 2.0], [3.0, 4.0], [5.0, 6.0]]), sc.KMeansParameters())
+    assert str(e2.value).startswith("Fit failed: CUDA backend unavailable")
+
+
+def test_product_package_never_touches_the_oracle():
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "smartcore_b200")):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".hpp", ".h")):
+                src = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in src.lower(), "%s mentions the oracle" % f
+
+
+def test_invalid_k(kat):  # kmeans.rs:426-443 (i32 matrix, validation before any device work)
+    x = sc.DenseMatrix.from_2d_array([[1, 2, 3], [4, 5, 6]], dtype=np.int32)
+    with pytest.raises(sc.Failed):
+        sc.KMeans.fit(x, sc.KMeansParameters.default().with_k(0))
+    with pytest.raises(sc.Failed) as e:
+        sc.KMeans.fit(x, sc.KMeansParameters.default().with_k(1))
+    assert str(e.value) == kat["invalid_k_message"]
+    with pytest.raises(sc.Failed) as e:
+        sc.KMeans.fit(x, sc.KMeansParameters.default().with_max_iter(0))
+    assert str(e.value) == "Fit failed: invalid maximum number of iterations: 0"
+
+
+def test_search_parameters():  # kmeans.rs:446-466
+    it = iter(sc.KMeansSearchParameters(k=[2, 4], max_iter=[10, 100]))
+    got = [(p.k, p.max_iter) for p in it]
+    assert got == [(2, 10), (4, 10), (2, 100), (4, 100)]
+    got = [(p.k, p.max_iter, p.seed) for p in sc.KMeansSearchParameters(k=[2, 3], max_iter=[5], seed=[None, 7])]
+    assert got == [(2, 5, None), (3, 5, None), (2, 5, 7), (3, 5, 7)]
+    d = sc.KMeansParameters.default()
+    assert (d.k, d.max_iter, d.seed) == (2, 100, None)
+
+
+def test_host_rng_draws_match_oracle_rng(O):
+    for seed, n, k in [(None, 150, 3), (42, 150, 3), (7, 10**7, 256), (2**63 + 5, 12345, 17)]:
+        first, u = cluster.kmeanspp_draws(seed, n, k)
+        r = O.Rng(0 if seed is None else seed)
+        assert first == r.gen_range(n)
+        assert u.tolist() == [r.gen_f64() for _ in range(k - 1)]
+
+
+def test_dense_matrix_layouts():
+    a = np.arange(12, dtype=np.float64).reshape(4, 3)
+    cm = sc.DenseMatrix.from_2d_array(a)          # column-major (matrix.rs:230-236)
+    rm = sc.DenseMatrix.new(4, 3, a.reshape(-1), False)
+    assert cm.column_major and not rm.column_major
+    assert cm.values.tolist() == a.T.reshape(-1).tolist()
+    for r in range(4):
+        for c in range(3):
+            assert cm.get((r, c)) == a[r, c] == rm.get((r, c))
+    with pytest.raises(sc.Failed):
+        sc.DenseMatrix.new(4, 3, np.zeros(11), True)
+
+
+def test_blob_generator_host_twin():
+    a = cabi.blobs_host(0, 64, 8, 4, 20260101)
+    b = cabi.blobs_host(16, 8, 8, 4, 20260101)
+    assert np.array_equal(a[16:24], b)            # any row regenerates independently of the shard
+    assert not np.array_equal(a, cabi.blobs_host(0, 64, 8, 4, 20260102))
+    f = cabi.blobs_host(0, 64, 8, 4, 20260101, dtype=np.float32)
+    assert np.array_equal(f, a.astype(np.float32))
+    big = cabi.blobs_host(0, 4000, 4, 4, 1)
+    for c in range(4):                             # centre + N(0,1); centres in [-10, 10)
+        pts = big[c::4]
+        assert np.all(np.abs(pts.mean(0)) < 10.2) and np.all(np.abs(pts.std(0) - 1.0) < 0.1)
+
+
+def test_shard_range_partitions_rows():
+    for n in (0, 1, 150, 1024, 1025, 10**6 + 7, 10**7):
+        for world in (1, 2, 3, 4, 8):
+            spans = [dist.shard_range(n, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            for (a0, a1), (b0, b1) in zip(spans, spans[1:]):
+                assert a1 == b0 and a0 <= a1
+            for lo, hi in spans[:-1]:
+                assert (hi - lo) % dist.SHARD_ALIGN == 0 or hi == n

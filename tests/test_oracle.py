@@ -1,0 +1,136 @@
+"""CPU: the oracle restatement against every known-answer the reference's own tests hold for the
+hot path and against the committed regression fixtures."""
+import numpy as np
+import pytest
+
+
+def test_xoshiro256pp_upstream_vector(O, kat):
+    r = O.Rng(0, state=[1, 2, 3, 4])
+    assert [r.next_u64() for _ in range(10)] == kat["xoshiro256pp_state_1234"]
+
+
+def test_splitmix_seeding_candidate(O, kat):
+    r = O.Rng(0, mode=O.SEED_MODE_SPLITMIX)
+    assert list(r.state) == kat["splitmix_seed0_state"]
+    assert [r.next_u64() for _ in range(4)] == kat["splitmix_seed0_out"]
+
+
+def test_pcg_seeding_is_deterministic_and_distinct(O):
+    a, b = O.Rng(42), O.Rng(42)
+    assert [a.next_u64() for _ in range(8)] == [b.next_u64() for _ in range(8)]
+    assert list(O.Rng(42).state) != list(O.Rng(42, mode=O.SEED_MODE_SPLITMIX).state)
+    assert list(O.Rng(0).state) != [0, 0, 0, 0]
+
+
+def test_gen_f64_and_gen_range_bounds(O):
+    r = O.Rng(7)
+    us = [r.gen_f64() for _ in range(2000)]
+    assert 0.0 <= min(us) and max(us) < 1.0 and 0.4 < np.mean(us) < 0.6
+    for n in (1, 2, 3, 150, 10**7, 2**40 + 17):
+        vals = [r.gen_range(n) for _ in range(200)]
+        assert 0 <= min(vals) and max(vals) < n
+    # Standard f64 = top 53 bits * 2^-53
+    r1, r2 = O.Rng(9), O.Rng(9)
+    assert r1.gen_f64() == (r2.next_u64() >> 11) * 2.0 ** -53
+
+
+def test_squared_distance_kat(O, kat):  # euclidian.rs:84-91 (i32 inputs -> f64)
+    k = kat["squared_distance"]
+    a = np.array(k["a"], dtype=np.int32); b = np.array(k["b"], dtype=np.int32)
+    assert abs(O.squared_distance(a, b) ** 0.5 - k["l2"]) < k["tol"]
+    assert O.squared_distance(a.astype(np.float64), b.astype(np.float64)) == 27.0
+
+
+def test_squared_distance_f32_rounds_in_f32(O):
+    a = np.array([0.1, 0.7, 1e-3], dtype=np.float32); b = np.array([0.3, -0.2, 5.0], dtype=np.float32)
+    want = 0.0
+    for x, y in zip(a, b):
+        r = np.float32(x - y)
+        want += float(np.float32(r * r))
+    assert O.squared_distance(a, b) == want
+
+
+def test_bbdtree_iris_golden(O, kat, iris20):  # bbd_tree.rs:324-364
+    g = kat["bbdtree_iris"]
+    tree = O.BBDTree(iris20)
+    dist, sums, counts, mem = tree.clustering(g["centroids"])
+    assert abs(dist - g["cost"]) < g["cost_tol"]
+    assert abs(sums[0][0] - g["sums_0_0"]) < g["sums_tol"]
+    assert abs(sums[1][3] - g["sums_1_3"]) < g["sums_tol"]
+    assert mem[17] == g["membership_17"]
+    assert counts.sum() == 20
+
+
+def test_tree_equals_dense_step(O, iris_f32):
+    x = iris_f32[0].astype(np.float64)
+    rng = np.random.default_rng(1)
+    tree = O.BBDTree(x)
+    for k in (2, 3, 7):
+        c = x[rng.choice(150, k, replace=False)] + 0.01
+        dt, st, ct, mt = tree.clustering(c)
+        db, sb, cb, mb, gap = O.brute_clustering(x, c, want_gap=True)
+        bad = mt != mb
+        assert np.all(gap[bad] < 1e-12)
+        assert np.array_equal(ct, cb) or bad.any()
+        np.testing.assert_allclose(st, sb, rtol=1e-12, atol=1e-12)
+        assert abs(dt - db) <= 1e-11 * abs(db)
+
+
+def test_fit_predict_self_consistency(O, iris20):  # kmeans.rs:473-505, any seed
+    for seed in (0, 1, 42, 12345):
+        for mode in (0, 1):
+            r = O.fit(iris20, 2, 100, seed, mode)
+            assert np.array_equal(O.predict(iris20, r.centroids), r.y)
+            assert r.size.sum() == 20 and r.iters >= 1
+
+
+def test_invalid_parameters(O, kat):  # kmeans.rs:426-443
+    x = np.array([[1, 2, 3], [4, 5, 6]], dtype=np.float64)
+    with pytest.raises(ValueError):
+        O.fit(x, 0)
+    with pytest.raises(ValueError) as e:
+        O.fit(x, 1)
+    assert str(e.value) == kat["invalid_k_message"]
+    with pytest.raises(ValueError) as e:
+        O.fit(x, 2, max_iter=0)
+    assert str(e.value) == "Fit failed: invalid maximum number of iterations: 0"
+
+
+def test_regression_fixtures(O, oracle_fits, iris_f32, iris20):
+    data = {"iris_f64_k3_seed42": iris_f32[0].astype(np.float64), "iris_f32_k3_seed42": iris_f32[0],
+            "iris20_f64_k2_seedNone": iris20}
+    for name, g in oracle_fits.items():
+        base, mode = name.rsplit("_mode", 1)
+        r = O.fit(data[base], g["k"], 100, g["seed"], int(mode))
+        assert r.y.tolist() == g["y"] and r.size.tolist() == g["size"] and r.iters == g["iters"]
+        assert r.seed_idx.tolist() == g["seed_idx"]
+        assert r.distortion == g["distortion"]
+        np.testing.assert_array_equal(r.centroids, np.array(g["centroids"]))
+
+
+def test_injected_seed_rows_bypass_rng(O, iris_f32):
+    x = iris_f32[0].astype(np.float64)
+    r = O.fit(x, 3, 100, 42)
+    r2 = O.fit(x, 3, 100, 999, inject=r.seed_idx)
+    assert np.array_equal(r.y, r2.y) and r.distortion == r2.distortion
+
+
+def test_duplicate_rows_leaf_rule(O):
+    # duplicate points form a leaf whose sum is first point x count (bbd_tree.rs:234-246)
+    x = np.array([[1.0, 1.0]] * 5 + [[4.0, 4.0]] * 3 + [[9.0, 0.5]])
+    tree = O.BBDTree(x)
+    dist, sums, counts, mem = tree.clustering([[1.0, 1.1], [4.2, 4.0], [9.0, 0.0]])
+    assert counts.tolist() == [5, 3, 1] and mem.tolist() == [0] * 5 + [1] * 3 + [2]
+    np.testing.assert_allclose(sums, [[5, 5], [12, 12], [9, 0.5]])
+    db = O.brute_clustering(x, [[1.0, 1.1], [4.2, 4.0], [9.0, 0.0]])[0]
+    assert abs(dist - db) < 1e-12
+
+
+def test_kmeanspp_labels_are_nearest_seed(O, iris_f32):
+    x = iris_f32[0]
+    y, idx, dd = O.kmeanspp(x, 4, seed=3)
+    seeds = x[idx].astype(np.float32)
+    for i in range(150):
+        ds = [O.squared_distance(x[i], s) for s in seeds]
+        assert dd[i] == min(ds)
+        assert y[i] == int(np.argmin(ds))  # strict <: first minimum wins

@@ -1,0 +1,277 @@
+#!/usr/bin/env python
+"""bench.py -- Lloyd point-iterations/sec on BASELINE.json's headline config.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU algorithm (oracle)
+
+A "step" is one Lloyd iteration (assignment + per-cluster sums/counts + all-reduce + centroid update +
+inertia) over all rows.  Workload at every N: config C3 of BASELINE.json, synthetic Gaussian blobs
+10M x 64, k = 256, f64, PER GPU (weak scaling: rank r holds rows [r*10M, (r+1)*10M) of an N*10M-row
+matrix; the only data-path collective is one NCCL all-reduce of [k*d sums | k counts | inertia] per step).
+
+  value : n_global * K / T, T = CUDA-event time of the K timed steps on the library's stream (max over
+          ranks), X resident in HBM.  Inputs (5.12 GB/GPU) are far larger than L2, so no flush is needed.
+  e2e   : the same metric through the reference-facing call sequence of KMeans::fit with HOST buffers:
+          upload of X from pinned host memory + kmeans++ + initial means + Lloyd loop (reference stop
+          rule, max_iter = K) + download of labels/centroids, all inside the timed region.
+  roofline : the assignment kernel (dominant), 2*k*d flops per point against the FP64 peak measured by
+          the library's own DFMA/DMMA micro-kernels on this GPU (MEASURED_PEAKS.json has no FP64 figure).
+  cpu_baseline : the CPU oracle (a port of smartcore's BBD-tree path; rustc is not available) timed on
+          this host, single-threaded like the reference, on a row sub-sample with the same k and d.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_PER_GPU, D, K_CLUSTERS, DATA_SEED, KMEANS_SEED = 10_000_000, 64, 256, 20260101, 42
+CPU_SAMPLE_ROWS = 100_000
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=N_PER_GPU, help="rows per GPU (default: config C3)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:  # noqa: BLE001
+                pass
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        # samples while the GPU is busy are the upper half of the clock distribution
+        busy = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_oracle_run(steps, warmup, rows):
+    """The reference's algorithm (BBD-tree filter) on this host: single thread, row sub-sample."""
+    from oracle import oracle_py as O
+    from smartcore_b200 import cabi
+    x = cabi.blobs_host(0, rows, D, K_CLUSTERS, DATA_SEED)
+    t0 = time.perf_counter()
+    tree = O.BBDTree(x)
+    t_tree = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    y, idx, _ = O.kmeanspp(x, K_CLUSTERS, seed=KMEANS_SEED)
+    t_kpp = time.perf_counter() - t0
+    cent = np.zeros((K_CLUSTERS, D))
+    for c in range(K_CLUSTERS):
+        cent[c] = x[y == c].mean(0) if np.any(y == c) else x[idx[c]]
+    for _ in range(warmup):
+        dist, sums, counts, _ = tree.clustering(cent)
+        nz = counts > 0
+        cent[nz] = sums[nz] / counts[nz, None]
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        dist, sums, counts, _ = tree.clustering(cent)
+        nz = counts > 0
+        cent[nz] = sums[nz] / counts[nz, None]
+    t_steps = time.perf_counter() - t0
+    return dict(rows=rows, t_tree=t_tree, t_kpp=t_kpp, t_steps=t_steps, steps=steps,
+                value=rows * steps / t_steps, e2e=rows * steps / (t_tree + t_kpp + t_steps))
+
+
+def reference_arm(args, world, rank):
+    if rank != 0:
+        return
+    r = cpu_oracle_run(args.steps, args.warmup, CPU_SAMPLE_ROWS)
+    cores = 1
+    line = {
+        "impl": "reference", "metric": "lloyd_point_iters_per_sec", "value": r["value"], "unit": "point-iters/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * r["t_steps"] / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "C3 blobs 10M x 64 k=256 f64 per GPU (BASELINE.json configs[2])", "k": K_CLUSTERS, "d": D,
+                   "sample_rows": r["rows"]},
+        "cpu_baseline": {"value": r["value"], "unit": "point-iters/s", "cores": cores, "kind": "port",
+                         "sample": "%d-row sub-sample of the C3 blobs, same k=%d d=%d; BBD-tree path of smartcore restated in "
+                                   "C++ (oracle/), single thread like the reference; host has %d cores; tree build %.2fs, "
+                                   "kmeans++ %.2fs" % (r["rows"], K_CLUSTERS, D, os.cpu_count(), r["t_tree"], r["t_kpp"])},
+        "e2e": {"value": r["e2e"], "unit": "point-iters/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    world, rank, local_rank = (int(os.environ.get(v, d)) for v, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    if args.impl == "reference":
+        return reference_arm(args, world, rank)
+
+    import torch
+    import smartcore_b200 as sc
+    from smartcore_b200 import cluster, dist as scd
+
+    torch.cuda.set_device(local_rank)
+    distributed = world > 1
+    if distributed:
+        import torch.distributed as tdist
+        tdist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if distributed:
+            tdist.barrier()
+        torch.cuda.synchronize()
+
+    ctx = sc.Context(local_rank)
+    if distributed:
+        scd.join_comm(ctx)
+    n_local, k, d = args.rows, K_CLUSTERS, D
+    n_global = n_local * world
+    row0 = rank * n_local
+
+    peaks = ctx.device_peaks()
+    ds = ctx.generate_blobs(n_local, d, k, DATA_SEED, row_offset=row0, n_global=n_global)
+    first, uniforms = cluster.kmeanspp_draws(KMEANS_SEED, n_global, k)
+    t0 = time.perf_counter()
+    ds.kmeanspp(k, first, uniforms)
+    cent0, _ = ds.init_centroids(k)
+    t_init = time.perf_counter() - t0
+
+    if args.warmup:
+        ds.lloyd_iterate(cent0, args.warmup)
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    l0 = ctx.launch_count()
+    w0 = time.perf_counter()
+    out = ds.lloyd_iterate(cent0, args.steps)
+    barrier()
+    wall = time.perf_counter() - w0
+    launches = ctx.launch_count() - l0
+    clocks = sampler.stop()
+    t_dev = float(out["ms"].sum()) * 1e-3
+    t_assign = float(out["assign_ms"].mean()) * 1e-3
+    if distributed:
+        t_dev = scd.max_over_ranks(t_dev)
+        t_assign = scd.max_over_ranks(t_assign)
+        wall = scd.max_over_ranks(wall)
+    value = n_global * args.steps / t_dev
+
+    # ---- e2e: KMeans::fit call sequence from pinned host buffers (per rank: its shard) ----
+    e2e = None
+    if not args.no_e2e:
+        host = torch.empty((n_local, d), dtype=torch.float64, pin_memory=True)
+        hx = host.numpy()
+        chunk = 1 << 20
+        for r in range(0, n_local, chunk):
+            m = min(chunk, n_local - r)
+            hx[r:r + m] = ds.download_rows(r, m)
+        ds.close()
+        barrier()
+        e0 = time.perf_counter()
+        ds2 = ctx.upload(hx, column_major=False, row_offset=row0, n_global=n_global)
+        t_up = time.perf_counter() - e0
+        ds2.kmeanspp(k, first, uniforms)
+        c0, _ = ds2.init_centroids(k)
+        t_seed = time.perf_counter() - e0 - t_up
+        fit = ds2.lloyd_fit(c0, args.steps)
+        labels = ds2.labels(width=8)
+        barrier()
+        t_e2e = time.perf_counter() - e0
+        if distributed:
+            t_e2e = scd.max_over_ranks(t_e2e)
+        e2e = {"value": n_global * fit["iters"] / t_e2e, "unit": "point-iters/s",
+               "h2d_bytes_per_step": int(hx.nbytes // max(fit["iters"], 1)),
+               "d2h_bytes_per_step": int((labels.nbytes + fit["centroids"].nbytes) // max(fit["iters"], 1)),
+               "detail": {"what": "upload(pinned host) + kmeans++ + init means + Lloyd loop (stop rule, max_iter=steps) + "
+                                  "labels/centroids download; bytes are per fit divided by iterations executed",
+                          "iters": int(fit["iters"]), "total_s": t_e2e, "upload_s": t_up, "kmeanspp_init_s": t_seed,
+                          "distortion": fit["distortion"]}}
+        ds2.close()
+    else:
+        ds.close()
+
+    cpu = None
+    if rank == 0 and not args.no_cpu:
+        r = cpu_oracle_run(5, 1, CPU_SAMPLE_ROWS)
+        cpu = {"value": r["value"], "unit": "point-iters/s", "cores": 1, "kind": "port",
+               "sample": "%d-row sub-sample, same k and d, 5 timed BBD-tree clustering steps (oracle/ C++ port of "
+                         "smartcore's path; single thread like the reference; host has %d cores); tree build %.2fs"
+                         % (r["rows"], os.cpu_count(), r["t_tree"])}
+
+    if rank == 0:
+        flops_per_launch = 2.0 * n_local * k * d
+        fp64_peak = max(peaks["fp64_dfma_tflops"], peaks["fp64_dmma_tflops"])
+        achieved = flops_per_launch / t_assign / 1e12
+        hbm_bytes = n_local * (d * 8 + 4)
+        try:
+            mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            mp = {}
+        line = {
+            "metric": "lloyd_point_iters_per_sec", "value": value, "unit": "point-iters/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "C3 blobs 10M x 64 k=256 f64 per GPU (BASELINE.json configs[2])", "n_per_gpu": n_local,
+                       "n_global": n_global, "d": d, "k": k, "l2": "inputs (5.12 GB/GPU) larger than L2; no flush",
+                       "parallelism": "rows sharded x%d, one NCCL all-reduce of k*d+k+1 f64 per step" % world,
+                       "kmeanspp_init_s": t_init, "wall_s_timed_region": wall},
+            "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "kernel": "assignment kernel (dominant), CUDA events on the library stream, mean of %d launches" % args.steps,
+                         "kernel_ms": 1e3 * t_assign,
+                         "peak_source": "FP64 peak measured now by the library's DFMA/DMMA micro-kernels (dfma %.1f, dmma %.1f "
+                                        "TFLOP/s); MEASURED_PEAKS.json carries no FP64 figure" % (peaks["fp64_dfma_tflops"], peaks["fp64_dmma_tflops"]),
+                         "hbm": {"achieved_gbs": hbm_bytes / t_assign / 1e9, "peak_gbs": mp.get("hbm_gbs", 6650.0),
+                                 "peak_source": "MEASURED_PEAKS.json" if mp else "fallback (B200_PROFILING.md)",
+                                 "copy_gbs_measured_now": peaks["hbm_copy_gbs"]}},
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if distributed:
+        tdist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -121,10 +121,12 @@ int sckm_lloyd_step(sckm_dataset* ds, const double* centroids, uint64_t k, doubl
 int sckm_lloyd_fit(sckm_dataset* ds, uint64_t k, uint64_t max_iter, double* centroids_inout,
                    int64_t* size_out, double* distortion_out, int64_t* iters_out);
 /* Same loop with the stop rule disabled (exactly n_iters steps) and device timing:
- * ms_per_iter_out[n_iters] (nullable) are CUDA-event times on the context's stream.
- * inertia_out (nullable) gets n_iters values. */
+ * ms_per_iter_out[n_iters] (nullable) are CUDA-event times of each whole iteration on the context's
+ * stream, assign_ms_out[n_iters] (nullable) those of the assignment kernel alone (the dominant
+ * kernel, for the roofline).  inertia_out (nullable) gets n_iters values. */
 int sckm_lloyd_iterate(sckm_dataset* ds, uint64_t k, uint64_t n_iters, double* centroids_inout,
-                       int64_t* size_out, double* inertia_out, float* ms_per_iter_out);
+                       int64_t* size_out, double* inertia_out, float* ms_per_iter_out,
+                       float* assign_ms_out);
 
 /* Labels of this rank's rows; width = 4 (uint32_t) or 8 (uint64_t, Rust usize). */
 int sckm_labels_download(sckm_dataset* ds, void* out, int width);

@@ -56,7 +56,7 @@ def _load():
     L.sckm_init_centroids.argtypes = [vp, u64, vp, vp]
     L.sckm_lloyd_step.argtypes = [vp, vp, u64, vp, vp, vp]
     L.sckm_lloyd_fit.argtypes = [vp, u64, u64, vp, vp, vp, vp]
-    L.sckm_lloyd_iterate.argtypes = [vp, u64, u64, vp, vp, vp, vp]
+    L.sckm_lloyd_iterate.argtypes = [vp, u64, u64, vp, vp, vp, vp, vp]
     L.sckm_labels_download.argtypes = [vp, vp, i32]
     L.sckm_mindist_download.argtypes = [vp, vp]
     L.sckm_predict.argtypes = [vp, vp, u64, u64, i32, i32, vp, u64, vp, i32]
@@ -227,9 +227,10 @@ class Dataset:
     def lloyd_iterate(self, centroids, n_iters, want_inertia=False):
         c = np.array(centroids, dtype=np.float64, order="C"); k = c.shape[0]
         size = np.zeros(k, dtype=np.int64); ms = np.zeros(n_iters, dtype=np.float32)
+        ams = np.zeros(n_iters, dtype=np.float32)
         inertia = np.zeros(n_iters) if want_inertia else None
-        self.ctx._check(lib.sckm_lloyd_iterate(self.h, k, n_iters, _p(c), _p(size), _p(inertia), _p(ms)))
-        return dict(centroids=c, size=size, ms=ms, inertia=inertia)
+        self.ctx._check(lib.sckm_lloyd_iterate(self.h, k, n_iters, _p(c), _p(size), _p(inertia), _p(ms), _p(ams)))
+        return dict(centroids=c, size=size, ms=ms, assign_ms=ams, inertia=inertia)
 
     def labels(self, width=8):
         out = np.empty(self.n, dtype=np.uint64 if width == 8 else np.uint32)

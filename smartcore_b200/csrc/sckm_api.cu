@@ -64,7 +64,7 @@ void sckm_ctx_destroy(sckm_ctx* ctx) {
     nccl_destroy(ctx);
     cudaFree(ctx->d_centroids); cudaFree(ctx->d_cnorm); cudaFree(ctx->d_packed); cudaFree(ctx->d_partials);
     cudaFree(ctx->d_size); cudaFree(ctx->d_blocksum); cudaFree(ctx->d_totals); cudaFree(ctx->d_seedrow);
-    cudaFree(ctx->d_seeds); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush);
+    cudaFree(ctx->d_seeds); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush); cudaFree(ctx->d_flagrows);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -260,11 +260,13 @@ static int pick_assign(const sckm_dataset* ds, uint64_t k) {
 }
 
 // one clustering step on the device: labels, packed = all-reduced [sums | counts | inertia]
-static int clustering_step(sckm_dataset* ds, uint64_t k) {
+static int clustering_step(sckm_dataset* ds, uint64_t k, cudaEvent_t ev_a0 = nullptr, cudaEvent_t ev_a1 = nullptr) {
     sckm_ctx* ctx = ds->ctx;
     const int which = pick_assign(ds, k);
+    if (ev_a0) SCKM_CUDA(ctx, cudaEventRecord(ev_a0, ctx->stream));
     if (which == SCKM_ASSIGN_DMMA) SCKM_TRY(launch_assign_dmma(ds, k));
     else SCKM_TRY(launch_assign_direct(ds, k));
+    if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
     SCKM_TRY(launch_update(ds, k, true));
     SCKM_TRY(nccl_allreduce_f64(ctx, ctx->d_packed, (size_t)k * ds->d + k + 1));
     ds->have_labels = true;
@@ -312,7 +314,7 @@ int sckm_lloyd_step(sckm_dataset* ds, const double* centroids, uint64_t k, doubl
 
 static int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop, double* centroids_inout,
                       int64_t* size_out, double* distortion_out, int64_t* iters_out, double* inertia_trace,
-                      float* ms_trace) {
+                      float* ms_trace, float* assign_ms_trace = nullptr) {
     sckm_ctx* ctx = ds->ctx;
     SCKM_TRY(check_k(ds, k));
     if (max_iter == 0) return fail(ctx, SCKM_ERR_INVALID, "max_iter must be >= 1");
@@ -323,20 +325,25 @@ static int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool hono
         SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->d_centroids, centroids_inout, kd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     double distortion = DBL_MAX;
     int64_t iters = 0;
-    std::vector<cudaEvent_t> evs;
+    std::vector<cudaEvent_t> evs, evs_a;
+    if (assign_ms_trace) {
+        evs_a.resize(2 * max_iter);
+        for (auto& e : evs_a) SCKM_CUDA(ctx, cudaEventCreate(&e));
+    }
     if (ms_trace) {
         evs.resize(max_iter + 1);
         for (auto& e : evs) SCKM_CUDA(ctx, cudaEventCreate(&e));
         SCKM_CUDA(ctx, cudaEventRecord(evs[0], ctx->stream));
     }
     for (uint64_t it = 1; it <= max_iter; it++) {
-        SCKM_TRY(clustering_step(ds, k));                         // bbd.clustering(...)        kmeans.rs:296
+        if (assign_ms_trace) SCKM_TRY(clustering_step(ds, k, evs_a[2 * (it - 1)], evs_a[2 * (it - 1) + 1]));
+        else SCKM_TRY(clustering_step(ds, k));                    // bbd.clustering(...)        kmeans.rs:296
         SCKM_TRY(launch_finalize(ctx, k, ds->d, /*guarded=*/true));  // centroids = sums / size   kmeans.rs:297-303
         iters++;
         if (ms_trace) SCKM_CUDA(ctx, cudaEventRecord(evs[it], ctx->stream));
         if (honor_stop || inertia_trace) {
             SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_packed + kd + k, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            if (honor_stop || it == max_iter || true) SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+            SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
             const double dist = ctx->h_pinned[0];
             if (inertia_trace) inertia_trace[it - 1] = dist;
             if (honor_stop) {
@@ -353,6 +360,10 @@ static int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool hono
         for (int64_t i = 0; i < iters; i++) SCKM_CUDA(ctx, cudaEventElapsedTime(&ms_trace[i], evs[i], evs[i + 1]));
         for (auto& e : evs) cudaEventDestroy(e);
     }
+    if (assign_ms_trace) {
+        for (int64_t i = 0; i < iters; i++) SCKM_CUDA(ctx, cudaEventElapsedTime(&assign_ms_trace[i], evs_a[2 * i], evs_a[2 * i + 1]));
+        for (auto& e : evs_a) cudaEventDestroy(e);
+    }
     if (distortion_out) *distortion_out = distortion;
     if (iters_out) *iters_out = iters;
     return SCKM_OK;
@@ -365,9 +376,10 @@ int sckm_lloyd_fit(sckm_dataset* ds, uint64_t k, uint64_t max_iter, double* cent
 }
 
 int sckm_lloyd_iterate(sckm_dataset* ds, uint64_t k, uint64_t n_iters, double* centroids_inout,
-                       int64_t* size_out, double* inertia_out, float* ms_per_iter_out) {
+                       int64_t* size_out, double* inertia_out, float* ms_per_iter_out, float* assign_ms_out) {
     if (!ds || !centroids_inout) return SCKM_ERR_INVALID;
-    return lloyd_loop(ds, k, n_iters, false, centroids_inout, size_out, nullptr, nullptr, inertia_out, ms_per_iter_out);
+    return lloyd_loop(ds, k, n_iters, false, centroids_inout, size_out, nullptr, nullptr, inertia_out, ms_per_iter_out,
+                      assign_ms_out);
 }
 
 static int download_labels(sckm_ctx* ctx, const uint32_t* d_labels, uint64_t n, void* out, int width) {

@@ -45,6 +45,8 @@ struct sckm_ctx {
     size_t cap_seedrow = 0;
     int64_t* d_seeds = nullptr;      // [k] chosen global rows
     unsigned long long* d_flags = nullptr;  // [8] misc device counters (near-tie count, ...)
+    uint32_t* d_flagrows = nullptr;  // rows flagged as near-ties by the GEMM-form kernel
+    size_t cap_flagrows = 0;
     void* d_flush = nullptr;         // L2 flush buffer
     size_t flush_bytes = 0;
     double* h_pinned = nullptr;      // small pinned scratch (>= 64 doubles)

@@ -480,7 +480,7 @@ int ensure_workspace(sckm_ctx* ctx, uint64_t k, uint64_t d, size_t partial_slots
     const size_t kd = (size_t)k * d, pk = kd + k + 1;
     SCKM_TRY(regrow(ctx, &ctx->d_centroids, &ctx->cap_centroids, kd, sizeof(double)));
     SCKM_TRY(regrow(ctx, &ctx->d_packed, &ctx->cap_packed, pk, sizeof(double)));
-    SCKM_TRY(regrow(ctx, &ctx->d_cnorm, &ctx->cap_cnorm, k, sizeof(double)));
+    SCKM_TRY(regrow(ctx, &ctx->d_cnorm, &ctx->cap_cnorm, k + 1, sizeof(double)));  // [k] norms + max
     SCKM_TRY(regrow(ctx, &ctx->d_size, &ctx->cap_size, k, sizeof(int64_t)));
     SCKM_TRY(regrow(ctx, &ctx->d_seeds, &ctx->cap_seeds, k, sizeof(int64_t)));
     if (partial_slots)

@@ -1,0 +1,238 @@
+"""GPU (-m gpu): the CUDA path against the CPU oracle, through the C ABI.
+
+Bars (BASELINE.json north_star): kmeans++ D^2 values, predict labels and direct-form Lloyd labels are
+BIT-EXACT; GEMM-form Lloyd labels are identical except where the oracle's (second-best)/best squared
+distance gap is < 1e-12 relative; centroids and inertia agree within 1e-9 relative (f64)."""
+import numpy as np
+import pytest
+
+import smartcore_b200 as sc
+from smartcore_b200 import cabi, cluster
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-9       # centroids / inertia, f64 (north_star)
+GAP_TOL = 1e-12   # label tolerance, relative best/second-best gap (north_star)
+
+
+def blobs(n, d, k, seed, dtype=np.float64, spread=4.0):
+    rng = np.random.default_rng(seed)
+    centers = rng.uniform(-10, 10, size=(k, d))
+    x = centers[np.arange(n) % k] * (spread / 4.0) + rng.normal(size=(n, d))
+    return x.astype(dtype)
+
+
+def assert_labels_match(got, want, gap):
+    bad = np.nonzero(np.asarray(got, dtype=np.int64) != np.asarray(want, dtype=np.int64))[0]
+    assert np.all(gap[bad] < GAP_TOL), "labels differ at %d rows with gap >= %g" % (len(bad), GAP_TOL)
+
+
+# ---- kmeans++ ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,k,dtype", [(150, 4, 3, np.float64), (150, 4, 3, np.float32), (1000, 16, 8, np.float64),
+                                         (5000, 7, 5, np.float64), (4097, 3, 4, np.float32), (33, 64, 6, np.float64)])
+def test_kmeanspp_bit_exact(ctx, O, n, d, k, dtype):
+    x = blobs(n, d, k, 100 + n + d, dtype)
+    first, u = cluster.kmeanspp_draws(42, n, k)
+    ds = ctx.upload(x)
+    seeds = ds.kmeanspp(k, first, u)
+    y_o, idx_o, dd_o = O.kmeanspp(x, k, seed=42)
+    assert seeds.tolist() == idx_o.tolist()
+    assert np.array_equal(ds.labels(), y_o.astype(np.uint64))
+    assert np.array_equal(ds.mindist(), dd_o)          # bit-identical D^2 (euclidian.rs:56-63 rounding)
+    ds.close()
+
+
+def test_kmeanspp_injected_rows_and_iris(ctx, O, iris_f32):
+    x = iris_f32[0]
+    inj = np.array([7, 77, 140, 3])
+    for data in (x, x.astype(np.float64)):
+        ds = ctx.upload(data)
+        seeds = ds.kmeanspp(4, inject_rows=inj)
+        y_o, idx_o, dd_o = O.kmeanspp(data, 4, inject=inj)
+        assert seeds.tolist() == inj.tolist() == idx_o.tolist()
+        assert np.array_equal(ds.labels(), y_o.astype(np.uint64)) and np.array_equal(ds.mindist(), dd_o)
+        ds.close()
+
+
+# ---- initial centroids / Lloyd step ------------------------------------------------------------
+def test_bbdtree_iris_golden_on_gpu(ctx, kat, iris20):  # the reference's only numeric golden (bbd_tree.rs:349-363)
+    g = kat["bbdtree_iris"]
+    for cm in (False, True):
+        ds = ctx.upload(iris20, column_major=cm)
+        inertia, sums, counts = ds.lloyd_step(g["centroids"])
+        assert abs(inertia - g["cost"]) < g["cost_tol"]
+        assert abs(sums[0][0] - g["sums_0_0"]) < g["sums_tol"] and abs(sums[1][3] - g["sums_1_3"]) < g["sums_tol"]
+        assert ds.labels()[17] == g["membership_17"] and counts.tolist() == [10, 10]
+        ds.close()
+
+
+@pytest.mark.parametrize("n,d,k,dtype", [(150, 4, 3, np.float64), (2000, 16, 8, np.float64), (3000, 64, 32, np.float64),
+                                         (1537, 5, 7, np.float64), (2048, 32, 16, np.float32), (999, 128, 10, np.float64)])
+@pytest.mark.parametrize("kernel", [cabi.ASSIGN_DIRECT, cabi.ASSIGN_AUTO])
+def test_lloyd_step_matches_oracle(ctx, O, n, d, k, dtype, kernel):
+    x = blobs(n, d, k, 7 * n + d, dtype)
+    cent = x[np.random.default_rng(3).choice(n, k, replace=False)].astype(np.float64) + 0.05
+    ctx.set_assign_kernel(kernel)
+    ds = ctx.upload(x)
+    inertia, sums, counts = ds.lloyd_step(cent)
+    ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+    labels = ds.labels()
+    if kernel == cabi.ASSIGN_DIRECT:
+        assert np.array_equal(labels, m_o.astype(np.uint64))       # direct form: bit-exact argmin
+        md = ds.mindist()                                          # and bit-exact min distances
+        for i in range(0, n, 97):
+            assert md[i] == O.squared_distance(x[i].astype(np.float64), cent[m_o[i]])
+    assert_labels_match(labels, m_o, gap)
+    if np.array_equal(labels.astype(np.int64), m_o):
+        assert counts.tolist() == c_o.tolist()
+        np.testing.assert_allclose(sums, s_o, rtol=RTOL, atol=1e-9)
+    assert abs(inertia - d_o) <= RTOL * d_o
+    # and against the reference's own tree-filter path
+    d_t, s_t, c_t, m_t = O.BBDTree(x).clustering(cent)
+    assert_labels_match(labels, m_t, gap)
+    assert abs(inertia - d_t) <= RTOL * d_t
+    ds.close()
+
+
+def test_init_centroids_are_label_means(ctx, O):
+    x = blobs(3000, 8, 6, 11)
+    first, u = cluster.kmeanspp_draws(5, 3000, 6)
+    ds = ctx.upload(x)
+    ds.kmeanspp(6, first, u)
+    cent, size = ds.init_centroids(6)
+    y = ds.labels().astype(np.int64)
+    for c in range(6):
+        assert size[c] == (y == c).sum()
+        np.testing.assert_allclose(cent[c], x[y == c].mean(0), rtol=1e-12)
+    ds.close()
+
+
+def test_empty_cluster_keeps_previous_centroid(ctx, O):  # kmeans.rs:298
+    x = blobs(500, 4, 2, 21)
+    cent = np.vstack([x[:2], [[1e6, 1e6, 1e6, 1e6]]])
+    ds = ctx.upload(x)
+    out = ds.lloyd_iterate(cent, 1)
+    assert out["size"][2] == 0 and np.array_equal(out["centroids"][2], cent[2])
+    ds.close()
+
+
+# ---- full fit ------------------------------------------------------------------------------------
+def fit_gpu(ctx, x, k, seed, max_iter=100, column_major=False):
+    first, u = cluster.kmeanspp_draws(seed, x.shape[0], k)
+    return ctx.kmeans_fit(x, k, max_iter, first, u, column_major=column_major)
+
+
+def check_fit(O, x, k, seed, got):
+    want = O.fit(x, k, 100, 0 if seed is None else seed, use_tree=True)
+    if not np.array_equal(got["labels"].astype(np.int64), want.y):
+        # tolerate only near-tie flips, judged against the final centroids
+        gap = O.brute_clustering(x, want.centroids, want_gap=True)[4]
+        assert_labels_match(got["labels"], want.y, gap)
+    np.testing.assert_allclose(got["centroids"], want.centroids, rtol=RTOL, atol=1e-12)
+    assert abs(got["distortion"] - want.distortion) <= RTOL * want.distortion
+    assert got["size"].tolist() == want.size.tolist()
+    assert got["iters"] == want.iters
+    return want
+
+
+def test_fit_iris_matches_oracle_and_fixture(ctx, O, iris_f32, oracle_fits):
+    for dtype, key in ((np.float64, "iris_f64_k3_seed42_mode0"), (np.float32, "iris_f32_k3_seed42_mode0")):
+        x = iris_f32[0].astype(dtype)
+        for cm in (False, True):
+            got = fit_gpu(ctx, x, 3, 42, column_major=cm)
+            check_fit(O, x, 3, 42, got)
+            g = oracle_fits[key]
+            assert got["labels"].tolist() == g["y"] and got["size"].tolist() == g["size"] and got["iters"] == g["iters"]
+            np.testing.assert_allclose(got["centroids"], np.array(g["centroids"]), rtol=RTOL)
+
+
+@pytest.mark.parametrize("n,d,k,dtype,seed", [(20000, 16, 8, np.float64, 42), (6000, 64, 32, np.float64, 1),
+                                              (10000, 32, 16, np.float32, 9), (4001, 3, 5, np.float64, None)])
+def test_fit_blobs_matches_oracle(ctx, O, n, d, k, dtype, seed):
+    x = blobs(n, d, k, n + 13, dtype, spread=2.0)
+    got = fit_gpu(ctx, x, k, seed)
+    check_fit(O, x, k, seed, got)
+
+
+def test_fit_is_run_to_run_deterministic(ctx):
+    x = blobs(30000, 16, 8, 77, spread=1.0)
+    a = fit_gpu(ctx, x, 8, 3); b = fit_gpu(ctx, x, 8, 3)
+    assert a["iters"] == b["iters"] and a["distortion"] == b["distortion"]
+    assert np.array_equal(a["centroids"], b["centroids"]) and np.array_equal(a["labels"], b["labels"])
+
+
+# ---- host mirror: the reference's own tests, re-expressed ----------------------------------------------
+def test_fit_predict_reference_test(iris20):  # kmeans.rs:473-505
+    x = sc.DenseMatrix.from_2d_array(iris20)
+    kmeans = sc.KMeans.fit(x, sc.KMeansParameters.default())
+    y = kmeans.predict(x)
+    assert np.array_equal(y, kmeans._y) and kmeans.size.sum() == 20
+
+
+def test_f32_model_and_u8_labels(iris20):  # doctest kmeans.rs:18-48 (Vec<u8>) and serde test's f32 model
+    x = sc.DenseMatrix.from_2d_array(iris20.astype(np.float32))
+    kmeans = sc.KMeans.fit(x, sc.KMeansParameters.default().with_k(2))
+    y = kmeans.predict(x, ty=np.uint8)
+    assert y.dtype == np.uint8 and np.array_equal(y, kmeans._y)
+    with pytest.raises(sc.Failed):
+        kmeans.predict(sc.DenseMatrix.from_2d_array(iris20[:, :3].astype(np.float32)))
+
+
+# ---- predict ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,d,k,dtype", [(1, 4, 2, np.float64), (777, 16, 8, np.float32), (5000, 64, 40, np.float64),
+                                         (300, 9, 3, np.float64)])
+def test_predict_bit_exact(ctx, O, n, d, k, dtype):
+    x = blobs(n, d, k, n + 5, dtype)
+    cent = blobs(k, d, k, 99).astype(np.float64)
+    want = O.predict(x, cent)
+    assert np.array_equal(ctx.predict(x, cent).astype(np.int64), want)
+    assert np.array_equal(ctx.predict(x, cent, column_major=True, width=4).astype(np.int64), want)
+
+
+def test_predict_tie_break_lowest_index(ctx):
+    x = np.zeros((40, 4)); cent = np.ones((5, 4)); cent[3] = 0.5
+    assert np.all(ctx.predict(x, cent) == 3)
+    cent[:] = 1.0
+    assert np.all(ctx.predict(x, cent) == 0)          # exact tie: strict < keeps the first
+
+
+# ---- generator twin, properties at scale --------------------------------------------------------------
+def test_device_blobs_equal_host_twin(ctx):
+    for dtype in (np.float64, np.float32):
+        ds = ctx.generate_blobs(5000, 16, 8, 20260101, dtype=dtype, row_offset=123, n_global=10000)
+        got = ds.download_rows(100, 64)
+        assert np.array_equal(got, cabi.blobs_host(223, 64, 16, 8, 20260101, dtype=dtype))
+        ds.close()
+
+
+def test_config2_1Mx16_k8_properties(ctx, O):
+    """BASELINE config 2 at full size: size-independent properties + sampled-row oracle check."""
+    n, d, k = 1_000_000, 16, 8
+    ds = ctx.generate_blobs(n, d, k, 20260101)
+    first, u = cluster.kmeanspp_draws(42, n, k)
+    seeds = ds.kmeanspp(k, first, u)
+    assert seeds[0] == first and len(set(seeds.tolist())) == k
+    cent, size = ds.init_centroids(k)
+    assert size.sum() == n
+    out = ds.lloyd_fit(cent, 100)
+    assert out["size"].sum() == n and 1 <= out["iters"] <= 100
+    labels = ds.labels().astype(np.int64)
+    assert np.array_equal(np.bincount(labels, minlength=k), out["size"])
+    # monotone inertia: one more step from the final centroids cannot increase it beyond rounding
+    inertia, sums, counts = ds.lloyd_step(out["centroids"])
+    assert inertia <= out["distortion"] * (1 + 1e-12)
+    np.testing.assert_allclose(sums.sum(0) / n, np.mean(cabi.blobs_host(0, 20000, d, k, 20260101), 0), atol=0.2)
+    # sampled rows regenerated on the host, labels recomputed by the oracle against the GPU's centroids
+    rows = np.random.default_rng(0).choice(n, 4096, replace=False)
+    xs = np.vstack([cabi.blobs_host(int(r), 1, d, k, 20260101) for r in rows])
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(xs, out["centroids"], want_gap=True)
+    assert_labels_match(ds.labels()[rows], m_o, gap)
+    ds.close()
+
+
+def test_config2_fit_parity_200k(ctx, O):
+    n, d, k = 200_000, 16, 8
+    x = cabi.blobs_host(0, n, d, k, 20260101)
+    got = fit_gpu(ctx, x, k, 42)
+    check_fit(O, x, k, 42, got)

@@ -13,6 +13,7 @@ namespace sckm {
 const char* create_error_text();
 int launch_assign_dmma(sckm_dataset* ds, uint64_t k);         // sckm_dmma.cu
 bool dmma_supported(const sckm_dataset* ds, uint64_t k);      // sckm_dmma.cu
+uint32_t dmma_partial_slots(const sckm_ctx* ctx);             // sckm_dmma.cu
 }
 using namespace sckm;
 
@@ -264,10 +265,15 @@ static int clustering_step(sckm_dataset* ds, uint64_t k, cudaEvent_t ev_a0 = nul
     sckm_ctx* ctx = ds->ctx;
     const int which = pick_assign(ds, k);
     if (ev_a0) SCKM_CUDA(ctx, cudaEventRecord(ev_a0, ctx->stream));
-    if (which == SCKM_ASSIGN_DMMA) SCKM_TRY(launch_assign_dmma(ds, k));
-    else SCKM_TRY(launch_assign_direct(ds, k));
-    if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
-    SCKM_TRY(launch_update(ds, k, true));
+    if (which == SCKM_ASSIGN_DMMA) {
+        SCKM_TRY(launch_assign_dmma(ds, k));                      // assignment + fused per-warp partial sums
+        if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
+        SCKM_TRY(launch_reduce_partials(ctx, dmma_partial_slots(ctx), (size_t)k * ds->d + k + 1));
+    } else {
+        SCKM_TRY(launch_assign_direct(ds, k));
+        if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
+        SCKM_TRY(launch_update(ds, k, true));
+    }
     SCKM_TRY(nccl_allreduce_f64(ctx, ctx->d_packed, (size_t)k * ds->d + k + 1));
     ds->have_labels = true;
     return SCKM_OK;

@@ -108,6 +108,7 @@ int launch_assign_direct_raw(sckm_ctx* ctx, const void* x, int dtype, uint64_t n
                              uint32_t* labels, double* mind);
 // deterministic per-label sums/counts/inertia of the local rows into ctx->d_packed
 int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia);
+int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk);
 // centroids = sums / counts (guarded: keep old when count == 0; unguarded for the initial means)
 int launch_finalize(sckm_ctx* ctx, uint64_t k, uint64_t d, bool guarded);
 int launch_labels_widen(sckm_ctx* ctx, const uint32_t* in, uint64_t* out, uint64_t n);

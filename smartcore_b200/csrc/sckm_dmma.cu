@@ -16,8 +16,12 @@
 //   * Accumulators start at -(||x||^2 + ||c||^2)/2, DMMA adds x.c: acc = -dist^2/2; the epilogue
 //     is max / second-max tracking only.
 //   * Rows whose best/second gap is within 1e-10*(||x||^2 + max||c||^2) (>= 1e4 x the rounding
-//     error bound of the GEMM form) are appended to a list and re-decided by refine_rows_kernel with
-//     the reference's exact arithmetic (euclidian.rs:56-63), so labels equal the dense oracle.
+//     error bound of the GEMM form) are marked and re-decided by refine_rows_kernel with the
+//     reference's exact arithmetic (euclidian.rs:56-63), so labels equal the dense oracle.
+//   * The centroid update (per-label sums, counts, inertia) is fused: while a slab's rows are still
+//     in registers they are added to the warp's PRIVATE partial [k*d | k | 1] in L2-resident global
+//     memory, in a fixed order, so results are bit-reproducible run to run (needed by the stop rule
+//     `distortion <= dist`, kmeans.rs:305) without any floating-point atomics.
 #include "sckm_common.cuh"
 #include <cfloat>
 #include <algorithm>
@@ -33,9 +37,13 @@ namespace sckm {
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
-constexpr int DMMA_WARPS = 8;
-constexpr int DMMA_NT = 8;                       // n-tiles per sub-block: 64 centroids
+constexpr int DMMA_WARPS = 12;                   // 3 warps per SM sub-partition (<= 168 registers/thread)
+constexpr int DMMA_NT = 4;                       // n-tiles per sub-block: 32 centroids
 constexpr double DMMA_TIE_REL = 1e-10;
+
+// max/min without NaN plumbing (DSETP + SEL); NaNs are caught by the tie test at the end
+__device__ __forceinline__ double dmax_(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin_(double a, double b) { return a < b ? a : b; }
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -47,14 +55,13 @@ template <int KSTEPS, int MT, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t* __restrict__ labels,
-                   double* __restrict__ mind, unsigned long long* __restrict__ flag_count,
-                   uint32_t* __restrict__ flag_rows) {
+                   double* __restrict__ mind, double* __restrict__ partials, size_t pk) {
     constexpr int DP = KSTEPS * 4;                 // padded feature count
     constexpr int PITCH = DP + 4;                  // doubles per staged centroid row (pitch = d*8+32 B)
     constexpr int ROWS = 8 * MT;
     extern __shared__ __align__(16) double smem_d[];
     double* cbuf = smem_d;                         // [bn][PITCH]
-    double* cn = smem_d + (size_t)bn * PITCH;      // [bn]  ||c||^2, +inf for padding columns
+    double* cn = smem_d + (size_t)bn * PITCH;      // [bn]  -||c||^2/2, -inf for padding columns
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const double cmax = cnorm[k];                  // max_j ||c_j||^2 (written by cnorm_max_kernel)
@@ -64,6 +71,9 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
     const uint64_t rounds = (nslabs + stride - 1) / stride;
     const uint32_t nchunks = (k + bn - 1) / bn;
     const double* bbase = cbuf + (size_t)g * PITCH + t;
+    double* part = partials + ((size_t)blockIdx.x * DMMA_WARPS + warp) * pk;   // this warp's private partial
+    unsigned lanemask_lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanemask_lt));
 
     for (uint64_t rd = 0; rd < rounds; rd++) {
         const uint64_t slab = rd * stride + (uint64_t)blockIdx.x * DMMA_WARPS + warp;
@@ -71,7 +81,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
         const uint64_t r0 = slab * ROWS;
         // ---- rows -> A fragments (registers), ||x||^2 ----
         double a[MT][KSTEPS];
-        double xn[MT];
+        double xn[MT], hxn[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
             const uint64_t row = r0 + mt * 8 + g;
@@ -89,6 +99,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             xn[mt] = s;
+            hxn[mt] = -0.5 * s;
         }
         double best[MT], second[MT];
         uint32_t bidx[MT];
@@ -107,7 +118,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                     cbuf[(size_t)r * PITCH + c] = v;
                 }
                 for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
-                    cn[r] = (c0 + r < k) ? cnorm[c0 + r] : INFINITY;
+                    cn[r] = (c0 + r < k) ? -0.5 * cnorm[c0 + r] : -INFINITY;
                 __syncthreads();
             }
             const uint32_t cols = min(bn, k - c0);
@@ -118,8 +129,8 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                     const double cn0 = cn[ns + nt * 8 + 2 * t], cn1 = cn[ns + nt * 8 + 2 * t + 1];
 #pragma unroll
                     for (int mt = 0; mt < MT; mt++) {
-                        acc[mt][nt][0] = -0.5 * (xn[mt] + cn0);
-                        acc[mt][nt][1] = -0.5 * (xn[mt] + cn1);
+                        acc[mt][nt][0] = hxn[mt] + cn0;
+                        acc[mt][nt][1] = hxn[mt] + cn1;
                     }
                 }
                 const double* bp = bbase + (size_t)ns * PITCH;
@@ -142,15 +153,16 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
 #pragma unroll
                         for (int mt = 0; mt < MT; mt++) {
                             const double v = acc[mt][nt][e];
-                            second[mt] = fmax(second[mt], fmin(v, best[mt]));
                             const bool gt = v > best[mt];
+                            second[mt] = dmax_(second[mt], gt ? best[mt] : v);
                             bidx[mt] = gt ? col : bidx[mt];
-                            best[mt] = fmax(best[mt], v);
+                            best[mt] = gt ? v : best[mt];
                         }
                     }
             }
         }
-        // ---- merge the 4 lanes that share a row, write out, flag near-ties ----
+        // ---- merge the 4 lanes that share a row, write out, mark near-ties, fused update ----
+        double slab_inertia = 0.0;
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
 #pragma unroll
@@ -159,57 +171,107 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                 const double os = __shfl_xor_sync(0xffffffffu, second[mt], o);
                 const uint32_t oi = __shfl_xor_sync(0xffffffffu, bidx[mt], o);
                 const bool take = ob > best[mt] || (ob == best[mt] && oi < bidx[mt]);
-                second[mt] = fmax(fmax(second[mt], os), fmin(best[mt], ob));
+                second[mt] = dmax_(dmax_(second[mt], os), dmin_(best[mt], ob));
                 bidx[mt] = take ? oi : bidx[mt];
-                best[mt] = fmax(best[mt], ob);
+                best[mt] = dmax_(best[mt], ob);
             }
             const uint64_t row = r0 + mt * 8 + g;
-            if (active && row < n && t == 0) {
-                labels[row] = bidx[mt];
-                mind[row] = fmax(0.0, -2.0 * best[mt]);
-                const double gap = 2.0 * (best[mt] - second[mt]);
-                if (!(gap > DMMA_TIE_REL * (xn[mt] + cmax))) {   // also catches NaN
-                    const unsigned long long slot = atomicAdd(flag_count, 1ull);
-                    flag_rows[slot] = (uint32_t)row;
+            const bool valid = active && row < n;
+            const double dist = fmax(0.0, -2.0 * best[mt]);
+            const double gap = 2.0 * (best[mt] - second[mt]);
+            const bool tie = !(gap > DMMA_TIE_REL * (xn[mt] + cmax));   // also catches NaN
+            if (valid && t == 0) {
+                labels[row] = tie ? 0xffffffffu : bidx[mt];             // ties are re-decided by refine_rows_kernel
+                mind[row] = dist;
+            }
+            // Deterministic per-label accumulation (the update of bbd_tree.rs:151-155) into this warp's
+            // private partial: the 4 lanes of a row add their A-fragment elements.  Rows of this m-tile that
+            // share a label are serialised in ascending row order (rank), so the order of every f64 addition is
+            // fixed by (n, grid) alone.
+            const bool part_ok = valid && !tie;
+            const uint32_t key = part_ok ? bidx[mt] : (0x80000000u | (uint32_t)g);
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int rank = __popc(peers & lanemask_lt) >> 2;
+            const int maxrank = __reduce_max_sync(0xffffffffu, part_ok ? rank : 0);
+            for (int r = 0; r <= maxrank; r++) {
+                if (r) { __threadfence(); __syncwarp(); }     // order the (rare) same-label rows of this m-tile
+                if (part_ok && rank == r) {
+                    // fire-and-forget RED.ADD.F64 into the warp-private partial: a given address only ever
+                    // receives adds from this warp, same-thread adds stay in program order and cross-lane
+                    // same-label adds are separated by the fence above => the summation order is fixed.
+                    double* p = part + (size_t)bidx[mt] * d + t;
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ks++)
+                        if (ks * 4 + t < d) atomicAdd(p + ks * 4, a[mt][ks]);
+                    if (t == 0) atomicAdd(part + (size_t)k * d + bidx[mt], 1.0);
                 }
             }
+            double v = (part_ok && t == 0) ? dist : 0.0;                 // fixed-order sum over the 8 rows
+            v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+            v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 8));
+            v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
+            slab_inertia = __dadd_rn(slab_inertia, v);
         }
+        if (lane == 0 && active) atomicAdd(part + pk - 1, slab_inertia);
     }
 }
 
-// exact re-decision of the flagged rows: one warp per row, lane l scans centroids l, l+32, ... with the
-// reference's arithmetic (widen to f64, diff, square, sequential sum, never fused), then a warp argmin
-// with strict < and lowest index on ties (kmeans.rs:334-347 / bbd_tree.rs:101-111).
+// Exact re-decision of the rows marked 0xffffffff by the tile kernel.  Warp w scans the fixed row range
+// [w*R, (w+1)*R) in order; for a marked row, lane l scans centroids l, l+32, ... with the reference's
+// arithmetic (widen to f64, diff, square, sequential sum, never fused), then a warp argmin with strict <
+// and lowest index on ties (kmeans.rs:334-347 / bbd_tree.rs:101-111); the row is then added to this
+// warp's private partial (lanes own columns), so the result does not depend on scheduling.
 template <typename TX>
-__global__ void __launch_bounds__(256)
-refine_rows_kernel(const TX* __restrict__ x, uint32_t d, const double* __restrict__ centroids, uint32_t k,
-                   const unsigned long long* __restrict__ flag_count, const uint32_t* __restrict__ flag_rows,
-                   uint32_t* __restrict__ labels, double* __restrict__ mind) {
-    const unsigned long long count = *flag_count;
+__global__ void __launch_bounds__(DMMA_WARPS * 32)
+refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids, uint32_t k,
+                   uint32_t* __restrict__ labels, double* __restrict__ mind, double* __restrict__ partials, size_t pk) {
     const int lane = threadIdx.x & 31;
-    const unsigned long long warp_global = ((unsigned long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const unsigned long long nwarps = ((unsigned long long)gridDim.x * blockDim.x) >> 5;
-    for (unsigned long long f = warp_global; f < count; f += nwarps) {
-        const uint64_t row = flag_rows[f];
-        const TX* xr = x + row * d;
-        double best = DBL_MAX; uint32_t bi = 0xffffffffu;
-        for (uint32_t c = lane; c < k; c += 32) {
-            const double* cr = centroids + (size_t)c * d;
-            double dist = 0.0;
-            for (uint32_t j = 0; j < d; j++) {
-                const double r = __dsub_rn((double)xr[j], cr[j]);
-                dist = __dadd_rn(dist, __dmul_rn(r, r));
+    const uint64_t w = (uint64_t)blockIdx.x * DMMA_WARPS + (threadIdx.x >> 5);
+    const uint64_t nw = (uint64_t)gridDim.x * DMMA_WARPS;
+    const uint64_t per = ((n + nw - 1) / nw + 31) / 32 * 32;
+    const uint64_t r_begin = min(n, w * per), r_end = min(n, r_begin + per);
+    double* part = partials + w * pk;
+    double inertia = 0.0;
+    bool any = false;
+    for (uint64_t base = r_begin; base < r_end; base += 32) {
+        const uint64_t mine = base + lane;
+        const bool marked = mine < r_end && labels[mine] == 0xffffffffu;
+        unsigned todo = __ballot_sync(0xffffffffu, marked);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const uint64_t row = base + src;
+            const TX* xr = x + row * d;
+            double best = DBL_MAX; uint32_t bi = 0xffffffffu;
+            for (uint32_t c = lane; c < k; c += 32) {
+                const double* cr = centroids + (size_t)c * d;
+                double dist = 0.0;
+                for (uint32_t j = 0; j < d; j++) {
+                    const double r = __dsub_rn((double)xr[j], cr[j]);
+                    dist = __dadd_rn(dist, __dmul_rn(r, r));
+                }
+                if (dist < best) { best = dist; bi = c; }
             }
-            if (dist < best) { best = dist; bi = c; }
-        }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            for (int o = 16; o > 0; o >>= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+            }
+            if (bi == 0xffffffffu) bi = 0;                      // all distances NaN: the reference keeps cluster 0
+            double* p = part + (size_t)bi * d;
+            for (uint32_t j = lane; j < d; j += 32) __stcg(p + j, __dadd_rn(__ldcg(p + j), (double)xr[j]));
+            if (lane == 0) {
+                labels[row] = bi; mind[row] = best;
+                double* pc = part + (size_t)k * d + bi;
+                __stcg(pc, __ldcg(pc) + 1.0);
+                inertia = __dadd_rn(inertia, best);
+                any = true;
+            }
+            __syncwarp();
         }
-        if (lane == 0) { labels[row] = bi == 0xffffffffu ? 0u : bi; mind[row] = best; }
     }
+    if (lane == 0 && any) __stcg(part + pk - 1, __dadd_rn(__ldcg(part + pk - 1), inertia));
 }
 
 // cnorm[k] = max_j cnorm[j]  (single warp; k is small)
@@ -235,60 +297,58 @@ bool dmma_supported(const sckm_dataset* ds, uint64_t k) {
     return ds->d >= 4 && ds->d <= 128 && k >= 16 && k <= (1u << 24) && ds->n < 0xFFFFFFFFull;
 }
 
+static unsigned dmma_grid(const sckm_ctx* ctx) { return (unsigned)ctx->num_sms; }
+
+// number of per-warp partial slots the fused kernels accumulate into (reduced by launch_reduce_partials)
+uint32_t dmma_partial_slots(const sckm_ctx* ctx) { return dmma_grid(ctx) * DMMA_WARPS; }
+
 template <int KSTEPS, int MT, typename TX>
-static int launch_t(sckm_dataset* ds, uint64_t k) {
+static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     sckm_ctx* ctx = ds->ctx;
     constexpr int DP = KSTEPS * 4, PITCH = DP + 4;
     const size_t row_bytes = (size_t)PITCH * 8 + 8;                   // staged row + its norm
     uint32_t bn = (uint32_t)(((size_t)ctx->smem_optin - 1024) / row_bytes);
-    bn = bn / 64 * 64;
-    const uint32_t kpad = (uint32_t)((k + 63) / 64 * 64);
+    bn = bn / (8 * DMMA_NT) * (8 * DMMA_NT);
+    const uint32_t kpad = (uint32_t)((k + 8 * DMMA_NT - 1) / (8 * DMMA_NT) * (8 * DMMA_NT));
     if (bn >= kpad) bn = kpad;                                         // whole centroid set resident
-    if (bn < 64) return fail(ctx, SCKM_ERR_INVALID, "shared memory too small for the DMMA tile");
+    if (bn < 8 * DMMA_NT) return fail(ctx, SCKM_ERR_INVALID, "shared memory too small for the DMMA tile");
     const size_t smem = (size_t)bn * row_bytes;
     auto kern = assign_dmma_kernel<KSTEPS, MT, TX>;
     SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const uint64_t nslabs = (ds->n + 8 * MT - 1) / (8 * MT);
-    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nslabs + DMMA_WARPS - 1) / DMMA_WARPS, ctx->num_sms));
-    kern<<<grid, DMMA_WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
-                                                      ctx->d_cnorm, (uint32_t)k, bn, ds->labels, ds->mind,
-                                                      ctx->d_flags, ctx->d_flagrows);
+    kern<<<dmma_grid(ctx), DMMA_WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
+                                                               ctx->d_cnorm, (uint32_t)k, bn, ds->labels, ds->mind,
+                                                               ctx->d_partials, pk);
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }
 
 template <typename TX>
-static int launch_by_d(sckm_dataset* ds, uint64_t k) {
+static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     const uint64_t d = ds->d;
-    if (d <= 16) return launch_t<4, 2, TX>(ds, k);
-    if (d <= 32) return launch_t<8, 2, TX>(ds, k);
-    if (d <= 64) return launch_t<16, 2, TX>(ds, k);
-    return launch_t<32, 1, TX>(ds, k);
+    if (d <= 16) return launch_t<4, 2, TX>(ds, k, pk);
+    if (d <= 32) return launch_t<8, 2, TX>(ds, k, pk);
+    if (d <= 64) return launch_t<16, 2, TX>(ds, k, pk);
+    return launch_t<32, 1, TX>(ds, k, pk);
 }
 
+// labels + mind + per-warp partial [sums | counts | inertia] (fused update); the caller reduces the slots.
 int launch_assign_dmma(sckm_dataset* ds, uint64_t k) {
     sckm_ctx* ctx = ds->ctx;
     if (!dmma_supported(ds, k)) return fail(ctx, SCKM_ERR_INVALID, "shape not supported by the DMMA kernel");
+    const size_t pk = (size_t)k * ds->d + k + 1;
+    SCKM_TRY(ensure_workspace(ctx, k, ds->d, dmma_partial_slots(ctx)));
     if (ds->n == 0) return SCKM_OK;
-    // near-tie list (one u32 per local row is the worst case: every row tied)
-    if (ctx->cap_flagrows < ds->n) {
-        if (ctx->d_flagrows) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_flagrows); ctx->d_flagrows = nullptr; }
-        SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_flagrows, ds->n * sizeof(uint32_t)));
-        ctx->cap_flagrows = ds->n;
-    }
-    SCKM_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(unsigned long long), ctx->stream));
     cnorm_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)ds->d, ctx->d_cnorm);
     LAUNCH_CHECK_D(ctx);
     cnorm_max_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_cnorm, (uint32_t)k);
     LAUNCH_CHECK_D(ctx);
-    SCKM_TRY(ds->dtype == SCKM_F32 ? launch_by_d<float>(ds, k) : launch_by_d<double>(ds, k));
-    const unsigned rgrid = (unsigned)ctx->num_sms * 2;
+    SCKM_TRY(ds->dtype == SCKM_F32 ? launch_by_d<float>(ds, k, pk) : launch_by_d<double>(ds, k, pk));
     if (ds->dtype == SCKM_F32)
-        refine_rows_kernel<float><<<rgrid, 256, 0, ctx->stream>>>((const float*)ds->x, (uint32_t)ds->d, ctx->d_centroids,
-            (uint32_t)k, ctx->d_flags, ctx->d_flagrows, ds->labels, ds->mind);
+        refine_rows_kernel<float><<<dmma_grid(ctx), DMMA_WARPS * 32, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d,
+            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
     else
-        refine_rows_kernel<double><<<rgrid, 256, 0, ctx->stream>>>((const double*)ds->x, (uint32_t)ds->d, ctx->d_centroids,
-            (uint32_t)k, ctx->d_flags, ctx->d_flagrows, ds->labels, ds->mind);
+        refine_rows_kernel<double><<<dmma_grid(ctx), DMMA_WARPS * 32, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d,
+            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }

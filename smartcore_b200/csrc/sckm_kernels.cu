@@ -342,18 +342,36 @@ __global__ void update_partial_kernel(const T* __restrict__ x, uint64_t n, uint3
     if (threadIdx.x == 0) part[pk - 1] = inertia;
 }
 
-// packed[e] = sum over partial slots in slot order; the slots are zeroed for the next step.
-__global__ void reduce_partials_kernel(double* __restrict__ partials, uint32_t nslots, size_t pk,
-                                       double* __restrict__ packed) {
-    const size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= pk) return;
+// packed[e] = sum over the partial slots in a FIXED order (8 slot groups summed sequentially by 8 thread rows,
+// then the 8 group sums in order); the slots are zeroed for the next step.  blockDim = (32, 8).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(double* __restrict__ partials, uint32_t nslots, size_t pk,
+                                                              double* __restrict__ packed) {
+    __shared__ double sh[8][33];
+    const size_t e = (size_t)blockIdx.x * 32 + threadIdx.x;
+    const uint32_t per = (nslots + 7) / 8;
+    const uint32_t p0 = min(nslots, threadIdx.y * per), p1 = min(nslots, p0 + per);
     double s = 0.0;
-    for (uint32_t p = 0; p < nslots; p++) {
-        double* q = partials + (size_t)p * pk + e;
-        s = __dadd_rn(s, *q);
-        *q = 0.0;
+    if (e < pk) {
+        double* q = partials + (size_t)p0 * pk + e;
+        uint32_t p = p0;
+        for (; p + 8 <= p1; p += 8) {            // 8 independent loads in flight, added in slot order
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) v[i] = __ldcg(q + (size_t)i * pk);
+#pragma unroll
+            for (int i = 0; i < 8; i++) { s = __dadd_rn(s, v[i]); __stcg(q + (size_t)i * pk, 0.0); }
+            q += 8 * pk;
+        }
+        for (; p < p1; p++) { s = __dadd_rn(s, __ldcg(q)); __stcg(q, 0.0); q += pk; }
     }
-    packed[e] = s;
+    sh[threadIdx.y][threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.y == 0 && e < pk) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t = __dadd_rn(t, sh[i][threadIdx.x]);
+        packed[e] = t;
+    }
 }
 
 // K6: centroids = sums / counts (kmeans.rs:288-292 unguarded, :297-303 guarded), sizes, ||c||^2
@@ -620,7 +638,12 @@ int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia) {
                 ds->labels, with_inertia ? ds->mind : nullptr, (uint32_t)k, rows_per_cta, ctx->d_partials);
         LAUNCH_CHECK(ctx);
     }
-    reduce_partials_kernel<<<(unsigned)((pk + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_partials, slots, pk, ctx->d_packed);
+    SCKM_TRY(launch_reduce_partials(ctx, slots, pk));
+    return SCKM_OK;
+}
+
+int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk) {
+    reduce_partials_kernel<<<(unsigned)((pk + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(ctx->d_partials, slots, pk, ctx->d_packed);
     LAUNCH_CHECK(ctx);
     return SCKM_OK;
 }

@@ -95,6 +95,54 @@ def test_lloyd_step_matches_oracle(ctx, O, n, d, k, dtype, kernel):
     ds.close()
 
 
+def test_dmma_ties_duplicates_and_exact_refine(ctx, O):
+    """Degenerate data: duplicated rows and duplicated centroids make every row an exact tie in GEMM form;
+    the refine pass must reproduce the reference's strict-< / lowest-index rule bit for bit."""
+    rng = np.random.default_rng(0)
+    base = rng.normal(size=(16, 32))
+    x = base[rng.integers(0, 16, size=4000)]
+    cent = np.vstack([base, base, base[:8] + 1e-13])            # k = 40: exact and 1e-13 near-duplicates
+    ctx.set_assign_kernel(cabi.ASSIGN_DMMA)
+    ds = ctx.upload(x)
+    inertia, sums, counts = ds.lloyd_step(cent)
+    ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+    assert np.array_equal(ds.labels().astype(np.int64), m_o)     # includes gap == 0 rows
+    assert counts.tolist() == c_o.tolist()
+    np.testing.assert_allclose(sums, s_o, rtol=RTOL, atol=1e-9)
+    assert abs(inertia - d_o) <= 1e-9 * max(d_o, 1e-30) + 1e-18
+    ds.close()
+
+
+def test_dmma_step_is_bit_reproducible(ctx):
+    x = blobs(50000, 64, 64, 5, spread=1.0)
+    cent = x[:64] + 0.01
+    ctx.set_assign_kernel(cabi.ASSIGN_DMMA)
+    ds = ctx.upload(x)
+    a = ds.lloyd_step(cent); la = ds.labels()
+    b = ds.lloyd_step(cent); lb = ds.labels()
+    ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+    assert a[0] == b[0] and np.array_equal(a[1], b[1]) and np.array_equal(a[2], b[2]) and np.array_equal(la, lb)
+    ds.close()
+
+
+@pytest.mark.parametrize("n,d,k,dtype", [(20000, 64, 256, np.float64), (9000, 128, 100, np.float64), (7777, 20, 33, np.float64),
+                                         (30000, 32, 512, np.float32), (5000, 12, 17, np.float32)])
+def test_dmma_step_shapes(ctx, O, n, d, k, dtype):
+    x = blobs(n, d, k, n + d, dtype, spread=1.5)
+    cent = x[np.random.default_rng(1).choice(n, k, replace=False)].astype(np.float64) * 1.001
+    ctx.set_assign_kernel(cabi.ASSIGN_DMMA)
+    ds = ctx.upload(x)
+    inertia, sums, counts = ds.lloyd_step(cent)
+    ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+    assert np.array_equal(ds.labels().astype(np.int64), m_o)
+    assert counts.tolist() == c_o.tolist()
+    np.testing.assert_allclose(sums, s_o, rtol=RTOL, atol=1e-9)
+    assert abs(inertia - d_o) <= RTOL * d_o
+    ds.close()
+
+
 def test_init_centroids_are_label_means(ctx, O):
     x = blobs(3000, 8, 6, 11)
     first, u = cluster.kmeanspp_draws(5, 3000, 6)

@@ -177,11 +177,11 @@ def main():
     cent0, _ = ds.init_centroids(k)
     t_init = time.perf_counter() - t0
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi takes a moment to start: begin before the warm-up steps
     if args.warmup:
         ds.lloyd_iterate(cent0, args.warmup)
-    sampler = ClockSampler(local_rank)
     barrier()
-    sampler.start()
     l0 = ctx.launch_count()
     w0 = time.perf_counter()
     out = ds.lloyd_iterate(cent0, args.steps)
@@ -215,9 +215,11 @@ def main():
         c0, _ = ds2.init_centroids(k)
         t_seed = time.perf_counter() - e0 - t_up
         fit = ds2.lloyd_fit(c0, args.steps)
+        t_lloyd = time.perf_counter() - e0 - t_up - t_seed
         labels = ds2.labels(width=8)
         barrier()
         t_e2e = time.perf_counter() - e0
+        t_down = t_e2e - t_lloyd - t_up - t_seed
         if distributed:
             t_e2e = scd.max_over_ranks(t_e2e)
         e2e = {"value": n_global * fit["iters"] / t_e2e, "unit": "point-iters/s",
@@ -225,7 +227,7 @@ def main():
                "d2h_bytes_per_step": int((labels.nbytes + fit["centroids"].nbytes) // max(fit["iters"], 1)),
                "detail": {"what": "upload(pinned host) + kmeans++ + init means + Lloyd loop (stop rule, max_iter=steps) + "
                                   "labels/centroids download; bytes are per fit divided by iterations executed",
-                          "iters": int(fit["iters"]), "total_s": t_e2e, "upload_s": t_up, "kmeanspp_init_s": t_seed,
+                          "iters": int(fit["iters"]), "total_s": t_e2e, "upload_s": t_up, "kmeanspp_init_s": t_seed, "lloyd_s": t_lloyd, "download_s": t_down,
                           "distortion": fit["distortion"]}}
         ds2.close()
     else:

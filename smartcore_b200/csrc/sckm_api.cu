@@ -268,7 +268,7 @@ static int clustering_step(sckm_dataset* ds, uint64_t k, cudaEvent_t ev_a0 = nul
     if (which == SCKM_ASSIGN_DMMA) {
         SCKM_TRY(launch_assign_dmma(ds, k));                      // assignment + fused per-warp partial sums
         if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
-        SCKM_TRY(launch_reduce_partials(ctx, dmma_partial_slots(ctx), (size_t)k * ds->d + k + 1));
+        SCKM_TRY(launch_reduce_partials(ctx, ctx->partial_slots_used, (size_t)k * ds->d + k + 1));
     } else {
         SCKM_TRY(launch_assign_direct(ds, k));
         if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));

@@ -18,6 +18,9 @@ constexpr int kWarpRows = 32;         // rows staged per warp slab in the direct
 
 struct NcclApi;  // dlopen'd entry points (sckm_nccl.cu)
 
+// pitch (in doubles) of one partial slot [k*d sums | k counts | inertia]: 128-byte aligned rows
+inline size_t slot_pitch(size_t pk) { return (pk + 15) / 16 * 16; }
+
 }  // namespace sckm
 
 struct sckm_ctx {
@@ -45,6 +48,7 @@ struct sckm_ctx {
     size_t cap_seedrow = 0;
     int64_t* d_seeds = nullptr;      // [k] chosen global rows
     unsigned long long* d_flags = nullptr;  // [8] misc device counters (near-tie count, ...)
+    uint32_t partial_slots_used = 0; // slots written by the last fused assignment launch
     uint32_t* d_flagrows = nullptr;  // rows flagged as near-ties by the GEMM-form kernel
     size_t cap_flagrows = 0;
     void* d_flush = nullptr;         // L2 flush buffer

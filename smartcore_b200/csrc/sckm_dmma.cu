@@ -25,6 +25,7 @@
 #include "sckm_common.cuh"
 #include <cfloat>
 #include <algorithm>
+#include <cstdlib>
 
 namespace sckm {
 
@@ -37,8 +38,7 @@ namespace sckm {
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
-constexpr int DMMA_WARPS = 12;                   // 3 warps per SM sub-partition (<= 168 registers/thread)
-constexpr int DMMA_NT = 4;                       // n-tiles per sub-block: 32 centroids
+constexpr int DMMA_MAX_WARPS = 16;
 constexpr double DMMA_TIE_REL = 1e-10;
 
 // max/min without NaN plumbing (DSETP + SEL); NaNs are caught by the tie test at the end
@@ -50,8 +50,9 @@ __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
-// KSTEPS: d padded to 4*KSTEPS; MT: m-tiles (8 rows each) per warp slab
-template <int KSTEPS, int MT, typename TX>
+// KSTEPS: d padded to 4*KSTEPS; MT: m-tiles (8 rows each) per warp slab; DMMA_NT: n-tiles (8 centroids each) per
+// accumulator sub-block; DMMA_WARPS: warps per CTA (one CTA per SM)
+template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t* __restrict__ labels,
@@ -71,7 +72,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
     const uint64_t rounds = (nslabs + stride - 1) / stride;
     const uint32_t nchunks = (k + bn - 1) / bn;
     const double* bbase = cbuf + (size_t)g * PITCH + t;
-    double* part = partials + ((size_t)blockIdx.x * DMMA_WARPS + warp) * pk;   // this warp's private partial
+    double* part = partials + ((size_t)blockIdx.x * DMMA_WARPS + warp) * ((pk + 15) / 16 * 16);   // this warp's private partial
     unsigned lanemask_lt;
     asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanemask_lt));
 
@@ -221,22 +222,29 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
 // arithmetic (widen to f64, diff, square, sequential sum, never fused), then a warp argmin with strict <
 // and lowest index on ties (kmeans.rs:334-347 / bbd_tree.rs:101-111); the row is then added to this
 // warp's private partial (lanes own columns), so the result does not depend on scheduling.
-template <typename TX>
+template <typename TX, int DMMA_WARPS>
 __global__ void __launch_bounds__(DMMA_WARPS * 32)
 refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids, uint32_t k,
                    uint32_t* __restrict__ labels, double* __restrict__ mind, double* __restrict__ partials, size_t pk) {
     const int lane = threadIdx.x & 31;
     const uint64_t w = (uint64_t)blockIdx.x * DMMA_WARPS + (threadIdx.x >> 5);
     const uint64_t nw = (uint64_t)gridDim.x * DMMA_WARPS;
-    const uint64_t per = ((n + nw - 1) / nw + 31) / 32 * 32;
+    const uint64_t per = ((n + nw - 1) / nw + 127) / 128 * 128;
     const uint64_t r_begin = min(n, w * per), r_end = min(n, r_begin + per);
-    double* part = partials + w * pk;
+    double* part = partials + w * ((pk + 15) / 16 * 16);
     double inertia = 0.0;
     bool any = false;
-    for (uint64_t base = r_begin; base < r_end; base += 32) {
-        const uint64_t mine = base + lane;
-        const bool marked = mine < r_end && labels[mine] == 0xffffffffu;
-        unsigned todo = __ballot_sync(0xffffffffu, marked);
+    for (uint64_t base4 = r_begin; base4 < r_end; base4 += 128) {
+        unsigned marks[4];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {                            // 4 independent label loads in flight
+            const uint64_t mine = base4 + u * 32 + lane;
+            marks[u] = (mine < r_end) ? labels[mine] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+        const uint64_t base = base4 + u * 32;
+        unsigned todo = __ballot_sync(0xffffffffu, marks[u] == 0xffffffffu);
         while (todo) {
             const int src = __ffs(todo) - 1;
             todo &= todo - 1;
@@ -270,6 +278,7 @@ refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
             }
             __syncwarp();
         }
+        }
     }
     if (lane == 0 && any) __stcg(part + pk - 1, __dadd_rn(__ldcg(part + pk - 1), inertia));
 }
@@ -299,36 +308,53 @@ bool dmma_supported(const sckm_dataset* ds, uint64_t k) {
 
 static unsigned dmma_grid(const sckm_ctx* ctx) { return (unsigned)ctx->num_sms; }
 
-// number of per-warp partial slots the fused kernels accumulate into (reduced by launch_reduce_partials)
-uint32_t dmma_partial_slots(const sckm_ctx* ctx) { return dmma_grid(ctx) * DMMA_WARPS; }
+// number of per-warp partial slots the fused kernels may accumulate into (reduced by launch_reduce_partials)
+uint32_t dmma_partial_slots(const sckm_ctx* ctx) { return dmma_grid(ctx) * DMMA_MAX_WARPS; }
 
-template <int KSTEPS, int MT, typename TX>
+template <int KSTEPS, int MT, int NT, int WARPS, typename TX>
 static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     sckm_ctx* ctx = ds->ctx;
     constexpr int DP = KSTEPS * 4, PITCH = DP + 4;
     const size_t row_bytes = (size_t)PITCH * 8 + 8;                   // staged row + its norm
     uint32_t bn = (uint32_t)(((size_t)ctx->smem_optin - 1024) / row_bytes);
-    bn = bn / (8 * DMMA_NT) * (8 * DMMA_NT);
-    const uint32_t kpad = (uint32_t)((k + 8 * DMMA_NT - 1) / (8 * DMMA_NT) * (8 * DMMA_NT));
+    bn = bn / (8 * NT) * (8 * NT);
+    const uint32_t kpad = (uint32_t)((k + 8 * NT - 1) / (8 * NT) * (8 * NT));
     if (bn >= kpad) bn = kpad;                                         // whole centroid set resident
-    if (bn < 8 * DMMA_NT) return fail(ctx, SCKM_ERR_INVALID, "shared memory too small for the DMMA tile");
+    if (bn < 8 * NT) return fail(ctx, SCKM_ERR_INVALID, "shared memory too small for the DMMA tile");
     const size_t smem = (size_t)bn * row_bytes;
-    auto kern = assign_dmma_kernel<KSTEPS, MT, TX>;
+    ctx->partial_slots_used = dmma_grid(ctx) * WARPS;
+    auto kern = assign_dmma_kernel<KSTEPS, MT, NT, WARPS, TX>;
     SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dmma_grid(ctx), DMMA_WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
-                                                               ctx->d_cnorm, (uint32_t)k, bn, ds->labels, ds->mind,
-                                                               ctx->d_partials, pk);
+    kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
+                                                          ctx->d_cnorm, (uint32_t)k, bn, ds->labels, ds->mind,
+                                                          ctx->d_partials, pk);
+    LAUNCH_CHECK_D(ctx);
+    refine_rows_kernel<TX, WARPS><<<dmma_grid(ctx), WARPS * 32, 0, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d,
+        ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
+}
+
+static int dmma_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("SCKM_DMMA_VARIANT"); v = e ? atoi(e) : 0; }
+    return v;
 }
 
 template <typename TX>
 static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     const uint64_t d = ds->d;
-    if (d <= 16) return launch_t<4, 2, TX>(ds, k, pk);
-    if (d <= 32) return launch_t<8, 2, TX>(ds, k, pk);
-    if (d <= 64) return launch_t<16, 2, TX>(ds, k, pk);
-    return launch_t<32, 1, TX>(ds, k, pk);
+    if (d <= 16) return launch_t<4, 2, 4, 12, TX>(ds, k, pk);
+    if (d <= 32) return launch_t<8, 2, 4, 12, TX>(ds, k, pk);
+    if (d <= 64) {
+        switch (dmma_variant()) {   // tuning variants (default 0)
+            case 1: return launch_t<16, 1, 8, 16, TX>(ds, k, pk);
+            case 2: return launch_t<16, 1, 4, 16, TX>(ds, k, pk);
+            case 3: return launch_t<16, 2, 8, 8, TX>(ds, k, pk);
+            default: return launch_t<16, 2, 4, 12, TX>(ds, k, pk);
+        }
+    }
+    return launch_t<32, 1, 4, 12, TX>(ds, k, pk);
 }
 
 // labels + mind + per-warp partial [sums | counts | inertia] (fused update); the caller reduces the slots.
@@ -342,15 +368,7 @@ int launch_assign_dmma(sckm_dataset* ds, uint64_t k) {
     LAUNCH_CHECK_D(ctx);
     cnorm_max_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_cnorm, (uint32_t)k);
     LAUNCH_CHECK_D(ctx);
-    SCKM_TRY(ds->dtype == SCKM_F32 ? launch_by_d<float>(ds, k, pk) : launch_by_d<double>(ds, k, pk));
-    if (ds->dtype == SCKM_F32)
-        refine_rows_kernel<float><<<dmma_grid(ctx), DMMA_WARPS * 32, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d,
-            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
-    else
-        refine_rows_kernel<double><<<dmma_grid(ctx), DMMA_WARPS * 32, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d,
-            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
-    LAUNCH_CHECK_D(ctx);
-    return SCKM_OK;
+    return ds->dtype == SCKM_F32 ? launch_by_d<float>(ds, k, pk) : launch_by_d<double>(ds, k, pk);
 }
 
 }  // namespace sckm

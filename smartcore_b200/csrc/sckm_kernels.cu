@@ -324,7 +324,7 @@ __global__ void update_partial_kernel(const T* __restrict__ x, uint64_t n, uint3
                                       const uint32_t* __restrict__ labels, const double* __restrict__ mind,
                                       uint32_t k, uint64_t rows_per_cta, double* __restrict__ partials) {
     const size_t pk = (size_t)k * d + k + 1;
-    double* part = partials + (size_t)blockIdx.x * pk;
+    double* part = partials + (size_t)blockIdx.x * ((pk + 15) / 16 * 16);
     const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_cta;
     const uint64_t r1 = min(n, r0 + rows_per_cta);
     double inertia = 0.0;
@@ -343,34 +343,45 @@ __global__ void update_partial_kernel(const T* __restrict__ x, uint64_t n, uint3
 }
 
 // packed[e] = sum over the partial slots in a FIXED order (8 slot groups summed sequentially by 8 thread rows,
-// then the 8 group sums in order); the slots are zeroed for the next step.  blockDim = (32, 8).
+// then the 8 group sums in order); the slots are zeroed for the next step.  blockDim = (32, 8); each thread owns
+// two adjacent elements (16-byte accesses; slot rows are 128-byte aligned).
 __global__ void __launch_bounds__(256) reduce_partials_kernel(double* __restrict__ partials, uint32_t nslots, size_t pk,
-                                                              double* __restrict__ packed) {
-    __shared__ double sh[8][33];
-    const size_t e = (size_t)blockIdx.x * 32 + threadIdx.x;
+                                                              size_t pitch, double* __restrict__ packed) {
+    __shared__ double2 sh[8][33];
+    const size_t e = ((size_t)blockIdx.x * 32 + threadIdx.x) * 2;
     const uint32_t per = (nslots + 7) / 8;
     const uint32_t p0 = min(nslots, threadIdx.y * per), p1 = min(nslots, p0 + per);
-    double s = 0.0;
-    if (e < pk) {
-        double* q = partials + (size_t)p0 * pk + e;
+    double2 s = make_double2(0.0, 0.0);
+    const double2 zero = make_double2(0.0, 0.0);
+    if (e < pitch) {
+        double2* q = reinterpret_cast<double2*>(partials + (size_t)p0 * pitch + e);
+        const size_t step = pitch / 2;
         uint32_t p = p0;
         for (; p + 8 <= p1; p += 8) {            // 8 independent loads in flight, added in slot order
-            double v[8];
+            double2 v[8];
 #pragma unroll
-            for (int i = 0; i < 8; i++) v[i] = __ldcg(q + (size_t)i * pk);
+            for (int i = 0; i < 8; i++) v[i] = __ldcg(q + (size_t)i * step);
 #pragma unroll
-            for (int i = 0; i < 8; i++) { s = __dadd_rn(s, v[i]); __stcg(q + (size_t)i * pk, 0.0); }
-            q += 8 * pk;
+            for (int i = 0; i < 8; i++) {
+                s.x = __dadd_rn(s.x, v[i].x); s.y = __dadd_rn(s.y, v[i].y);
+                __stcg(q + (size_t)i * step, zero);
+            }
+            q += 8 * step;
         }
-        for (; p < p1; p++) { s = __dadd_rn(s, __ldcg(q)); __stcg(q, 0.0); q += pk; }
+        for (; p < p1; p++) {
+            const double2 v = __ldcg(q);
+            s.x = __dadd_rn(s.x, v.x); s.y = __dadd_rn(s.y, v.y);
+            __stcg(q, zero); q += step;
+        }
     }
     sh[threadIdx.y][threadIdx.x] = s;
     __syncthreads();
-    if (threadIdx.y == 0 && e < pk) {
-        double t = 0.0;
+    if (threadIdx.y == 0) {
+        double2 t = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int i = 0; i < 8; i++) t = __dadd_rn(t, sh[i][threadIdx.x]);
-        packed[e] = t;
+        for (int i = 0; i < 8; i++) { t.x = __dadd_rn(t.x, sh[i][threadIdx.x].x); t.y = __dadd_rn(t.y, sh[i][threadIdx.x].y); }
+        if (e < pk) packed[e] = t.x;
+        if (e + 1 < pk) packed[e + 1] = t.y;
     }
 }
 
@@ -502,7 +513,7 @@ int ensure_workspace(sckm_ctx* ctx, uint64_t k, uint64_t d, size_t partial_slots
     SCKM_TRY(regrow(ctx, &ctx->d_size, &ctx->cap_size, k, sizeof(int64_t)));
     SCKM_TRY(regrow(ctx, &ctx->d_seeds, &ctx->cap_seeds, k, sizeof(int64_t)));
     if (partial_slots)
-        SCKM_TRY(regrow(ctx, &ctx->d_partials, &ctx->cap_partials, partial_slots * pk, sizeof(double)));
+        SCKM_TRY(regrow(ctx, &ctx->d_partials, &ctx->cap_partials, partial_slots * slot_pitch(pk), sizeof(double)));
     return SCKM_OK;
 }
 
@@ -643,7 +654,8 @@ int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia) {
 }
 
 int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk) {
-    reduce_partials_kernel<<<(unsigned)((pk + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(ctx->d_partials, slots, pk, ctx->d_packed);
+    const size_t pitch = slot_pitch(pk);
+    reduce_partials_kernel<<<(unsigned)((pitch / 2 + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed);
     LAUNCH_CHECK(ctx);
     return SCKM_OK;
 }

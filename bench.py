@@ -44,6 +44,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=N_PER_GPU, help="rows per GPU (default: config C3)")
+    ap.add_argument("--d", type=int, default=D, help="features (default: config C3; other shapes are for tuning only)")
+    ap.add_argument("--k", type=int, default=K_CLUSTERS, help="clusters (default: config C3)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -165,7 +167,7 @@ def main():
     ctx = sc.Context(local_rank)
     if distributed:
         scd.join_comm(ctx)
-    n_local, k, d = args.rows, K_CLUSTERS, D
+    n_local, k, d = args.rows, args.k, args.d
     n_global = n_local * world
     row0 = rank * n_local
 
@@ -258,7 +260,7 @@ def main():
                        "n_global": n_global, "d": d, "k": k, "l2": "inputs (5.12 GB/GPU) larger than L2; no flush",
                        "parallelism": "rows sharded x%d, one NCCL all-reduce of k*d+k+1 f64 per step" % world,
                        "kmeanspp_init_s": t_init, "wall_s_timed_region": wall},
-            "roofline": {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+            "roofline": {"bound": "tensor" if k >= 4 * 6 else "hbm", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
                          "kernel": "assignment kernel (dominant), CUDA events on the library stream, mean of %d launches" % args.steps,
                          "kernel_ms": 1e3 * t_assign,

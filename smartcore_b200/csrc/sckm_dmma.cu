@@ -41,18 +41,86 @@ namespace sckm {
 constexpr int DMMA_MAX_WARPS = 16;
 constexpr double DMMA_TIE_REL = 1e-10;
 
-// max/min without NaN plumbing (DSETP + SEL); NaNs are caught by the tie test at the end
-__device__ __forceinline__ double dmax_(double a, double b) { return a > b ? a : b; }
-__device__ __forceinline__ double dmin_(double a, double b) { return a < b ? a : b; }
+// Order-preserving map double -> int64 (an involution on the bit pattern): scalar FP64 instructions share the
+// datapath with DMMA on B200 (bench/dmma_mix.cu: one DADD per DMMA costs 14 % of the DMMA rate, eight IMADs 2 %),
+// so the whole top-2 tracking of the epilogue runs on integer keys.  NaNs sort to the extremes and are caught by
+// the tie test at the end (gap is NaN -> exact re-decision).
+typedef long long key_t;
+__device__ __forceinline__ key_t dkey(double v) {
+    const key_t b = __double_as_longlong(v);
+    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
+}
+__device__ __forceinline__ double dunkey(key_t k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL)); }
+constexpr key_t KEY_MIN = (key_t)0x8000000000000000ULL;
 
 __device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                  : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
 }
 
+
+// ---- building blocks of the tile kernel (all force-inlined; arrays stay in registers) ----
+// accumulators start at -||c||^2/2 (plain copies out of shared memory, no FP64 instruction); the row's own
+// -||x||^2/2 is constant over the centroids and is only added back once per row at the very end
+template <int MT, int NT>
+__device__ __forceinline__ void acc_init(double (&acc)[MT][NT][2], const double* __restrict__ cn_sub, int t) {
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+        const double2 c2 = *reinterpret_cast<const double2*>(cn_sub + nt * 8 + 2 * t);
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) { acc[mt][nt][0] = c2.x; acc[mt][nt][1] = c2.y; }
+    }
+}
+
+// one epilogue item: element (nt, e) of m-tile mt -> running max / second max / argmax (ascending column order)
+template <int MT, int NT>
+__device__ __forceinline__ void epi_item(const double (&acc)[MT][NT][2], int item, uint32_t col_base, int t,
+                                         key_t (&best)[MT], key_t (&second)[MT], uint32_t (&bidx)[MT]) {
+    const int mt = item % MT, j = item / MT, nt = j >> 1, e = j & 1;
+    const uint32_t col = col_base + nt * 8 + 2 * t + e;
+    const key_t v = dkey(acc[mt][nt][e]);
+    const bool gt = v > best[mt];
+    const key_t lose = gt ? best[mt] : v;
+    second[mt] = lose > second[mt] ? lose : second[mt];
+    bidx[mt] = gt ? col : bidx[mt];
+    best[mt] = gt ? v : best[mt];
+}
+
+// K loop of one sub-block into accC; when EPI, the epilogue items of the PREVIOUS sub-block (accE) are spread over
+// the k-steps so that their FP64-ALU work issues in the shadow of this sub-block's DMMAs (software pipelining).
+template <int KSTEPS, int MT, int NT, int PITCH, bool EPI>
+__device__ __forceinline__ void kloop(double (&accC)[MT][NT][2], const double (&accE)[MT][NT][2],
+                                      const double (&a)[MT][KSTEPS], const double* __restrict__ bp,
+                                      uint32_t colE_base, int t, key_t (&best)[MT], key_t (&second)[MT],
+                                      uint32_t (&bidx)[MT]) {
+    constexpr int ITEMS = MT * NT * 2;
+#pragma unroll
+    for (int ks = 0; ks < KSTEPS; ks++) {
+        double b[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) b[nt] = bp[(size_t)nt * 8 * PITCH + ks * 4];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++)
+#pragma unroll
+            for (int nt = 0; nt < NT; nt++) dmma884(accC[mt][nt][0], accC[mt][nt][1], a[mt][ks], b[nt]);
+        if (EPI) {
+#pragma unroll
+            for (int item = 0; item < ITEMS; item++)
+                if (item * KSTEPS / ITEMS == ks) epi_item<MT, NT>(accE, item, colE_base, t, best, second, bidx);
+        }
+    }
+}
+
+template <int MT, int NT>
+__device__ __forceinline__ void epilogue_all(const double (&acc)[MT][NT][2], uint32_t col_base, int t,
+                                             key_t (&best)[MT], key_t (&second)[MT], uint32_t (&bidx)[MT]) {
+#pragma unroll
+    for (int item = 0; item < MT * NT * 2; item++) epi_item<MT, NT>(acc, item, col_base, t, best, second, bidx);
+}
+
 // KSTEPS: d padded to 4*KSTEPS; MT: m-tiles (8 rows each) per warp slab; DMMA_NT: n-tiles (8 centroids each) per
 // accumulator sub-block; DMMA_WARPS: warps per CTA (one CTA per SM)
-template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, typename TX>
+template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool PIPE, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t* __restrict__ labels,
@@ -82,7 +150,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
         const uint64_t r0 = slab * ROWS;
         // ---- rows -> A fragments (registers), ||x||^2 ----
         double a[MT][KSTEPS];
-        double xn[MT], hxn[MT];
+        double xn[MT];
 #pragma unroll
         for (int mt = 0; mt < MT; mt++) {
             const uint64_t row = r0 + mt * 8 + g;
@@ -100,12 +168,11 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
             s += __shfl_xor_sync(0xffffffffu, s, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2);
             xn[mt] = s;
-            hxn[mt] = -0.5 * s;
         }
-        double best[MT], second[MT];
+        key_t best[MT], second[MT];
         uint32_t bidx[MT];
 #pragma unroll
-        for (int mt = 0; mt < MT; mt++) { best[mt] = -DBL_MAX; second[mt] = -DBL_MAX; bidx[mt] = 0; }
+        for (int mt = 0; mt < MT; mt++) { best[mt] = KEY_MIN; second[mt] = KEY_MIN; bidx[mt] = 0; }
 
         for (uint32_t ch = 0; ch < nchunks; ch++) {
             const uint32_t c0 = ch * bn;
@@ -123,43 +190,38 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                 __syncthreads();
             }
             const uint32_t cols = min(bn, k - c0);
-            for (uint32_t ns = 0; ns < cols; ns += 8 * DMMA_NT) {
-                double acc[MT][DMMA_NT][2];
-#pragma unroll
-                for (int nt = 0; nt < DMMA_NT; nt++) {
-                    const double cn0 = cn[ns + nt * 8 + 2 * t], cn1 = cn[ns + nt * 8 + 2 * t + 1];
-#pragma unroll
-                    for (int mt = 0; mt < MT; mt++) {
-                        acc[mt][nt][0] = hxn[mt] + cn0;
-                        acc[mt][nt][1] = hxn[mt] + cn1;
-                    }
+            constexpr int SUB = 8 * DMMA_NT;                       // centroids per accumulator sub-block
+            const uint32_t nsub = (cols + SUB - 1) / SUB;
+            if (PIPE) {
+                // two accumulator sets: the epilogue of sub-block i-1 rides under the DMMAs of sub-block i
+                double acc0[MT][DMMA_NT][2], acc1[MT][DMMA_NT][2];
+                acc_init<MT, DMMA_NT>(acc0, cn, t);
+                kloop<KSTEPS, MT, DMMA_NT, PITCH, false>(acc0, acc0, a, bbase, 0, t, best, second, bidx);
+                uint32_t sb = 1;
+                for (; sb + 1 < nsub; sb += 2) {
+                    acc_init<MT, DMMA_NT>(acc1, cn + sb * SUB, t);
+                    kloop<KSTEPS, MT, DMMA_NT, PITCH, true>(acc1, acc0, a, bbase + (size_t)sb * SUB * PITCH,
+                                                             c0 + (sb - 1) * SUB, t, best, second, bidx);
+                    acc_init<MT, DMMA_NT>(acc0, cn + (sb + 1) * SUB, t);
+                    kloop<KSTEPS, MT, DMMA_NT, PITCH, true>(acc0, acc1, a, bbase + (size_t)(sb + 1) * SUB * PITCH,
+                                                             c0 + sb * SUB, t, best, second, bidx);
                 }
-                const double* bp = bbase + (size_t)ns * PITCH;
-#pragma unroll
-                for (int ks = 0; ks < KSTEPS; ks++) {
-                    double b[DMMA_NT];
-#pragma unroll
-                    for (int nt = 0; nt < DMMA_NT; nt++) b[nt] = bp[(size_t)nt * 8 * PITCH + ks * 4];
-#pragma unroll
-                    for (int mt = 0; mt < MT; mt++)
-#pragma unroll
-                        for (int nt = 0; nt < DMMA_NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt][ks], b[nt]);
+                if (sb < nsub) {
+                    acc_init<MT, DMMA_NT>(acc1, cn + sb * SUB, t);
+                    kloop<KSTEPS, MT, DMMA_NT, PITCH, true>(acc1, acc0, a, bbase + (size_t)sb * SUB * PITCH,
+                                                             c0 + (sb - 1) * SUB, t, best, second, bidx);
+                    epilogue_all<MT, DMMA_NT>(acc1, c0 + sb * SUB, t, best, second, bidx);
+                } else {
+                    epilogue_all<MT, DMMA_NT>(acc0, c0 + (sb - 1) * SUB, t, best, second, bidx);
                 }
-                // epilogue: running max / second max of acc = -dist^2/2, ascending column order
-#pragma unroll
-                for (int nt = 0; nt < DMMA_NT; nt++)
-#pragma unroll
-                    for (int e = 0; e < 2; e++) {
-                        const uint32_t col = c0 + ns + nt * 8 + 2 * t + e;
-#pragma unroll
-                        for (int mt = 0; mt < MT; mt++) {
-                            const double v = acc[mt][nt][e];
-                            const bool gt = v > best[mt];
-                            second[mt] = dmax_(second[mt], gt ? best[mt] : v);
-                            bidx[mt] = gt ? col : bidx[mt];
-                            best[mt] = gt ? v : best[mt];
-                        }
-                    }
+            } else {
+                for (uint32_t sb = 0; sb < nsub; sb++) {
+                    double acc[MT][DMMA_NT][2];
+                    acc_init<MT, DMMA_NT>(acc, cn + sb * SUB, t);
+                    kloop<KSTEPS, MT, DMMA_NT, PITCH, false>(acc, acc, a, bbase + (size_t)sb * SUB * PITCH, 0, t, best,
+                                                              second, bidx);
+                    epilogue_all<MT, DMMA_NT>(acc, c0 + sb * SUB, t, best, second, bidx);
+                }
             }
         }
         // ---- merge the 4 lanes that share a row, write out, mark near-ties, fused update ----
@@ -168,18 +230,21 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
         for (int mt = 0; mt < MT; mt++) {
 #pragma unroll
             for (int o = 1; o <= 2; o <<= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best[mt], o);
-                const double os = __shfl_xor_sync(0xffffffffu, second[mt], o);
+                const key_t ob = __shfl_xor_sync(0xffffffffu, best[mt], o);
+                const key_t os = __shfl_xor_sync(0xffffffffu, second[mt], o);
                 const uint32_t oi = __shfl_xor_sync(0xffffffffu, bidx[mt], o);
                 const bool take = ob > best[mt] || (ob == best[mt] && oi < bidx[mt]);
-                second[mt] = dmax_(dmax_(second[mt], os), dmin_(best[mt], ob));
+                const key_t lo_best = ob < best[mt] ? ob : best[mt];
+                key_t s2 = os > second[mt] ? os : second[mt];
+                second[mt] = lo_best > s2 ? lo_best : s2;
                 bidx[mt] = take ? oi : bidx[mt];
-                best[mt] = dmax_(best[mt], ob);
+                best[mt] = ob > best[mt] ? ob : best[mt];
             }
             const uint64_t row = r0 + mt * 8 + g;
             const bool valid = active && row < n;
-            const double dist = fmax(0.0, -2.0 * best[mt]);
-            const double gap = 2.0 * (best[mt] - second[mt]);
+            const double bestv = dunkey(best[mt]), secondv = dunkey(second[mt]);   // x.c - ||c||^2/2
+            const double dist = fmax(0.0, fma(-2.0, bestv, xn[mt]));
+            const double gap = 2.0 * (bestv - secondv);
             const bool tie = !(gap > DMMA_TIE_REL * (xn[mt] + cmax));   // also catches NaN
             if (valid && t == 0) {
                 labels[row] = tie ? 0xffffffffu : bidx[mt];             // ties are re-decided by refine_rows_kernel
@@ -311,7 +376,7 @@ static unsigned dmma_grid(const sckm_ctx* ctx) { return (unsigned)ctx->num_sms; 
 // number of per-warp partial slots the fused kernels may accumulate into (reduced by launch_reduce_partials)
 uint32_t dmma_partial_slots(const sckm_ctx* ctx) { return dmma_grid(ctx) * DMMA_MAX_WARPS; }
 
-template <int KSTEPS, int MT, int NT, int WARPS, typename TX>
+template <int KSTEPS, int MT, int NT, int WARPS, bool PIPE, typename TX>
 static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     sckm_ctx* ctx = ds->ctx;
     constexpr int DP = KSTEPS * 4, PITCH = DP + 4;
@@ -323,7 +388,7 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     if (bn < 8 * NT) return fail(ctx, SCKM_ERR_INVALID, "shared memory too small for the DMMA tile");
     const size_t smem = (size_t)bn * row_bytes;
     ctx->partial_slots_used = dmma_grid(ctx) * WARPS;
-    auto kern = assign_dmma_kernel<KSTEPS, MT, NT, WARPS, TX>;
+    auto kern = assign_dmma_kernel<KSTEPS, MT, NT, WARPS, PIPE, TX>;
     SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
                                                           ctx->d_cnorm, (uint32_t)k, bn, ds->labels, ds->mind,
@@ -344,17 +409,20 @@ static int dmma_variant() {
 template <typename TX>
 static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     const uint64_t d = ds->d;
-    if (d <= 16) return launch_t<4, 2, 4, 12, TX>(ds, k, pk);
-    if (d <= 32) return launch_t<8, 2, 4, 12, TX>(ds, k, pk);
+    if (d <= 16) return launch_t<4, 2, 4, 12, false, TX>(ds, k, pk);
+    if (d <= 32) return launch_t<8, 2, 4, 12, false, TX>(ds, k, pk);
     if (d <= 64) {
         switch (dmma_variant()) {   // tuning variants (default 0)
-            case 1: return launch_t<16, 1, 8, 16, TX>(ds, k, pk);
-            case 2: return launch_t<16, 1, 4, 16, TX>(ds, k, pk);
-            case 3: return launch_t<16, 2, 8, 8, TX>(ds, k, pk);
-            default: return launch_t<16, 2, 4, 12, TX>(ds, k, pk);
+            case 1: return launch_t<16, 2, 4, 8, true, TX>(ds, k, pk);
+            case 2: return launch_t<16, 1, 4, 16, false, TX>(ds, k, pk);
+            case 3: return launch_t<16, 2, 4, 10, true, TX>(ds, k, pk);
+            case 4: return launch_t<16, 1, 8, 12, true, TX>(ds, k, pk);
+            case 5: return launch_t<16, 1, 4, 16, true, TX>(ds, k, pk);
+            case 6: return launch_t<16, 2, 4, 12, true, TX>(ds, k, pk);
+            default: return launch_t<16, 2, 4, 12, false, TX>(ds, k, pk);
         }
     }
-    return launch_t<32, 1, 4, 12, TX>(ds, k, pk);
+    return launch_t<32, 1, 4, 12, false, TX>(ds, k, pk);
 }
 
 // labels + mind + per-warp partial [sums | counts | inertia] (fused update); the caller reduces the slots.

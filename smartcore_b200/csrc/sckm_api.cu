@@ -14,6 +14,8 @@ const char* create_error_text();
 int launch_assign_dmma(sckm_dataset* ds, uint64_t k);         // sckm_dmma.cu
 bool dmma_supported(const sckm_dataset* ds, uint64_t k);      // sckm_dmma.cu
 uint32_t dmma_partial_slots(const sckm_ctx* ctx);             // sckm_dmma.cu
+int launch_assign_stream(sckm_dataset* ds, uint64_t k);       // sckm_stream.cu
+bool stream_supported(const sckm_dataset* ds, uint64_t k);    // sckm_stream.cu
 }
 using namespace sckm;
 
@@ -254,9 +256,10 @@ int sckm_kmeanspp(sckm_dataset* ds, uint64_t k, uint64_t first_index, const doub
 static int pick_assign(const sckm_dataset* ds, uint64_t k) {
     const sckm_ctx* ctx = ds->ctx;
     int which = ctx->assign_kernel;
-    if (which == SCKM_ASSIGN_AUTO) which = dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA : SCKM_ASSIGN_DIRECT;
+    if (which == SCKM_ASSIGN_AUTO)
+        which = dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA : stream_supported(ds, k) ? SCKM_ASSIGN_STREAM : SCKM_ASSIGN_DIRECT;
     if (which == SCKM_ASSIGN_DMMA && !dmma_supported(ds, k)) which = SCKM_ASSIGN_DIRECT;
-    if (which == SCKM_ASSIGN_STREAM) which = SCKM_ASSIGN_DIRECT;  // streaming kernel: see sckm_dmma.cu notes
+    if (which == SCKM_ASSIGN_STREAM && !stream_supported(ds, k)) which = SCKM_ASSIGN_DIRECT;
     return which;
 }
 
@@ -265,8 +268,9 @@ static int clustering_step(sckm_dataset* ds, uint64_t k, cudaEvent_t ev_a0 = nul
     sckm_ctx* ctx = ds->ctx;
     const int which = pick_assign(ds, k);
     if (ev_a0) SCKM_CUDA(ctx, cudaEventRecord(ev_a0, ctx->stream));
-    if (which == SCKM_ASSIGN_DMMA) {
-        SCKM_TRY(launch_assign_dmma(ds, k));                      // assignment + fused per-warp partial sums
+    if (which == SCKM_ASSIGN_DMMA || which == SCKM_ASSIGN_STREAM) {
+        if (which == SCKM_ASSIGN_DMMA) SCKM_TRY(launch_assign_dmma(ds, k));   // assignment + fused partial sums
+        else SCKM_TRY(launch_assign_stream(ds, k));
         if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
         SCKM_TRY(launch_reduce_partials(ctx, ctx->partial_slots_used, (size_t)k * ds->d + k + 1));
     } else {

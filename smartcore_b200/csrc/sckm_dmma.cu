@@ -23,6 +23,7 @@
 //     memory, in a fixed order, so results are bit-reproducible run to run (needed by the stop rule
 //     `distortion <= dist`, kmeans.rs:305) without any floating-point atomics.
 #include "sckm_common.cuh"
+#include "sckm_tile.cuh"
 #include <cfloat>
 #include <algorithm>
 #include <cstdlib>
@@ -40,23 +41,6 @@ namespace sckm {
 
 constexpr int DMMA_MAX_WARPS = 16;
 constexpr double DMMA_TIE_REL = 1e-10;
-
-// Order-preserving map double -> int64 (an involution on the bit pattern): scalar FP64 instructions share the
-// datapath with DMMA on B200 (bench/dmma_mix.cu: one DADD per DMMA costs 14 % of the DMMA rate, eight IMADs 2 %),
-// so the whole top-2 tracking of the epilogue runs on integer keys.  NaNs sort to the extremes and are caught by
-// the tie test at the end (gap is NaN -> exact re-decision).
-typedef long long key_t;
-__device__ __forceinline__ key_t dkey(double v) {
-    const key_t b = __double_as_longlong(v);
-    return b ^ ((b >> 63) & 0x7fffffffffffffffLL);
-}
-__device__ __forceinline__ double dunkey(key_t k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL)); }
-constexpr key_t KEY_MIN = (key_t)0x8000000000000000ULL;
-
-__device__ __forceinline__ void dmma884(double& c0, double& c1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                 : "+d"(c0), "+d"(c1) : "d"(a), "d"(b));
-}
 
 
 // ---- building blocks of the tile kernel (all force-inlined; arrays stay in registers) ----
@@ -425,6 +409,27 @@ static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     return launch_t<32, 1, 4, 12, false, TX>(ds, k, pk);
 }
 
+int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d) {
+    cnorm_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_cnorm);
+    LAUNCH_CHECK_D(ctx);
+    cnorm_max_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_cnorm, (uint32_t)k);
+    LAUNCH_CHECK_D(ctx);
+    return SCKM_OK;
+}
+
+// refine pass for the streaming kernel's launch geometry (8 warps per CTA)
+int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas) {
+    sckm_ctx* ctx = ds->ctx;
+    if (ds->dtype == SCKM_F32)
+        refine_rows_kernel<float, 8><<<grid_ctas, 256, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d,
+            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
+    else
+        refine_rows_kernel<double, 8><<<grid_ctas, 256, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d,
+            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
+    LAUNCH_CHECK_D(ctx);
+    return SCKM_OK;
+}
+
 // labels + mind + per-warp partial [sums | counts | inertia] (fused update); the caller reduces the slots.
 int launch_assign_dmma(sckm_dataset* ds, uint64_t k) {
     sckm_ctx* ctx = ds->ctx;
@@ -432,10 +437,7 @@ int launch_assign_dmma(sckm_dataset* ds, uint64_t k) {
     const size_t pk = (size_t)k * ds->d + k + 1;
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, dmma_partial_slots(ctx)));
     if (ds->n == 0) return SCKM_OK;
-    cnorm_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)ds->d, ctx->d_cnorm);
-    LAUNCH_CHECK_D(ctx);
-    cnorm_max_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_cnorm, (uint32_t)k);
-    LAUNCH_CHECK_D(ctx);
+    SCKM_TRY(launch_cnorm(ctx, k, ds->d));
     return ds->dtype == SCKM_F32 ? launch_by_d<float>(ds, k, pk) : launch_by_d<double>(ds, k, pk);
 }
 

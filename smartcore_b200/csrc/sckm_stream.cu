@@ -1,0 +1,331 @@
+// sckm_stream.cu -- K3s: streaming Lloyd step for small k*d (config C2: 1M x 16, k = 8), where the step is
+// HBM-bound (k/4 flop per byte < ~6): one pass over X does assignment AND the per-cluster update.
+//
+// Replaces BBDTree::clustering (src/algorithm/neighbour/bbd_tree.rs:62-163) for shapes the DMMA tile kernel
+// does not take (k < 16).
+//
+//   * a warp owns batches of 32 consecutive rows; the rows go from HBM straight into DMMA A-fragment registers
+//     (16-byte loads, every request = full 32-byte sectors; the feature order is permuted consistently in both
+//     GEMM operands so a lane's elements are contiguous in memory) -- no staging, no shared memory in the loop;
+//   * scores  x.c_j - ||c_j||^2/2  as 8x8x4 DMMAs against centroid B-fragments that stay in registers for the
+//     whole launch; top-2 per row on integer keys; rows whose gap is within 1e-10*(||x||^2 + max||c||^2) are
+//     marked and re-decided exactly by refine_rows_kernel (same rule as the DMMA tile kernel), so labels equal
+//     the dense oracle;
+//   * update: sums[cluster][feature] += onehot(label)^T . X, again as DMMAs whose accumulators live in registers
+//     for the whole launch (the FP64 tensor path used as a wide adder with a fixed, hardware-defined order: no
+//     atomics, no read-modify-write traffic); counts are integer adds; one store per CTA into its partial slot at
+//     the end => bit-reproducible for a fixed (n, grid).
+#include "sckm_common.cuh"
+#include "sckm_tile.cuh"
+#include <cfloat>
+#include <algorithm>
+#include <type_traits>
+
+namespace sckm {
+
+#define LAUNCH_CHECK_S(ctx)                                                                        \
+    do {                                                                                           \
+        (ctx)->launches++;                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess)                                                                     \
+            return fail((ctx), SCKM_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+constexpr int STREAM_WARPS = 8;
+constexpr int STREAM_MAX_K = 15;
+constexpr double STREAM_TIE_REL = 1e-10;
+
+int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas);   // sckm_dmma.cu
+
+// Feature (k-dimension) permutation used by both operands of the scoring GEMM so that a lane's KS elements of a
+// row are VW-element vectors in memory (one 16-byte LDG per VW k-steps): the dot product does not care about the
+// order of its terms, only that A and B agree.  VW = 1 is the textbook layout col = 4*ks + t.
+template <int VW> __device__ __forceinline__ constexpr int kcol(int t, int ks) { return (ks / VW) * (4 * VW) + t * VW + (ks % VW); }
+
+template <typename TX, int VW> struct VecLoad;
+template <typename TX> struct VecLoad<TX, 1> {
+    static __device__ __forceinline__ void ld(const TX* p, double (&o)[1]) { o[0] = (double)__ldg(p); }
+};
+template <> struct VecLoad<double, 2> {
+    static __device__ __forceinline__ void ld(const double* p, double (&o)[2]) {
+        const double2 v = __ldg(reinterpret_cast<const double2*>(p)); o[0] = v.x; o[1] = v.y; }
+};
+template <> struct VecLoad<float, 2> {
+    static __device__ __forceinline__ void ld(const float* p, double (&o)[2]) {
+        const float2 v = __ldg(reinterpret_cast<const float2*>(p)); o[0] = v.x; o[1] = v.y; }
+};
+template <> struct VecLoad<float, 4> {
+    static __device__ __forceinline__ void ld(const float* p, double (&o)[4]) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+};
+
+// KS: k-steps of the scoring GEMM (features padded to 4*KS); KT: 8-cluster tiles (k <= 8*KT); VW: see kcol
+template <int KS, int KT, int VW, typename TX>
+__global__ void __launch_bounds__(STREAM_WARPS * 32, (KS * KT <= 8) ? 2 : 1)
+assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
+                     const double* __restrict__ cnorm, uint32_t k, uint32_t* __restrict__ labels,
+                     double* __restrict__ mind, double* __restrict__ partials, size_t pk) {
+    constexpr int NTU = KS / 2 > 0 ? KS / 2 : 1;         // feature n-tiles of the update GEMM (8 features each)
+    extern __shared__ __align__(16) double smem_s[];     // [warps][k*d] sums | [warps][16] counts | [warps] inertia
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const double cmax = cnorm[k];
+
+    // centroid B fragments and -||c||^2/2, resident in registers for the whole launch
+    double bc[KT][KS], hc[KT][2];
+#pragma unroll
+    for (int nt = 0; nt < KT; nt++) {
+        const uint32_t c = nt * 8 + g;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            const uint32_t col = kcol<VW>(t, ks);
+            bc[nt][ks] = (c < k && col < d) ? centroids[(size_t)c * d + col] : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const uint32_t ce = nt * 8 + 2 * t + e;
+            hc[nt][e] = ce < k ? -0.5 * cnorm[ce] : -INFINITY;
+        }
+    }
+    double cu[KT][NTU][2];                               // per-cluster sums: cluster ct*8+g, feature nt*8+2t+e
+#pragma unroll
+    for (int ct = 0; ct < KT; ct++)
+#pragma unroll
+        for (int nt = 0; nt < NTU; nt++) { cu[ct][nt][0] = 0.0; cu[ct][nt][1] = 0.0; }
+    uint32_t cnt[KT];
+#pragma unroll
+    for (int ct = 0; ct < KT; ct++) cnt[ct] = 0;
+    double inertia = 0.0;
+
+    const uint64_t nbatches = (n + 31) / 32;
+    const uint64_t wglobal = (uint64_t)blockIdx.x * STREAM_WARPS + warp;
+    const uint64_t nwarps = (uint64_t)gridDim.x * STREAM_WARPS;
+
+    // rows -> A fragments straight from HBM (8 rows x full 32-byte sectors per request)
+    double a[4][KS];
+    auto load_rows = [&](uint64_t row0) {
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+            const uint64_t row = row0 + mt * 8 + g;
+            const TX* xr = x + row * d;
+#pragma unroll
+            for (int i = 0; i < KS / VW; i++) {
+                const uint32_t col0 = kcol<VW>(t, i * VW);
+                double v[VW];
+#pragma unroll
+                for (int e = 0; e < VW; e++) v[e] = 0.0;
+                if (row < n && col0 < d) VecLoad<TX, VW>::ld(xr + col0, v);
+#pragma unroll
+                for (int e = 0; e < VW; e++) a[mt][i * VW + e] = v[e];
+            }
+        }
+    };
+    if (wglobal < nbatches) load_rows(wglobal * 32);
+
+    for (uint64_t b = wglobal; b < nbatches; b += nwarps) {
+        const uint64_t row0 = b * 32;
+        double xn[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+            double sq = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) sq = fma(a[mt][ks], a[mt][ks], sq);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 1);
+            sq += __shfl_xor_sync(0xffffffffu, sq, 2);
+            xn[mt] = sq;
+        }
+        // ---- scores x.c - ||c||^2/2 on the FP64 tensor path ----
+        double acc[4][KT][2];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+            for (int nt = 0; nt < KT; nt++) { acc[mt][nt][0] = hc[nt][0]; acc[mt][nt][1] = hc[nt][1]; }
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++)
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int nt = 0; nt < KT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt][ks], bc[nt][ks]);
+        // the A registers are dead now: prefetch the next batch so its HBM latency hides under epilogue + update
+        if (b + nwarps < nbatches) load_rows((b + nwarps) * 32);
+        // ---- argmax per row: each lane holds 2*KT scores of row (mt, g); butterfly over the 4 lanes of the row
+        // (strict >, lowest index on ties).  Near-ties are detected afterwards by one more pass over the scores:
+        // some OTHER column within the tolerance of the winner <=> (best - second) within tolerance. ----
+        uint32_t lab[4];
+#pragma unroll
+        for (int mt = 0; mt < 4; mt++) {
+            double best = acc[mt][0][0]; uint32_t bi = 2 * t;
+#pragma unroll
+            for (int nt = 0; nt < KT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++) {
+                    if (nt == 0 && e == 0) continue;
+                    const double v = acc[mt][nt][e];
+                    const bool gt = v > best;
+                    bi = gt ? (uint32_t)(nt * 8 + 2 * t + e) : bi;
+                    best = gt ? v : best;
+                }
+#pragma unroll
+            for (int o = 1; o <= 2; o <<= 1) {
+                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
+                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+                const bool take = ob > best || (ob == best && oi < bi);
+                bi = take ? oi : bi;
+                best = take ? ob : best;
+            }
+            const uint64_t row = row0 + mt * 8 + g;
+            const bool valid = row < n;
+            const double dist = fmax(0.0, fma(-2.0, best, xn[mt]));
+            // gap = 2*(best - v) <= tol  <=>  v >= best - tol/2 ; NaN scores fail every comparison and are caught below
+            const double thr = best - 0.5 * STREAM_TIE_REL * (xn[mt] + cmax);
+            bool near = false;
+#pragma unroll
+            for (int nt = 0; nt < KT; nt++)
+#pragma unroll
+                for (int e = 0; e < 2; e++)
+                    near = near || (acc[mt][nt][e] >= thr && (uint32_t)(nt * 8 + 2 * t + e) != bi);
+            near = near || !(best == best);                                  // NaN winner
+            const unsigned nb = __ballot_sync(0xffffffffu, near);
+            const bool tie = ((nb >> (lane & ~3)) & 0xfu) != 0u;
+            const bool ok = valid && !tie;
+            if (valid && t == 0) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = dist; }
+            if (ok && t == 0) inertia = __dadd_rn(inertia, dist);
+            lab[mt] = ok ? bi : 0xffffffffu;
+        }
+        // ---- update: sums[cluster][feature] += onehot(label)^T . X as DMMAs accumulating in registers.
+        // K dimension = the 32 rows (row 4*ks+t), A = one-hot of the labels, B = the rows again (L1 hits). ----
+#pragma unroll
+        for (int ks = 0; ks < 8; ks++) {
+            const uint32_t lr = __shfl_sync(0xffffffffu, lab[ks >> 1], ((4 * (ks & 1) + t) << 2));
+            const uint64_t row = row0 + 4 * ks + t;
+            const TX* xr = x + row * d;
+            double xb[NTU];
+#pragma unroll
+            for (int nt = 0; nt < NTU; nt++) {
+                const uint32_t col = nt * 8 + g;
+                xb[nt] = (row < n && col < d) ? (double)__ldg(xr + col) : 0.0;
+            }
+#pragma unroll
+            for (int ct = 0; ct < KT; ct++) {
+                const bool hit = lr == (uint32_t)(ct * 8 + g);
+                cnt[ct] += hit ? 1u : 0u;
+                const double oh = hit ? 1.0 : 0.0;
+#pragma unroll
+                for (int nt = 0; nt < NTU; nt++) dmma884(cu[ct][nt][0], cu[ct][nt][1], oh, xb[nt]);
+            }
+        }
+    }
+    // ---- per-warp results -> shared memory, CTA combine in warp order, store this CTA's partial slot ----
+    const uint32_t kd = k * d;
+    double* s_sum = smem_s + (size_t)warp * kd;
+    uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_s + (size_t)STREAM_WARPS * kd) + warp * 16;
+    double* s_in = smem_s + (size_t)STREAM_WARPS * kd + STREAM_WARPS * 8;
+#pragma unroll
+    for (int ct = 0; ct < KT; ct++) {
+        const uint32_t c = ct * 8 + g;
+#pragma unroll
+        for (int nt = 0; nt < NTU; nt++)
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const uint32_t f = nt * 8 + 2 * t + e;
+                if (c < k && f < d) s_sum[(size_t)c * d + f] = cu[ct][nt][e];
+            }
+        uint32_t cc = cnt[ct];
+        cc += __shfl_xor_sync(0xffffffffu, cc, 1);
+        cc += __shfl_xor_sync(0xffffffffu, cc, 2);
+        if (t == 0 && c < 16) s_cnt[c] = cc;
+    }
+    double v = inertia;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+    if (lane == 0) s_in[warp] = v;
+    __syncthreads();
+    double* part = partials + (size_t)blockIdx.x * ((pk + 15) / 16 * 16);
+    for (uint32_t e = threadIdx.x; e < kd; e += blockDim.x) {
+        double tsum = 0.0;
+#pragma unroll
+        for (int w = 0; w < STREAM_WARPS; w++) tsum = __dadd_rn(tsum, smem_s[(size_t)w * kd + e]);
+        part[e] = tsum;
+    }
+    if (threadIdx.x < k) {
+        const uint32_t* cbase = reinterpret_cast<const uint32_t*>(smem_s + (size_t)STREAM_WARPS * kd);
+        uint32_t c = 0;
+#pragma unroll
+        for (int w = 0; w < STREAM_WARPS; w++) c += cbase[w * 16 + threadIdx.x];
+        part[(size_t)kd + threadIdx.x] = (double)c;
+    }
+    if (threadIdx.x == 0) {
+        double tsum = 0.0;
+#pragma unroll
+        for (int w = 0; w < STREAM_WARPS; w++) tsum = __dadd_rn(tsum, s_in[w]);
+        part[pk - 1] = tsum;
+    }
+}
+
+bool stream_supported(const sckm_dataset* ds, uint64_t k) {
+    return k >= 1 && k <= STREAM_MAX_K && ds->d >= 1 && ds->d <= 32 && ds->n < 0xFFFFFFFFull;
+}
+
+template <int KS, int KT, int VW, typename TX>
+static int launch_stream_t(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* grid_out) {
+    sckm_ctx* ctx = ds->ctx;
+    const uint32_t d = (uint32_t)ds->d;
+    const size_t smem = ((size_t)STREAM_WARPS * k * d + STREAM_WARPS * 8 + STREAM_WARPS) * sizeof(double);
+    auto kern = assign_stream_kernel<KS, KT, VW, TX>;
+    if (smem > 48 * 1024) SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int ctas_per_sm = 0;
+    SCKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, STREAM_WARPS * 32, smem));
+    ctas_per_sm = std::max(1, std::min(ctas_per_sm, 4));
+    const uint64_t nbatches = (ds->n + 31) / 32;
+    const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbatches + STREAM_WARPS - 1) / STREAM_WARPS,
+                                                                              (uint64_t)ctx->num_sms * ctas_per_sm));
+    kern<<<grid, STREAM_WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, d, ctx->d_centroids, ctx->d_cnorm,
+                                                        (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
+    LAUNCH_CHECK_S(ctx);
+    *grid_out = grid;
+    return SCKM_OK;
+}
+
+template <int KS, int KT, typename TX>
+static int launch_stream_vw(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* grid_out) {
+    constexpr int VMAX = (16 / sizeof(TX)) < KS ? (16 / sizeof(TX)) : KS;     // widest 16-byte vector that fits KS
+    if (ds->d % VMAX == 0) return launch_stream_t<KS, KT, VMAX, TX>(ds, k, pk, grid_out);
+    if (VMAX > 2 && ds->d % 2 == 0) return launch_stream_t<KS, KT, 2, TX>(ds, k, pk, grid_out);
+    return launch_stream_t<KS, KT, 1, TX>(ds, k, pk, grid_out);
+}
+
+template <typename TX>
+static int launch_stream_by_d(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* grid_out) {
+    const uint64_t d = ds->d;
+    if (k <= 8) {
+        if (d <= 8) return launch_stream_vw<2, 1, TX>(ds, k, pk, grid_out);
+        if (d <= 16) return launch_stream_vw<4, 1, TX>(ds, k, pk, grid_out);
+        return launch_stream_vw<8, 1, TX>(ds, k, pk, grid_out);
+    }
+    if (d <= 8) return launch_stream_vw<2, 2, TX>(ds, k, pk, grid_out);
+    if (d <= 16) return launch_stream_vw<4, 2, TX>(ds, k, pk, grid_out);
+    return launch_stream_vw<8, 2, TX>(ds, k, pk, grid_out);
+}
+
+int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d);   // sckm_dmma.cu
+
+// labels + mind + per-warp partials (fused update); the caller reduces ctx->partial_slots_used slots
+int launch_assign_stream(sckm_dataset* ds, uint64_t k) {
+    sckm_ctx* ctx = ds->ctx;
+    if (!stream_supported(ds, k)) return fail(ctx, SCKM_ERR_INVALID, "shape not supported by the streaming kernel");
+    const size_t pk = (size_t)k * ds->d + k + 1;
+    SCKM_TRY(ensure_workspace(ctx, k, ds->d, (size_t)ctx->num_sms * 4 * STREAM_WARPS));
+    ctx->partial_slots_used = 0;
+    if (ds->n == 0) return SCKM_OK;
+    SCKM_TRY(launch_cnorm(ctx, k, ds->d));
+    unsigned grid = 0;
+    SCKM_TRY(ds->dtype == SCKM_F32 ? launch_stream_by_d<float>(ds, k, pk, &grid) : launch_stream_by_d<double>(ds, k, pk, &grid));
+    // exact re-decision of marked rows: (grid/8) CTAs x 8 warps, warp w adds into slot w -- the slots the streaming
+    // kernel just stored, or still-zero ones beyond them (kernel order on the stream makes that safe)
+    const unsigned rgrid = (grid + STREAM_WARPS - 1) / STREAM_WARPS;
+    ctx->partial_slots_used = std::max(grid, rgrid * STREAM_WARPS);
+    return launch_refine_rows(ds, k, pk, rgrid);
+}
+
+}  // namespace sckm

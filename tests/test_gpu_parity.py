@@ -114,6 +114,31 @@ def test_dmma_ties_duplicates_and_exact_refine(ctx, O):
     ds.close()
 
 
+def test_stream_kernel_ties_and_shapes(ctx, O):
+    """Small-k streaming kernel (k < 16): exact ties, odd d (scalar staging path), f32, ragged n."""
+    rng = np.random.default_rng(2)
+    base = rng.normal(size=(6, 16))
+    x = base[rng.integers(0, 6, size=3001)]
+    cent = np.vstack([base, base])                                # k = 12, every row an exact tie
+    for data, c in ((x, cent), (blobs(5003, 7, 5, 3), None), (blobs(4097, 32, 15, 4, np.float32), None),
+                    (blobs(31, 2, 3, 5), None), (blobs(6000, 12, 9, 6, np.float32), None)):
+        if c is None:
+            kk = {7: 5, 32: 15, 2: 3, 12: 9}[data.shape[1]]
+            c = data[np.random.default_rng(9).choice(len(data), kk, replace=False)].astype(np.float64) + 0.01
+        ctx.set_assign_kernel(cabi.ASSIGN_STREAM)
+        ds = ctx.upload(data)
+        inertia, sums, counts = ds.lloyd_step(c)
+        again = ds.lloyd_step(c)
+        ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+        d_o, s_o, c_o, m_o, gap = O.brute_clustering(data, c, want_gap=True)
+        assert np.array_equal(ds.labels().astype(np.int64), m_o)
+        assert counts.tolist() == c_o.tolist()
+        np.testing.assert_allclose(sums, s_o, rtol=RTOL, atol=1e-9)
+        assert abs(inertia - d_o) <= RTOL * max(d_o, 1e-30) + 1e-18
+        assert again[0] == inertia and np.array_equal(again[1], sums)        # bit-reproducible
+        ds.close()
+
+
 def test_dmma_step_is_bit_reproducible(ctx):
     x = blobs(50000, 64, 64, 5, spread=1.0)
     cent = x[:64] + 0.01

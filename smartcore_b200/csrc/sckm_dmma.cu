@@ -102,11 +102,13 @@ __device__ __forceinline__ void epilogue_all(const double (&acc)[MT][NT][2], uin
     for (int item = 0; item < MT * NT * 2; item++) epi_item<MT, NT>(acc, item, col_base, t, best, second, bidx);
 }
 
+// Resident-centroid specialisation (the whole centroid set fits in shared memory: config C3).  Kept as its own
+// kernel: it is the headline path and its instruction schedule is tuned (87.8 % of the FP64 peak).
 // KSTEPS: d padded to 4*KSTEPS; MT: m-tiles (8 rows each) per warp slab; DMMA_NT: n-tiles (8 centroids each) per
 // accumulator sub-block; DMMA_WARPS: warps per CTA (one CTA per SM)
 template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool PIPE, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
-assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
+assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t* __restrict__ labels,
                    double* __restrict__ mind, double* __restrict__ partials, size_t pk) {
     constexpr int DP = KSTEPS * 4;                 // padded feature count
@@ -266,6 +268,181 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
     }
 }
 
+// KSTEPS: d padded to 4*KSTEPS; MT: m-tiles (8 rows each) per warp slab; DMMA_NT: n-tiles (8 centroids each) per
+// accumulator sub-block; DMMA_WARPS: warps per CTA (one CTA per SM).
+// When the centroids do not fit in shared memory they are streamed through it in blocks of `bn`; to amortise each
+// block load (and its two CTA barriers) a warp then runs `sl` slabs against the resident block, keeping the running
+// (best, second, argbest) of every row in a small per-warp shared-memory table between blocks.  Rows are re-read per
+// block, but a round's working set (148 CTAs x warps x sl slabs) is L2-resident, so HBM still sees X once.
+// MULTI = false is the compile-time specialisation for a fully resident centroid set (one block, sl = 1, no state).
+template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool MULTI, typename TX>
+__global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
+assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
+                   const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t sl_arg, uint32_t* __restrict__ labels,
+                   double* __restrict__ mind, double* __restrict__ partials, size_t pk) {
+    const uint32_t sl = MULTI ? sl_arg : 1u;
+    constexpr int DP = KSTEPS * 4;                 // padded feature count
+    constexpr int PITCH = DP + 4;                  // doubles per staged centroid row (pitch = d*8+32 B)
+    constexpr int ROWS = 8 * MT;
+    constexpr int SUB = 8 * DMMA_NT;               // centroids per accumulator sub-block
+    extern __shared__ __align__(16) double smem_d[];
+    double* cbuf = smem_d;                         // [bn][PITCH]
+    double* cn = smem_d + (size_t)bn * PITCH;      // [bn]  -||c||^2/2, -inf for padding columns
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    // per-warp row state between centroid blocks: [sl][ROWS] x {best, second, idx}
+    key_t* st_best = reinterpret_cast<key_t*>(cn + bn) + (size_t)warp * sl * ROWS * 3;
+    key_t* st_second = st_best + (size_t)sl * ROWS;
+    key_t* st_idx = st_second + (size_t)sl * ROWS;
+    const double cmax = cnorm[k];                  // max_j ||c_j||^2 (written by cnorm_max_kernel)
+
+    const uint64_t nslabs = (n + ROWS - 1) / ROWS;
+    const uint64_t stride = (uint64_t)gridDim.x * DMMA_WARPS;
+    const uint64_t rounds = (nslabs + stride * sl - 1) / (stride * sl);
+    const uint32_t nchunks = MULTI ? (k + bn - 1) / bn : 1u;
+    const double* bbase = cbuf + (size_t)g * PITCH + t;
+    double* part = partials + ((size_t)blockIdx.x * DMMA_WARPS + warp) * ((pk + 15) / 16 * 16);   // this warp's private partial
+    unsigned lanemask_lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanemask_lt));
+
+    for (uint64_t rd = 0; rd < rounds; rd++) {
+        for (uint32_t ch = 0; ch < nchunks; ch++) {
+            const uint32_t c0 = ch * bn;
+            if (nchunks > 1 || rd == 0) {
+                // (re)load the centroid block; resident for the whole launch when it is the only one
+                if (nchunks > 1) __syncthreads();
+                for (uint32_t e = threadIdx.x; e < bn * DP; e += blockDim.x) {
+                    const uint32_t r = e / DP, c = e - r * DP;
+                    double v = 0.0;
+                    if (c0 + r < k && c < d) v = centroids[(size_t)(c0 + r) * d + c];
+                    cbuf[(size_t)r * PITCH + c] = v;
+                }
+                for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
+                    cn[r] = (c0 + r < k) ? -0.5 * cnorm[c0 + r] : -INFINITY;
+                __syncthreads();
+            }
+            const uint32_t cols = min(bn, k - c0);
+            const uint32_t nsub = (cols + SUB - 1) / SUB;
+            const bool last = ch + 1 == nchunks;
+
+            for (uint32_t si = 0; si < sl; si++) {
+                const uint64_t slab = (rd * sl + si) * stride + (uint64_t)blockIdx.x * DMMA_WARPS + warp;
+                const bool active = slab < nslabs;
+                if (!active) continue;                                    // warp-uniform
+                const uint64_t r0 = slab * ROWS;
+                // ---- rows -> A fragments (registers), ||x||^2 ----
+                double a[MT][KSTEPS];
+                double xn[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const uint64_t row = r0 + mt * 8 + g;
+                    const bool rok = row < n;
+                    const TX* xr = x + row * d;
+                    double s = 0.0;
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ks++) {
+                        const uint32_t col = ks * 4 + t;
+                        double v = 0.0;
+                        if (rok && col < d) v = (double)__ldg(xr + col);
+                        a[mt][ks] = v;
+                        s = fma(v, v, s);
+                    }
+                    s += __shfl_xor_sync(0xffffffffu, s, 1);
+                    s += __shfl_xor_sync(0xffffffffu, s, 2);
+                    xn[mt] = s;
+                }
+                // ---- running top-2 of every row: fresh on the first block, else resumed (lane t == 0 carries it) ----
+                key_t best[MT], second[MT];
+                uint32_t bidx[MT];
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    best[mt] = KEY_MIN; second[mt] = KEY_MIN; bidx[mt] = 0;
+                    if (MULTI && ch > 0 && t == 0) {
+                        const uint32_t o = si * ROWS + mt * 8 + g;
+                        best[mt] = st_best[o]; second[mt] = st_second[o]; bidx[mt] = (uint32_t)st_idx[o];
+                    }
+                }
+                for (uint32_t sb = 0; sb < nsub; sb++) {
+                    double acc[MT][DMMA_NT][2];
+                    acc_init<MT, DMMA_NT>(acc, cn + sb * SUB, t);
+                    kloop<KSTEPS, MT, DMMA_NT, PITCH, false>(acc, acc, a, bbase + (size_t)sb * SUB * PITCH, 0, t, best,
+                                                              second, bidx);
+                    epilogue_all<MT, DMMA_NT>(acc, c0 + sb * SUB, t, best, second, bidx);
+                }
+                // ---- merge the 4 lanes that share a row ----
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+                    for (int o = 1; o <= 2; o <<= 1) {
+                        const key_t ob = __shfl_xor_sync(0xffffffffu, best[mt], o);
+                        const key_t os = __shfl_xor_sync(0xffffffffu, second[mt], o);
+                        const uint32_t oi = __shfl_xor_sync(0xffffffffu, bidx[mt], o);
+                        const bool take = ob > best[mt] || (ob == best[mt] && oi < bidx[mt]);
+                        const key_t lo_best = ob < best[mt] ? ob : best[mt];
+                        key_t s2 = os > second[mt] ? os : second[mt];
+                        second[mt] = lo_best > s2 ? lo_best : s2;
+                        bidx[mt] = take ? oi : bidx[mt];
+                        best[mt] = ob > best[mt] ? ob : best[mt];
+                    }
+                }
+                if (MULTI && !last) {                                     // park the row state until the next block
+                    if (t == 0) {
+#pragma unroll
+                        for (int mt = 0; mt < MT; mt++) {
+                            const uint32_t o = si * ROWS + mt * 8 + g;
+                            st_best[o] = best[mt]; st_second[o] = second[mt]; st_idx[o] = (key_t)bidx[mt];
+                        }
+                    }
+                    continue;
+                }
+                // ---- last block: write out, mark near-ties, fused update ----
+                double slab_inertia = 0.0;
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const uint64_t row = r0 + mt * 8 + g;
+                    const bool valid = row < n;
+                    const double bestv = dunkey(best[mt]), secondv = dunkey(second[mt]);   // x.c - ||c||^2/2
+                    const double dist = fmax(0.0, fma(-2.0, bestv, xn[mt]));
+                    const double gap = 2.0 * (bestv - secondv);
+                    const bool tie = !(gap > DMMA_TIE_REL * (xn[mt] + cmax));   // also catches NaN
+                    if (valid && t == 0) {
+                        labels[row] = tie ? 0xffffffffu : bidx[mt];             // ties are re-decided by refine_rows_kernel
+                        mind[row] = dist;
+                    }
+                    // Deterministic per-label accumulation (the update of bbd_tree.rs:151-155) into this warp's
+                    // private partial: the 4 lanes of a row add their A-fragment elements.  Rows of this m-tile that
+                    // share a label are serialised in ascending row order (rank), so the order of every f64 addition
+                    // is fixed by (n, grid) alone.
+                    const bool part_ok = valid && !tie;
+                    const uint32_t key = part_ok ? bidx[mt] : (0x80000000u | (uint32_t)g);
+                    const unsigned peers = __match_any_sync(0xffffffffu, key);
+                    const int rank = __popc(peers & lanemask_lt) >> 2;
+                    const int maxrank = __reduce_max_sync(0xffffffffu, part_ok ? rank : 0);
+                    for (int r = 0; r <= maxrank; r++) {
+                        if (r) { __threadfence(); __syncwarp(); }     // order the (rare) same-label rows of this m-tile
+                        if (part_ok && rank == r) {
+                            // fire-and-forget RED.ADD.F64 into the warp-private partial: a given address only ever
+                            // receives adds from this warp, same-thread adds stay in program order and cross-lane
+                            // same-label adds are separated by the fence above => the summation order is fixed.
+                            double* p = part + (size_t)bidx[mt] * d + t;
+#pragma unroll
+                            for (int ks = 0; ks < KSTEPS; ks++)
+                                if (ks * 4 + t < d) atomicAdd(p + ks * 4, a[mt][ks]);
+                            if (t == 0) atomicAdd(part + (size_t)k * d + bidx[mt], 1.0);
+                        }
+                    }
+                    double v = (part_ok && t == 0) ? dist : 0.0;                 // fixed-order sum over the 8 rows
+                    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+                    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 8));
+                    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
+                    slab_inertia = __dadd_rn(slab_inertia, v);
+                }
+                if (lane == 0) atomicAdd(part + pk - 1, slab_inertia);
+            }
+        }
+    }
+}
+
 // Exact re-decision of the rows marked 0xffffffff by the tile kernel.  Warp w scans the fixed row range
 // [w*R, (w+1)*R) in order; for a marked row, lane l scans centroids l, l+32, ... with the reference's
 // arithmetic (widen to f64, diff, square, sequential sum, never fused), then a warp argmin with strict <
@@ -360,23 +537,45 @@ static unsigned dmma_grid(const sckm_ctx* ctx) { return (unsigned)ctx->num_sms; 
 // number of per-warp partial slots the fused kernels may accumulate into (reduced by launch_reduce_partials)
 uint32_t dmma_partial_slots(const sckm_ctx* ctx) { return dmma_grid(ctx) * DMMA_MAX_WARPS; }
 
-template <int KSTEPS, int MT, int NT, int WARPS, bool PIPE, typename TX>
+template <int KSTEPS, int MT, int NT, int WARPS, typename TX>
 static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     sckm_ctx* ctx = ds->ctx;
-    constexpr int DP = KSTEPS * 4, PITCH = DP + 4;
+    constexpr int DP = KSTEPS * 4, PITCH = DP + 4, ROWS = 8 * MT;
     const size_t row_bytes = (size_t)PITCH * 8 + 8;                   // staged row + its norm
+    const uint32_t kpad = (uint32_t)((k + 8 * NT - 1) / (8 * NT) * (8 * NT));
+    uint32_t sl = 1;
+    bool multi = false;
     uint32_t bn = (uint32_t)(((size_t)ctx->smem_optin - 1024) / row_bytes);
     bn = bn / (8 * NT) * (8 * NT);
-    const uint32_t kpad = (uint32_t)((k + 8 * NT - 1) / (8 * NT) * (8 * NT));
-    if (bn >= kpad) bn = kpad;                                         // whole centroid set resident
+    if (bn >= kpad) {
+        bn = kpad;                                                     // whole centroid set resident, no row state
+    } else {
+        multi = true;
+        sl = 12;                                                       // slabs per warp per resident centroid block
+        if (const char* e = getenv("SCKM_DMMA_SL")) sl = (uint32_t)std::max(1, std::min(16, atoi(e)));   // tuning knob
+        const size_t state = (size_t)WARPS * sl * ROWS * 3 * sizeof(long long);
+        bn = (uint32_t)(((size_t)ctx->smem_optin - 1024 - state) / row_bytes);
+        bn = bn / (8 * NT) * (8 * NT);
+        // balance the blocks: same count, even sizes
+        const uint32_t nch = (kpad + bn - 1) / bn;
+        bn = ((kpad + nch - 1) / nch + 8 * NT - 1) / (8 * NT) * (8 * NT);
+    }
     if (bn < 8 * NT) return fail(ctx, SCKM_ERR_INVALID, "shared memory too small for the DMMA tile");
-    const size_t smem = (size_t)bn * row_bytes;
+    const size_t smem = (size_t)bn * row_bytes + (multi ? (size_t)WARPS * sl * ROWS * 3 * sizeof(long long) : 0);
     ctx->partial_slots_used = dmma_grid(ctx) * WARPS;
-    auto kern = assign_dmma_kernel<KSTEPS, MT, NT, WARPS, PIPE, TX>;
-    SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
-                                                          ctx->d_cnorm, (uint32_t)k, bn, ds->labels, ds->mind,
-                                                          ctx->d_partials, pk);
+    if (!multi) {
+        auto kern = assign_dmma_resident_kernel<KSTEPS, MT, NT, WARPS, false, TX>;
+        SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
+                                                              ctx->d_cnorm, (uint32_t)k, bn, ds->labels, ds->mind,
+                                                              ctx->d_partials, pk);
+    } else {
+        auto kern = assign_dmma_kernel<KSTEPS, MT, NT, WARPS, true, TX>;
+        SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
+                                                              ctx->d_cnorm, (uint32_t)k, bn, sl, ds->labels, ds->mind,
+                                                              ctx->d_partials, pk);
+    }
     LAUNCH_CHECK_D(ctx);
     refine_rows_kernel<TX, WARPS><<<dmma_grid(ctx), WARPS * 32, 0, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d,
         ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
@@ -384,29 +583,13 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     return SCKM_OK;
 }
 
-static int dmma_variant() {
-    static int v = -1;
-    if (v < 0) { const char* e = getenv("SCKM_DMMA_VARIANT"); v = e ? atoi(e) : 0; }
-    return v;
-}
-
 template <typename TX>
 static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     const uint64_t d = ds->d;
-    if (d <= 16) return launch_t<4, 2, 4, 12, false, TX>(ds, k, pk);
-    if (d <= 32) return launch_t<8, 2, 4, 12, false, TX>(ds, k, pk);
-    if (d <= 64) {
-        switch (dmma_variant()) {   // tuning variants (default 0)
-            case 1: return launch_t<16, 2, 4, 8, true, TX>(ds, k, pk);
-            case 2: return launch_t<16, 1, 4, 16, false, TX>(ds, k, pk);
-            case 3: return launch_t<16, 2, 4, 10, true, TX>(ds, k, pk);
-            case 4: return launch_t<16, 1, 8, 12, true, TX>(ds, k, pk);
-            case 5: return launch_t<16, 1, 4, 16, true, TX>(ds, k, pk);
-            case 6: return launch_t<16, 2, 4, 12, true, TX>(ds, k, pk);
-            default: return launch_t<16, 2, 4, 12, false, TX>(ds, k, pk);
-        }
-    }
-    return launch_t<32, 1, 4, 12, false, TX>(ds, k, pk);
+    if (d <= 16) return launch_t<4, 2, 4, 12, TX>(ds, k, pk);
+    if (d <= 32) return launch_t<8, 2, 4, 12, TX>(ds, k, pk);
+    if (d <= 64) return launch_t<16, 2, 4, 12, TX>(ds, k, pk);
+    return launch_t<32, 1, 4, 12, TX>(ds, k, pk);
 }
 
 int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d) {

@@ -152,7 +152,9 @@ def test_dmma_step_is_bit_reproducible(ctx):
 
 
 @pytest.mark.parametrize("n,d,k,dtype", [(20000, 64, 256, np.float64), (9000, 128, 100, np.float64), (7777, 20, 33, np.float64),
-                                         (30000, 32, 512, np.float32), (5000, 12, 17, np.float32)])
+                                         (30000, 32, 512, np.float32), (5000, 12, 17, np.float32),
+                                         # centroid sets larger than shared memory: streamed in blocks, row state parked
+                                         (6001, 128, 300, np.float64), (20000, 64, 700, np.float64), (40000, 32, 1500, np.float32)])
 def test_dmma_step_shapes(ctx, O, n, d, k, dtype):
     x = blobs(n, d, k, n + d, dtype, spread=1.5)
     cent = x[np.random.default_rng(1).choice(n, k, replace=False)].astype(np.float64) * 1.001

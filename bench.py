@@ -94,6 +94,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def ncu_traffic_bytes():
+    """dram__bytes_read + dram__bytes_write of one assignment launch at the default C3 shape, from the committed
+    `ncu --set full` capture (profiles/ncu_r1_assign_dmma_v6_summary.csv); None when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_r1_assign_dmma_v6_summary.csv")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+    total, seen = 0.0, 0
+    try:
+        for line in open(path):
+            parts = line.strip().split(",")
+            if len(parts) == 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum") and parts[1] in scale:
+                total += float(parts[2]) * scale[parts[1]]
+                seen += 1
+    except OSError:
+        return None
+    return total if seen == 2 else None
+
+
 def cpu_oracle_run(steps, warmup, rows):
     """The reference's algorithm (BBD-tree filter) on this host: single thread, row sub-sample."""
     from oracle import oracle_py as O
@@ -261,7 +278,11 @@ def main():
                        "parallelism": "rows sharded x%d, one NCCL all-reduce of k*d+k+1 f64 per step" % world,
                        "kmeanspp_init_s": t_init, "wall_s_timed_region": wall},
             "roofline": {"bound": "tensor" if k >= 4 * 6 else "hbm", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None, "traffic": None,
+                         "frac": achieved / fp64_peak if fp64_peak else None,
+                         "traffic": ncu_traffic_bytes() if (n_local, k, d) == (N_PER_GPU, K_CLUSTERS, D) else None,
+                         "traffic_note": "DRAM read+write bytes of one assignment launch from the committed ncu --set full capture "
+                                         "(profiles/ncu_r1_assign_dmma_v6_summary.csv); algorithmic bytes per launch = n*(d*8+4) = %.3e"
+                                         % hbm_bytes,
                          "kernel": "assignment kernel (dominant), CUDA events on the library stream, mean of %d launches" % args.steps,
                          "kernel_ms": 1e3 * t_assign,
                          "peak_source": "FP64 peak measured now by the library's DFMA/DMMA micro-kernels (dfma %.1f, dmma %.1f "

@@ -8,6 +8,7 @@
 #include "sckm_blobs.cuh"
 #include <cfloat>
 #include <algorithm>
+#include <cstdlib>
 
 namespace sckm {
 const char* create_error_text();
@@ -67,7 +68,7 @@ void sckm_ctx_destroy(sckm_ctx* ctx) {
     nccl_destroy(ctx);
     cudaFree(ctx->d_centroids); cudaFree(ctx->d_cnorm); cudaFree(ctx->d_packed); cudaFree(ctx->d_partials);
     cudaFree(ctx->d_size); cudaFree(ctx->d_blocksum); cudaFree(ctx->d_totals); cudaFree(ctx->d_seedrow);
-    cudaFree(ctx->d_seeds); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush); cudaFree(ctx->d_flagrows);
+    cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush); cudaFree(ctx->d_flagrows);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -204,6 +205,17 @@ static int ensure_kpp(sckm_dataset* ds, uint64_t k) {
         SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_blocksum, nb * sizeof(double)));
         ctx->cap_blocks = nb;
     }
+    const size_t tab_bytes = (size_t)k * ds->d * ds->elem();
+    if (tab_bytes > ctx->cap_seedtab) {
+        if (ctx->d_seedtab) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_seedtab); ctx->d_seedtab = nullptr; }
+        SCKM_CUDA(ctx, cudaMalloc(&ctx->d_seedtab, tab_bytes));
+        ctx->cap_seedtab = tab_bytes;
+    }
+    if (k > ctx->cap_skiptab) {
+        if (ctx->d_skiptab) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_skiptab); ctx->d_skiptab = nullptr; }
+        SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_skiptab, k * sizeof(double)));
+        ctx->cap_skiptab = k;
+    }
     const size_t seed_bytes = ((size_t)ds->d * ds->elem() + 7) / 8 * 8 + 8;
     if (seed_bytes > ctx->cap_seedrow) {
         if (ctx->d_seedrow) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_seedrow); ctx->d_seedrow = nullptr; }
@@ -236,13 +248,18 @@ int sckm_kmeanspp(sckm_dataset* ds, uint64_t k, uint64_t first_index, const doub
     // seed 0: the row drawn by gen_range (kmeans.rs:358-362)
     SCKM_TRY(launch_kpp_select(ds, 0.0, inject_rows ? inject_rows[0] : (int64_t)first_index, 0));
     SCKM_TRY(nccl_allreduce_u64(ctx, (unsigned long long*)ctx->d_seedrow, seed_words));
+    // Triangle-inequality pruning: a row whose D^2 to its nearest seed s is <= ||s_new - s||^2 / 4 cannot improve, so
+    // it is neither read nor touched.  Exact (the skipped rows are exactly rows the reference would leave unchanged).
+    const bool prune = getenv("SCKM_KPP_NOPRUNE") == nullptr && (size_t)k * sizeof(double) <= 64 * 1024;
+    SCKM_TRY(launch_kpp_seedtab(ds, 0));
     for (uint64_t j = 1; j < k; j++) {
-        SCKM_TRY(launch_kpp_refresh(ds, (uint32_t)(j - 1), j == 1));
+        SCKM_TRY(launch_kpp_refresh(ds, (uint32_t)(j - 1), j == 1, prune));
         if (ctx->nranks > 1) SCKM_TRY(nccl_allgather_f64(ctx, ctx->d_totals + ctx->rank, ctx->d_totals));
         SCKM_TRY(launch_kpp_select(ds, inject_rows ? 0.0 : uniforms[j - 1], inject_rows ? inject_rows[j] : -1, (uint32_t)j));
         SCKM_TRY(nccl_allreduce_u64(ctx, (unsigned long long*)ctx->d_seedrow, seed_words));
+        SCKM_TRY(launch_kpp_seedtab(ds, (uint32_t)j));
     }
-    SCKM_TRY(launch_kpp_refresh(ds, (uint32_t)(k - 1), k == 1));  // final pass, label k-1 (kmeans.rs:399-410)
+    SCKM_TRY(launch_kpp_refresh(ds, (uint32_t)(k - 1), k == 1, prune));  // final pass, label k-1 (kmeans.rs:399-410)
     if (seed_rows_out) {
         if (ctx->nranks > 1) SCKM_TRY(nccl_allreduce_u64(ctx, (unsigned long long*)ctx->d_seeds, k));
         SCKM_CUDA(ctx, cudaMemcpyAsync(seed_rows_out, ctx->d_seeds, k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));

@@ -47,6 +47,9 @@ struct sckm_ctx {
     void* d_seedrow = nullptr;       // [d elements of TX, padded] + global index (8 B)
     size_t cap_seedrow = 0;
     int64_t* d_seeds = nullptr;      // [k] chosen global rows
+    void* d_seedtab = nullptr;       // [k][d] of TX: the chosen seed rows (kmeans++ pruning)
+    double* d_skiptab = nullptr;     // [k] pruning thresholds of the current pass
+    size_t cap_seedtab = 0, cap_skiptab = 0;
     unsigned long long* d_flags = nullptr;  // [8] misc device counters (near-tie count, ...)
     uint32_t partial_slots_used = 0; // slots written by the last fused assignment launch
     uint32_t* d_flagrows = nullptr;  // rows flagged as near-ties by the GEMM-form kernel
@@ -101,7 +104,8 @@ int launch_blobs(sckm_ctx* ctx, void* x, int dtype, uint64_t row0, uint64_t nrow
                  uint64_t n_centers, uint64_t seed);
 // kmeans++ pass: D^2 refresh against the seed row in ctx->d_seedrow, label = `label` where improved;
 // writes per-1024-row block sums to ctx->d_blocksum and the rank total to ctx->d_totals[rank].
-int launch_kpp_refresh(sckm_dataset* ds, uint32_t label, bool first_pass);
+int launch_kpp_refresh(sckm_dataset* ds, uint32_t label, bool first_pass, bool prune);
+int launch_kpp_seedtab(sckm_dataset* ds, uint32_t slot);
 // pick the next seed: cutoff = u * sum(totals); the owning rank locates the row and publishes it
 // (row + global index) in ctx->d_seedrow; other ranks publish zeros (all-reduced by the caller).
 // inject_row >= 0 bypasses sampling.  Stores the global row in ctx->d_seeds[slot] (owner only; zero elsewhere).

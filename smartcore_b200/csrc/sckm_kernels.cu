@@ -61,6 +61,24 @@ __device__ __forceinline__ void stage_rows_vec(const T* __restrict__ x, uint64_t
     __syncwarp();
 }
 
+// same, but rows whose bit is set in `skipmask` are not fetched at all (kmeans++ triangle-inequality pruning)
+template <typename T>
+__device__ __forceinline__ void stage_rows_vec_masked(const T* __restrict__ x, uint64_t row0, uint32_t nrows, uint32_t d,
+                                                      unsigned char* slab, uint32_t pitch16, int lane, unsigned skipmask) {
+    const uint32_t chunks_per_row = d * sizeof(T) / 16;
+    const uint32_t total = nrows * chunks_per_row;
+    const unsigned char* src = reinterpret_cast<const unsigned char*>(x + row0 * d);
+    uint32_t r = lane / chunks_per_row, q = lane % chunks_per_row;
+    const uint32_t step_r = 32 / chunks_per_row, step_q = 32 % chunks_per_row;
+    for (uint32_t c = lane; c < total; c += 32) {
+        if (!((skipmask >> r) & 1u)) cp_async16(slab + ((size_t)r * pitch16 + q) * 16, src + (size_t)c * 16);
+        r += step_r; q += step_q;
+        if (q >= chunks_per_row) { q -= chunks_per_row; r++; }
+    }
+    cp_async_wait_all();
+    __syncwarp();
+}
+
 // ------------------------------------------------------------------------------------------
 // K5: kmeans++ D^2 refresh (kmeans.rs:368-379 / 399-410) + per-1024-row block sums (kmeans.rs:381-384)
 // One CTA per 1024-row block, 4 warps, each warp stages 32 rows at a time; one lane = one row.
@@ -72,15 +90,21 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(KPP_WARPS * 32)
 kpp_refresh_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __restrict__ seedrow,
                    double* __restrict__ mind, uint32_t* __restrict__ labels, uint32_t label, int first_pass,
-                   double* __restrict__ blocksum, uint32_t pitch16) {
+                   double* __restrict__ blocksum, uint32_t pitch16, const double* __restrict__ skiptab, uint32_t ntab) {
+    // skiptab[j] (nullable) = (1 - margin) * ||new seed - seed j||^2 / 4: a row whose current D^2 (to its nearest
+    // seed j = labels[row]) is <= skiptab[j] cannot be closer to the new seed (triangle inequality), so the
+    // reference's `if dist < d[i]` (kmeans.rs:375) is false for it and the row need not even be read.
     extern __shared__ __align__(16) unsigned char smem[];
     T* cent = reinterpret_cast<T*>(smem);                       // [d] (padded to 16 B)
     const uint32_t cent_bytes = (d * sizeof(T) + 15) / 16 * 16;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     unsigned char* slab = smem + cent_bytes + (size_t)warp * 32 * pitch16 * 16;
+    double* tab = reinterpret_cast<double*>(smem + cent_bytes + (size_t)KPP_WARPS * 32 * pitch16 * 16 * (VEC ? 1 : 0));
     __shared__ double warp_part[KPP_WARPS];
+    const bool prune = skiptab != nullptr && !first_pass;
 
     for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) cent[j] = seedrow[j];
+    if (prune) for (uint32_t j = threadIdx.x; j < ntab; j += blockDim.x) tab[j] = skiptab[j];
     __syncthreads();
 
     const uint64_t block_row0 = (uint64_t)blockIdx.x * kKppBlockRows;
@@ -90,33 +114,41 @@ kpp_refresh_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __r
         if (row0 >= n) break;
         const uint32_t nrows = (uint32_t)min((uint64_t)32, n - row0);
         double dist = 0.0;
+        // current D^2 / label of my row, and the pruning decision
+        double old = DBL_MAX; bool skip = false;
+        if (lane < nrows && !first_pass) {
+            old = mind[row0 + lane];
+            if (prune) skip = old <= tab[labels[row0 + lane]];
+        }
+        const unsigned skipmask = __ballot_sync(0xffffffffu, skip || lane >= nrows);
         if (VEC) {
-            stage_rows_vec<T>(x, row0, nrows, d, slab, pitch16, lane);
-            if (lane < nrows) {
-                using V = typename Vec16<T>::type;
-                const V* xr = reinterpret_cast<const V*>(slab + (size_t)lane * pitch16 * 16);
-                const V* cr = reinterpret_cast<const V*>(cent);
-                const uint32_t nv = d / Vec16<T>::N;
-                for (uint32_t q = 0; q < nv; q++) {
-                    V xv = xr[q], cv = cr[q];
-                    const T* xe = reinterpret_cast<const T*>(&xv);
-                    const T* ce = reinterpret_cast<const T*>(&cv);
+            if (skipmask != 0xffffffffu) {
+                stage_rows_vec_masked<T>(x, row0, nrows, d, slab, pitch16, lane, skipmask);
+                if (lane < nrows && !skip) {
+                    using V = typename Vec16<T>::type;
+                    const V* xr = reinterpret_cast<const V*>(slab + (size_t)lane * pitch16 * 16);
+                    const V* cr = reinterpret_cast<const V*>(cent);
+                    const uint32_t nv = d / Vec16<T>::N;
+                    for (uint32_t q = 0; q < nv; q++) {
+                        V xv = xr[q], cv = cr[q];
+                        const T* xe = reinterpret_cast<const T*>(&xv);
+                        const T* ce = reinterpret_cast<const T*>(&cv);
 #pragma unroll
-                    for (int e = 0; e < Vec16<T>::N; e++) dist = __dadd_rn(dist, sqdiff(xe[e], ce[e]));
+                        for (int e = 0; e < Vec16<T>::N; e++) dist = __dadd_rn(dist, sqdiff(xe[e], ce[e]));
+                    }
                 }
+                __syncwarp();
             }
-            __syncwarp();
         } else {
-            if (lane < nrows) {
+            if (lane < nrows && !skip) {
                 const T* xr = x + (row0 + lane) * d;
                 for (uint32_t j = 0; j < d; j++) dist = __dadd_rn(dist, sqdiff(xr[j], cent[j]));
             }
         }
         if (lane < nrows) {
             const uint64_t r = row0 + lane;
-            double old = first_pass ? DBL_MAX : mind[r];
             if (first_pass) labels[r] = 0;
-            if (dist < old) { old = dist; mind[r] = dist; labels[r] = label; }
+            if (!skip && dist < old) { old = dist; mind[r] = dist; labels[r] = label; }
             else if (first_pass) mind[r] = old;
             acc_rows = __dadd_rn(acc_rows, old);
         }
@@ -132,6 +164,25 @@ kpp_refresh_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __r
         for (int w = 0; w < KPP_WARPS; w++) s = __dadd_rn(s, warp_part[w]);
         blocksum[blockIdx.x] = s;
     }
+}
+
+// seedtab[slot] = the seed just published in seedrow; skiptab[j] = (1-margin) * ||seed_slot - seed_j||^2 / 4, j < slot
+template <typename T>
+__global__ void __launch_bounds__(256)
+kpp_seedtab_kernel(const T* __restrict__ seedrow, T* __restrict__ seedtab, uint32_t d, uint32_t slot,
+                   double* __restrict__ skiptab, double margin) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (blockIdx.x == 0) for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) seedtab[(size_t)slot * d + j] = seedrow[j];
+    const uint32_t j = blockIdx.x * 8 + warp;
+    if (j >= slot) return;
+    double s = 0.0;
+    for (uint32_t f = lane; f < d; f += 32) {
+        const double r = (double)seedrow[f] - (double)seedtab[(size_t)j * d + f];
+        s = fma(r, r, s);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) skiptab[j] = 0.25 * s * (1.0 - margin);
 }
 
 // rank total = fixed-order reduction of the block sums (one CTA)
@@ -542,26 +593,29 @@ template <typename K> static int set_smem(sckm_ctx* ctx, K kernel, size_t bytes)
 }
 
 template <typename T>
-static int kpp_refresh_t(sckm_dataset* ds, uint32_t label, bool first_pass) {
+static int kpp_refresh_t(sckm_dataset* ds, uint32_t label, bool first_pass, bool prune) {
     sckm_ctx* ctx = ds->ctx;
     const uint32_t d = (uint32_t)ds->d;
     const uint32_t nb = (uint32_t)((ds->n + kKppBlockRows - 1) / kKppBlockRows);
     const uint32_t row_bytes = d * sizeof(T), pitch16 = slab_pitch16(row_bytes);
     const size_t cent_bytes = ((size_t)row_bytes + 15) / 16 * 16;
-    const size_t smem_vec = cent_bytes + (size_t)KPP_WARPS * 32 * pitch16 * 16;
+    const uint32_t ntab = prune ? label : 0;                      // seeds 0 .. label-1 precede the new one
+    const size_t tab_bytes = (size_t)ntab * sizeof(double);
+    const size_t smem_vec = cent_bytes + (size_t)KPP_WARPS * 32 * pitch16 * 16 + tab_bytes;
     const bool vec = vec_ok(d, ds->dtype) && smem_vec <= (size_t)ctx->smem_optin;
+    const double* tab = prune && ntab ? ctx->d_skiptab : nullptr;
     if (nb) {
         if (vec) {
             SCKM_TRY(set_smem(ctx, kpp_refresh_kernel<T, true>, smem_vec));
             kpp_refresh_kernel<T, true><<<nb, KPP_WARPS * 32, smem_vec, ctx->stream>>>(
                 (const T*)ds->x, ds->n, d, (const T*)ctx->d_seedrow, ds->mind, ds->labels, label, first_pass ? 1 : 0,
-                ctx->d_blocksum, pitch16);
+                ctx->d_blocksum, pitch16, tab, ntab);
         } else {
-            if (cent_bytes > (size_t)ctx->smem_optin) return fail(ctx, SCKM_ERR_INVALID, "d=%u too large", d);
-            SCKM_TRY(set_smem(ctx, kpp_refresh_kernel<T, false>, cent_bytes));
-            kpp_refresh_kernel<T, false><<<nb, KPP_WARPS * 32, cent_bytes, ctx->stream>>>(
+            if (cent_bytes + tab_bytes > (size_t)ctx->smem_optin) return fail(ctx, SCKM_ERR_INVALID, "d=%u too large", d);
+            SCKM_TRY(set_smem(ctx, kpp_refresh_kernel<T, false>, cent_bytes + tab_bytes));
+            kpp_refresh_kernel<T, false><<<nb, KPP_WARPS * 32, cent_bytes + tab_bytes, ctx->stream>>>(
                 (const T*)ds->x, ds->n, d, (const T*)ctx->d_seedrow, ds->mind, ds->labels, label, first_pass ? 1 : 0,
-                ctx->d_blocksum, pitch16);
+                ctx->d_blocksum, pitch16, tab, ntab);
         }
         LAUNCH_CHECK(ctx);
     }
@@ -570,8 +624,25 @@ static int kpp_refresh_t(sckm_dataset* ds, uint32_t label, bool first_pass) {
     return SCKM_OK;
 }
 
-int launch_kpp_refresh(sckm_dataset* ds, uint32_t label, bool first_pass) {
-    return ds->dtype == SCKM_F32 ? kpp_refresh_t<float>(ds, label, first_pass) : kpp_refresh_t<double>(ds, label, first_pass);
+int launch_kpp_refresh(sckm_dataset* ds, uint32_t label, bool first_pass, bool prune) {
+    return ds->dtype == SCKM_F32 ? kpp_refresh_t<float>(ds, label, first_pass, prune)
+                                 : kpp_refresh_t<double>(ds, label, first_pass, prune);
+}
+
+// remember the seed just published (slot) and build the pruning table against all earlier seeds
+int launch_kpp_seedtab(sckm_dataset* ds, uint32_t slot) {
+    sckm_ctx* ctx = ds->ctx;
+    const unsigned grid = (unsigned)std::max<uint32_t>(1, (slot + 7) / 8);
+    // margin: the bound is exact in real arithmetic; computed D^2 values carry <= d*eps relative rounding
+    // (eps = 2^-24 for f32 element arithmetic, 2^-53 for f64), so leave orders of magnitude of slack
+    if (ds->dtype == SCKM_F32)
+        kpp_seedtab_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)ctx->d_seedrow, (float*)ctx->d_seedtab,
+                                                              (uint32_t)ds->d, slot, ctx->d_skiptab, 1e-3);
+    else
+        kpp_seedtab_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double*)ctx->d_seedrow, (double*)ctx->d_seedtab,
+                                                               (uint32_t)ds->d, slot, ctx->d_skiptab, 1e-9);
+    LAUNCH_CHECK(ctx);
+    return SCKM_OK;
 }
 
 int launch_kpp_select(sckm_dataset* ds, double u, int64_t inject_row, uint32_t slot) {

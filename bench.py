@@ -44,8 +44,9 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=N_PER_GPU, help="rows per GPU (default: config C3)")
-    ap.add_argument("--d", type=int, default=D, help="features (default: config C3; other shapes are for tuning only)")
-    ap.add_argument("--k", type=int, default=K_CLUSTERS, help="clusters (default: config C3)")
+    # (--dim/--clusters rather than --d/--k: torchrun's own parser treats a bare --d as an abbreviation of its options)
+    ap.add_argument("--dim", dest="d", type=int, default=D, help="features (default: config C3; other shapes: tuning only)")
+    ap.add_argument("--clusters", dest="k", type=int, default=K_CLUSTERS, help="clusters (default: config C3)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -70,17 +71,26 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append([time.perf_counter()] + [c.strip() for c in line.split(",")])
 
-    def stop(self):
+    def mark(self):
+        return time.perf_counter()
+
+    def stop(self, t0=None, t1=None):
+        """Summarise the samples taken in [t0, t1] (the timed region); if the region was shorter than the sampling
+        period, fall back to the samples nearest to it."""
         if self.proc:
             self.proc.terminate()
             try:
                 self.proc.wait(timeout=5)
             except Exception:  # noqa: BLE001
                 pass
+        rows = [r[1:] for r in self.rows if t0 is None or (t0 <= r[0] <= t1 + 0.15)]
+        if not rows and self.rows:
+            mid = 0.5 * ((t0 or 0) + (t1 or 0))
+            rows = [r[1:] for r in sorted(self.rows, key=lambda r: abs(r[0] - mid))[:3]]
         sm, mx, reasons = [], [], set()
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[1])); mx.append(float(r[2]))
             except (ValueError, IndexError):
@@ -88,9 +98,7 @@ class ClockSampler:
             for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
                 if len(r) > col and r[col].lower().startswith("active"):
                     reasons.add(name)
-        # samples while the GPU is busy are the upper half of the clock distribution
-        busy = sorted(sm)[len(sm) // 2:] if sm else []
-        return {"sm_mhz": float(np.median(busy)) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
@@ -166,6 +174,8 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, world, rank)
 
+    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     import torch
     import smartcore_b200 as sc
     from smartcore_b200 import cluster, dist as scd
@@ -181,6 +191,8 @@ def main():
             tdist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # nvidia-smi takes seconds to start: begin now, select the timed window later
     ctx = sc.Context(local_rank)
     if distributed:
         scd.join_comm(ctx)
@@ -196,8 +208,6 @@ def main():
     cent0, _ = ds.init_centroids(k)
     t_init = time.perf_counter() - t0
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()                      # nvidia-smi takes a moment to start: begin before the warm-up steps
     if args.warmup:
         ds.lloyd_iterate(cent0, args.warmup)
     barrier()
@@ -205,9 +215,9 @@ def main():
     w0 = time.perf_counter()
     out = ds.lloyd_iterate(cent0, args.steps)
     barrier()
-    wall = time.perf_counter() - w0
+    w1 = time.perf_counter()
+    wall = w1 - w0
     launches = ctx.launch_count() - l0
-    clocks = sampler.stop()
     t_dev = float(out["ms"].sum()) * 1e-3
     t_assign = float(out["assign_ms"].mean()) * 1e-3
     if distributed:
@@ -252,6 +262,7 @@ def main():
     else:
         ds.close()
 
+    clocks = sampler.stop(w0, w1)
     cpu = None
     if rank == 0 and not args.no_cpu:
         r = cpu_oracle_run(5, 1, CPU_SAMPLE_ROWS)

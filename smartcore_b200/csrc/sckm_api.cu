@@ -68,7 +68,7 @@ void sckm_ctx_destroy(sckm_ctx* ctx) {
     nccl_destroy(ctx);
     cudaFree(ctx->d_centroids); cudaFree(ctx->d_cnorm); cudaFree(ctx->d_packed); cudaFree(ctx->d_partials);
     cudaFree(ctx->d_size); cudaFree(ctx->d_blocksum); cudaFree(ctx->d_totals); cudaFree(ctx->d_seedrow);
-    cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush); cudaFree(ctx->d_flagrows);
+    cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -191,7 +191,7 @@ int sckm_dataset_download_rows(sckm_dataset* ds, uint64_t local_row0, uint64_t n
 void sckm_dataset_destroy(sckm_dataset* ds) {
     if (!ds) return;
     if (ds->ctx) { cudaSetDevice(ds->ctx->device); cudaStreamSynchronize(ds->ctx->stream); }
-    cudaFree(ds->x); cudaFree(ds->labels); cudaFree(ds->mind);
+    cudaFree(ds->x); cudaFree(ds->labels); cudaFree(ds->mind); cudaFree(ds->labels64);
     delete ds;
 }
 
@@ -409,29 +409,27 @@ int sckm_lloyd_iterate(sckm_dataset* ds, uint64_t k, uint64_t n_iters, double* c
                       assign_ms_out);
 }
 
-static int download_labels(sckm_ctx* ctx, const uint32_t* d_labels, uint64_t n, void* out, int width) {
+static int download_labels(sckm_dataset* ds, void* out, int width) {
+    sckm_ctx* ctx = ds->ctx;
+    const uint64_t n = ds->n;
     if (width == 4) {
-        SCKM_CUDA(ctx, cudaMemcpyAsync(out, d_labels, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        SCKM_CUDA(ctx, cudaMemcpyAsync(out, ds->labels, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
         SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
         return SCKM_OK;
     }
     if (width != 8) return fail(ctx, SCKM_ERR_INVALID, "label width must be 4 or 8");
-    uint64_t* tmp = nullptr;
-    SCKM_CUDA(ctx, cudaMalloc((void**)&tmp, std::max<uint64_t>(n, 1) * 8));
-    int rc = launch_labels_widen(ctx, d_labels, tmp, n);
-    cudaError_t e = cudaSuccess;
-    if (rc == SCKM_OK) e = cudaMemcpyAsync(out, tmp, n * 8, cudaMemcpyDeviceToHost, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    cudaFree(tmp);
-    if (rc == SCKM_OK && e != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "label download failed: %s", cudaGetErrorString(e));
-    return rc;
+    if (!ds->labels64) SCKM_CUDA(ctx, cudaMalloc((void**)&ds->labels64, std::max<uint64_t>(n, 1) * 8));
+    SCKM_TRY(launch_labels_widen(ctx, ds->labels, ds->labels64, n));
+    SCKM_CUDA(ctx, cudaMemcpyAsync(out, ds->labels64, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return SCKM_OK;
 }
 
 int sckm_labels_download(sckm_dataset* ds, void* out, int width) {
     if (!ds || !out) return SCKM_ERR_INVALID;
     if (!ds->have_labels) return fail(ds->ctx, SCKM_ERR_STATE, "no labels on the dataset yet");
     SCKM_CUDA(ds->ctx, cudaSetDevice(ds->ctx->device));
-    return download_labels(ds->ctx, ds->labels, ds->n, out, width);
+    return download_labels(ds, out, width);
 }
 
 int sckm_mindist_download(sckm_dataset* ds, double* out) {
@@ -458,7 +456,7 @@ int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int 
     if (rc == SCKM_OK && cudaMemcpyAsync(ctx->d_centroids, centroids, k * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         rc = fail(ctx, SCKM_ERR_CUDA, "centroid upload failed");
     if (rc == SCKM_OK) rc = launch_assign_direct_raw(ctx, ds->x, dtype, n, d, k, ds->labels, nullptr);
-    if (rc == SCKM_OK) rc = download_labels(ctx, ds->labels, n, labels_out, width);
+    if (rc == SCKM_OK) rc = download_labels(ds, labels_out, width);
     sckm_dataset_destroy(ds);
     return rc;
 }
@@ -478,7 +476,7 @@ int sckm_kmeans_fit(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, i
     if (rc == SCKM_OK) rc = lloyd_loop(ds, k, max_iter, true, nullptr, size_out, distortion_out, iters_out, nullptr, nullptr);
     if (rc == SCKM_OK && cudaMemcpy(centroids_out, ctx->d_centroids, k * d * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
         rc = fail(ctx, SCKM_ERR_CUDA, "centroid download failed");
-    if (rc == SCKM_OK && labels_out) rc = download_labels(ctx, ds->labels, n, labels_out, width);
+    if (rc == SCKM_OK && labels_out) rc = download_labels(ds, labels_out, width);
     sckm_dataset_destroy(ds);
     return rc;
 }

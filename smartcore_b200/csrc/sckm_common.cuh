@@ -12,11 +12,7 @@
 
 namespace sckm {
 
-constexpr int kNumSMsB200 = 148;
 constexpr int kKppBlockRows = 1024;   // fixed summation unit of the kmeans++ D^2 array
-constexpr int kWarpRows = 32;         // rows staged per warp slab in the direct kernels
-
-struct NcclApi;  // dlopen'd entry points (sckm_nccl.cu)
 
 // pitch (in doubles) of one partial slot [k*d sums | k counts | inertia]: 128-byte aligned rows
 inline size_t slot_pitch(size_t pk) { return (pk + 15) / 16 * 16; }
@@ -50,10 +46,8 @@ struct sckm_ctx {
     void* d_seedtab = nullptr;       // [k][d] of TX: the chosen seed rows (kmeans++ pruning)
     double* d_skiptab = nullptr;     // [k] pruning thresholds of the current pass
     size_t cap_seedtab = 0, cap_skiptab = 0;
-    unsigned long long* d_flags = nullptr;  // [8] misc device counters (near-tie count, ...)
+    unsigned long long* d_flags = nullptr;  // [8] scratch words (sink of the peak micro-kernels)
     uint32_t partial_slots_used = 0; // slots written by the last fused assignment launch
-    uint32_t* d_flagrows = nullptr;  // rows flagged as near-ties by the GEMM-form kernel
-    size_t cap_flagrows = 0;
     void* d_flush = nullptr;         // L2 flush buffer
     size_t flush_bytes = 0;
     double* h_pinned = nullptr;      // small pinned scratch (>= 64 doubles)
@@ -68,6 +62,7 @@ struct sckm_dataset {
     uint64_t row_offset = 0, n_global = 0;
     uint32_t* labels = nullptr;      // [n]
     double* mind = nullptr;          // [n] kmeans++ D^2 / per-point min distance
+    uint64_t* labels64 = nullptr;    // lazily allocated widening buffer for usize downloads
     bool have_labels = false;
     size_t elem() const { return dtype == SCKM_F32 ? 4 : 8; }
 };

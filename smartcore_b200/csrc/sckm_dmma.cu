@@ -17,7 +17,7 @@
 //     is max / second-max tracking only.
 //   * Rows whose best/second gap is within 1e-10*(||x||^2 + max||c||^2) (>= 1e4 x the rounding
 //     error bound of the GEMM form) are marked and re-decided by refine_rows_kernel with the
-//     reference's exact arithmetic (euclidian.rs:56-63), so labels equal the dense oracle.
+//     reference's exact arithmetic (euclidian.rs:56-63), so labels equal the exact direct-form argmin.
 //   * The centroid update (per-label sums, counts, inertia) is fused: while a slab's rows are still
 //     in registers they are added to the warp's PRIVATE partial [k*d | k | 1] in L2-resident global
 //     memory, in a fixed order, so results are bit-reproducible run to run (needed by the stop rule

@@ -108,49 +108,108 @@ kpp_refresh_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __r
     __syncthreads();
 
     const uint64_t block_row0 = (uint64_t)blockIdx.x * kKppBlockRows;
-    double acc_rows = 0.0;  // this lane's rows of the block, in ascending row order
-    for (int t = 0; t < kKppBlockRows / (KPP_WARPS * 32); t++) {
-        const uint64_t row0 = block_row0 + (uint64_t)(t * KPP_WARPS + warp) * 32;
-        if (row0 >= n) break;
-        const uint32_t nrows = (uint32_t)min((uint64_t)32, n - row0);
-        double dist = 0.0;
-        // current D^2 / label of my row, and the pruning decision
-        double old = DBL_MAX; bool skip = false;
-        if (lane < nrows && !first_pass) {
-            old = mind[row0 + lane];
-            if (prune) skip = old <= tab[labels[row0 + lane]];
-        }
-        const unsigned skipmask = __ballot_sync(0xffffffffu, skip || lane >= nrows);
-        if (VEC) {
-            if (skipmask != 0xffffffffu) {
-                stage_rows_vec_masked<T>(x, row0, nrows, d, slab, pitch16, lane, skipmask);
-                if (lane < nrows && !skip) {
-                    using V = typename Vec16<T>::type;
-                    const V* xr = reinterpret_cast<const V*>(slab + (size_t)lane * pitch16 * 16);
-                    const V* cr = reinterpret_cast<const V*>(cent);
-                    const uint32_t nv = d / Vec16<T>::N;
-                    for (uint32_t q = 0; q < nv; q++) {
-                        V xv = xr[q], cv = cr[q];
-                        const T* xe = reinterpret_cast<const T*>(&xv);
-                        const T* ce = reinterpret_cast<const T*>(&cv);
+    double acc_rows = 0.0;  // D^2 values this thread is responsible for, in a fixed order
+    constexpr int SEGS = kKppBlockRows / 32;                    // 32-row segments of the block
+
+    if (VEC) {
+        // ---- phase 1: decide per row (coalesced reads of D^2 / label), compact the surviving rows of the block.
+        // Pruned rows only contribute their unchanged D^2 to the block sum; with clustered data most of the block
+        // vanishes here after the first few seeds, and phase 2 runs dense warps over what is left. ----
+        __shared__ uint16_t list[kKppBlockRows];
+        __shared__ uint32_t seg_cnt[SEGS];
+        unsigned ball[SEGS / KPP_WARPS];
 #pragma unroll
-                        for (int e = 0; e < Vec16<T>::N; e++) dist = __dadd_rn(dist, sqdiff(xe[e], ce[e]));
-                    }
+        for (int t = 0; t < SEGS / KPP_WARPS; t++) {
+            const uint32_t local = (uint32_t)(t * KPP_WARPS + warp) * 32 + lane;
+            const uint64_t r = block_row0 + local;
+            bool active = false;
+            if (r < n) {
+                active = true;
+                if (first_pass) labels[r] = 0;
+                else if (prune) {
+                    const double old = mind[r];
+                    if (old <= tab[labels[r]]) { active = false; acc_rows = __dadd_rn(acc_rows, old); }
                 }
+            }
+            ball[t] = __ballot_sync(0xffffffffu, active);
+            if (lane == 0) seg_cnt[t * KPP_WARPS + warp] = __popc(ball[t]);
+        }
+        __syncthreads();
+        uint32_t total = 0;
+        {
+            uint32_t run = 0, mybase[SEGS / KPP_WARPS];
+#pragma unroll
+            for (int sgi = 0; sgi < SEGS; sgi++) {                 // exclusive prefix over the 32 segments
+                const uint32_t c = seg_cnt[sgi];
+#pragma unroll
+                for (int t = 0; t < SEGS / KPP_WARPS; t++) if (sgi == t * KPP_WARPS + warp) mybase[t] = run;
+                run += c;
+            }
+            total = run;
+#pragma unroll
+            for (int t = 0; t < SEGS / KPP_WARPS; t++)
+                if ((ball[t] >> lane) & 1u)
+                    list[mybase[t] + __popc(ball[t] & ((1u << lane) - 1u))] = (uint16_t)((t * KPP_WARPS + warp) * 32 + lane);
+        }
+        __syncthreads();
+        // ---- phase 2: dense warps over the compacted rows; each row's 16-byte chunks are fetched individually ----
+        const uint32_t cpr = d * sizeof(T) / 16;
+        const uint32_t lane_e = lane / cpr, lane_q = lane % cpr, step_e = 32 / cpr, step_q = 32 % cpr;
+        for (uint32_t base = warp * 32; base < total; base += KPP_WARPS * 32) {
+            const uint32_t cnt = min(32u, total - base);
+            {
+                uint32_t e = lane_e, q = lane_q;
+                const uint32_t nchunks = cnt * cpr;
+                for (uint32_t c = lane; c < nchunks; c += 32) {
+                    const uint64_t r = block_row0 + list[base + e];
+                    cp_async16(slab + ((size_t)e * pitch16 + q) * 16,
+                               reinterpret_cast<const unsigned char*>(x + r * d) + (size_t)q * 16);
+                    e += step_e; q += step_q;
+                    if (q >= cpr) { q -= cpr; e++; }
+                }
+                cp_async_wait_all();
                 __syncwarp();
             }
-        } else {
-            if (lane < nrows && !skip) {
-                const T* xr = x + (row0 + lane) * d;
-                for (uint32_t j = 0; j < d; j++) dist = __dadd_rn(dist, sqdiff(xr[j], cent[j]));
+            if (lane < cnt) {
+                const uint64_t r = block_row0 + list[base + lane];
+                using V = typename Vec16<T>::type;
+                const V* xr = reinterpret_cast<const V*>(slab + (size_t)lane * pitch16 * 16);
+                const V* cr = reinterpret_cast<const V*>(cent);
+                const uint32_t nv = d / Vec16<T>::N;
+                double dist = 0.0;
+                for (uint32_t q = 0; q < nv; q++) {
+                    V xv = xr[q], cv = cr[q];
+                    const T* xe = reinterpret_cast<const T*>(&xv);
+                    const T* ce = reinterpret_cast<const T*>(&cv);
+#pragma unroll
+                    for (int e = 0; e < Vec16<T>::N; e++) dist = __dadd_rn(dist, sqdiff(xe[e], ce[e]));
+                }
+                double old = first_pass ? DBL_MAX : mind[r];
+                if (dist < old) { old = dist; mind[r] = dist; labels[r] = label; }
+                else if (first_pass) mind[r] = old;
+                acc_rows = __dadd_rn(acc_rows, old);
             }
+            __syncwarp();
         }
-        if (lane < nrows) {
-            const uint64_t r = row0 + lane;
-            if (first_pass) labels[r] = 0;
-            if (!skip && dist < old) { old = dist; mind[r] = dist; labels[r] = label; }
-            else if (first_pass) mind[r] = old;
-            acc_rows = __dadd_rn(acc_rows, old);
+    } else {
+        for (int t = 0; t < SEGS / KPP_WARPS; t++) {
+            const uint64_t row0 = block_row0 + (uint64_t)(t * KPP_WARPS + warp) * 32;
+            if (row0 >= n) break;
+            const uint32_t nrows = (uint32_t)min((uint64_t)32, n - row0);
+            if (lane < nrows) {
+                const uint64_t r = row0 + lane;
+                double old = first_pass ? DBL_MAX : mind[r];
+                const bool skip = prune && old <= tab[labels[r]];
+                if (first_pass) labels[r] = 0;
+                if (!skip) {
+                    const T* xr = x + r * d;
+                    double dist = 0.0;
+                    for (uint32_t j = 0; j < d; j++) dist = __dadd_rn(dist, sqdiff(xr[j], cent[j]));
+                    if (dist < old) { old = dist; mind[r] = dist; labels[r] = label; }
+                    else if (first_pass) mind[r] = old;
+                }
+                acc_rows = __dadd_rn(acc_rows, old);
+            }
         }
     }
     // fixed-order block reduction: lanes (xor tree), then warps 0..3 sequentially

@@ -92,6 +92,14 @@ int nccl_init_rank(sckm_ctx* ctx, int nranks, int rank, const void* id128) {
     if (ctx->d_totals) { cudaFree(ctx->d_totals); ctx->d_totals = nullptr; }
     SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_totals, sizeof(double) * (size_t)std::max(nranks, 1)));
     SCKM_CUDA(ctx, cudaMemset(ctx->d_totals, 0, sizeof(double) * (size_t)std::max(nranks, 1)));
+    if (nranks > 1) {
+        // NCCL sets up its channels lazily on the first collective of each kind (~1 s on 8 GPUs): pay that here,
+        // not inside the first kmeans++ pass / Lloyd step.  The buffer holds zeros, so the results are zeros again.
+        SCKM_TRY(nccl_allgather_f64(ctx, ctx->d_totals + rank, ctx->d_totals));
+        SCKM_TRY(nccl_allreduce_f64(ctx, ctx->d_totals, 1));
+        SCKM_TRY(nccl_allreduce_u64(ctx, (unsigned long long*)ctx->d_totals, 1));
+        SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    }
     return SCKM_OK;
 }
 

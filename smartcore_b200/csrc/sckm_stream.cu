@@ -10,7 +10,7 @@
 //   * scores  x.c_j - ||c_j||^2/2  as 8x8x4 DMMAs against centroid B-fragments that stay in registers for the
 //     whole launch; top-2 per row on integer keys; rows whose gap is within 1e-10*(||x||^2 + max||c||^2) are
 //     marked and re-decided exactly by refine_rows_kernel (same rule as the DMMA tile kernel), so labels equal
-//     the dense oracle;
+//     the exact direct-form argmin;
 //   * update: sums[cluster][feature] += onehot(label)^T . X, again as DMMAs whose accumulators live in registers
 //     for the whole launch (the FP64 tensor path used as a wide adder with a fixed, hardware-defined order: no
 //     atomics, no read-modify-write traffic); counts are integer adds; one store per CTA into its partial slot at

@@ -1,0 +1,54 @@
+"""Small end-to-end exercise of every CUDA kernel, meant to run under compute-sanitizer on a B200:
+
+    compute-sanitizer --tool memcheck  python tests/sanitizer_smoke.py
+    compute-sanitizer --tool racecheck python tests/sanitizer_smoke.py
+
+Shapes are tiny (the tools slow kernels down 10-100x); results are still checked against the oracle."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import smartcore_b200 as sc  # noqa: E402
+from smartcore_b200 import cabi, cluster  # noqa: E402
+from oracle import oracle_py as O  # noqa: E402
+
+
+def main():
+    ctx = sc.Context(0)
+    rng = np.random.default_rng(0)
+    cases = [(1500, 16, 8, np.float64, cabi.ASSIGN_STREAM), (1111, 7, 5, np.float32, cabi.ASSIGN_STREAM),
+             (2000, 64, 48, np.float64, cabi.ASSIGN_DMMA), (1777, 20, 33, np.float32, cabi.ASSIGN_DMMA),
+             (1200, 128, 300, np.float64, cabi.ASSIGN_DMMA),          # streamed centroid blocks
+             (900, 9, 4, np.float64, cabi.ASSIGN_DIRECT), (700, 40, 6, np.float64, cabi.ASSIGN_DIRECT)]
+    for n, d, k, dt, kern in cases:
+        x = (rng.normal(size=(n, d)) + 3.0 * rng.integers(0, k, size=(n, 1))).astype(dt)
+        first, u = cluster.kmeanspp_draws(3, n, k)
+        ds = ctx.upload(x)
+        seeds = ds.kmeanspp(k, first, u)
+        y_o, idx_o, dd_o = O.kmeanspp(x, k, seed=3)
+        assert seeds.tolist() == idx_o.tolist() and np.array_equal(ds.mindist(), dd_o)
+        cent, size = ds.init_centroids(k)
+        ctx.set_assign_kernel(kern)
+        inertia, sums, counts = ds.lloyd_step(cent)
+        ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+        d_o, s_o, c_o, m_o = O.brute_clustering(x, cent)
+        assert np.array_equal(ds.labels().astype(np.int64), m_o) and counts.tolist() == c_o.tolist()
+        assert abs(inertia - d_o) <= 1e-9 * d_o
+        fit = ds.lloyd_fit(cent, 5)
+        assert fit["size"].sum() == n
+        assert np.array_equal(ctx.predict(x, fit["centroids"]).astype(np.int64), O.predict(x, fit["centroids"]))
+        assert np.array_equal(ctx.predict(x, fit["centroids"], column_major=True).astype(np.int64), O.predict(x, fit["centroids"]))
+        ds.close()
+        print("ok", n, d, k, np.dtype(dt).name, kern, flush=True)
+    g = ctx.generate_blobs(3000, 16, 8, 5)
+    assert np.array_equal(g.download_rows(10, 20), cabi.blobs_host(10, 20, 16, 8, 5))
+    g.close()
+    ctx.close()
+    print("sanitizer smoke done")
+
+
+if __name__ == "__main__":
+    main()

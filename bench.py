@@ -47,6 +47,10 @@ def parse():
     # (--dim/--clusters rather than --d/--k: torchrun's own parser treats a bare --d as an abbreviation of its options)
     ap.add_argument("--dim", dest="d", type=int, default=D, help="features (default: config C3; other shapes: tuning only)")
     ap.add_argument("--clusters", dest="k", type=int, default=K_CLUSTERS, help="clusters (default: config C3)")
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"], help="element type of X (default: config C3 = f64)")
+    ap.add_argument("--init", default="kmeanspp", choices=["kmeanspp", "rows"],
+                    help="tuning only: 'rows' seeds the timed steps from k evenly spaced rows instead of running kmeans++")
+    ap.add_argument("--assign", type=int, default=0, help="tuning only: force an assignment kernel (SCKM_ASSIGN_*)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     return ap.parse_args()
@@ -201,11 +205,19 @@ def main():
     row0 = rank * n_local
 
     peaks = ctx.device_peaks()
-    ds = ctx.generate_blobs(n_local, d, k, DATA_SEED, row_offset=row0, n_global=n_global)
+    np_dtype = np.float32 if args.dtype == "f32" else np.float64
+    esize = 4 if args.dtype == "f32" else 8
+    if args.assign:
+        ctx.set_assign_kernel(args.assign)
+    ds = ctx.generate_blobs(n_local, d, k, DATA_SEED, dtype=np_dtype, row_offset=row0, n_global=n_global)
     first, uniforms = cluster.kmeanspp_draws(KMEANS_SEED, n_global, k)
     t0 = time.perf_counter()
-    ds.kmeanspp(k, first, uniforms)
-    cent0, _ = ds.init_centroids(k)
+    if args.init == "rows":
+        step = max(1, n_local // k)
+        cent0 = np.vstack([ds.download_rows(i * step, 1) for i in range(k)]).astype(np.float64)
+    else:
+        ds.kmeanspp(k, first, uniforms)
+        cent0, _ = ds.init_centroids(k)
     t_init = time.perf_counter() - t0
 
     if args.warmup:
@@ -229,7 +241,7 @@ def main():
     # ---- e2e: KMeans::fit call sequence from pinned host buffers (per rank: its shard) ----
     e2e = None
     if not args.no_e2e:
-        host = torch.empty((n_local, d), dtype=torch.float64, pin_memory=True)
+        host = torch.empty((n_local, d), dtype=torch.float32 if args.dtype == "f32" else torch.float64, pin_memory=True)
         hx = host.numpy()
         chunk = 1 << 20
         for r in range(0, n_local, chunk):
@@ -275,7 +287,7 @@ def main():
         flops_per_launch = 2.0 * n_local * k * d
         fp64_peak = max(peaks["fp64_dfma_tflops"], peaks["fp64_dmma_tflops"])
         achieved = flops_per_launch / t_assign / 1e12
-        hbm_bytes = n_local * (d * 8 + 4)
+        hbm_bytes = n_local * (d * esize + 4)
         try:
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:  # noqa: BLE001
@@ -283,8 +295,10 @@ def main():
         line = {
             "metric": "lloyd_point_iters_per_sec", "value": value, "unit": "point-iters/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "C3 blobs 10M x 64 k=256 f64 per GPU (BASELINE.json configs[2])", "n_per_gpu": n_local,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
+            "config": {"workload": "C3 blobs 10M x 64 k=256 f64 per GPU (BASELINE.json configs[2])"
+                                   if (n_local, k, d, args.dtype) == (N_PER_GPU, K_CLUSTERS, D, "f64")
+                                   else "tuning shape %d x %d k=%d %s per GPU" % (n_local, d, k, args.dtype), "n_per_gpu": n_local,
                        "n_global": n_global, "d": d, "k": k, "l2": "inputs (5.12 GB/GPU) larger than L2; no flush",
                        "parallelism": "rows sharded x%d, one NCCL all-reduce of k*d+k+1 f64 per step" % world,
                        "kmeanspp_init_s": t_init, "wall_s_timed_region": wall},

@@ -60,7 +60,8 @@ enum {
     SCKM_ASSIGN_AUTO = 0,
     SCKM_ASSIGN_DIRECT = 1, /* direct-difference form, bit-exact distances (euclidian.rs:56-63) */
     SCKM_ASSIGN_DMMA = 2,   /* ||x||^2 - 2 X.C^T + ||c||^2 on FP64 DMMA tiles + exact near-tie refine */
-    SCKM_ASSIGN_STREAM = 3  /* small k*d: rows in registers, DFMA scores, HBM-bound */
+    SCKM_ASSIGN_STREAM = 3, /* small k (<16), d <= 32: one HBM pass does assignment and update */
+    SCKM_ASSIGN_TC5 = 4     /* f32 data, d <= 32: 3xTF32 on tcgen05 (TMA + TMEM) + exact f64 decision */
 };
 
 int sckm_abi_version(void);

@@ -12,7 +12,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsmartcore_kmeans_cuda.so")
 
 F32, F64 = 0, 1
-ASSIGN_AUTO, ASSIGN_DIRECT, ASSIGN_DMMA, ASSIGN_STREAM = 0, 1, 2, 3
+ASSIGN_AUTO, ASSIGN_DIRECT, ASSIGN_DMMA, ASSIGN_STREAM, ASSIGN_TC5 = 0, 1, 2, 3, 4
 
 # every symbol include/smartcore_kmeans_cuda.h declares (checked by tests/test_cabi_symbols.py)
 SYMBOLS = [

@@ -17,6 +17,8 @@ bool dmma_supported(const sckm_dataset* ds, uint64_t k);      // sckm_dmma.cu
 uint32_t dmma_partial_slots(const sckm_ctx* ctx);             // sckm_dmma.cu
 int launch_assign_stream(sckm_dataset* ds, uint64_t k);       // sckm_stream.cu
 bool stream_supported(const sckm_dataset* ds, uint64_t k);    // sckm_stream.cu
+int launch_assign_tc5(sckm_dataset* ds, uint64_t k);          // sckm_tc5.cu
+bool tc5_supported(const sckm_dataset* ds, uint64_t k);       // sckm_tc5.cu
 }
 using namespace sckm;
 
@@ -68,7 +70,7 @@ void sckm_ctx_destroy(sckm_ctx* ctx) {
     nccl_destroy(ctx);
     cudaFree(ctx->d_centroids); cudaFree(ctx->d_cnorm); cudaFree(ctx->d_packed); cudaFree(ctx->d_partials);
     cudaFree(ctx->d_size); cudaFree(ctx->d_blocksum); cudaFree(ctx->d_totals); cudaFree(ctx->d_seedrow);
-    cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush);
+    cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush); cudaFree(ctx->d_tc5);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -80,7 +82,7 @@ const char* sckm_last_error(const sckm_ctx* ctx) { return ctx ? ctx->err.c_str()
 
 int sckm_ctx_set_assign_kernel(sckm_ctx* ctx, int which) {
     if (!ctx) return SCKM_ERR_INVALID;
-    if (which < SCKM_ASSIGN_AUTO || which > SCKM_ASSIGN_STREAM) return fail(ctx, SCKM_ERR_INVALID, "unknown assign kernel %d", which);
+    if (which < SCKM_ASSIGN_AUTO || which > SCKM_ASSIGN_TC5) return fail(ctx, SCKM_ERR_INVALID, "unknown assign kernel %d", which);
     ctx->assign_kernel = which;
     return SCKM_OK;
 }
@@ -274,7 +276,9 @@ static int pick_assign(const sckm_dataset* ds, uint64_t k) {
     const sckm_ctx* ctx = ds->ctx;
     int which = ctx->assign_kernel;
     if (which == SCKM_ASSIGN_AUTO)
-        which = dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA : stream_supported(ds, k) ? SCKM_ASSIGN_STREAM : SCKM_ASSIGN_DIRECT;
+        which = tc5_supported(ds, k) ? SCKM_ASSIGN_TC5 : dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA
+                : stream_supported(ds, k) ? SCKM_ASSIGN_STREAM : SCKM_ASSIGN_DIRECT;
+    if (which == SCKM_ASSIGN_TC5 && !tc5_supported(ds, k)) which = dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA : SCKM_ASSIGN_DIRECT;
     if (which == SCKM_ASSIGN_DMMA && !dmma_supported(ds, k)) which = SCKM_ASSIGN_DIRECT;
     if (which == SCKM_ASSIGN_STREAM && !stream_supported(ds, k)) which = SCKM_ASSIGN_DIRECT;
     return which;
@@ -285,8 +289,9 @@ static int clustering_step(sckm_dataset* ds, uint64_t k, cudaEvent_t ev_a0 = nul
     sckm_ctx* ctx = ds->ctx;
     const int which = pick_assign(ds, k);
     if (ev_a0) SCKM_CUDA(ctx, cudaEventRecord(ev_a0, ctx->stream));
-    if (which == SCKM_ASSIGN_DMMA || which == SCKM_ASSIGN_STREAM) {
+    if (which == SCKM_ASSIGN_DMMA || which == SCKM_ASSIGN_STREAM || which == SCKM_ASSIGN_TC5) {
         if (which == SCKM_ASSIGN_DMMA) SCKM_TRY(launch_assign_dmma(ds, k));   // assignment + fused partial sums
+        else if (which == SCKM_ASSIGN_TC5) SCKM_TRY(launch_assign_tc5(ds, k));
         else SCKM_TRY(launch_assign_stream(ds, k));
         if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
         SCKM_TRY(launch_reduce_partials(ctx, ctx->partial_slots_used, (size_t)k * ds->d + k + 1));

@@ -48,6 +48,8 @@ struct sckm_ctx {
     size_t cap_seedtab = 0, cap_skiptab = 0;
     unsigned long long* d_flags = nullptr;  // [8] scratch words (sink of the peak micro-kernels)
     uint32_t partial_slots_used = 0; // slots written by the last fused assignment launch
+    float* d_tc5 = nullptr;          // tcgen05 path: centroid hi | lo parts (TF32) and -||c||^2/2 in f32
+    size_t cap_tc5 = 0;
     void* d_flush = nullptr;         // L2 flush buffer
     size_t flush_bytes = 0;
     double* h_pinned = nullptr;      // small pinned scratch (>= 64 doubles)

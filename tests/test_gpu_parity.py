@@ -170,6 +170,41 @@ def test_dmma_step_shapes(ctx, O, n, d, k, dtype):
     ds.close()
 
 
+@pytest.mark.parametrize("n,d,k", [(5000, 32, 16), (33333, 32, 300), (20000, 16, 128), (7001, 8, 100), (9000, 28, 257),
+                                   (50000, 32, 1500), (255, 32, 64)])
+def test_tc5_f32_tile_kernel(ctx, O, n, d, k):
+    """f32 data on the tcgen05 3xTF32 kernel: the ranking runs in reduced precision, the decision must still be
+    exact (labels equal the f64 direct-form argmin), sums/inertia in f64, bit-reproducible."""
+    x = blobs(n, d, k, 3 * n + d, np.float32, spread=1.5)
+    cent = x[np.random.default_rng(2).choice(n, k, replace=False)].astype(np.float64) * 1.001
+    ctx.set_assign_kernel(cabi.ASSIGN_TC5)
+    ds = ctx.upload(x)
+    inertia, sums, counts = ds.lloyd_step(cent)
+    again = ds.lloyd_step(cent)
+    ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+    assert np.array_equal(ds.labels().astype(np.int64), m_o)
+    assert counts.tolist() == c_o.tolist()
+    np.testing.assert_allclose(sums, s_o, rtol=RTOL, atol=1e-9)
+    assert abs(inertia - d_o) <= RTOL * d_o
+    assert again[0] == inertia and np.array_equal(again[1], sums) and np.array_equal(again[2], counts)
+    ds.close()
+
+
+def test_tc5_ties_and_duplicates(ctx, O):
+    rng = np.random.default_rng(0)
+    base = rng.normal(size=(16, 32)).astype(np.float32)
+    x = base[rng.integers(0, 16, size=3000)]
+    cent = np.vstack([base, base, base[:8] * (1 + 1e-7)]).astype(np.float64)     # exact and near duplicates (k = 40)
+    ctx.set_assign_kernel(cabi.ASSIGN_TC5)
+    ds = ctx.upload(x)
+    inertia, sums, counts = ds.lloyd_step(cent)
+    ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+    d_o, s_o, c_o, m_o = O.brute_clustering(x, cent)
+    assert np.array_equal(ds.labels().astype(np.int64), m_o) and counts.tolist() == c_o.tolist()
+    ds.close()
+
+
 def test_init_centroids_are_label_means(ctx, O):
     x = blobs(3000, 8, 6, 11)
     first, u = cluster.kmeanspp_draws(5, 3000, 6)

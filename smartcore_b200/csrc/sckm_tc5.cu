@@ -85,7 +85,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
                    "=r"(v[30]), "=r"(v[31]) : "r"(addr));
 }
 
-struct TcSmem {                       // dynamic shared memory image (base aligned to 1024 B)
+struct alignas(16) TcSmem {           // dynamic shared memory image (base aligned to 1024 B)
     float xh[2][TC_TILES][TC_BM * TC_K];   // raw rows on arrival, TF32 hi part after the split
     float xl[2][TC_TILES][TC_BM * TC_K];   // TF32 lo part
     float ch[2][TC_BN * TC_K];             // centroid block, hi
@@ -107,6 +107,8 @@ __global__ void tc5_prep_kernel(const double* __restrict__ centroids, const doub
     if (e < kpad) hcn[e] = e < k ? (float)(-0.5 * cnorm[e]) : -INFINITY;
 }
 
+// HCN_SMEM: -||c||^2/2 of all centroids resident in shared memory (fits up to ~7000 centroids), else read through L1
+template <bool HCN_SMEM>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapCh,
                   const __grid_constant__ CUtensorMap mapCl, uint64_t n, uint32_t d,
@@ -118,6 +120,8 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t rows_per_super = TC_TILES * TC_BM;
     const uint64_t nsuper = (n + rows_per_super - 1) / rows_per_super;
+    float* s_hcn = reinterpret_cast<float*>(&S + 1);                 // [nblocks * TC_BN] when HCN_SMEM
+    if (HCN_SMEM) for (uint32_t i = threadIdx.x; i < nblocks * TC_BN; i += blockDim.x) s_hcn[i] = hcn[i];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) {
@@ -198,12 +202,9 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         double* part = partials + ((size_t)blockIdx.x * TC_EPI_WARPS + ew) * ((pk + 15) / 16 * 16);
         unsigned lanemask_lt;
         asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanemask_lt));
-        uint32_t it = 0, j = 0;
-        for (uint64_t st = blockIdx.x; st < nsuper; st += gridDim.x, it++) {
-            const int xs = it & 1; const uint32_t xph = (it >> 1) & 1;
-            const uint64_t row = st * rows_per_super + (uint64_t)m * TC_BM + rloc;
-            const bool valid = row < n;
-            // ---- split my row in place (128 bytes at rloc*128; the swizzle only permutes 16-byte chunks inside it) ----
+        // split my row of X stage `xs` in place (128 bytes at rloc*128; the swizzle only permutes 16-byte chunks
+        // inside it) and return ||x||^2; then tell the MMA warp that the stage is ready
+        auto split_stage = [&](int xs, uint32_t xph) -> double {
             mbar_wait(&S.x_full[xs], xph);
             float4* ph4 = reinterpret_cast<float4*>(S.xh[xs][m] + rloc * TC_K);
             float4* pl4 = reinterpret_cast<float4*>(S.xl[xs][m] + rloc * TC_K);
@@ -223,38 +224,60 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.x_ready[xs]);
+            return xn;
+        };
+        uint32_t it = 0, j = 0;
+        double xn_next = blockIdx.x < nsuper ? split_stage(0, 0) : 0.0;
+        for (uint64_t st = blockIdx.x; st < nsuper; st += gridDim.x, it++) {
+            const int xs = it & 1;
+            const uint64_t row = st * rows_per_super + (uint64_t)m * TC_BM + rloc;
+            const bool valid = row < n;
+            const double xn = xn_next;
+            float4* ph4 = reinterpret_cast<float4*>(S.xh[xs][m] + rloc * TC_K);
+            float4* pl4 = reinterpret_cast<float4*>(S.xl[xs][m] + rloc * TC_K);
             // ---- running top-2 over all centroid blocks ----
             float best = -FLT_MAX, second = -FLT_MAX; uint32_t bi = 0;
             for (uint32_t b = 0; b < nblocks; b++, j++) {
                 const int ts = j & 1; const uint32_t ph = (j >> 1) & 1;
+                // split the NEXT super-tile as soon as this one is under way, so the MMA warp never waits for it
+                if (b == (nblocks > 1 ? 1u : 0u) && st + gridDim.x < nsuper) xn_next = split_stage((it + 1) & 1, ((it + 1) >> 1) & 1);
                 mbar_wait(&S.t_full[ts], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * 256 + m * TC_BN);
-                const float4* h4 = reinterpret_cast<const float4*>(hcn + (size_t)b * TC_BN);
-#pragma unroll 1
-                for (int c0 = 0; c0 < TC_BN; c0 += 32) {
-                    uint32_t v[32];
-                    tmem_ld32(taddr + c0, v);
-                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (c0 + 32 == TC_BN) {                          // all of this stage's columns are in registers
-                        asm volatile("tcgen05.fence::before_thread_sync;");
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&S.t_empty[ts]);
-                    }
+                const float4* h4 = reinterpret_cast<const float4*>((HCN_SMEM ? s_hcn : hcn) + (size_t)b * TC_BN);
+                // software pipeline over the four 32-column chunks: chunk c+1 is in flight (tcgen05.ld is asynchronous
+                // until tcgen05.wait::ld) while chunk c goes through the top-2 update
+                uint32_t va[32], vb[32];
+                auto consume = [&](const uint32_t (&v)[32], int c0) {
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
-                        const float4 hv = __ldg(h4 + (c0 >> 2) + u);
+                        const float4 hv = HCN_SMEM ? h4[(c0 >> 2) + u] : __ldg(h4 + (c0 >> 2) + u);
                         const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
-                            const float s = __uint_as_float(v[u * 4 + e]) + hh[e];
-                            const bool gt = s > best;
-                            second = fmaxf(second, gt ? best : s);
+                            const float sc = __uint_as_float(v[u * 4 + e]) + hh[e];
+                            const bool gt = sc > best;
+                            second = fmaxf(second, gt ? best : sc);
                             bi = gt ? (b * TC_BN + c0 + u * 4 + e) : bi;
-                            best = fmaxf(best, s);
+                            best = fmaxf(best, sc);
                         }
                     }
-                }
+                };
+                tmem_ld32(taddr, va);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(taddr + 32, vb);
+                consume(va, 0);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(taddr + 64, va);
+                consume(vb, 32);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(taddr + 96, vb);
+                consume(va, 64);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;");   // all of this stage's columns are in registers
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.t_empty[ts]);
+                consume(vb, 96);
             }
             // ---- decide: exact f64 distance to the winner, near-tie mark ----
             // my row again in logical order: chunk c of row r sits at physical chunk c ^ (r & 7)
@@ -274,21 +297,24 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                     if ((uint32_t)f < d) { const double r = (double)xr[f] - cr[f]; dist = fma(r, r, dist); }
             }
             if (valid) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = dist; }
-            // ---- deterministic fused update (see sckm_dmma.cu): rows of this warp that share a label go in rank order ----
+            // ---- deterministic fused update: the warp walks its 32 rows in order; lane f adds feature f of the row
+            // (read back from the staged tile) to the warp's private partial with a fire-and-forget RED.  Every
+            // address only ever receives adds from one thread, in program order => fixed summation order. ----
             const bool part_ok = valid && !tie;
-            const uint32_t key = part_ok ? bi : (0x80000000u | (uint32_t)lane);
-            const unsigned peers = __match_any_sync(0xffffffffu, key);
-            const int rank = __popc(peers & lanemask_lt);
-            const int maxrank = __reduce_max_sync(0xffffffffu, part_ok ? rank : 0);
-            for (int r = 0; r <= maxrank; r++) {
-                if (r) { __threadfence(); __syncwarp(); }
-                if (part_ok && rank == r) {
-                    double* p = part + (size_t)bi * d;
-#pragma unroll
-                    for (int f = 0; f < TC_K; f++)
-                        if ((uint32_t)f < d) atomicAdd(p + f, (double)xr[f]);
-                    atomicAdd(part + (size_t)k * d + bi, 1.0);
+            const uint32_t lab = part_ok ? bi : 0xffffffffu;
+            {
+                const float* th = S.xh[xs][m] + (size_t)(q * 32) * TC_K;   // first row of this warp's quadrant
+                const float* tl = S.xl[xs][m] + (size_t)(q * 32) * TC_K;
+#pragma unroll 4
+                for (int r = 0; r < 32; r++) {
+                    const uint32_t lr = __shfl_sync(0xffffffffu, lab, r);
+                    if (lr == 0xffffffffu) continue;                       // warp-uniform
+                    const int phys = r * TC_K + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3));   // undo the 128-byte swizzle
+                    if ((uint32_t)lane < d) atomicAdd(part + (size_t)lr * d + lane, (double)th[phys] + (double)tl[phys]);
                 }
+                // counts: one add per distinct label of the warp (the lowest lane of each group adds the group size)
+                const unsigned peers = __match_any_sync(0xffffffffu, part_ok ? bi : (0x80000000u | (uint32_t)lane));
+                if (part_ok && (peers & lanemask_lt) == 0) atomicAdd(part + (size_t)k * d + bi, (double)__popc(peers));
             }
             double v = part_ok ? dist : 0.0;                          // fixed-order sum over the warp's 32 rows
 #pragma unroll
@@ -362,11 +388,13 @@ int launch_assign_tc5(sckm_dataset* ds, uint64_t k) {
     SCKM_TRY(make_map(ctx, &mapX, ds->x, ds->n, ds->d));
     SCKM_TRY(make_map(ctx, &mapCh, ch, kpad, TC_K));
     SCKM_TRY(make_map(ctx, &mapCl, cl, kpad, TC_K));
-    const size_t smem = sizeof(TcSmem) + 1024;
-    SCKM_CUDA(ctx, cudaFuncSetAttribute(assign_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    assign_tc5_kernel<<<grid, TC_THREADS, smem, ctx->stream>>>(mapX, mapCh, mapCl, ds->n, (uint32_t)ds->d,
-                                                              ctx->d_centroids, ctx->d_cnorm, hcn, (uint32_t)k, nblocks,
-                                                              ds->labels, ds->mind, ctx->d_partials, pk);
+    const size_t hcn_bytes = (size_t)kpad * sizeof(float);
+    const bool hcn_smem = sizeof(TcSmem) + 1024 + hcn_bytes <= (size_t)ctx->smem_optin;
+    const size_t smem = sizeof(TcSmem) + 1024 + (hcn_smem ? hcn_bytes : 0);
+    auto kern = hcn_smem ? assign_tc5_kernel<true> : assign_tc5_kernel<false>;
+    SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TC_THREADS, smem, ctx->stream>>>(mapX, mapCh, mapCl, ds->n, (uint32_t)ds->d, ctx->d_centroids, ctx->d_cnorm,
+                                                  hcn, (uint32_t)k, nblocks, ds->labels, ds->mind, ctx->d_partials, pk);
     LAUNCH_CHECK_T(ctx);
     return launch_refine_rows(ds, k, pk, grid);   // 8 warps per CTA: the same partial slots as the epilogue warps
 }

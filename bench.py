@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--assign", type=int, default=0, help="tuning only: force an assignment kernel (SCKM_ASSIGN_*)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra tcgen05-ranked measurement on f64 data")
     return ap.parse_args()
 
 
@@ -232,6 +233,26 @@ def main():
     launches = ctx.launch_count() - l0
     t_dev = float(out["ms"].sum()) * 1e-3
     t_assign = float(out["assign_ms"].mean()) * 1e-3
+    # ---- optional second figure: same steps with the tcgen05 kernel ranking an f32 shadow of X in 3xTF32 while every
+    # decision, distance and sum stays exact f64 (opt-in kernel, SCKM_ASSIGN_TC5); reported beside the FP64 headline ----
+    alt = None
+    if args.dtype == "f64" and not args.assign and d <= 64 and d % 4 == 0 and k >= 16 and not args.no_alt:
+        from smartcore_b200 import cabi as _cabi
+        ctx.set_assign_kernel(_cabi.ASSIGN_TC5)
+        ds.lloyd_iterate(cent0, max(args.warmup, 1))
+        barrier()
+        out2 = ds.lloyd_iterate(cent0, args.steps)
+        barrier()
+        ctx.set_assign_kernel(_cabi.ASSIGN_AUTO)
+        t2 = float(out2["ms"].sum()) * 1e-3
+        if distributed:
+            t2 = scd.max_over_ranks(t2)
+        denom = np.maximum(np.abs(out["centroids"]), 1e-300)
+        alt = {"what": "same K steps with the tcgen05 kernel: 3xTF32 ranking of an f32 shadow of X on the tensor cores, "
+                       "near-ties re-decided exactly, distances and sums in f64 (SCKM_ASSIGN_TC5, opt-in for f64 data)",
+               "ms_per_step": 1e3 * t2 / args.steps, "value": n_global * args.steps / t2, "unit": "point-iters/s",
+               "max_rel_diff_final_centroids_vs_fp64_path": float(np.max(np.abs(out2["centroids"] - out["centroids"]) / denom)),
+               "sizes_equal": bool(np.array_equal(out2["size"], out["size"]))}
     if distributed:
         t_dev = scd.max_over_ranks(t_dev)
         t_assign = scd.max_over_ranks(t_assign)
@@ -315,7 +336,7 @@ def main():
                          "hbm": {"achieved_gbs": hbm_bytes / t_assign / 1e9, "peak_gbs": mp.get("hbm_gbs", 6650.0),
                                  "peak_source": "MEASURED_PEAKS.json" if mp else "fallback (B200_PROFILING.md)",
                                  "copy_gbs_measured_now": peaks["hbm_copy_gbs"]}},
-            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "tf32_ranked": alt,
         }
         print(json.dumps(line), flush=True)
     ctx.close()

@@ -19,6 +19,7 @@ int launch_assign_stream(sckm_dataset* ds, uint64_t k);       // sckm_stream.cu
 bool stream_supported(const sckm_dataset* ds, uint64_t k);    // sckm_stream.cu
 int launch_assign_tc5(sckm_dataset* ds, uint64_t k);          // sckm_tc5.cu
 bool tc5_supported(const sckm_dataset* ds, uint64_t k);       // sckm_tc5.cu
+bool tc5_auto(const sckm_dataset* ds, uint64_t k);            // sckm_tc5.cu
 }
 using namespace sckm;
 
@@ -193,7 +194,7 @@ int sckm_dataset_download_rows(sckm_dataset* ds, uint64_t local_row0, uint64_t n
 void sckm_dataset_destroy(sckm_dataset* ds) {
     if (!ds) return;
     if (ds->ctx) { cudaSetDevice(ds->ctx->device); cudaStreamSynchronize(ds->ctx->stream); }
-    cudaFree(ds->x); cudaFree(ds->labels); cudaFree(ds->mind); cudaFree(ds->labels64);
+    cudaFree(ds->x); cudaFree(ds->labels); cudaFree(ds->mind); cudaFree(ds->labels64); cudaFree(ds->x32);
     delete ds;
 }
 
@@ -276,7 +277,7 @@ static int pick_assign(const sckm_dataset* ds, uint64_t k) {
     const sckm_ctx* ctx = ds->ctx;
     int which = ctx->assign_kernel;
     if (which == SCKM_ASSIGN_AUTO)
-        which = tc5_supported(ds, k) ? SCKM_ASSIGN_TC5 : dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA
+        which = tc5_auto(ds, k) ? SCKM_ASSIGN_TC5 : dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA
                 : stream_supported(ds, k) ? SCKM_ASSIGN_STREAM : SCKM_ASSIGN_DIRECT;
     if (which == SCKM_ASSIGN_TC5 && !tc5_supported(ds, k)) which = dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA : SCKM_ASSIGN_DIRECT;
     if (which == SCKM_ASSIGN_DMMA && !dmma_supported(ds, k)) which = SCKM_ASSIGN_DIRECT;

@@ -65,6 +65,7 @@ struct sckm_dataset {
     uint32_t* labels = nullptr;      // [n]
     double* mind = nullptr;          // [n] kmeans++ D^2 / per-point min distance
     uint64_t* labels64 = nullptr;    // lazily allocated widening buffer for usize downloads
+    float* x32 = nullptr;            // f32 shadow of an f64 X (tcgen05 ranking only; lazily built)
     bool have_labels = false;
     size_t elem() const { return dtype == SCKM_F32 ? 4 : 8; }
 };

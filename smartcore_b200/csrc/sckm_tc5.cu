@@ -36,15 +36,11 @@ namespace sckm {
 int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas);   // sckm_dmma.cu
 int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d);                               // sckm_dmma.cu
 
-constexpr int TC_K = 32;                 // padded feature count = one 128-byte swizzle row of f32
 constexpr int TC_BM = 128;               // rows per MMA tile (TMEM lanes)
-constexpr int TC_TILES = 2;              // tiles per super-tile
-constexpr int TC_BN = 128;               // centroids per block
 constexpr int TC_EPI_WARPS = 8;
 constexpr int TC_THREADS = 11 * 32;      // warps: 0 X-producer, 1 MMA, 2..9 epilogue, 10 C-producer
-constexpr uint32_t TC_TILE_BYTES = TC_BM * TC_K * 4;   // 16 KB
+constexpr uint32_t TC_ATOM_FLOATS = TC_BM * 32;        // one 128-row x 128-byte swizzle atom of f32
 constexpr double TC_TIE_REL = 2e-5;      // >= 10x the 3xTF32 + FP32-accumulate error bound (bench/tc5_probe.cu: 1e-6)
-constexpr uint32_t TC_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
 
 // ---- PTX wrappers -----------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -70,9 +66,9 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
     return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
            ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
 }
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t accumulate) {
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
     asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n }"
-                 ::"r"(tmem_c), "l"(da), "l"(db), "r"(TC_IDESC), "r"(accumulate) : "memory");
+                 ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
@@ -85,21 +81,28 @@ __device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
                    "=r"(v[30]), "=r"(v[31]) : "r"(addr));
 }
 
-struct alignas(16) TcSmem {           // dynamic shared memory image (base aligned to 1024 B)
-    float xh[2][TC_TILES][TC_BM * TC_K];   // raw rows on arrival, TF32 hi part after the split
-    float xl[2][TC_TILES][TC_BM * TC_K];   // TF32 lo part
-    float ch[2][TC_BN * TC_K];             // centroid block, hi
-    float cl[2][TC_BN * TC_K];             // centroid block, lo
+// NK: 128-byte swizzle atoms along K (d <= 32*NK); TILES: 128-row tiles per super-tile; BN: centroids per block.
+// The 8 epilogue warps cover TILES tiles x 4 TMEM lane quadrants x CP column parts (CP = 2 / TILES).
+template <int NK, int TILES, int BN>
+struct alignas(16) TcSmemT {                  // dynamic shared memory image (base aligned to 1024 B)
+    float xh[2][TILES][NK][TC_ATOM_FLOATS];   // raw rows on arrival, TF32 hi part after the split
+    float xl[2][TILES][NK][TC_ATOM_FLOATS];   // TF32 lo part
+    float ch[2][NK][BN * 32];                 // centroid block, hi
+    float cl[2][NK][BN * 32];                 // centroid block, lo
     uint64_t x_full[2], x_ready[2], x_empty[2], c_full[2], c_empty[2], t_full[2], t_empty[2];
+    double m_xn[2][TC_BM];                    // column-part merge scratch (CP == 2), double-buffered by super-tile
+    float m_best[2][TC_BM], m_second[2][TC_BM];
+    uint32_t m_idx[2][TC_BM];
     uint32_t tmem_base;
 };
 
-// centroids (f64 [k][d]) -> TF32 hi / lo parts in f32 [kpad][32] (zero padded) and -||c||^2/2 in f32
+// centroids (f64 [k][d]) -> TF32 hi / lo parts in f32 [kpad][kdim] (zero padded) and -||c||^2/2 in f32
 __global__ void tc5_prep_kernel(const double* __restrict__ centroids, const double* __restrict__ cnorm, uint32_t k, uint32_t d,
-                                uint32_t kpad, float* __restrict__ ch, float* __restrict__ cl, float* __restrict__ hcn) {
+                                uint32_t kpad, uint32_t kdim, float* __restrict__ ch, float* __restrict__ cl,
+                                float* __restrict__ hcn) {
     const uint32_t e = blockIdx.x * blockDim.x + threadIdx.x;
-    if (e < kpad * TC_K) {
-        const uint32_t r = e / TC_K, c = e - r * TC_K;
+    if (e < kpad * kdim) {
+        const uint32_t r = e / kdim, c = e - r * kdim;
         float v = (r < k && c < d) ? (float)centroids[(size_t)r * d + c] : 0.f;
         const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
         ch[e] = h; cl[e] = v - h;
@@ -107,21 +110,34 @@ __global__ void tc5_prep_kernel(const double* __restrict__ centroids, const doub
     if (e < kpad) hcn[e] = e < k ? (float)(-0.5 * cnorm[e]) : -INFINITY;
 }
 
-// HCN_SMEM: -||c||^2/2 of all centroids resident in shared memory (fits up to ~7000 centroids), else read through L1
-template <bool HCN_SMEM>
+__global__ void tc5_shadow_kernel(const double* __restrict__ x, float* __restrict__ x32, uint64_t total) {
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x)
+        x32[i] = (float)x[i];
+}
+
+// HCN_SMEM: -||c||^2/2 of all centroids resident in shared memory, else read through L1.
+// TXS: type of the rows used for the exact part (distance to the winner, sums): float = the staged tile itself,
+// double = the original f64 rows in HBM (the tensor cores then only see an f32 shadow copy, for the ranking).
+template <int NK, int TILES, int BN, bool HCN_SMEM, typename TXS>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapCh,
-                  const __grid_constant__ CUtensorMap mapCl, uint64_t n, uint32_t d,
+                  const __grid_constant__ CUtensorMap mapCl, const TXS* __restrict__ xsrc, uint64_t n, uint32_t d,
                   const double* __restrict__ centroids, const double* __restrict__ cnorm, const float* __restrict__ hcn,
                   uint32_t k, uint32_t nblocks, uint32_t* __restrict__ labels, double* __restrict__ mind,
                   double* __restrict__ partials, size_t pk) {
+    using Smem = TcSmemT<NK, TILES, BN>;
+    constexpr int CP = 2 / TILES;                    // column parts per row
+    constexpr int COLS = BN / CP;                    // columns per epilogue thread per block
+    constexpr int TSTAGE = TILES * BN;               // TMEM columns per accumulator stage
+    constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    static_assert(COLS % 32 == 0, "epilogue threads read TMEM in 32-column chunks");
     extern __shared__ unsigned char smem_raw[];
-    TcSmem& S = *reinterpret_cast<TcSmem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    Smem& S = *reinterpret_cast<Smem*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint64_t rows_per_super = TC_TILES * TC_BM;
+    const uint64_t rows_per_super = (uint64_t)TILES * TC_BM;
     const uint64_t nsuper = (n + rows_per_super - 1) / rows_per_super;
-    float* s_hcn = reinterpret_cast<float*>(&S + 1);                 // [nblocks * TC_BN] when HCN_SMEM
-    if (HCN_SMEM) for (uint32_t i = threadIdx.x; i < nblocks * TC_BN; i += blockDim.x) s_hcn[i] = hcn[i];
+    float* s_hcn = reinterpret_cast<float*>(&S + 1);                 // [nblocks * BN] when HCN_SMEM
+    if (HCN_SMEM) for (uint32_t i = threadIdx.x; i < nblocks * BN; i += blockDim.x) s_hcn[i] = hcn[i];
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) {
@@ -131,8 +147,9 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
+    constexpr uint32_t TMEM_COLS = 2 * TSTAGE < 32 ? 32 : 2 * TSTAGE;   // 128 / 256 / 512: a power of two >= 32
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(512));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&S.tmem_base)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -147,9 +164,10 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             for (uint64_t st = blockIdx.x; st < nsuper; st += gridDim.x, it++) {
                 const int xs = it & 1; const uint32_t ph = (it >> 1) & 1;
                 mbar_wait(&S.x_empty[xs], ph ^ 1);
-                mbar_expect_tx(&S.x_full[xs], TC_TILES * TC_TILE_BYTES);
-                for (int m = 0; m < TC_TILES; m++)
-                    tma_load_2d(S.xh[xs][m], &mapX, 0, (int)(st * rows_per_super + (uint64_t)m * TC_BM), &S.x_full[xs]);
+                mbar_expect_tx(&S.x_full[xs], TILES * NK * TC_ATOM_FLOATS * 4);
+                for (int m = 0; m < TILES; m++)
+                    for (int a = 0; a < NK; a++)
+                        tma_load_2d(S.xh[xs][m][a], &mapX, 32 * a, (int)(st * rows_per_super + (uint64_t)m * TC_BM), &S.x_full[xs]);
             }
         }
     } else if (warp == 10) {
@@ -160,9 +178,11 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 for (uint32_t b = 0; b < nblocks; b++, j++) {
                     const int cs = j & 1; const uint32_t ph = (j >> 1) & 1;
                     mbar_wait(&S.c_empty[cs], ph ^ 1);
-                    mbar_expect_tx(&S.c_full[cs], 2 * TC_TILE_BYTES);
-                    tma_load_2d(S.ch[cs], &mapCh, 0, (int)(b * TC_BN), &S.c_full[cs]);
-                    tma_load_2d(S.cl[cs], &mapCl, 0, (int)(b * TC_BN), &S.c_full[cs]);
+                    mbar_expect_tx(&S.c_full[cs], 2 * NK * BN * 128);
+                    for (int a = 0; a < NK; a++) {
+                        tma_load_2d(S.ch[cs][a], &mapCh, 32 * a, (int)(b * BN), &S.c_full[cs]);
+                        tma_load_2d(S.cl[cs][a], &mapCl, 32 * a, (int)(b * BN), &S.c_full[cs]);
+                    }
                 }
         }
     } else if (warp == 1) {
@@ -178,13 +198,15 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                     mbar_wait(&S.c_full[cs], ph);
                     mbar_wait(&S.t_empty[cs], ph ^ 1);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    const uint64_t dCh = umma_desc_sw128(S.ch[cs]), dCl = umma_desc_sw128(S.cl[cs]);
-                    for (int m = 0; m < TC_TILES; m++) {
-                        const uint64_t dXh = umma_desc_sw128(S.xh[xs][m]), dXl = umma_desc_sw128(S.xl[xs][m]);
-                        const uint32_t tcol = tmem + (uint32_t)(cs * 256 + m * TC_BN);
-                        for (int ks = 0; ks < TC_K / 8; ks++) umma_tf32(tcol, dXh + 2 * ks, dCh + 2 * ks, ks > 0);
-                        for (int ks = 0; ks < TC_K / 8; ks++) umma_tf32(tcol, dXh + 2 * ks, dCl + 2 * ks, 1);
-                        for (int ks = 0; ks < TC_K / 8; ks++) umma_tf32(tcol, dXl + 2 * ks, dCh + 2 * ks, 1);
+                    for (int m = 0; m < TILES; m++) {
+                        const uint32_t tcol = tmem + (uint32_t)(cs * TSTAGE + m * BN);
+                        uint32_t acc = 0;
+                        for (int prod = 0; prod < 3; prod++)          // Xh.Ch + Xh.Cl + Xl.Ch
+                            for (int a = 0; a < NK; a++) {
+                                const uint64_t dX = umma_desc_sw128(prod == 2 ? S.xl[xs][m][a] : S.xh[xs][m][a]);
+                                const uint64_t dC = umma_desc_sw128(prod == 1 ? S.cl[cs][a] : S.ch[cs][a]);
+                                for (int ks = 0; ks < 4; ks++) { umma_tf32(tcol, dX + 2 * ks, dC + 2 * ks, IDESC, acc); acc = 1; }
+                            }
                     }
                     umma_commit(&S.c_empty[cs]);                     // centroid stage free once these MMAs have read it
                     umma_commit(&S.t_full[cs]);                      // accumulators ready for the epilogue
@@ -193,33 +215,35 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             }
         }
     } else {
-        // ================= epilogue warps: thread = row =================
+        // ================= epilogue warps: one thread per (row, column part) =================
         const int ew = warp - 2;                                     // 0..7
-        const int m = ew >> 2;                                       // tile of the super-tile
+        const int m = TILES == 2 ? (ew >> 2) : 0;                    // tile of the super-tile
+        const int cp = TILES == 2 ? 0 : (ew >> 2);                   // column part
         const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
         const int rloc = q * 32 + lane;                              // row within the tile
         const double cmax = cnorm[k];
         double* part = partials + ((size_t)blockIdx.x * TC_EPI_WARPS + ew) * ((pk + 15) / 16 * 16);
-        unsigned lanemask_lt;
-        asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanemask_lt));
-        // split my row of X stage `xs` in place (128 bytes at rloc*128; the swizzle only permutes 16-byte chunks
-        // inside it) and return ||x||^2; then tell the MMA warp that the stage is ready
+        // split my share of X stage `xs` in place (a row is 128 bytes at rloc*128 inside each atom; the swizzle only
+        // permutes 16-byte chunks inside it), return my part of ||x||^2, and tell the MMA warp the stage is ready
         auto split_stage = [&](int xs, uint32_t xph) -> double {
             mbar_wait(&S.x_full[xs], xph);
-            float4* ph4 = reinterpret_cast<float4*>(S.xh[xs][m] + rloc * TC_K);
-            float4* pl4 = reinterpret_cast<float4*>(S.xl[xs][m] + rloc * TC_K);
             double xn = 0.0;
 #pragma unroll
-            for (int c0 = 0; c0 < 8; c0++) {
-                const int c = (c0 + lane) & 7;                         // rotate: 8 lanes hit 8 different 16-byte columns
-                float4 v = ph4[c], h, l;
-                h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
-                h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
-                h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
-                h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
-                ph4[c] = h; pl4[c] = l;
-                xn = fma((double)v.x, (double)v.x, xn); xn = fma((double)v.y, (double)v.y, xn);
-                xn = fma((double)v.z, (double)v.z, xn); xn = fma((double)v.w, (double)v.w, xn);
+            for (int a = cp; a < NK; a += CP) {
+                float4* ph4 = reinterpret_cast<float4*>(S.xh[xs][m][a] + rloc * 32);
+                float4* pl4 = reinterpret_cast<float4*>(S.xl[xs][m][a] + rloc * 32);
+#pragma unroll
+                for (int c0 = 0; c0 < 8; c0++) {
+                    const int c = (c0 + lane) & 7;                     // rotate: 8 lanes hit 8 different 16-byte columns
+                    float4 v = ph4[c], h, l;
+                    h.x = __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.x = v.x - h.x;
+                    h.y = __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u); l.y = v.y - h.y;
+                    h.z = __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.z = v.z - h.z;
+                    h.w = __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u); l.w = v.w - h.w;
+                    ph4[c] = h; pl4[c] = l;
+                    xn = fma((double)v.x, (double)v.x, xn); xn = fma((double)v.y, (double)v.y, xn);
+                    xn = fma((double)v.z, (double)v.z, xn); xn = fma((double)v.w, (double)v.w, xn);
+                }
             }
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic writes -> visible to the MMA (async proxy)
             __syncwarp();
@@ -232,10 +256,8 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             const int xs = it & 1;
             const uint64_t row = st * rows_per_super + (uint64_t)m * TC_BM + rloc;
             const bool valid = row < n;
-            const double xn = xn_next;
-            float4* ph4 = reinterpret_cast<float4*>(S.xh[xs][m] + rloc * TC_K);
-            float4* pl4 = reinterpret_cast<float4*>(S.xl[xs][m] + rloc * TC_K);
-            // ---- running top-2 over all centroid blocks ----
+            double xn = xn_next;
+            // ---- running top-2 over all centroid blocks (my columns only) ----
             float best = -FLT_MAX, second = -FLT_MAX; uint32_t bi = 0;
             for (uint32_t b = 0; b < nblocks; b++, j++) {
                 const int ts = j & 1; const uint32_t ph = (j >> 1) & 1;
@@ -243,9 +265,10 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 if (b == (nblocks > 1 ? 1u : 0u) && st + gridDim.x < nsuper) xn_next = split_stage((it + 1) & 1, ((it + 1) >> 1) & 1);
                 mbar_wait(&S.t_full[ts], ph);
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * 256 + m * TC_BN);
-                const float4* h4 = reinterpret_cast<const float4*>((HCN_SMEM ? s_hcn : hcn) + (size_t)b * TC_BN);
-                // software pipeline over the four 32-column chunks: chunk c+1 is in flight (tcgen05.ld is asynchronous
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TSTAGE + m * BN + cp * COLS);
+                const uint32_t col0 = b * BN + cp * COLS;
+                const float4* h4 = reinterpret_cast<const float4*>((HCN_SMEM ? s_hcn : hcn) + col0);
+                // software pipeline over the 32-column chunks: chunk c+1 is in flight (tcgen05.ld is asynchronous
                 // until tcgen05.wait::ld) while chunk c goes through the top-2 update
                 uint32_t va[32], vb[32];
                 auto consume = [&](const uint32_t (&v)[32], int c0) {
@@ -258,75 +281,99 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                             const float sc = __uint_as_float(v[u * 4 + e]) + hh[e];
                             const bool gt = sc > best;
                             second = fmaxf(second, gt ? best : sc);
-                            bi = gt ? (b * TC_BN + c0 + u * 4 + e) : bi;
+                            bi = gt ? (col0 + c0 + u * 4 + e) : bi;
                             best = fmaxf(best, sc);
                         }
                     }
                 };
+                auto release_stage = [&]() {                           // all of this stage's columns are in registers
+                    asm volatile("tcgen05.fence::before_thread_sync;");
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&S.t_empty[ts]);
+                };
                 tmem_ld32(taddr, va);
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tmem_ld32(taddr + 32, vb);
-                consume(va, 0);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tmem_ld32(taddr + 64, va);
-                consume(vb, 32);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tmem_ld32(taddr + 96, vb);
-                consume(va, 64);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;");   // all of this stage's columns are in registers
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.t_empty[ts]);
-                consume(vb, 96);
-            }
-            // ---- decide: exact f64 distance to the winner, near-tie mark ----
-            // my row again in logical order: chunk c of row r sits at physical chunk c ^ (r & 7)
-            float xr[TC_K];
+                if (COLS == 32) {
+                    release_stage();
+                    consume(va, 0);
+                } else {
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const float4 h = ph4[c ^ (rloc & 7)], l = pl4[c ^ (rloc & 7)];
-                xr[4 * c + 0] = h.x + l.x; xr[4 * c + 1] = h.y + l.y; xr[4 * c + 2] = h.z + l.z; xr[4 * c + 3] = h.w + l.w;
+                    for (int c0 = 0; c0 < COLS; c0 += 64) {
+                        tmem_ld32(taddr + c0 + 32, vb);
+                        consume(va, c0);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (c0 + 64 < COLS) tmem_ld32(taddr + c0 + 64, va); else release_stage();
+                        consume(vb, c0 + 32);
+                        if (c0 + 64 < COLS) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
+                }
             }
-            const double gap = 2.0 * ((double)best - (double)second);
-            const bool tie = !(gap > TC_TIE_REL * (xn + cmax)) || bi >= k;
-            double dist = 0.0;
-            if (valid && !tie) {
-                const double* cr = centroids + (size_t)bi * d;
-#pragma unroll
-                for (int f = 0; f < TC_K; f++)
-                    if ((uint32_t)f < d) { const double r = (double)xr[f] - cr[f]; dist = fma(r, r, dist); }
+            // ---- CP == 2: the two column parts of a row live in different warps: merge through shared memory ----
+            if (CP == 2) {
+                const int mb = it & 1;
+                if (cp == 1) { S.m_best[mb][rloc] = best; S.m_second[mb][rloc] = second; S.m_idx[mb][rloc] = bi; S.m_xn[mb][rloc] = xn; }
+                asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 epilogue warps
+                if (cp == 0) {
+                    const float ob = S.m_best[mb][rloc], os = S.m_second[mb][rloc]; const uint32_t oi = S.m_idx[mb][rloc];
+                    xn += S.m_xn[mb][rloc];
+                    const bool take = ob > best || (ob == best && oi < bi);
+                    second = fmaxf(fmaxf(second, os), fminf(best, ob));
+                    bi = take ? oi : bi;
+                    best = fmaxf(best, ob);
+                }
             }
-            if (valid) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = dist; }
-            // ---- deterministic fused update: the warp walks its 32 rows in order; lane f adds feature f of the row
-            // (read back from the staged tile) to the warp's private partial with a fire-and-forget RED.  Every
-            // address only ever receives adds from one thread, in program order => fixed summation order. ----
-            const bool part_ok = valid && !tie;
-            const uint32_t lab = part_ok ? bi : 0xffffffffu;
-            {
-                const float* th = S.xh[xs][m] + (size_t)(q * 32) * TC_K;   // first row of this warp's quadrant
-                const float* tl = S.xl[xs][m] + (size_t)(q * 32) * TC_K;
-#pragma unroll 4
+            if (cp == 0) {
+                // ---- decide: near-tie mark; exact f64 distance to the winner and the update, cooperatively per row ----
+                const double gap = 2.0 * ((double)best - (double)second);
+                const bool tie = !(gap > TC_TIE_REL * (xn + cmax)) || bi >= k;
+                const bool part_ok = valid && !tie;
+                const uint32_t lab = part_ok ? bi : 0xffffffffu;
+                const uint64_t wrow0 = st * rows_per_super + (uint64_t)m * TC_BM + (uint64_t)q * 32;   // first row of this warp
+                double mydist = 0.0;
+                // The warp walks its 32 rows in order; lane f handles features f, f+32, ...: it adds the row's value
+                // to the warp's private partial with a fire-and-forget RED (an address only ever receives adds from one
+                // thread, in program order => fixed summation order) and contributes (x - c)^2 to the row's distance.
+#pragma unroll 2
                 for (int r = 0; r < 32; r++) {
                     const uint32_t lr = __shfl_sync(0xffffffffu, lab, r);
-                    if (lr == 0xffffffffu) continue;                       // warp-uniform
-                    const int phys = r * TC_K + ((((lane >> 2) ^ (r & 7)) << 2) | (lane & 3));   // undo the 128-byte swizzle
-                    if ((uint32_t)lane < d) atomicAdd(part + (size_t)lr * d + lane, (double)th[phys] + (double)tl[phys]);
+                    if (lr == 0xffffffffu) continue;                   // warp-uniform
+                    double acc = 0.0;
+                    for (uint32_t f = lane; f < d; f += 32) {
+                        double xv;
+                        if (sizeof(TXS) == 8) {
+                            xv = (double)__ldg(xsrc + (wrow0 + r) * d + f);
+                        } else {
+                            const int a = f >> 5, fi = f & 31, rt = q * 32 + r;
+                            const int phys = rt * 32 + ((((fi >> 2) ^ (rt & 7)) << 2) | (fi & 3));   // undo the 128-byte swizzle
+                            xv = (double)S.xh[xs][m][a][phys] + (double)S.xl[xs][m][a][phys];
+                        }
+                        const double dv = xv - __ldg(centroids + (size_t)lr * d + f);
+                        acc = fma(dv, dv, acc);
+                        atomicAdd(part + (size_t)lr * d + f, xv);
+                    }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
+                    if (lane == r) mydist = acc;
                 }
+                if (valid) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = mydist; }
                 // counts: one add per distinct label of the warp (the lowest lane of each group adds the group size)
+                unsigned lanemask_lt;
+                asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanemask_lt));
                 const unsigned peers = __match_any_sync(0xffffffffu, part_ok ? bi : (0x80000000u | (uint32_t)lane));
                 if (part_ok && (peers & lanemask_lt) == 0) atomicAdd(part + (size_t)k * d + bi, (double)__popc(peers));
-            }
-            double v = part_ok ? dist : 0.0;                          // fixed-order sum over the warp's 32 rows
+                double v = part_ok ? mydist : 0.0;                    // fixed-order sum over the warp's 32 rows
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
-            if (lane == 0) { atomicAdd(part + pk - 1, v); mbar_arrive(&S.x_empty[xs]); }
+                for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+                if (lane == 0) atomicAdd(part + pk - 1, v);
+            }
             __syncwarp();
+            if (lane == 0) mbar_arrive(&S.x_empty[xs]);
         }
     }
     // ---- teardown ----
     asm volatile("tcgen05.fence::before_thread_sync;");
     __syncthreads();
-    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
+    if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
 // ---- host side --------------------------------------------------------------------------------------------------
@@ -346,11 +393,11 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int make_map(sckm_ctx* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols) {
+static int make_map(sckm_ctx* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     EncodeTiledFn enc = encode_fn();
     if (!enc) return fail(ctx, SCKM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
     cuuint64_t dims[2] = {cols, rows}, strides[1] = {cols * 4};
-    cuuint32_t box[2] = {TC_K, TC_BM}, estr[2] = {1, 1};
+    cuuint32_t box[2] = {32, box_rows}, estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -359,9 +406,45 @@ static int make_map(sckm_ctx* ctx, CUtensorMap* map, const void* base, uint64_t 
     return SCKM_OK;
 }
 
+// f32 data: d <= 64.  f64 data only on explicit request (SCKM_ASSIGN_TC5): the tensor cores then rank an f32 shadow
+// copy of X and everything that reaches the result (decision of near-ties, distances, sums) is still exact f64.
 bool tc5_supported(const sckm_dataset* ds, uint64_t k) {
-    return ds->dtype == SCKM_F32 && ds->d >= 4 && ds->d <= TC_K && ds->d % 4 == 0 && k >= 16 && k <= (1u << 20) &&
-           ds->n < 0x7FFFFFFFull && encode_fn() != nullptr;
+    return ds->d >= 4 && ds->d <= 64 && ds->d % 4 == 0 && k >= 16 && k <= (1u << 20) && ds->n < 0x7FFFFFFFull &&
+           encode_fn() != nullptr;
+}
+bool tc5_auto(const sckm_dataset* ds, uint64_t k) { return ds->dtype == SCKM_F32 && tc5_supported(ds, k); }
+
+template <int NK, int TILES, int BN, typename TXS>
+static int launch_tc5_t(sckm_dataset* ds, uint64_t k, size_t pk, const float* x32) {
+    sckm_ctx* ctx = ds->ctx;
+    const unsigned grid = (unsigned)ctx->num_sms;
+    const uint32_t kdim = 32 * NK;
+    const uint32_t nblocks = (uint32_t)((k + BN - 1) / BN), kpad = nblocks * BN;
+    const size_t need = (size_t)kpad * kdim * 2 + kpad;               // ch | cl | hcn   (floats)
+    if (need > ctx->cap_tc5) {
+        if (ctx->d_tc5) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_tc5); ctx->d_tc5 = nullptr; }
+        SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_tc5, need * sizeof(float)));
+        ctx->cap_tc5 = need;
+    }
+    float* ch = ctx->d_tc5; float* cl = ch + (size_t)kpad * kdim; float* hcn = cl + (size_t)kpad * kdim;
+    tc5_prep_kernel<<<(kpad * kdim + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_centroids, ctx->d_cnorm, (uint32_t)k, (uint32_t)ds->d,
+                                                                     kpad, kdim, ch, cl, hcn);
+    LAUNCH_CHECK_T(ctx);
+    CUtensorMap mapX, mapCh, mapCl;
+    SCKM_TRY(make_map(ctx, &mapX, x32, ds->n, ds->d, TC_BM));
+    SCKM_TRY(make_map(ctx, &mapCh, ch, kpad, kdim, BN));
+    SCKM_TRY(make_map(ctx, &mapCl, cl, kpad, kdim, BN));
+    using Smem = TcSmemT<NK, TILES, BN>;
+    const size_t hcn_bytes = (size_t)kpad * sizeof(float);
+    const bool hcn_smem = sizeof(Smem) + 1024 + hcn_bytes <= (size_t)ctx->smem_optin;
+    const size_t smem = sizeof(Smem) + 1024 + (hcn_smem ? hcn_bytes : 0);
+    auto kern = hcn_smem ? assign_tc5_kernel<NK, TILES, BN, true, TXS> : assign_tc5_kernel<NK, TILES, BN, false, TXS>;
+    SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, TC_THREADS, smem, ctx->stream>>>(mapX, mapCh, mapCl, (const TXS*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
+                                                  ctx->d_cnorm, hcn, (uint32_t)k, nblocks, ds->labels, ds->mind,
+                                                  ctx->d_partials, pk);
+    LAUNCH_CHECK_T(ctx);
+    return SCKM_OK;
 }
 
 int launch_assign_tc5(sckm_dataset* ds, uint64_t k) {
@@ -373,29 +456,19 @@ int launch_assign_tc5(sckm_dataset* ds, uint64_t k) {
     ctx->partial_slots_used = grid * TC_EPI_WARPS;
     if (ds->n == 0) return SCKM_OK;
     SCKM_TRY(launch_cnorm(ctx, k, ds->d));
-    const uint32_t nblocks = (uint32_t)((k + TC_BN - 1) / TC_BN), kpad = nblocks * TC_BN;
-    const size_t need = (size_t)kpad * TC_K * 2 + kpad;               // ch | cl | hcn   (floats)
-    if (need > ctx->cap_tc5) {
-        if (ctx->d_tc5) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_tc5); ctx->d_tc5 = nullptr; }
-        SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_tc5, need * sizeof(float)));
-        ctx->cap_tc5 = need;
+    const float* x32 = (const float*)ds->x;
+    if (ds->dtype == SCKM_F64) {                                      // f32 shadow copy of X for the ranking, built once
+        if (!ds->x32) {
+            SCKM_CUDA(ctx, cudaMalloc((void**)&ds->x32, ds->n * ds->d * sizeof(float)));
+            tc5_shadow_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>((const double*)ds->x, ds->x32, ds->n * ds->d);
+            LAUNCH_CHECK_T(ctx);
+        }
+        x32 = ds->x32;
     }
-    float* ch = ctx->d_tc5; float* cl = ch + (size_t)kpad * TC_K; float* hcn = cl + (size_t)kpad * TC_K;
-    tc5_prep_kernel<<<(kpad * TC_K + 255) / 256, 256, 0, ctx->stream>>>(ctx->d_centroids, ctx->d_cnorm, (uint32_t)k, (uint32_t)ds->d,
-                                                                     kpad, ch, cl, hcn);
-    LAUNCH_CHECK_T(ctx);
-    CUtensorMap mapX, mapCh, mapCl;
-    SCKM_TRY(make_map(ctx, &mapX, ds->x, ds->n, ds->d));
-    SCKM_TRY(make_map(ctx, &mapCh, ch, kpad, TC_K));
-    SCKM_TRY(make_map(ctx, &mapCl, cl, kpad, TC_K));
-    const size_t hcn_bytes = (size_t)kpad * sizeof(float);
-    const bool hcn_smem = sizeof(TcSmem) + 1024 + hcn_bytes <= (size_t)ctx->smem_optin;
-    const size_t smem = sizeof(TcSmem) + 1024 + (hcn_smem ? hcn_bytes : 0);
-    auto kern = hcn_smem ? assign_tc5_kernel<true> : assign_tc5_kernel<false>;
-    SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, TC_THREADS, smem, ctx->stream>>>(mapX, mapCh, mapCl, ds->n, (uint32_t)ds->d, ctx->d_centroids, ctx->d_cnorm,
-                                                  hcn, (uint32_t)k, nblocks, ds->labels, ds->mind, ctx->d_partials, pk);
-    LAUNCH_CHECK_T(ctx);
+    int rc;
+    if (ds->d <= 32) rc = ds->dtype == SCKM_F64 ? launch_tc5_t<1, 2, 128, double>(ds, k, pk, x32) : launch_tc5_t<1, 2, 128, float>(ds, k, pk, x32);
+    else             rc = ds->dtype == SCKM_F64 ? launch_tc5_t<2, 1, 64, double>(ds, k, pk, x32) : launch_tc5_t<2, 1, 64, float>(ds, k, pk, x32);
+    SCKM_TRY(rc);
     return launch_refine_rows(ds, k, pk, grid);   // 8 warps per CTA: the same partial slots as the epilogue warps
 }
 

@@ -170,12 +170,17 @@ def test_dmma_step_shapes(ctx, O, n, d, k, dtype):
     ds.close()
 
 
-@pytest.mark.parametrize("n,d,k", [(5000, 32, 16), (33333, 32, 300), (20000, 16, 128), (7001, 8, 100), (9000, 28, 257),
-                                   (50000, 32, 1500), (255, 32, 64)])
-def test_tc5_f32_tile_kernel(ctx, O, n, d, k):
-    """f32 data on the tcgen05 3xTF32 kernel: the ranking runs in reduced precision, the decision must still be
-    exact (labels equal the f64 direct-form argmin), sums/inertia in f64, bit-reproducible."""
-    x = blobs(n, d, k, 3 * n + d, np.float32, spread=1.5)
+@pytest.mark.parametrize("n,d,k,dtype", [(5000, 32, 16, np.float32), (33333, 32, 300, np.float32), (20000, 16, 128, np.float32),
+                                         (7001, 8, 100, np.float32), (9000, 28, 257, np.float32), (50000, 32, 1500, np.float32),
+                                         (255, 32, 64, np.float32),
+                                         # two swizzle atoms along K (d <= 64), rows split over two column parts
+                                         (30000, 64, 256, np.float32), (12345, 48, 100, np.float32), (9999, 36, 17, np.float32),
+                                         # f64 data: tensor cores rank an f32 shadow copy, everything else stays f64
+                                         (30000, 64, 256, np.float64), (20000, 32, 500, np.float64), (5001, 20, 40, np.float64)])
+def test_tc5_tile_kernel(ctx, O, n, d, k, dtype):
+    """tcgen05 3xTF32 kernel: the ranking runs in reduced precision, the decision must still be exact (labels equal
+    the f64 direct-form argmin), sums/inertia in f64, bit-reproducible."""
+    x = blobs(n, d, k, 3 * n + d, dtype, spread=1.5)
     cent = x[np.random.default_rng(2).choice(n, k, replace=False)].astype(np.float64) * 1.001
     ctx.set_assign_kernel(cabi.ASSIGN_TC5)
     ds = ctx.upload(x)

@@ -53,7 +53,8 @@ def parse():
     ap.add_argument("--assign", type=int, default=0, help="tuning only: force an assignment kernel (SCKM_ASSIGN_*)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--no-alt", action="store_true", help="skip the extra tcgen05-ranked measurement on f64 data")
+    ap.add_argument("--alt", action="store_true",
+                    help="also time the experimental tcgen05-ranked path on f64 data (3xTF32 ranking of an f32 shadow, exact f64 result)")
     return ap.parse_args()
 
 
@@ -179,8 +180,9 @@ def main():
     if args.impl == "reference":
         return reference_arm(args, world, rank)
 
-    if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+    # NCCL prints its version banner on stdout at any debug level >= VERSION; rank 0 must print ONE JSON line, so send
+    # NCCL's own log to a file instead (override with NCCL_DEBUG_FILE)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sckm_nccl_%h_%p.log")
     import torch
     import smartcore_b200 as sc
     from smartcore_b200 import cluster, dist as scd
@@ -236,7 +238,7 @@ def main():
     # ---- optional second figure: same steps with the tcgen05 kernel ranking an f32 shadow of X in 3xTF32 while every
     # decision, distance and sum stays exact f64 (opt-in kernel, SCKM_ASSIGN_TC5); reported beside the FP64 headline ----
     alt = None
-    if args.dtype == "f64" and not args.assign and d <= 64 and d % 4 == 0 and k >= 16 and not args.no_alt:
+    if args.alt and args.dtype == "f64" and not args.assign and d <= 64 and d % 4 == 0 and k >= 16:
         from smartcore_b200 import cabi as _cabi
         ctx.set_assign_kernel(_cabi.ASSIGN_TC5)
         ds.lloyd_iterate(cent0, max(args.warmup, 1))

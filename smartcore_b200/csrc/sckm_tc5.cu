@@ -21,6 +21,7 @@
 #include <cuda.h>
 #include <cfloat>
 #include <algorithm>
+#include <cstdlib>
 
 namespace sckm {
 
@@ -329,15 +330,13 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 const bool part_ok = valid && !tie;
                 const uint32_t lab = part_ok ? bi : 0xffffffffu;
                 const uint64_t wrow0 = st * rows_per_super + (uint64_t)m * TC_BM + (uint64_t)q * 32;   // first row of this warp
-                double mydist = 0.0;
-                // The warp walks its 32 rows in order; lane f handles features f, f+32, ...: it adds the row's value
-                // to the warp's private partial with a fire-and-forget RED (an address only ever receives adds from one
-                // thread, in program order => fixed summation order) and contributes (x - c)^2 to the row's distance.
-#pragma unroll 2
+                // (a) update: the warp walks its 32 rows in order; lane f handles features f, f+32, ... and adds the
+                // row's value to the warp's private partial with a fire-and-forget RED (an address only ever receives
+                // adds from one thread, in program order => fixed summation order).  No dependent loads: nothing waits.
+#pragma unroll 4
                 for (int r = 0; r < 32; r++) {
                     const uint32_t lr = __shfl_sync(0xffffffffu, lab, r);
                     if (lr == 0xffffffffu) continue;                   // warp-uniform
-                    double acc = 0.0;
                     for (uint32_t f = lane; f < d; f += 32) {
                         double xv;
                         if (sizeof(TXS) == 8) {
@@ -347,13 +346,33 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                             const int phys = rt * 32 + ((((fi >> 2) ^ (rt & 7)) << 2) | (fi & 3));   // undo the 128-byte swizzle
                             xv = (double)S.xh[xs][m][a][phys] + (double)S.xl[xs][m][a][phys];
                         }
-                        const double dv = xv - __ldg(centroids + (size_t)lr * d + f);
-                        acc = fma(dv, dv, acc);
                         atomicAdd(part + (size_t)lr * d + f, xv);
                     }
-#pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) acc = __dadd_rn(acc, __shfl_xor_sync(0xffffffffu, acc, o));
-                    if (lane == r) mydist = acc;
+                }
+                // (b) exact f64 distance of my row to its winner: all loads independent (one memory round trip)
+                double mydist = 0.0;
+                if (part_ok) {
+                    const double* cr = centroids + (size_t)bi * d;
+                    double a0 = 0.0, a1 = 0.0;
+                    for (uint32_t c = 0; c < d; c += 4) {              // d % 4 == 0
+                        double xv[4];
+                        if (sizeof(TXS) == 8) {
+                            const double2 p0 = __ldg(reinterpret_cast<const double2*>(xsrc + row * d + c));
+                            const double2 p1 = __ldg(reinterpret_cast<const double2*>(xsrc + row * d + c + 2));
+                            xv[0] = p0.x; xv[1] = p0.y; xv[2] = p1.x; xv[3] = p1.y;
+                        } else {
+                            const int a = c >> 5, ch4 = (c & 31) >> 2;
+                            const float4 h = reinterpret_cast<const float4*>(S.xh[xs][m][a] + rloc * 32)[ch4 ^ (rloc & 7)];
+                            const float4 l = reinterpret_cast<const float4*>(S.xl[xs][m][a] + rloc * 32)[ch4 ^ (rloc & 7)];
+                            xv[0] = (double)h.x + (double)l.x; xv[1] = (double)h.y + (double)l.y;
+                            xv[2] = (double)h.z + (double)l.z; xv[3] = (double)h.w + (double)l.w;
+                        }
+                        const double2 c0 = __ldg(reinterpret_cast<const double2*>(cr + c));
+                        const double2 c1 = __ldg(reinterpret_cast<const double2*>(cr + c + 2));
+                        const double d0 = xv[0] - c0.x, d1 = xv[1] - c0.y, d2 = xv[2] - c1.x, d3 = xv[3] - c1.y;
+                        a0 = fma(d0, d0, a0); a1 = fma(d1, d1, a1); a0 = fma(d2, d2, a0); a1 = fma(d3, d3, a1);
+                    }
+                    mydist = a0 + a1;
                 }
                 if (valid) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = mydist; }
                 // counts: one add per distinct label of the warp (the lowest lane of each group adds the group size)

@@ -335,6 +335,7 @@ int sckm_lloyd_step(sckm_dataset* ds, const double* centroids, uint64_t k, doubl
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, 0));
     const size_t kd = (size_t)k * ds->d;
     SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->d_centroids, centroids, kd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    ctx->cnorm_valid = false;
     SCKM_TRY(clustering_step(ds, k));
     std::vector<double> packed(kd + k + 1);
     SCKM_CUDA(ctx, cudaMemcpyAsync(packed.data(), ctx->d_packed, packed.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -354,8 +355,10 @@ static int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool hono
     SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, 0));
     const size_t kd = (size_t)k * ds->d;
-    if (centroids_inout)
+    if (centroids_inout) {
         SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->d_centroids, centroids_inout, kd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+        ctx->cnorm_valid = false;
+    }
     double distortion = DBL_MAX;
     int64_t iters = 0;
     std::vector<cudaEvent_t> evs, evs_a;
@@ -461,6 +464,7 @@ int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int 
     int rc = ensure_workspace(ctx, k, d, 0);
     if (rc == SCKM_OK && cudaMemcpyAsync(ctx->d_centroids, centroids, k * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         rc = fail(ctx, SCKM_ERR_CUDA, "centroid upload failed");
+    ctx->cnorm_valid = false;
     if (rc == SCKM_OK) rc = launch_assign_direct_raw(ctx, ds->x, dtype, n, d, k, ds->labels, nullptr);
     if (rc == SCKM_OK) rc = download_labels(ds, labels_out, width);
     sckm_dataset_destroy(ds);

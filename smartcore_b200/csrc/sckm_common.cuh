@@ -46,7 +46,9 @@ struct sckm_ctx {
     void* d_seedtab = nullptr;       // [k][d] of TX: the chosen seed rows (kmeans++ pruning)
     double* d_skiptab = nullptr;     // [k] pruning thresholds of the current pass
     size_t cap_seedtab = 0, cap_skiptab = 0;
-    unsigned long long* d_flags = nullptr;  // [8] scratch words (sink of the peak micro-kernels)
+    unsigned long long* d_flags = nullptr;  // [0] rows marked as near-ties in the current step; rest: scratch
+    bool cnorm_valid = false;        // d_cnorm matches d_centroids
+    uint64_t ws_k = 0, ws_d = 0;     // shape the centroid workspaces currently hold
     uint32_t partial_slots_used = 0; // slots written by the last fused assignment launch
     float* d_tc5 = nullptr;          // tcgen05 path: centroid hi | lo parts (TF32) and -||c||^2/2 in f32
     size_t cap_tc5 = 0;

@@ -110,7 +110,7 @@ template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool PIPE, typename T
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t* __restrict__ labels,
-                   double* __restrict__ mind, double* __restrict__ partials, size_t pk) {
+                   double* __restrict__ mind, double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked) {
     constexpr int DP = KSTEPS * 4;                 // padded feature count
     constexpr int PITCH = DP + 4;                  // doubles per staged centroid row (pitch = d*8+32 B)
     constexpr int ROWS = 8 * MT;
@@ -119,7 +119,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
     double* cn = smem_d + (size_t)bn * PITCH;      // [bn]  -||c||^2/2, -inf for padding columns
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const double cmax = cnorm[k];                  // max_j ||c_j||^2 (written by cnorm_max_kernel)
+    const double cmax = cta_max(cnorm, k);         // max_j ||c_j||^2
 
     const uint64_t nslabs = (n + ROWS - 1) / ROWS;
     const uint64_t stride = (uint64_t)gridDim.x * DMMA_WARPS;
@@ -235,6 +235,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
             if (valid && t == 0) {
                 labels[row] = tie ? 0xffffffffu : bidx[mt];             // ties are re-decided by refine_rows_kernel
                 mind[row] = dist;
+                if (tie) atomicAdd(nmarked, 1ull);
             }
             // Deterministic per-label accumulation (the update of bbd_tree.rs:151-155) into this warp's
             // private partial: the 4 lanes of a row add their A-fragment elements.  Rows of this m-tile that
@@ -279,7 +280,7 @@ template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool MULTI, typename 
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t sl_arg, uint32_t* __restrict__ labels,
-                   double* __restrict__ mind, double* __restrict__ partials, size_t pk) {
+                   double* __restrict__ mind, double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked) {
     const uint32_t sl = MULTI ? sl_arg : 1u;
     constexpr int DP = KSTEPS * 4;                 // padded feature count
     constexpr int PITCH = DP + 4;                  // doubles per staged centroid row (pitch = d*8+32 B)
@@ -294,7 +295,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
     key_t* st_best = reinterpret_cast<key_t*>(cn + bn) + (size_t)warp * sl * ROWS * 3;
     key_t* st_second = st_best + (size_t)sl * ROWS;
     key_t* st_idx = st_second + (size_t)sl * ROWS;
-    const double cmax = cnorm[k];                  // max_j ||c_j||^2 (written by cnorm_max_kernel)
+    const double cmax = cta_max(cnorm, k);         // max_j ||c_j||^2
 
     const uint64_t nslabs = (n + ROWS - 1) / ROWS;
     const uint64_t stride = (uint64_t)gridDim.x * DMMA_WARPS;
@@ -408,6 +409,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                     if (valid && t == 0) {
                         labels[row] = tie ? 0xffffffffu : bidx[mt];             // ties are re-decided by refine_rows_kernel
                         mind[row] = dist;
+                        if (tie) atomicAdd(nmarked, 1ull);
                     }
                     // Deterministic per-label accumulation (the update of bbd_tree.rs:151-155) into this warp's
                     // private partial: the 4 lanes of a row add their A-fragment elements.  Rows of this m-tile that
@@ -451,7 +453,9 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
 template <typename TX, int DMMA_WARPS>
 __global__ void __launch_bounds__(DMMA_WARPS * 32)
 refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids, uint32_t k,
-                   uint32_t* __restrict__ labels, double* __restrict__ mind, double* __restrict__ partials, size_t pk) {
+                   uint32_t* __restrict__ labels, double* __restrict__ mind, double* __restrict__ partials, size_t pk,
+                   const unsigned long long* __restrict__ nmarked) {
+    if (*nmarked == 0ull) return;                                // nothing was marked in this step (the common case)
     const int lane = threadIdx.x & 31;
     const uint64_t w = (uint64_t)blockIdx.x * DMMA_WARPS + (threadIdx.x >> 5);
     const uint64_t nw = (uint64_t)gridDim.x * DMMA_WARPS;
@@ -509,15 +513,6 @@ refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
     if (lane == 0 && any) __stcg(part + pk - 1, __dadd_rn(__ldcg(part + pk - 1), inertia));
 }
 
-// cnorm[k] = max_j cnorm[j]  (single warp; k is small)
-__global__ void cnorm_max_kernel(double* __restrict__ cnorm, uint32_t k) {
-    double m = 0.0;
-    for (uint32_t j = threadIdx.x; j < k; j += 32) m = fmax(m, cnorm[j]);
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) cnorm[k] = m;
-}
-
 // ||c||^2 of the centroids currently in ctx->d_centroids (the finalize kernel also writes them, but
 // sckm_lloyd_step uploads centroids from the host)
 __global__ void cnorm_kernel(const double* __restrict__ centroids, uint32_t k, uint32_t d, double* __restrict__ cnorm) {
@@ -568,17 +563,17 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
         SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
                                                               ctx->d_cnorm, (uint32_t)k, bn, ds->labels, ds->mind,
-                                                              ctx->d_partials, pk);
+                                                              ctx->d_partials, pk, ctx->d_flags);
     } else {
         auto kern = assign_dmma_kernel<KSTEPS, MT, NT, WARPS, true, TX>;
         SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
                                                               ctx->d_cnorm, (uint32_t)k, bn, sl, ds->labels, ds->mind,
-                                                              ctx->d_partials, pk);
+                                                              ctx->d_partials, pk, ctx->d_flags);
     }
     LAUNCH_CHECK_D(ctx);
     refine_rows_kernel<TX, WARPS><<<dmma_grid(ctx), WARPS * 32, 0, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d,
-        ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
+        ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags);
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }
@@ -592,11 +587,13 @@ static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     return launch_t<32, 1, 4, 12, TX>(ds, k, pk);
 }
 
+// ||c||^2 of ctx->d_centroids -- only needed when the centroids came from the host; inside the Lloyd loop the
+// finalize kernel keeps the norms current (an unchanged centroid keeps its norm)
 int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d) {
+    if (ctx->cnorm_valid) return SCKM_OK;
     cnorm_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_cnorm);
     LAUNCH_CHECK_D(ctx);
-    cnorm_max_kernel<<<1, 32, 0, ctx->stream>>>(ctx->d_cnorm, (uint32_t)k);
-    LAUNCH_CHECK_D(ctx);
+    ctx->cnorm_valid = true;
     return SCKM_OK;
 }
 
@@ -605,10 +602,10 @@ int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ct
     sckm_ctx* ctx = ds->ctx;
     if (ds->dtype == SCKM_F32)
         refine_rows_kernel<float, 8><<<grid_ctas, 256, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d,
-            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
+            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags);
     else
         refine_rows_kernel<double, 8><<<grid_ctas, 256, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d,
-            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
+            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags);
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }

@@ -455,11 +455,14 @@ __global__ void update_partial_kernel(const T* __restrict__ x, uint64_t n, uint3
 // packed[e] = sum over the partial slots in a FIXED order (8 slot groups summed sequentially by 8 thread rows,
 // then the 8 group sums in order); the slots are zeroed for the next step.  blockDim = (32, 8); each thread owns
 // two adjacent elements (16-byte accesses; slot rows are 128-byte aligned).
-__global__ void __launch_bounds__(256) reduce_partials_kernel(double* __restrict__ partials, uint32_t nslots, size_t pk,
-                                                              size_t pitch, double* __restrict__ packed) {
-    __shared__ double2 sh[8][33];
+template <int GROUPS>
+__global__ void __launch_bounds__(32 * GROUPS) reduce_partials_kernel(double* __restrict__ partials, uint32_t nslots, size_t pk,
+                                                                     size_t pitch, double* __restrict__ packed,
+                                                                     unsigned long long* __restrict__ nmarked) {
+    __shared__ double2 sh[GROUPS][33];
+    if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *nmarked = 0ull;   // consumed by the refine pass of this step
     const size_t e = ((size_t)blockIdx.x * 32 + threadIdx.x) * 2;
-    const uint32_t per = (nslots + 7) / 8;
+    const uint32_t per = (nslots + GROUPS - 1) / GROUPS;
     const uint32_t p0 = min(nslots, threadIdx.y * per), p1 = min(nslots, p0 + per);
     double2 s = make_double2(0.0, 0.0);
     const double2 zero = make_double2(0.0, 0.0);
@@ -489,7 +492,7 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(double* __restrict
     if (threadIdx.y == 0) {
         double2 t = make_double2(0.0, 0.0);
 #pragma unroll
-        for (int i = 0; i < 8; i++) { t.x = __dadd_rn(t.x, sh[i][threadIdx.x].x); t.y = __dadd_rn(t.y, sh[i][threadIdx.x].y); }
+        for (int i = 0; i < GROUPS; i++) { t.x = __dadd_rn(t.x, sh[i][threadIdx.x].x); t.y = __dadd_rn(t.y, sh[i][threadIdx.x].y); }
         if (e < pk) packed[e] = t.x;
         if (e + 1 < pk) packed[e + 1] = t.y;
     }
@@ -617,6 +620,7 @@ template <typename P> static int regrow(sckm_ctx* ctx, P** p, size_t* cap, size_
 
 int ensure_workspace(sckm_ctx* ctx, uint64_t k, uint64_t d, size_t partial_slots) {
     const size_t kd = (size_t)k * d, pk = kd + k + 1;
+    if (k != ctx->ws_k || d != ctx->ws_d) { ctx->cnorm_valid = false; ctx->ws_k = k; ctx->ws_d = d; }
     SCKM_TRY(regrow(ctx, &ctx->d_centroids, &ctx->cap_centroids, kd, sizeof(double)));
     SCKM_TRY(regrow(ctx, &ctx->d_packed, &ctx->cap_packed, pk, sizeof(double)));
     SCKM_TRY(regrow(ctx, &ctx->d_cnorm, &ctx->cap_cnorm, k + 1, sizeof(double)));  // [k] norms + max
@@ -785,7 +789,11 @@ int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia) {
 
 int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk) {
     const size_t pitch = slot_pitch(pk);
-    reduce_partials_kernel<<<(unsigned)((pitch / 2 + 31) / 32), dim3(32, 8), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed);
+    const unsigned blocks = (unsigned)((pitch / 2 + 31) / 32);
+    if (blocks < (unsigned)ctx->num_sms)   // small payload: more slot groups per block so the few blocks are not latency-bound
+        reduce_partials_kernel<32><<<blocks, dim3(32, 32), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags);
+    else
+        reduce_partials_kernel<8><<<blocks, dim3(32, 8), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags);
     LAUNCH_CHECK(ctx);
     return SCKM_OK;
 }
@@ -795,6 +803,7 @@ int launch_finalize(sckm_ctx* ctx, uint64_t k, uint64_t d, bool guarded) {
     finalize_kernel<<<(unsigned)k, threads, 0, ctx->stream>>>(ctx->d_packed, (uint32_t)k, (uint32_t)d, guarded ? 1 : 0,
                                                             ctx->d_centroids, ctx->d_cnorm, (long long*)ctx->d_size);
     LAUNCH_CHECK(ctx);
+    ctx->cnorm_valid = ctx->cnorm_valid || !guarded;   // a guarded update keeps stale norms of empty clusters stale
     return SCKM_OK;
 }
 

@@ -65,12 +65,12 @@ template <int KS, int KT, int VW, typename TX>
 __global__ void __launch_bounds__(STREAM_WARPS * 32, (KS * KT <= 8) ? 2 : 1)
 assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                      const double* __restrict__ cnorm, uint32_t k, uint32_t* __restrict__ labels,
-                     double* __restrict__ mind, double* __restrict__ partials, size_t pk) {
+                     double* __restrict__ mind, double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked) {
     constexpr int NTU = KS / 2 > 0 ? KS / 2 : 1;         // feature n-tiles of the update GEMM (8 features each)
     extern __shared__ __align__(16) double smem_s[];     // [warps][k*d] sums | [warps][16] counts | [warps] inertia
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const double cmax = cnorm[k];
+    const double cmax = cta_max(cnorm, k);
 
     // centroid B fragments and -||c||^2/2, resident in registers for the whole launch
     double bc[KT][KS], hc[KT][2];
@@ -189,7 +189,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const dou
             const unsigned nb = __ballot_sync(0xffffffffu, near);
             const bool tie = ((nb >> (lane & ~3)) & 0xfu) != 0u;
             const bool ok = valid && !tie;
-            if (valid && t == 0) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = dist; }
+            if (valid && t == 0) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = dist; if (tie) atomicAdd(nmarked, 1ull); }
             if (ok && t == 0) inertia = __dadd_rn(inertia, dist);
             lab[mt] = ok ? bi : 0xffffffffu;
         }
@@ -281,7 +281,7 @@ static int launch_stream_t(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* gr
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbatches + STREAM_WARPS - 1) / STREAM_WARPS,
                                                                               (uint64_t)ctx->num_sms * ctas_per_sm));
     kern<<<grid, STREAM_WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, d, ctx->d_centroids, ctx->d_cnorm,
-                                                        (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk);
+                                                        (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags);
     LAUNCH_CHECK_S(ctx);
     *grid_out = grid;
     return SCKM_OK;

@@ -18,6 +18,7 @@
 //            fire-and-forget RED.ADD.F64 into the warp's private partial, same-label rows serialised by rank).
 // mbarrier rings: x_full/x_ready/x_empty (2 stages), c_full/c_empty (2 stages), t_full/t_empty (2 TMEM stages).
 #include "sckm_common.cuh"
+#include "sckm_tile.cuh"
 #include <cuda.h>
 #include <cfloat>
 #include <algorithm>
@@ -125,7 +126,7 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                   const __grid_constant__ CUtensorMap mapCl, const TXS* __restrict__ xsrc, uint64_t n, uint32_t d,
                   const double* __restrict__ centroids, const double* __restrict__ cnorm, const float* __restrict__ hcn,
                   uint32_t k, uint32_t nblocks, uint32_t* __restrict__ labels, double* __restrict__ mind,
-                  double* __restrict__ partials, size_t pk) {
+                  double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked) {
     using Smem = TcSmemT<NK, TILES, BN>;
     constexpr int CP = 2 / TILES;                    // column parts per row
     constexpr int COLS = BN / CP;                    // columns per epilogue thread per block
@@ -137,6 +138,7 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint64_t rows_per_super = (uint64_t)TILES * TC_BM;
     const uint64_t nsuper = (n + rows_per_super - 1) / rows_per_super;
+    const double cmax = cta_max(cnorm, k);                            // max_j ||c_j||^2 (all threads take part)
     float* s_hcn = reinterpret_cast<float*>(&S + 1);                 // [nblocks * BN] when HCN_SMEM
     if (HCN_SMEM) for (uint32_t i = threadIdx.x; i < nblocks * BN; i += blockDim.x) s_hcn[i] = hcn[i];
 
@@ -222,7 +224,6 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const int cp = TILES == 2 ? 0 : (ew >> 2);                   // column part
         const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
         const int rloc = q * 32 + lane;                              // row within the tile
-        const double cmax = cnorm[k];
         double* part = partials + ((size_t)blockIdx.x * TC_EPI_WARPS + ew) * ((pk + 15) / 16 * 16);
         // split my share of X stage `xs` in place (a row is 128 bytes at rloc*128 inside each atom; the swizzle only
         // permutes 16-byte chunks inside it), return my part of ||x||^2, and tell the MMA warp the stage is ready
@@ -374,7 +375,7 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                     }
                     mydist = a0 + a1;
                 }
-                if (valid) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = mydist; }
+                if (valid) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = mydist; if (tie) atomicAdd(nmarked, 1ull); }
                 // counts: one add per distinct label of the warp (the lowest lane of each group adds the group size)
                 unsigned lanemask_lt;
                 asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanemask_lt));
@@ -461,7 +462,7 @@ static int launch_tc5_t(sckm_dataset* ds, uint64_t k, size_t pk, const float* x3
     SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, TC_THREADS, smem, ctx->stream>>>(mapX, mapCh, mapCl, (const TXS*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
                                                   ctx->d_cnorm, hcn, (uint32_t)k, nblocks, ds->labels, ds->mind,
-                                                  ctx->d_partials, pk);
+                                                  ctx->d_partials, pk, ctx->d_flags);
     LAUNCH_CHECK_T(ctx);
     return SCKM_OK;
 }

@@ -26,4 +26,23 @@ __device__ __forceinline__ key_t dkey(double v) {
 __device__ __forceinline__ double dunkey(key_t k) { return __longlong_as_double(k ^ ((k >> 63) & 0x7fffffffffffffffLL)); }
 constexpr key_t KEY_MIN = (key_t)0x8000000000000000ULL;
 
+// max of v[0..k) computed by the whole CTA (every thread must call it, every thread gets the result)
+__device__ __forceinline__ double cta_max(const double* __restrict__ v, uint32_t k) {
+    __shared__ double s_part[32];
+    __shared__ double s_all;
+    double m = 0.0;
+    for (uint32_t j = threadIdx.x; j < k; j += blockDim.x) m = fmax(m, v[j]);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = m;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; w++) t = fmax(t, s_part[w]);
+        s_all = t;
+    }
+    __syncthreads();
+    return s_all;
+}
+
 }  // namespace sckm

@@ -110,8 +110,8 @@ class ClockSampler:
 
 def ncu_traffic_bytes():
     """dram__bytes_read + dram__bytes_write of one assignment launch at the default C3 shape, from the committed
-    `ncu --set full` capture (profiles/ncu_r1_assign_dmma_v6_summary.csv); None when the file is absent."""
-    path = os.path.join(ROOT, "profiles", "ncu_r1_assign_dmma_v6_summary.csv")
+    `ncu --set full` capture (profiles/ncu_r1_assign_dmma_final_summary.csv); None when the file is absent."""
+    path = os.path.join(ROOT, "profiles", "ncu_r1_assign_dmma_final_summary.csv")
     scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
     total, seen = 0.0, 0
     try:
@@ -329,7 +329,7 @@ def main():
                          "frac": achieved / fp64_peak if fp64_peak else None,
                          "traffic": ncu_traffic_bytes() if (n_local, k, d) == (N_PER_GPU, K_CLUSTERS, D) else None,
                          "traffic_note": "DRAM read+write bytes of one assignment launch from the committed ncu --set full capture "
-                                         "(profiles/ncu_r1_assign_dmma_v6_summary.csv); algorithmic bytes per launch = n*(d*8+4) = %.3e"
+                                         "(profiles/ncu_r1_assign_dmma_final_summary.csv); algorithmic bytes per launch = n*(d*8+4) = %.3e"
                                          % hbm_bytes,
                          "kernel": "assignment kernel (dominant), CUDA events on the library stream, mean of %d launches" % args.steps,
                          "kernel_ms": 1e3 * t_assign,

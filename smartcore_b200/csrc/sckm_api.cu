@@ -15,6 +15,7 @@ const char* create_error_text();
 int launch_assign_dmma(sckm_dataset* ds, uint64_t k);         // sckm_dmma.cu
 bool dmma_supported(const sckm_dataset* ds, uint64_t k);      // sckm_dmma.cu
 uint32_t dmma_partial_slots(const sckm_ctx* ctx);             // sckm_dmma.cu
+int launch_predict_dmma(sckm_dataset* ds, uint64_t k);        // sckm_dmma.cu
 int launch_assign_stream(sckm_dataset* ds, uint64_t k);       // sckm_stream.cu
 bool stream_supported(const sckm_dataset* ds, uint64_t k);    // sckm_stream.cu
 int launch_assign_tc5(sckm_dataset* ds, uint64_t k);          // sckm_tc5.cu
@@ -465,7 +466,11 @@ int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int 
     if (rc == SCKM_OK && cudaMemcpyAsync(ctx->d_centroids, centroids, k * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         rc = fail(ctx, SCKM_ERR_CUDA, "centroid upload failed");
     ctx->cnorm_valid = false;
-    if (rc == SCKM_OK) rc = launch_assign_direct_raw(ctx, ds->x, dtype, n, d, k, ds->labels, nullptr);
+    // large k: rank on the DMMA tiles and re-decide near-ties exactly (same labels as the direct form, much faster);
+    // otherwise the direct-form kernel
+    if (rc == SCKM_OK) rc = (dmma_supported(ds, k) && k >= 32 && ctx->assign_kernel != SCKM_ASSIGN_DIRECT)
+                                ? launch_predict_dmma(ds, k)
+                                : launch_assign_direct_raw(ctx, ds->x, dtype, n, d, k, ds->labels, nullptr);
     if (rc == SCKM_OK) rc = download_labels(ds, labels_out, width);
     sckm_dataset_destroy(ds);
     return rc;

@@ -70,14 +70,10 @@ __device__ __forceinline__ void epi_item(const double (&acc)[MT][NT][2], int ite
     best[mt] = gt ? v : best[mt];
 }
 
-// K loop of one sub-block into accC; when EPI, the epilogue items of the PREVIOUS sub-block (accE) are spread over
-// the k-steps so that their FP64-ALU work issues in the shadow of this sub-block's DMMAs (software pipelining).
-template <int KSTEPS, int MT, int NT, int PITCH, bool EPI>
-__device__ __forceinline__ void kloop(double (&accC)[MT][NT][2], const double (&accE)[MT][NT][2],
-                                      const double (&a)[MT][KSTEPS], const double* __restrict__ bp,
-                                      uint32_t colE_base, int t, key_t (&best)[MT], key_t (&second)[MT],
-                                      uint32_t (&bidx)[MT]) {
-    constexpr int ITEMS = MT * NT * 2;
+// K loop of one sub-block: acc += A(rows x d) * B(d x 8*NT centroids), B fragments read from shared memory
+template <int KSTEPS, int MT, int NT, int PITCH>
+__device__ __forceinline__ void kloop(double (&acc)[MT][NT][2], const double (&a)[MT][KSTEPS],
+                                      const double* __restrict__ bp) {
 #pragma unroll
     for (int ks = 0; ks < KSTEPS; ks++) {
         double b[NT];
@@ -86,12 +82,7 @@ __device__ __forceinline__ void kloop(double (&accC)[MT][NT][2], const double (&
 #pragma unroll
         for (int mt = 0; mt < MT; mt++)
 #pragma unroll
-            for (int nt = 0; nt < NT; nt++) dmma884(accC[mt][nt][0], accC[mt][nt][1], a[mt][ks], b[nt]);
-        if (EPI) {
-#pragma unroll
-            for (int item = 0; item < ITEMS; item++)
-                if (item * KSTEPS / ITEMS == ks) epi_item<MT, NT>(accE, item, colE_base, t, best, second, bidx);
-        }
+            for (int nt = 0; nt < NT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt][ks], b[nt]);
     }
 }
 
@@ -106,7 +97,7 @@ __device__ __forceinline__ void epilogue_all(const double (&acc)[MT][NT][2], uin
 // kernel: it is the headline path and its instruction schedule is tuned (87.8 % of the FP64 peak).
 // KSTEPS: d padded to 4*KSTEPS; MT: m-tiles (8 rows each) per warp slab; DMMA_NT: n-tiles (8 centroids each) per
 // accumulator sub-block; DMMA_WARPS: warps per CTA (one CTA per SM)
-template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool PIPE, typename TX>
+template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool UPDATE, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t* __restrict__ labels,
@@ -178,36 +169,11 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
             const uint32_t cols = min(bn, k - c0);
             constexpr int SUB = 8 * DMMA_NT;                       // centroids per accumulator sub-block
             const uint32_t nsub = (cols + SUB - 1) / SUB;
-            if (PIPE) {
-                // two accumulator sets: the epilogue of sub-block i-1 rides under the DMMAs of sub-block i
-                double acc0[MT][DMMA_NT][2], acc1[MT][DMMA_NT][2];
-                acc_init<MT, DMMA_NT>(acc0, cn, t);
-                kloop<KSTEPS, MT, DMMA_NT, PITCH, false>(acc0, acc0, a, bbase, 0, t, best, second, bidx);
-                uint32_t sb = 1;
-                for (; sb + 1 < nsub; sb += 2) {
-                    acc_init<MT, DMMA_NT>(acc1, cn + sb * SUB, t);
-                    kloop<KSTEPS, MT, DMMA_NT, PITCH, true>(acc1, acc0, a, bbase + (size_t)sb * SUB * PITCH,
-                                                             c0 + (sb - 1) * SUB, t, best, second, bidx);
-                    acc_init<MT, DMMA_NT>(acc0, cn + (sb + 1) * SUB, t);
-                    kloop<KSTEPS, MT, DMMA_NT, PITCH, true>(acc0, acc1, a, bbase + (size_t)(sb + 1) * SUB * PITCH,
-                                                             c0 + sb * SUB, t, best, second, bidx);
-                }
-                if (sb < nsub) {
-                    acc_init<MT, DMMA_NT>(acc1, cn + sb * SUB, t);
-                    kloop<KSTEPS, MT, DMMA_NT, PITCH, true>(acc1, acc0, a, bbase + (size_t)sb * SUB * PITCH,
-                                                             c0 + (sb - 1) * SUB, t, best, second, bidx);
-                    epilogue_all<MT, DMMA_NT>(acc1, c0 + sb * SUB, t, best, second, bidx);
-                } else {
-                    epilogue_all<MT, DMMA_NT>(acc0, c0 + (sb - 1) * SUB, t, best, second, bidx);
-                }
-            } else {
-                for (uint32_t sb = 0; sb < nsub; sb++) {
-                    double acc[MT][DMMA_NT][2];
-                    acc_init<MT, DMMA_NT>(acc, cn + sb * SUB, t);
-                    kloop<KSTEPS, MT, DMMA_NT, PITCH, false>(acc, acc, a, bbase + (size_t)sb * SUB * PITCH, 0, t, best,
-                                                              second, bidx);
-                    epilogue_all<MT, DMMA_NT>(acc, c0 + sb * SUB, t, best, second, bidx);
-                }
+            for (uint32_t sb = 0; sb < nsub; sb++) {
+                double acc[MT][DMMA_NT][2];
+                acc_init<MT, DMMA_NT>(acc, cn + sb * SUB, t);
+                kloop<KSTEPS, MT, DMMA_NT, PITCH>(acc, a, bbase + (size_t)sb * SUB * PITCH);
+                epilogue_all<MT, DMMA_NT>(acc, c0 + sb * SUB, t, best, second, bidx);
             }
         }
         // ---- merge the 4 lanes that share a row, write out, mark near-ties, fused update ----
@@ -234,14 +200,14 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
             const bool tie = !(gap > DMMA_TIE_REL * (xn[mt] + cmax));   // also catches NaN
             if (valid && t == 0) {
                 labels[row] = tie ? 0xffffffffu : bidx[mt];             // ties are re-decided by refine_rows_kernel
-                mind[row] = dist;
+                if (UPDATE) mind[row] = dist;
                 if (tie) atomicAdd(nmarked, 1ull);
             }
             // Deterministic per-label accumulation (the update of bbd_tree.rs:151-155) into this warp's
             // private partial: the 4 lanes of a row add their A-fragment elements.  Rows of this m-tile that
             // share a label are serialised in ascending row order (rank), so the order of every f64 addition is
             // fixed by (n, grid) alone.
-            const bool part_ok = valid && !tie;
+            const bool part_ok = UPDATE && valid && !tie;        // UPDATE = false: labels only (predict)
             const uint32_t key = part_ok ? bidx[mt] : (0x80000000u | (uint32_t)g);
             const unsigned peers = __match_any_sync(0xffffffffu, key);
             const int rank = __popc(peers & lanemask_lt) >> 2;
@@ -265,7 +231,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
             v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
             slab_inertia = __dadd_rn(slab_inertia, v);
         }
-        if (lane == 0 && active) atomicAdd(part + pk - 1, slab_inertia);
+        if (UPDATE && lane == 0 && active) atomicAdd(part + pk - 1, slab_inertia);
     }
 }
 
@@ -276,7 +242,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
 // (best, second, argbest) of every row in a small per-warp shared-memory table between blocks.  Rows are re-read per
 // block, but a round's working set (148 CTAs x warps x sl slabs) is L2-resident, so HBM still sees X once.
 // MULTI = false is the compile-time specialisation for a fully resident centroid set (one block, sl = 1, no state).
-template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool MULTI, typename TX>
+template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool MULTI, bool UPDATE, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t sl_arg, uint32_t* __restrict__ labels,
@@ -366,8 +332,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                 for (uint32_t sb = 0; sb < nsub; sb++) {
                     double acc[MT][DMMA_NT][2];
                     acc_init<MT, DMMA_NT>(acc, cn + sb * SUB, t);
-                    kloop<KSTEPS, MT, DMMA_NT, PITCH, false>(acc, acc, a, bbase + (size_t)sb * SUB * PITCH, 0, t, best,
-                                                              second, bidx);
+                    kloop<KSTEPS, MT, DMMA_NT, PITCH>(acc, a, bbase + (size_t)sb * SUB * PITCH);
                     epilogue_all<MT, DMMA_NT>(acc, c0 + sb * SUB, t, best, second, bidx);
                 }
                 // ---- merge the 4 lanes that share a row ----
@@ -408,14 +373,14 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                     const bool tie = !(gap > DMMA_TIE_REL * (xn[mt] + cmax));   // also catches NaN
                     if (valid && t == 0) {
                         labels[row] = tie ? 0xffffffffu : bidx[mt];             // ties are re-decided by refine_rows_kernel
-                        mind[row] = dist;
+                        if (UPDATE) mind[row] = dist;
                         if (tie) atomicAdd(nmarked, 1ull);
                     }
                     // Deterministic per-label accumulation (the update of bbd_tree.rs:151-155) into this warp's
                     // private partial: the 4 lanes of a row add their A-fragment elements.  Rows of this m-tile that
                     // share a label are serialised in ascending row order (rank), so the order of every f64 addition
                     // is fixed by (n, grid) alone.
-                    const bool part_ok = valid && !tie;
+                    const bool part_ok = UPDATE && valid && !tie;        // UPDATE = false: labels only (predict)
                     const uint32_t key = part_ok ? bidx[mt] : (0x80000000u | (uint32_t)g);
                     const unsigned peers = __match_any_sync(0xffffffffu, key);
                     const int rank = __popc(peers & lanemask_lt) >> 2;
@@ -439,7 +404,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                     v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
                     slab_inertia = __dadd_rn(slab_inertia, v);
                 }
-                if (lane == 0) atomicAdd(part + pk - 1, slab_inertia);
+                if (UPDATE && lane == 0) atomicAdd(part + pk - 1, slab_inertia);
             }
         }
     }
@@ -450,7 +415,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
 // arithmetic (widen to f64, diff, square, sequential sum, never fused), then a warp argmin with strict <
 // and lowest index on ties (kmeans.rs:334-347 / bbd_tree.rs:101-111); the row is then added to this
 // warp's private partial (lanes own columns), so the result does not depend on scheduling.
-template <typename TX, int DMMA_WARPS>
+template <typename TX, int DMMA_WARPS, bool UPDATE = true>
 __global__ void __launch_bounds__(DMMA_WARPS * 32)
 refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids, uint32_t k,
                    uint32_t* __restrict__ labels, double* __restrict__ mind, double* __restrict__ partials, size_t pk,
@@ -497,20 +462,25 @@ refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                 if (ob < best || (ob == best && oi < bi)) { best = ob; bi = oi; }
             }
             if (bi == 0xffffffffu) bi = 0;                      // all distances NaN: the reference keeps cluster 0
-            double* p = part + (size_t)bi * d;
-            for (uint32_t j = lane; j < d; j += 32) __stcg(p + j, __dadd_rn(__ldcg(p + j), (double)xr[j]));
+            if (UPDATE) {
+                double* p = part + (size_t)bi * d;
+                for (uint32_t j = lane; j < d; j += 32) __stcg(p + j, __dadd_rn(__ldcg(p + j), (double)xr[j]));
+            }
             if (lane == 0) {
-                labels[row] = bi; mind[row] = best;
-                double* pc = part + (size_t)k * d + bi;
-                __stcg(pc, __ldcg(pc) + 1.0);
-                inertia = __dadd_rn(inertia, best);
-                any = true;
+                labels[row] = bi;
+                if (UPDATE) {
+                    mind[row] = best;
+                    double* pc = part + (size_t)k * d + bi;
+                    __stcg(pc, __ldcg(pc) + 1.0);
+                    inertia = __dadd_rn(inertia, best);
+                    any = true;
+                }
             }
             __syncwarp();
         }
         }
     }
-    if (lane == 0 && any) __stcg(part + pk - 1, __dadd_rn(__ldcg(part + pk - 1), inertia));
+    if (UPDATE && lane == 0 && any) __stcg(part + pk - 1, __dadd_rn(__ldcg(part + pk - 1), inertia));
 }
 
 // ||c||^2 of the centroids currently in ctx->d_centroids (the finalize kernel also writes them, but
@@ -532,7 +502,7 @@ static unsigned dmma_grid(const sckm_ctx* ctx) { return (unsigned)ctx->num_sms; 
 // number of per-warp partial slots the fused kernels may accumulate into (reduced by launch_reduce_partials)
 uint32_t dmma_partial_slots(const sckm_ctx* ctx) { return dmma_grid(ctx) * DMMA_MAX_WARPS; }
 
-template <int KSTEPS, int MT, int NT, int WARPS, typename TX>
+template <int KSTEPS, int MT, int NT, int WARPS, bool UPDATE, typename TX>
 static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     sckm_ctx* ctx = ds->ctx;
     constexpr int DP = KSTEPS * 4, PITCH = DP + 4, ROWS = 8 * MT;
@@ -559,32 +529,32 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     const size_t smem = (size_t)bn * row_bytes + (multi ? (size_t)WARPS * sl * ROWS * 3 * sizeof(long long) : 0);
     ctx->partial_slots_used = dmma_grid(ctx) * WARPS;
     if (!multi) {
-        auto kern = assign_dmma_resident_kernel<KSTEPS, MT, NT, WARPS, false, TX>;
+        auto kern = assign_dmma_resident_kernel<KSTEPS, MT, NT, WARPS, UPDATE, TX>;
         SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
                                                               ctx->d_cnorm, (uint32_t)k, bn, ds->labels, ds->mind,
                                                               ctx->d_partials, pk, ctx->d_flags);
     } else {
-        auto kern = assign_dmma_kernel<KSTEPS, MT, NT, WARPS, true, TX>;
+        auto kern = assign_dmma_kernel<KSTEPS, MT, NT, WARPS, true, UPDATE, TX>;
         SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
                                                               ctx->d_cnorm, (uint32_t)k, bn, sl, ds->labels, ds->mind,
                                                               ctx->d_partials, pk, ctx->d_flags);
     }
     LAUNCH_CHECK_D(ctx);
-    refine_rows_kernel<TX, WARPS><<<dmma_grid(ctx), WARPS * 32, 0, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d,
+    refine_rows_kernel<TX, WARPS, UPDATE><<<dmma_grid(ctx), WARPS * 32, 0, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d,
         ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags);
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }
 
-template <typename TX>
+template <bool UPDATE, typename TX>
 static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     const uint64_t d = ds->d;
-    if (d <= 16) return launch_t<4, 2, 4, 12, TX>(ds, k, pk);
-    if (d <= 32) return launch_t<8, 2, 4, 12, TX>(ds, k, pk);
-    if (d <= 64) return launch_t<16, 2, 4, 12, TX>(ds, k, pk);
-    return launch_t<32, 1, 4, 12, TX>(ds, k, pk);
+    if (d <= 16) return launch_t<4, 2, 4, 12, UPDATE, TX>(ds, k, pk);
+    if (d <= 32) return launch_t<8, 2, 4, 12, UPDATE, TX>(ds, k, pk);
+    if (d <= 64) return launch_t<16, 2, 4, 12, UPDATE, TX>(ds, k, pk);
+    return launch_t<32, 1, 4, 12, UPDATE, TX>(ds, k, pk);
 }
 
 // ||c||^2 of ctx->d_centroids -- only needed when the centroids came from the host; inside the Lloyd loop the
@@ -618,7 +588,22 @@ int launch_assign_dmma(sckm_dataset* ds, uint64_t k) {
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, dmma_partial_slots(ctx)));
     if (ds->n == 0) return SCKM_OK;
     SCKM_TRY(launch_cnorm(ctx, k, ds->d));
-    return ds->dtype == SCKM_F32 ? launch_by_d<float>(ds, k, pk) : launch_by_d<double>(ds, k, pk);
+    return ds->dtype == SCKM_F32 ? launch_by_d<true, float>(ds, k, pk) : launch_by_d<true, double>(ds, k, pk);
+}
+
+// labels only (KMeans::predict at scale): same ranking + exact re-decision of near-ties, no update, no distances.
+// For every row the result equals the exact direct-form argmin (kmeans.rs:334-347).
+int launch_predict_dmma(sckm_dataset* ds, uint64_t k) {
+    sckm_ctx* ctx = ds->ctx;
+    if (!dmma_supported(ds, k)) return fail(ctx, SCKM_ERR_INVALID, "shape not supported by the DMMA kernel");
+    const size_t pk = (size_t)k * ds->d + k + 1;
+    SCKM_TRY(ensure_workspace(ctx, k, ds->d, 0));                 // no partial sums in this mode
+    if (ds->n == 0) return SCKM_OK;
+    SCKM_TRY(launch_cnorm(ctx, k, ds->d));
+    SCKM_TRY(ds->dtype == SCKM_F32 ? (launch_by_d<false, float>(ds, k, pk)) : (launch_by_d<false, double>(ds, k, pk)));
+    // the marked-row counter is normally cleared by the reduce of the step; there is none here
+    SCKM_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(unsigned long long), ctx->stream));
+    return SCKM_OK;
 }
 
 }  // namespace sckm

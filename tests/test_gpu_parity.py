@@ -312,6 +312,79 @@ def test_predict_tie_break_lowest_index(ctx):
     assert np.all(ctx.predict(x, cent) == 0)          # exact tie: strict < keeps the first
 
 
+@pytest.mark.parametrize("n,d,k,dtype", [(200000, 64, 256, np.float64), (50000, 32, 100, np.float32), (30000, 128, 300, np.float64),
+                                         (40000, 64, 1000, np.float64), (25000, 20, 33, np.float32), (65537, 16, 64, np.float64)])
+def test_predict_at_scale_bit_exact(ctx, O, n, d, k, dtype):
+    """k >= 32 routes predict through the DMMA ranking + exact re-decision of near-ties; the labels must still be
+    those of the direct form (kmeans.rs:334-347) for EVERY row, duplicates and exact ties included."""
+    x = blobs(n, d, min(k, 50), n + d, dtype, spread=1.0)
+    cent = x[np.random.default_rng(5).choice(n, k, replace=False)].astype(np.float64)
+    cent[7] = cent[3]                                  # duplicate centroid: rows of cluster 3 tie exactly -> lowest index
+    x[100:110] = 0.5 * (cent[1] + cent[2]).astype(dtype)   # rows (nearly) equidistant from two centroids
+    want = O.predict(x, cent)
+    got = ctx.predict(x, cent).astype(np.int64)
+    assert np.array_equal(got, want)
+    assert not np.any(got == 7)
+    assert np.array_equal(ctx.predict(x, cent, column_major=True, width=4).astype(np.int64), want)
+    ctx.set_assign_kernel(cabi.ASSIGN_DIRECT)          # and the direct-form kernel agrees
+    try:
+        assert np.array_equal(ctx.predict(x, cent).astype(np.int64), want)
+    finally:
+        ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+
+
+# ---- edge cases: tiny, ragged and degenerate inputs ------------------------------------------------------
+@pytest.mark.parametrize("n,d,k", [(2, 1, 2), (3, 2, 2), (5, 3, 5), (17, 1, 4), (64, 2, 63), (31, 3, 30), (257, 5, 256),
+                                   (100, 4, 99), (40, 130, 7), (1000, 1, 16), (129, 4, 16), (4096, 6, 17)])
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fit_edge_shapes(ctx, O, n, d, k, dtype):
+    x = blobs(n, d, max(2, k // 2), 31 * n + d, dtype, spread=3.0)
+    got = fit_gpu(ctx, x, k, 11)
+    want = O.fit(x, k, 100, 11, use_tree=True)
+    assert got["iters"] == want.iters and got["size"].tolist() == want.size.tolist()
+    if not np.array_equal(got["labels"].astype(np.int64), want.y):
+        gap = O.brute_clustering(x, want.centroids, want_gap=True)[4]
+        assert_labels_match(got["labels"], want.y, gap)
+    np.testing.assert_allclose(got["centroids"], want.centroids, rtol=RTOL if dtype == np.float64 else 1e-4, atol=1e-12,
+                               equal_nan=True)
+    assert abs(got["distortion"] - want.distortion) <= RTOL * max(want.distortion, 1e-300)
+    pred = ctx.predict(x, got["centroids"]).astype(np.int64)
+    assert np.array_equal(pred, O.predict(x, got["centroids"]))
+
+
+@pytest.mark.parametrize("kernel", [cabi.ASSIGN_DIRECT, cabi.ASSIGN_AUTO, cabi.ASSIGN_DMMA])
+def test_step_duplicates_and_constant_columns(ctx, O, kernel):
+    """Every row duplicated 4x, two constant columns, centroids ON data points (zero distances)."""
+    base = blobs(600, 8, 20, 5)
+    base[:, 2] = 3.25; base[:, 5] = 0.0
+    x = np.repeat(base, 4, axis=0)
+    cent = base[:20].copy()
+    ctx.set_assign_kernel(kernel)
+    try:
+        ds = ctx.upload(x)
+        inertia, sums, counts = ds.lloyd_step(cent)
+        labels = ds.labels()
+        ds.close()
+    finally:
+        ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+    assert_labels_match(labels, m_o, gap)
+    assert np.array_equal(labels.reshape(-1, 4), np.repeat(labels[::4, None], 4, axis=1))   # duplicates stay together
+    assert counts.tolist() == c_o.tolist() and abs(inertia - d_o) <= RTOL * d_o
+    np.testing.assert_allclose(sums, s_o, rtol=RTOL, atol=1e-9)
+
+
+def test_all_rows_identical(ctx, O):
+    """All D^2 are zero: kmeans++ keeps drawing row 0, k-1 clusters start empty (0/0 centroids, kmeans.rs:276-280)."""
+    x = np.full((50, 4), 2.5)
+    got = fit_gpu(ctx, x, 3, 1)
+    want = O.fit(x, 3, 100, 1, use_tree=True)
+    assert got["size"].tolist() == want.size.tolist() and got["iters"] == want.iters
+    assert np.array_equal(got["labels"].astype(np.int64), want.y)
+    assert np.array_equal(np.isnan(got["centroids"]), np.isnan(want.centroids))
+    np.testing.assert_allclose(got["centroids"], want.centroids, rtol=RTOL, equal_nan=True)
+
+
 # ---- generator twin, properties at scale --------------------------------------------------------------
 def test_device_blobs_equal_host_twin(ctx):
     for dtype in (np.float64, np.float32):

@@ -60,17 +60,24 @@ template <> struct VecLoad<float, 4> {
         const float4 v = __ldg(reinterpret_cast<const float4*>(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 };
 
-// KS: k-steps of the scoring GEMM (features padded to 4*KS); KT: 8-cluster tiles (k <= 8*KT); VW: see kcol
-template <int KS, int KT, int VW, typename TX>
+// Column of update n-tile `nt`, tile column `g`: a lane's VU n-tiles are VU consecutive features (one vector load)
+template <int VU> __device__ __forceinline__ constexpr int ucol(int g, int nt) { return (nt / VU) * (8 * VU) + g * VU + (nt % VU); }
+
+// KS: k-steps of the scoring GEMM (features padded to 4*KS); KT: 8-cluster tiles (k <= 8*KT); VW: see kcol;
+// DFULL: d == 4*KS exactly (then every offset is a compile-time constant and full batches run without predicates)
+template <int KS, int KT, int VW, bool DFULL, typename TX>
 __global__ void __launch_bounds__(STREAM_WARPS * 32, (KS * KT <= 8) ? 2 : 1)
-assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
+assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const double* __restrict__ centroids,
                      const double* __restrict__ cnorm, uint32_t k, uint32_t* __restrict__ labels,
-                     double* __restrict__ mind, double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked) {
+                     double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked) {
     constexpr int NTU = KS / 2 > 0 ? KS / 2 : 1;         // feature n-tiles of the update GEMM (8 features each)
+    constexpr int VU = VW < NTU ? VW : NTU;              // features per update load
+    const uint32_t d = DFULL ? (uint32_t)(4 * KS) : d_rt;
     extern __shared__ __align__(16) double smem_s[];     // [warps][k*d] sums | [warps][16] counts | [warps] inertia
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     const double cmax = cta_max(cnorm, k);
+    const double tie_half = 0.5 * STREAM_TIE_REL;
 
     // centroid B fragments and -||c||^2/2, resident in registers for the whole launch
     double bc[KT][KS], hc[KT][2];
@@ -88,7 +95,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const dou
             hc[nt][e] = ce < k ? -0.5 * cnorm[ce] : -INFINITY;
         }
     }
-    double cu[KT][NTU][2];                               // per-cluster sums: cluster ct*8+g, feature nt*8+2t+e
+    double cu[KT][NTU][2];                               // per-cluster sums: cluster ct*8+g, feature ucol(2t+e, nt)
 #pragma unroll
     for (int ct = 0; ct < KT; ct++)
 #pragma unroll
@@ -96,45 +103,50 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const dou
     uint32_t cnt[KT];
 #pragma unroll
     for (int ct = 0; ct < KT; ct++) cnt[ct] = 0;
-    double inertia = 0.0;
+    double inertia = 0.0;                                // this lane's share (rows whose winning score it holds)
+    uint32_t nties = 0;
 
     const uint64_t nbatches = (n + 31) / 32;
     const uint64_t wglobal = (uint64_t)blockIdx.x * STREAM_WARPS + warp;
     const uint64_t nwarps = (uint64_t)gridDim.x * STREAM_WARPS;
 
-    // rows -> A fragments straight from HBM (8 rows x full 32-byte sectors per request)
+    // rows -> A fragments straight from HBM (8 rows x full 32-byte sectors per request).  FULL: all 32 rows exist
+    // and d == 4*KS, so there is nothing to predicate and every offset folds into the instruction.
     double a[4][KS];
-    auto load_rows = [&](uint64_t row0) {
+    auto load_rows = [&](uint64_t row0, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
+        const TX* base = x + (row0 + g) * d + t * VW;
 #pragma unroll
         for (int mt = 0; mt < 4; mt++) {
-            const uint64_t row = row0 + mt * 8 + g;
-            const TX* xr = x + row * d;
 #pragma unroll
             for (int i = 0; i < KS / VW; i++) {
-                const uint32_t col0 = kcol<VW>(t, i * VW);
                 double v[VW];
+                if (FULL) {
+                    VecLoad<TX, VW>::ld(base + (size_t)mt * 8 * d + i * 4 * VW, v);
+                } else {
 #pragma unroll
-                for (int e = 0; e < VW; e++) v[e] = 0.0;
-                if (row < n && col0 < d) VecLoad<TX, VW>::ld(xr + col0, v);
+                    for (int e = 0; e < VW; e++) v[e] = 0.0;
+                    if (row0 + mt * 8 + g < n && (uint32_t)(i * 4 * VW + t * VW) < d)
+                        VecLoad<TX, VW>::ld(base + (size_t)mt * 8 * d + i * 4 * VW, v);
+                }
 #pragma unroll
                 for (int e = 0; e < VW; e++) a[mt][i * VW + e] = v[e];
             }
         }
     };
-    if (wglobal < nbatches) load_rows(wglobal * 32);
+    auto load_any = [&](uint64_t row0) {
+        if (DFULL && row0 + 32 <= n) load_rows(row0, std::true_type{});
+        else load_rows(row0, std::false_type{});
+    };
 
-    for (uint64_t b = wglobal; b < nbatches; b += nwarps) {
+    // per-warp staging tile for the epilogue: [32 rows][8*KT scores | 4 partial norms | pad], pitch = odd multiple
+    // of 16 bytes so that the row-per-lane 16-byte reads are conflict-free
+    constexpr int RP = 8 * KT + 6;
+    double* tw = smem_s + (size_t)warp * 32 * RP;
+
+    auto batch = [&](uint64_t b, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
         const uint64_t row0 = b * 32;
-        double xn[4];
-#pragma unroll
-        for (int mt = 0; mt < 4; mt++) {
-            double sq = 0.0;
-#pragma unroll
-            for (int ks = 0; ks < KS; ks++) sq = fma(a[mt][ks], a[mt][ks], sq);
-            sq += __shfl_xor_sync(0xffffffffu, sq, 1);
-            sq += __shfl_xor_sync(0xffffffffu, sq, 2);
-            xn[mt] = sq;
-        }
         // ---- scores x.c - ||c||^2/2 on the FP64 tensor path ----
         double acc[4][KT][2];
 #pragma unroll
@@ -147,64 +159,77 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const dou
             for (int mt = 0; mt < 4; mt++)
 #pragma unroll
                 for (int nt = 0; nt < KT; nt++) dmma884(acc[mt][nt][0], acc[mt][nt][1], a[mt][ks], bc[nt][ks]);
-        // the A registers are dead now: prefetch the next batch so its HBM latency hides under epilogue + update
-        if (b + nwarps < nbatches) load_rows((b + nwarps) * 32);
-        // ---- argmax per row: each lane holds 2*KT scores of row (mt, g); butterfly over the 4 lanes of the row
-        // (strict >, lowest index on ties).  Near-ties are detected afterwards by one more pass over the scores:
-        // some OTHER column within the tolerance of the winner <=> (best - second) within tolerance. ----
-        uint32_t lab[4];
+        // this lane's share of ||x||^2 for its 4 rows, and the scores, go through the staging tile so that the
+        // epilogue runs one row per lane (no butterflies): lane L then owns row row0 + L
 #pragma unroll
         for (int mt = 0; mt < 4; mt++) {
-            double best = acc[mt][0][0]; uint32_t bi = 2 * t;
+            double sq = 0.0;
+#pragma unroll
+            for (int ks = 0; ks < KS; ks++) sq = fma(a[mt][ks], a[mt][ks], sq);
+            double* tr = tw + (mt * 8 + g) * RP;
+            tr[8 * KT + t] = sq;
 #pragma unroll
             for (int nt = 0; nt < KT; nt++)
-#pragma unroll
-                for (int e = 0; e < 2; e++) {
-                    if (nt == 0 && e == 0) continue;
-                    const double v = acc[mt][nt][e];
-                    const bool gt = v > best;
-                    bi = gt ? (uint32_t)(nt * 8 + 2 * t + e) : bi;
-                    best = gt ? v : best;
-                }
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                const double ob = __shfl_xor_sync(0xffffffffu, best, o);
-                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-                const bool take = ob > best || (ob == best && oi < bi);
-                bi = take ? oi : bi;
-                best = take ? ob : best;
-            }
-            const uint64_t row = row0 + mt * 8 + g;
-            const bool valid = row < n;
-            const double dist = fmax(0.0, fma(-2.0, best, xn[mt]));
-            // gap = 2*(best - v) <= tol  <=>  v >= best - tol/2 ; NaN scores fail every comparison and are caught below
-            const double thr = best - 0.5 * STREAM_TIE_REL * (xn[mt] + cmax);
-            bool near = false;
-#pragma unroll
-            for (int nt = 0; nt < KT; nt++)
-#pragma unroll
-                for (int e = 0; e < 2; e++)
-                    near = near || (acc[mt][nt][e] >= thr && (uint32_t)(nt * 8 + 2 * t + e) != bi);
-            near = near || !(best == best);                                  // NaN winner
-            const unsigned nb = __ballot_sync(0xffffffffu, near);
-            const bool tie = ((nb >> (lane & ~3)) & 0xfu) != 0u;
-            const bool ok = valid && !tie;
-            if (valid && t == 0) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = dist; if (tie) atomicAdd(nmarked, 1ull); }
-            if (ok && t == 0) inertia = __dadd_rn(inertia, dist);
-            lab[mt] = ok ? bi : 0xffffffffu;
+                *reinterpret_cast<double2*>(tr + nt * 8 + 2 * t) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         }
+        __syncwarp();
+        // the A registers are dead now: prefetch the next batch so its HBM latency hides under epilogue + update
+        if (b + nwarps < nbatches) load_any((b + nwarps) * 32);
+        double sc[8 * KT];
+        double xn;
+        {
+            const double* tr = tw + lane * RP;
+#pragma unroll
+            for (int j = 0; j < 4 * KT; j++) {
+                const double2 v = *reinterpret_cast<const double2*>(tr + 2 * j);
+                sc[2 * j] = v.x; sc[2 * j + 1] = v.y;
+            }
+            const double2 p01 = *reinterpret_cast<const double2*>(tr + 8 * KT);
+            const double2 p23 = *reinterpret_cast<const double2*>(tr + 8 * KT + 2);
+            xn = (p01.x + p01.y) + (p23.x + p23.y);
+        }
+        __syncwarp();
+        // ---- argmax of this lane's row (strict >: lowest index first); rows with another score within the tolerance
+        // of the winner (exact ties and NaN included) are marked and re-decided exactly by refine_rows_kernel ----
+        double best = sc[0]; uint32_t bi = 0;
+#pragma unroll
+        for (int j = 1; j < 8 * KT; j++) {
+            const bool gt = sc[j] > best;
+            bi = gt ? (uint32_t)j : bi;
+            best = gt ? sc[j] : best;
+        }
+        const double thr = fma(-tie_half, xn + cmax, best);      // gap = 2*(best - v) <= tol  <=>  v >= best - tol/2
+        uint32_t nnear = 0;
+#pragma unroll
+        for (int j = 0; j < 8 * KT; j++) nnear += (sc[j] >= thr) ? 1u : 0u;
+        const bool valid = FULL || row0 + lane < n;
+        const bool ok = valid && nnear == 1u;                      // exactly the winner itself (NaN winner: 0)
+        double dist = fma(-2.0, best, xn);
+        dist = dist < 0.0 ? 0.0 : dist;
+        if (ok) inertia = __dadd_rn(inertia, dist);
+        nties += (valid && !ok) ? 1u : 0u;
+        const uint32_t lab = ok ? bi : 0xffffffffu;
+        if (valid) labels[row0 + lane] = lab;
         // ---- update: sums[cluster][feature] += onehot(label)^T . X as DMMAs accumulating in registers.
         // K dimension = the 32 rows (row 4*ks+t), A = one-hot of the labels, B = the rows again (L1 hits). ----
+        const TX* ub = x + (row0 + t) * d + g * VU;
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) {
-            const uint32_t lr = __shfl_sync(0xffffffffu, lab[ks >> 1], ((4 * (ks & 1) + t) << 2));
-            const uint64_t row = row0 + 4 * ks + t;
-            const TX* xr = x + row * d;
+            const uint32_t lr = __shfl_sync(0xffffffffu, lab, 4 * ks + t);
             double xb[NTU];
 #pragma unroll
-            for (int nt = 0; nt < NTU; nt++) {
-                const uint32_t col = nt * 8 + g;
-                xb[nt] = (row < n && col < d) ? (double)__ldg(xr + col) : 0.0;
+            for (int j = 0; j < NTU / VU; j++) {
+                double v[VU];
+                if (FULL) {
+                    VecLoad<TX, VU>::ld(ub + (size_t)ks * 4 * d + j * 8 * VU, v);
+                } else {
+#pragma unroll
+                    for (int e = 0; e < VU; e++) v[e] = 0.0;
+                    if (row0 + 4 * ks + t < n && (uint32_t)(j * 8 * VU + g * VU) < d)
+                        VecLoad<TX, VU>::ld(ub + (size_t)ks * 4 * d + j * 8 * VU, v);
+                }
+#pragma unroll
+                for (int e = 0; e < VU; e++) xb[j * VU + e] = v[e];
             }
 #pragma unroll
             for (int ct = 0; ct < KT; ct++) {
@@ -215,7 +240,18 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const dou
                 for (int nt = 0; nt < NTU; nt++) dmma884(cu[ct][nt][0], cu[ct][nt][1], oh, xb[nt]);
             }
         }
+    };
+
+    if (wglobal < nbatches) load_any(wglobal * 32);
+    for (uint64_t b = wglobal; b < nbatches; b += nwarps) {
+        if (DFULL && b * 32 + 32 <= n) batch(b, std::true_type{});
+        else batch(b, std::false_type{});
     }
+    // rows handed to refine_rows_kernel (rare); the reduction is unconditional: every lane must reach the shuffles
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) nties += __shfl_xor_sync(0xffffffffu, nties, o);
+    if (lane == 0 && nties) atomicAdd(nmarked, (unsigned long long)nties);
+    __syncthreads();                                      // the staging tiles are reused by the combine below
     // ---- per-warp results -> shared memory, CTA combine in warp order, store this CTA's partial slot ----
     const uint32_t kd = k * d;
     double* s_sum = smem_s + (size_t)warp * kd;
@@ -228,7 +264,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const dou
         for (int nt = 0; nt < NTU; nt++)
 #pragma unroll
             for (int e = 0; e < 2; e++) {
-                const uint32_t f = nt * 8 + 2 * t + e;
+                const uint32_t f = ucol<VU>(2 * t + e, nt);
                 if (c < k && f < d) s_sum[(size_t)c * d + f] = cu[ct][nt][e];
             }
         uint32_t cc = cnt[ct];
@@ -267,12 +303,13 @@ bool stream_supported(const sckm_dataset* ds, uint64_t k) {
     return k >= 1 && k <= STREAM_MAX_K && ds->d >= 1 && ds->d <= 32 && ds->n < 0xFFFFFFFFull;
 }
 
-template <int KS, int KT, int VW, typename TX>
-static int launch_stream_t(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* grid_out) {
+template <int KS, int KT, int VW, bool DFULL, typename TX>
+static int launch_stream_f(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* grid_out) {
     sckm_ctx* ctx = ds->ctx;
     const uint32_t d = (uint32_t)ds->d;
-    const size_t smem = ((size_t)STREAM_WARPS * k * d + STREAM_WARPS * 8 + STREAM_WARPS) * sizeof(double);
-    auto kern = assign_stream_kernel<KS, KT, VW, TX>;
+    const size_t smem = std::max(((size_t)STREAM_WARPS * k * d + STREAM_WARPS * 8 + STREAM_WARPS) * sizeof(double),
+                                 (size_t)STREAM_WARPS * 32 * (8 * KT + 6) * sizeof(double));   // combine | staging tiles
+    auto kern = assign_stream_kernel<KS, KT, VW, DFULL, TX>;
     if (smem > 48 * 1024) SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 0;
     SCKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, STREAM_WARPS * 32, smem));
@@ -281,10 +318,16 @@ static int launch_stream_t(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* gr
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbatches + STREAM_WARPS - 1) / STREAM_WARPS,
                                                                               (uint64_t)ctx->num_sms * ctas_per_sm));
     kern<<<grid, STREAM_WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, d, ctx->d_centroids, ctx->d_cnorm,
-                                                        (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags);
+                                                        (uint32_t)k, ds->labels, ctx->d_partials, pk, ctx->d_flags);
     LAUNCH_CHECK_S(ctx);
     *grid_out = grid;
     return SCKM_OK;
+}
+
+template <int KS, int KT, int VW, typename TX>
+static int launch_stream_t(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* grid_out) {
+    if (ds->d == 4 * KS) return launch_stream_f<KS, KT, VW, true, TX>(ds, k, pk, grid_out);
+    return launch_stream_f<KS, KT, VW, false, TX>(ds, k, pk, grid_out);
 }
 
 template <int KS, int KT, typename TX>
@@ -310,7 +353,7 @@ static int launch_stream_by_d(sckm_dataset* ds, uint64_t k, size_t pk, unsigned*
 
 int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d);   // sckm_dmma.cu
 
-// labels + mind + per-warp partials (fused update); the caller reduces ctx->partial_slots_used slots
+// labels + per-warp partials (fused update); the caller reduces ctx->partial_slots_used slots
 int launch_assign_stream(sckm_dataset* ds, uint64_t k) {
     sckm_ctx* ctx = ds->ctx;
     if (!stream_supported(ds, k)) return fail(ctx, SCKM_ERR_INVALID, "shape not supported by the streaming kernel");

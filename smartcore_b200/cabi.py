@@ -141,6 +141,13 @@ class Context:
                                             row_offset, n_global or n, C.byref(h)))
         return Dataset(self, h, n, d, buf.dtype)
 
+    def upload_colmajor_image(self, image, n, d):
+        """image: C-contiguous (d, n) array = the column-major image of an n x d matrix (no host transpose here)."""
+        assert image.shape == (d, n) and image.flags.c_contiguous
+        h = C.c_void_p()
+        self._check(lib.sckm_dataset_upload(self.h, _p(image), n, d, dtype_code(image), 1, 0, n, C.byref(h)))
+        return Dataset(self, h, n, d, image.dtype)
+
     def generate_blobs(self, n_local, d, n_centers, seed, dtype=np.float64, row_offset=0, n_global=0):
         h = C.c_void_p()
         code = F32 if np.dtype(dtype) == np.float32 else F64

@@ -70,6 +70,7 @@ void sckm_ctx_destroy(sckm_ctx* ctx) {
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     nccl_destroy(ctx);
+    ingest_destroy(ctx);
     cudaFree(ctx->d_centroids); cudaFree(ctx->d_cnorm); cudaFree(ctx->d_packed); cudaFree(ctx->d_partials);
     cudaFree(ctx->d_size); cudaFree(ctx->d_blocksum); cudaFree(ctx->d_totals); cudaFree(ctx->d_seedrow);
     cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush); cudaFree(ctx->d_tc5);
@@ -138,14 +139,15 @@ int sckm_dataset_upload(sckm_ctx* ctx, const void* host, uint64_t n_local, uint6
     int rc = SCKM_OK;
     if (bytes) {
         if (!column_major) {
-            cudaError_t e = cudaMemcpyAsync(ds->x, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
-            if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-            if (e != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "H2D copy failed: %s", cudaGetErrorString(e));
+            rc = copy_to_device(ctx, ds->x, host, bytes);
         } else {
+            // from_2d_array's layout (matrix.rs:215-237): land the column-major image, transpose on the device
             void* tmp = nullptr;
-            cudaError_t e = cudaMalloc(&tmp, bytes);
-            if (e == cudaSuccess) e = cudaMemcpyAsync(tmp, host, bytes, cudaMemcpyHostToDevice, ctx->stream);
-            if (e != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "H2D staging failed: %s", cudaGetErrorString(e));
+            if (cudaMalloc(&tmp, bytes) != cudaSuccess) {
+                cudaGetLastError();
+                rc = fail(ctx, SCKM_ERR_CUDA, "cudaMalloc of the %zu-byte column-major staging image failed", bytes);
+            }
+            if (rc == SCKM_OK) rc = copy_to_device(ctx, tmp, host, bytes);
             if (rc == SCKM_OK) rc = launch_transpose(ctx, tmp, ds->x, n_local, d, dtype);
             cudaStreamSynchronize(ctx->stream);
             cudaFree(tmp);
@@ -423,16 +425,12 @@ static int download_labels(sckm_dataset* ds, void* out, int width) {
     sckm_ctx* ctx = ds->ctx;
     const uint64_t n = ds->n;
     if (width == 4) {
-        SCKM_CUDA(ctx, cudaMemcpyAsync(out, ds->labels, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        return SCKM_OK;
+        return copy_to_host(ctx, out, ds->labels, n * 4);
     }
     if (width != 8) return fail(ctx, SCKM_ERR_INVALID, "label width must be 4 or 8");
     if (!ds->labels64) SCKM_CUDA(ctx, cudaMalloc((void**)&ds->labels64, std::max<uint64_t>(n, 1) * 8));
     SCKM_TRY(launch_labels_widen(ctx, ds->labels, ds->labels64, n));
-    SCKM_CUDA(ctx, cudaMemcpyAsync(out, ds->labels64, n * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return SCKM_OK;
+    return copy_to_host(ctx, out, ds->labels64, n * 8);
 }
 
 int sckm_labels_download(sckm_dataset* ds, void* out, int width) {
@@ -446,33 +444,71 @@ int sckm_mindist_download(sckm_dataset* ds, double* out) {
     if (!ds || !out) return SCKM_ERR_INVALID;
     sckm_ctx* ctx = ds->ctx;
     SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
-    SCKM_CUDA(ctx, cudaMemcpyAsync(out, ds->mind, ds->n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    return SCKM_OK;
+    return copy_to_host(ctx, out, ds->mind, ds->n * sizeof(double));
 }
 
 // ---- predict --------------------------------------------------------------------------------
+// KMeans::predict (kmeans.rs:327-352) for any n: X streams through two device buffers of <= ~256 MB, the upload of
+// chunk i+1 (threaded pinned ring, sckm_ingest.cu) overlapping the kernels of chunk i, so device memory stays
+// bounded and a prediction set need not fit in HBM.  Labels are those of the direct form for every row.
+static int predict_chunk(sckm_dataset* ds, uint64_t k) {
+    sckm_ctx* ctx = ds->ctx;
+    // large k: rank on the DMMA tiles and re-decide near-ties exactly (same labels as the direct form, much faster);
+    // otherwise the direct-form kernel
+    if (dmma_supported(ds, k) && k >= 32 && ctx->assign_kernel != SCKM_ASSIGN_DIRECT) return launch_predict_dmma(ds, k);
+    return launch_assign_direct_raw(ctx, ds->x, ds->dtype, ds->n, ds->d, k, ds->labels, nullptr);
+}
+
 int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int dtype,
                  int column_major, const double* centroids, uint64_t k, void* labels_out, int width) {
     if (!ctx) return SCKM_ERR_INVALID;
     if ((!x_host || !labels_out) && n) return fail(ctx, SCKM_ERR_INVALID, "NULL buffer");
     if (!centroids || k < 1) return fail(ctx, SCKM_ERR_INVALID, "no centroids");
     if (width != 4 && width != 8) return fail(ctx, SCKM_ERR_INVALID, "label width must be 4 or 8");
+    if (dtype != SCKM_F32 && dtype != SCKM_F64) return fail(ctx, SCKM_ERR_INVALID, "dtype must be SCKM_F32 or SCKM_F64");
     if (n == 0) return SCKM_OK;
     SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
-    sckm_dataset* ds = nullptr;
-    SCKM_TRY(sckm_dataset_upload(ctx, x_host, n, d, dtype, column_major, 0, n, &ds));
-    int rc = ensure_workspace(ctx, k, d, 0);
+    const size_t elem = dtype == SCKM_F32 ? 4 : 8, row_bytes = (size_t)d * elem;
+    uint64_t chunk_rows = std::max<uint64_t>(4096, ((size_t)256 << 20) / std::max<size_t>(row_bytes, 1));
+    if (const char* e = getenv("SCKM_PREDICT_CHUNK_ROWS")) chunk_rows = std::max<uint64_t>(1, strtoull(e, nullptr, 10));   // tests
+    chunk_rows = std::min(chunk_rows, n);
+    const uint64_t nchunks = (n + chunk_rows - 1) / chunk_rows;
+
+    sckm_dataset* buf[2] = {nullptr, nullptr};
+    void* cm_tmp = nullptr;                                   // column-major image of one chunk
+    int rc = dataset_alloc(ctx, chunk_rows, d, dtype, 0, chunk_rows, &buf[0]);
+    if (rc == SCKM_OK && nchunks > 1) rc = dataset_alloc(ctx, chunk_rows, d, dtype, 0, chunk_rows, &buf[1]);
+    if (rc == SCKM_OK && column_major && cudaMalloc(&cm_tmp, chunk_rows * row_bytes) != cudaSuccess) {
+        cudaGetLastError();
+        rc = fail(ctx, SCKM_ERR_CUDA, "cudaMalloc of the column-major staging image failed");
+    }
+    if (rc == SCKM_OK) rc = ensure_workspace(ctx, k, d, 0);
     if (rc == SCKM_OK && cudaMemcpyAsync(ctx->d_centroids, centroids, k * d * sizeof(double), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess)
         rc = fail(ctx, SCKM_ERR_CUDA, "centroid upload failed");
     ctx->cnorm_valid = false;
-    // large k: rank on the DMMA tiles and re-decide near-ties exactly (same labels as the direct form, much faster);
-    // otherwise the direct-form kernel
-    if (rc == SCKM_OK) rc = (dmma_supported(ds, k) && k >= 32 && ctx->assign_kernel != SCKM_ASSIGN_DIRECT)
-                                ? launch_predict_dmma(ds, k)
-                                : launch_assign_direct_raw(ctx, ds->x, dtype, n, d, k, ds->labels, nullptr);
-    if (rc == SCKM_OK) rc = download_labels(ds, labels_out, width);
-    sckm_dataset_destroy(ds);
+
+    // chunk c covers rows [c*chunk_rows, ...): row-major = one contiguous block; column-major = d strided pieces,
+    // landed as a [d][rows] image (2-D copy, stream-ordered) and transposed on the device
+    auto upload = [&](uint64_t c, bool first) -> int {
+        sckm_dataset* ds = buf[c & 1];
+        const uint64_t r0 = c * chunk_rows, rows = std::min(chunk_rows, n - r0);
+        ds->n = rows;
+        if (!column_major) return copy_to_device(ctx, ds->x, (const char*)x_host + r0 * row_bytes, rows * row_bytes, first);
+        SCKM_CUDA(ctx, cudaMemcpy2DAsync(cm_tmp, rows * elem, (const char*)x_host + r0 * elem, n * elem, rows * elem, d,
+                                         cudaMemcpyHostToDevice, ctx->stream));
+        return launch_transpose(ctx, cm_tmp, ds->x, rows, d, dtype);
+    };
+    if (rc == SCKM_OK) rc = upload(0, true);
+    for (uint64_t c = 0; c < nchunks && rc == SCKM_OK; c++) {
+        sckm_dataset* ds = buf[c & 1];
+        rc = predict_chunk(ds, k);                                            // asynchronous on ctx->stream
+        if (rc == SCKM_OK && c + 1 < nchunks) rc = upload(c + 1, false);      // other buffer: idle since its labels came back
+        if (rc == SCKM_OK) rc = download_labels(ds, (char*)labels_out + c * chunk_rows * (size_t)width, width);
+    }
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(cm_tmp);
+    sckm_dataset_destroy(buf[0]);
+    sckm_dataset_destroy(buf[1]);
     return rc;
 }
 

@@ -17,6 +17,8 @@ constexpr int kKppBlockRows = 1024;   // fixed summation unit of the kmeans++ D^
 // pitch (in doubles) of one partial slot [k*d sums | k counts | inertia]: 128-byte aligned rows
 inline size_t slot_pitch(size_t pk) { return (pk + 15) / 16 * 16; }
 
+struct StagePool;   // pinned staging ring of the host<->device transfer engine (sckm_ingest.cu)
+
 }  // namespace sckm
 
 struct sckm_ctx {
@@ -56,6 +58,8 @@ struct sckm_ctx {
     size_t flush_bytes = 0;
     double* h_pinned = nullptr;      // small pinned scratch (>= 64 doubles)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    cudaStream_t copy_stream = nullptr;      // transfers that must not queue behind the kernels on `stream`
+    sckm::StagePool* stage_pool = nullptr;   // created on the first large transfer from/to pageable memory
 };
 
 struct sckm_dataset {
@@ -97,6 +101,11 @@ void nccl_destroy(sckm_ctx* ctx);
 int nccl_allreduce_f64(sckm_ctx* ctx, double* buf, size_t count);
 int nccl_allreduce_u64(sckm_ctx* ctx, unsigned long long* buf, size_t count);
 int nccl_allgather_f64(sckm_ctx* ctx, const double* send1, double* recv);  // 1 double per rank
+
+// ---- host <-> device transfers (sckm_ingest.cu): blocking, pageable memory goes through a threaded pinned ring ----
+int copy_to_device(sckm_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, bool sync_first = true);
+int copy_to_host(sckm_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
+void ingest_destroy(sckm_ctx* ctx);
 
 // ---- kernel launchers (sckm_kernels.cu) ----
 int launch_transpose(sckm_ctx* ctx, const void* src_colmajor, void* dst_rowmajor, uint64_t n, uint64_t d, int dtype);

@@ -333,6 +333,37 @@ def test_predict_at_scale_bit_exact(ctx, O, n, d, k, dtype):
         ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
 
 
+def test_predict_streams_in_chunks(ctx, O, monkeypatch):
+    """sckm_predict double-buffers X through the device in row chunks (ragged last chunk, both layouts, both widths)."""
+    monkeypatch.setenv("SCKM_PREDICT_CHUNK_ROWS", "1000")
+    for n, d, k, dtype in ((4321, 16, 40, np.float64), (2500, 8, 5, np.float32), (1000, 64, 64, np.float64), (999, 4, 3, np.float64)):
+        x = blobs(n, d, k, n, dtype)
+        cent = blobs(k, d, k, 7).astype(np.float64)
+        want = O.predict(x, cent)
+        assert np.array_equal(ctx.predict(x, cent).astype(np.int64), want)
+        assert np.array_equal(ctx.predict(x, cent, column_major=True, width=4).astype(np.int64), want)
+
+
+def test_pageable_transfers_through_the_pinned_ring(ctx, O):
+    """> 32 MB from/to ordinary (pageable) numpy memory goes through the threaded staging ring in both directions."""
+    n, d = 5_000_011, 2                                    # 40 MB of f32 rows, 40 MB of u64 labels; ragged tail chunk
+    x = blobs(n, d, 2, 17, np.float32, spread=8.0)
+    ds = ctx.upload(x)
+    assert np.array_equal(ds.download_rows(0, 4096), x[:4096])
+    assert np.array_equal(ds.download_rows(n - 4099, 4099), x[n - 4099:])
+    assert np.array_equal(ds.download_rows(2_500_000, 1000), x[2_500_000:2_501_000])
+    cent = np.array([x[0], x[1]], dtype=np.float64)
+    inertia, sums, counts = ds.lloyd_step(cent)
+    labels = ds.labels()                                   # staged D2H
+    ds.close()
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+    assert_labels_match(labels, m_o, gap)
+    assert counts.sum() == n
+    dsc = ctx.upload(x, column_major=True)                 # column-major image + device transpose
+    assert np.array_equal(dsc.download_rows(n - 50, 50), x[n - 50:])
+    dsc.close()
+
+
 # ---- edge cases: tiny, ragged and degenerate inputs ------------------------------------------------------
 @pytest.mark.parametrize("n,d,k", [(2, 1, 2), (3, 2, 2), (5, 3, 5), (17, 1, 4), (64, 2, 63), (31, 3, 30), (257, 5, 256),
                                    (100, 4, 99), (40, 130, 7), (1000, 1, 16), (129, 4, 16), (4096, 6, 17)])

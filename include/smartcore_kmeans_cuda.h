@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define SCKM_ABI_VERSION 1
+#define SCKM_ABI_VERSION 2
 
 typedef struct sckm_ctx sckm_ctx;         /* device + stream + workspaces (+ NCCL communicator) */
 typedef struct sckm_dataset sckm_dataset; /* this rank's rows of X, labels y and D^2 array, on device */
@@ -145,6 +145,18 @@ int sckm_kmeans_fit(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, i
                     int column_major, uint64_t k, uint64_t max_iter, uint64_t first_index,
                     const double* uniforms, void* labels_out, int width, int64_t* size_out,
                     double* centroids_out, double* distortion_out, int64_t* iters_out);
+
+/* ---- cluster quality (src/metrics/cluster_helpers.rs:7-25 contingency_matrix) --------
+ * out[n_classes][k] (row-major) = number of rows with class id c and cluster label j, counted on the device.
+ * sckm_contingency: cluster labels = the dataset's resident labels (after a fit / Lloyd step); class_ids_host holds
+ * this rank's n_local dense class ids in [0, n_classes).  With a communicator the table is summed over ranks.
+ * sckm_contingency_host: both id arrays come from the host (any two labelings of n rows).
+ * An id outside its range is an error (SCKM_ERR_INVALID).  Entropy / mutual information / homogeneity,
+ * completeness and V-measure (cluster_hcv.rs:36-55) follow from the table on the host. */
+int sckm_contingency(sckm_dataset* ds, const uint32_t* class_ids_host, uint64_t n_classes, uint64_t k,
+                     int64_t* out);
+int sckm_contingency_host(sckm_ctx* ctx, const uint32_t* a_host, const uint32_t* b_host, uint64_t n,
+                          uint64_t na, uint64_t nb, int64_t* out);
 
 /* ---- measurement helpers ------------------------------------------------------- */
 /* out[0] = HBM copy GB/s (read+write), out[1] = FP64 DFMA TFLOP/s, out[2] = FP64 DMMA TFLOP/s,

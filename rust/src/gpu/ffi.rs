@@ -55,4 +55,11 @@ extern "C" {
         max_iter: u64, first_index: u64, uniforms: *const f64, labels_out: *mut c_void, width: c_int,
         size_out: *mut i64, centroids_out: *mut f64, distortion_out: *mut f64, iters_out: *mut i64,
     ) -> c_int;
+    // cluster quality (metrics/cluster_helpers.rs:7-25): contingency table counted on the device
+    pub fn sckm_contingency(
+        ds: *mut sckm_dataset, class_ids_host: *const u32, n_classes: u64, k: u64, out: *mut i64,
+    ) -> c_int;
+    pub fn sckm_contingency_host(
+        ctx: *mut sckm_ctx, a_host: *const u32, b_host: *const u32, n: u64, na: u64, nb: u64, out: *mut i64,
+    ) -> c_int;
 }

@@ -21,6 +21,7 @@ SYMBOLS = [
     "sckm_dataset_generate_blobs", "sckm_blobs_fill_host", "sckm_dataset_download_rows", "sckm_dataset_destroy",
     "sckm_kmeanspp", "sckm_init_centroids", "sckm_lloyd_step", "sckm_lloyd_fit", "sckm_lloyd_iterate",
     "sckm_labels_download", "sckm_mindist_download", "sckm_predict", "sckm_kmeans_fit", "sckm_device_peaks",
+    "sckm_contingency", "sckm_contingency_host",
     "sckm_flush_l2",
 ]
 
@@ -62,6 +63,8 @@ def _load():
     L.sckm_predict.argtypes = [vp, vp, u64, u64, i32, i32, vp, u64, vp, i32]
     L.sckm_kmeans_fit.argtypes = [vp, vp, u64, u64, i32, i32, u64, u64, u64, vp, vp, i32, vp, vp, vp, vp]
     L.sckm_device_peaks.argtypes = [vp, vp]
+    L.sckm_contingency.argtypes = [vp, vp, u64, u64, vp]
+    L.sckm_contingency_host.argtypes = [vp, vp, vp, u64, u64, u64, vp]
     L.sckm_flush_l2.argtypes = [vp]
     return L
 
@@ -242,6 +245,14 @@ class Dataset:
     def labels(self, width=8):
         out = np.empty(self.n, dtype=np.uint64 if width == 8 else np.uint32)
         self.ctx._check(lib.sckm_labels_download(self.h, _p(out), width))
+        return out
+
+    def contingency(self, class_ids, n_classes, k):
+        """sckm_contingency: table[n_classes][k] of (class id, resident cluster label) pairs, counted on the device."""
+        a = np.ascontiguousarray(class_ids, dtype=np.uint32)
+        assert a.size == self.n
+        out = np.zeros((n_classes, k), dtype=np.int64)
+        self.ctx._check(lib.sckm_contingency(self.h, _p(a), n_classes, k, _p(out)))
         return out
 
     def mindist(self):

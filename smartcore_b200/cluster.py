@@ -26,6 +26,9 @@ _h.sch_kmeans_predict.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp
 _h.sch_kmeans_dims.argtypes = [_vp, _vp, _vp, _vp]; _h.sch_kmeans_dims.restype = None
 _h.sch_kmeans_get.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp]; _h.sch_kmeans_get.restype = None
 _h.sch_kmeans_free.argtypes = [_vp]; _h.sch_kmeans_free.restype = None
+_h.sch_kmeans_serialize.argtypes = [_vp, C.c_int, _vp, C.c_size_t]; _h.sch_kmeans_serialize.restype = C.c_size_t
+_h.sch_kmeans_deserialize.argtypes = [C.c_int, C.c_int, C.c_char_p, C.c_size_t, _vp, C.c_char_p, C.c_size_t]
+_h.sch_kmeans_eq.argtypes = [_vp, _vp]
 _h.sch_search_parameters.argtypes = [_vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, C.c_size_t]
 _h.sch_search_parameters.restype = C.c_size_t
 _h.sch_kmeanspp_draws.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, _vp, _vp]; _h.sch_kmeanspp_draws.restype = None
@@ -146,6 +149,43 @@ class KMeans:
         if rc:
             raise Failed(err.value.decode())
         return cls(model, data.values.dtype)
+
+    # ---- serde (kmeans.rs:70-83): images interchangeable with the reference's derive(Serialize, Deserialize) ----
+    def _serialize(self, fmt):
+        size = _h.sch_kmeans_serialize(self._h, fmt, None, 0)
+        buf = C.create_string_buffer(size)
+        _h.sch_kmeans_serialize(self._h, fmt, buf, size)
+        return buf.raw[:size]
+
+    @classmethod
+    def _deserialize(cls, fmt, image, dtype):
+        model = _vp(); err = C.create_string_buffer(1024)
+        dtype = np.dtype(dtype)
+        if _h.sch_kmeans_deserialize(_DT[dtype], fmt, image, len(image), C.byref(model), err, len(err)):
+            raise Failed(err.value.decode())
+        return cls(model, dtype)
+
+    def to_json(self):
+        """serde_json::to_string(&kmeans)"""
+        return self._serialize(0).decode()
+
+    def to_bincode(self):
+        """bincode::serialize(&kmeans) (bincode 1.3 default options)"""
+        return self._serialize(1)
+
+    @classmethod
+    def from_json(cls, text, dtype=np.float64):
+        """serde_json::from_str::<KMeans<TX, ..>>(text); dtype = TX"""
+        return cls._deserialize(0, text.encode() if isinstance(text, str) else text, dtype)
+
+    @classmethod
+    def from_bincode(cls, image, dtype=np.float64):
+        return cls._deserialize(1, bytes(image), dtype)
+
+    def __eq__(self, other):  # PartialEq (kmeans.rs:85-107)
+        return isinstance(other, KMeans) and bool(_h.sch_kmeans_eq(self._h, other._h))
+
+    __hash__ = None
 
     def predict(self, x, ty=np.int64):
         out = np.zeros(x.nrows, dtype=np.int64); err = C.create_string_buffer(1024)

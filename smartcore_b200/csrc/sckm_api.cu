@@ -16,6 +16,8 @@ int launch_assign_dmma(sckm_dataset* ds, uint64_t k);         // sckm_dmma.cu
 bool dmma_supported(const sckm_dataset* ds, uint64_t k);      // sckm_dmma.cu
 uint32_t dmma_partial_slots(const sckm_ctx* ctx);             // sckm_dmma.cu
 int launch_predict_dmma(sckm_dataset* ds, uint64_t k);        // sckm_dmma.cu
+int launch_contingency(sckm_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, uint64_t n, uint64_t na, uint64_t nb,
+                       unsigned long long* d_out);            // sckm_metrics.cu
 int launch_assign_stream(sckm_dataset* ds, uint64_t k);       // sckm_stream.cu
 bool stream_supported(const sckm_dataset* ds, uint64_t k);    // sckm_stream.cu
 int launch_assign_tc5(sckm_dataset* ds, uint64_t k);          // sckm_tc5.cu
@@ -510,6 +512,52 @@ int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int 
     sckm_dataset_destroy(buf[0]);
     sckm_dataset_destroy(buf[1]);
     return rc;
+}
+
+// ---- cluster quality: contingency table --------------------------------------------------------
+static int contingency_common(sckm_ctx* ctx, const uint32_t* a_host, const uint32_t* d_b, const uint32_t* b_host, uint64_t n,
+                              uint64_t na, uint64_t nb, bool allreduce, int64_t* out) {
+    if (!out || na == 0 || nb == 0) return fail(ctx, SCKM_ERR_INVALID, "empty contingency table");
+    if (na > (1u << 20) || nb > (1u << 20) || na * nb > (1ull << 26)) return fail(ctx, SCKM_ERR_INVALID, "contingency table too large");
+    if (n && (!a_host || (!d_b && !b_host))) return fail(ctx, SCKM_ERR_INVALID, "NULL id array");
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint64_t ncell = na * nb;
+    uint32_t *d_a = nullptr, *d_b2 = nullptr;
+    unsigned long long* d_out = nullptr;
+    int rc = SCKM_OK;
+    auto cleanup = [&]() { cudaFree(d_a); cudaFree(d_b2); cudaFree(d_out); };
+    if (cudaMalloc((void**)&d_a, std::max<uint64_t>(n, 1) * 4) != cudaSuccess ||
+        cudaMalloc((void**)&d_out, (ncell + 1) * 8) != cudaSuccess ||
+        (!d_b && cudaMalloc((void**)&d_b2, std::max<uint64_t>(n, 1) * 4) != cudaSuccess)) {
+        cudaGetLastError(); cleanup();
+        return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc for the contingency table failed");
+    }
+    rc = copy_to_device(ctx, d_a, a_host, n * 4);
+    if (rc == SCKM_OK && !d_b) rc = copy_to_device(ctx, d_b2, b_host, n * 4);
+    if (rc == SCKM_OK) rc = launch_contingency(ctx, d_a, d_b ? d_b : d_b2, n, na, nb, d_out);
+    if (rc == SCKM_OK && allreduce) rc = nccl_allreduce_u64(ctx, d_out, ncell + 1);
+    std::vector<unsigned long long> h(ncell + 1);
+    if (rc == SCKM_OK && (cudaMemcpyAsync(h.data(), d_out, (ncell + 1) * 8, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                          cudaStreamSynchronize(ctx->stream) != cudaSuccess))
+        rc = fail(ctx, SCKM_ERR_CUDA, "contingency download failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cleanup();
+    if (rc != SCKM_OK) return rc;
+    if (h[ncell]) return fail(ctx, SCKM_ERR_INVALID, "%llu rows carry an id outside [0,%llu) x [0,%llu)", h[ncell],
+                              (unsigned long long)na, (unsigned long long)nb);
+    for (uint64_t i = 0; i < ncell; i++) out[i] = (int64_t)h[i];
+    return SCKM_OK;
+}
+
+int sckm_contingency(sckm_dataset* ds, const uint32_t* class_ids_host, uint64_t n_classes, uint64_t k, int64_t* out) {
+    if (!ds) return SCKM_ERR_INVALID;
+    if (!ds->have_labels) return fail(ds->ctx, SCKM_ERR_STATE, "no labels on the dataset yet");
+    return contingency_common(ds->ctx, class_ids_host, ds->labels, nullptr, ds->n, n_classes, k, true, out);
+}
+
+int sckm_contingency_host(sckm_ctx* ctx, const uint32_t* a_host, const uint32_t* b_host, uint64_t n, uint64_t na,
+                          uint64_t nb, int64_t* out) {
+    if (!ctx) return SCKM_ERR_INVALID;
+    return contingency_common(ctx, a_host, nullptr, b_host, n, na, nb, false, out);
 }
 
 // ---- whole fit from host buffers ----------------------------------------------------------------

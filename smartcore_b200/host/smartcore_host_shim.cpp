@@ -3,6 +3,7 @@
 // a Rust caller would.  No arithmetic here: validation + RNG draws live in the header, the compute in
 // libsmartcore_kmeans_cuda.so.
 #include "smartcore_kmeans.hpp"
+#include "smartcore_metrics.hpp"
 #include <cstring>
 
 using namespace smartcore;
@@ -109,6 +110,39 @@ void sch_kmeans_get(void* model, int64_t* y, int64_t* size, double* centroids, d
 }
 void sch_kmeans_free(void* model) { delete (Model*)model; }
 
+// serde images of the model (format 0 = serde_json, 1 = bincode).  Returns the image size; copies it when it fits.
+size_t sch_kmeans_serialize(void* model, int format, char* buf, size_t cap) {
+    std::string img;
+    WITH_MODEL(model, { img = format == 0 ? M.to_json() : M.to_bincode(); })
+    if (buf && img.size() <= cap) memcpy(buf, img.data(), img.size());
+    return img.size();
+}
+int sch_kmeans_deserialize(int dtype, int format, const char* bytes, size_t len, void** model_out, char* err, size_t errlen) {
+    Model* m = new Model(); m->dtype = dtype;
+    const std::string img(bytes, len);
+    int rc = 0;
+    WITH_MODEL(m, {
+        auto r = format == 0 ? std::decay_t<decltype(M)>::from_json(img) : std::decay_t<decltype(M)>::from_bincode(img);
+        if (r.is_err()) { set_err(err, errlen, r.unwrap_err().to_string()); rc = 1; }
+        else M = std::move(r.unwrap());
+    })
+    if (rc) { delete m; return rc; }
+    *model_out = m;
+    return 0;
+}
+// PartialEq (kmeans.rs:85-107)
+int sch_kmeans_eq(void* a, void* b) {
+    if (((Model*)a)->dtype != ((Model*)b)->dtype) return 0;
+    int eq = 0;
+    switch (((Model*)a)->dtype) {
+        case SCH_F32: eq = ((Model*)a)->f32 == ((Model*)b)->f32; break;
+        case SCH_F64: eq = ((Model*)a)->f64 == ((Model*)b)->f64; break;
+        case SCH_I32: eq = ((Model*)a)->i32 == ((Model*)b)->i32; break;
+        default: eq = ((Model*)a)->i64 == ((Model*)b)->i64; break;
+    }
+    return eq;
+}
+
 // KMeansSearchParameters{k, max_iter, seed}.into_iter() flattened; returns the number of items written
 size_t sch_search_parameters(const size_t* k, size_t nk, const size_t* max_iter, size_t nm, const uint64_t* seed,
                              const int* has_seed, size_t ns, size_t* out_k, size_t* out_max_iter, uint64_t* out_seed,
@@ -137,6 +171,45 @@ void sch_kmeanspp_draws(int has_seed, uint64_t seed, uint64_t n, size_t k, uint6
 double sch_dense_get_f64(const double* values, size_t nrows, size_t ncols, int column_major, size_t r, size_t c) {
     DenseMatrix<double> m; m.nrows = nrows; m.ncols = ncols; m.column_major = column_major != 0;
     return column_major ? values[c * nrows + r] : values[c + ncols * r];
+}
+
+// ---- metrics::cluster_helpers / cluster_hcv over i64 labels ------------------------------------------------
+// contingency_matrix(labels_true, labels_pred): writes the table row-major into out (capacity cap cells) and its
+// shape into nr / nc; returns 0, 1 (error, message in err) or 3 (cap too small; shape still reported)
+int sch_contingency_matrix(const int64_t* y_true, const int64_t* y_pred, size_t n, int64_t* out, size_t cap, size_t* nr,
+                           size_t* nc, char* err, size_t errlen) {
+    std::vector<int64_t> a(y_true, y_true + n), b(y_pred, y_pred + n);
+    auto r = metrics::cluster_helpers::contingency_matrix(a, b);
+    if (r.is_err()) { set_err(err, errlen, r.unwrap_err().to_string()); return 1; }
+    auto& t = r.unwrap();
+    *nr = t.size(); *nc = t.empty() ? 0 : t[0].size();
+    if (*nr * *nc > cap) return 3;
+    for (size_t i = 0; i < *nr; i++) for (size_t j = 0; j < *nc; j++) out[i * *nc + j] = (int64_t)t[i][j];
+    return 0;
+}
+double sch_entropy(const int64_t* y, size_t n) {
+    return *metrics::cluster_helpers::entropy(std::vector<int64_t>(y, y + n));
+}
+double sch_mutual_info_score(const int64_t* table, size_t nr, size_t nc) {
+    std::vector<std::vector<size_t>> t(nr, std::vector<size_t>(nc));
+    for (size_t i = 0; i < nr; i++) for (size_t j = 0; j < nc; j++) t[i][j] = (size_t)table[i * nc + j];
+    return metrics::cluster_helpers::mutual_info_score(t);
+}
+// HCVScore::compute: out3 = homogeneity, completeness, v_measure
+int sch_hcv_score(const int64_t* y_true, const int64_t* y_pred, size_t n, double* out3, char* err, size_t errlen) {
+    metrics::cluster_hcv::HCVScore<int64_t> s;
+    auto r = s.compute(std::vector<int64_t>(y_true, y_true + n), std::vector<int64_t>(y_pred, y_pred + n));
+    if (r.is_err()) { set_err(err, errlen, r.unwrap_err().to_string()); return 1; }
+    out3[0] = *s.homogeneity(); out3[1] = *s.completeness(); out3[2] = *s.v_measure();
+    return 0;
+}
+// the same scores from a table that was counted elsewhere (sckm_contingency on resident labels)
+void sch_hcv_from_table(const int64_t* table, size_t nr, size_t nc, double* out3) {
+    std::vector<std::vector<size_t>> t(nr, std::vector<size_t>(nc));
+    for (size_t i = 0; i < nr; i++) for (size_t j = 0; j < nc; j++) t[i][j] = (size_t)table[i * nc + j];
+    metrics::cluster_hcv::HCVScore<int64_t> s;
+    s.compute_from_table(t);
+    out3[0] = *s.homogeneity(); out3[1] = *s.completeness(); out3[2] = *s.v_measure();
 }
 
 }  // extern "C"

@@ -25,6 +25,7 @@
 #include <vector>
 
 #include "../../include/smartcore_kmeans_cuda.h"
+#include "smartcore_persist.hpp"
 
 namespace smartcore {
 
@@ -262,6 +263,32 @@ public:
         std::vector<TY> out(n);
         for (size_t i = 0; i < n; i++) out[i] = (TY)lab[i];
         return R::Ok(std::move(out));
+    }
+
+    // serde (kmeans.rs:70-83): serde_json and bincode images interchangeable with the reference's derive
+    persist::KMeansFields fields() const {
+        persist::KMeansFields f;
+        f.k = k; f.y.assign(_y.begin(), _y.end()); f.size.assign(size.begin(), size.end());
+        f.distortion = _distortion; f.centroids = centroids;
+        return f;
+    }
+    static KMeans from_fields(const persist::KMeansFields& f) {
+        KMeans m;
+        m.k = (size_t)f.k; m._y.assign(f.y.begin(), f.y.end()); m.size.assign(f.size.begin(), f.size.end());
+        m._distortion = f.distortion; m.centroids = f.centroids;
+        return m;
+    }
+    std::string to_json() const { return persist::to_json(fields()); }
+    std::string to_bincode() const { return persist::to_bincode(fields()); }
+    static error::Result<KMeans> from_json(const std::string& text) {
+        persist::KMeansFields f; std::string e;
+        if (!persist::from_json(text, f, e)) return error::Result<KMeans>::Err(error::Failed::input(e));
+        return error::Result<KMeans>::Ok(from_fields(f));
+    }
+    static error::Result<KMeans> from_bincode(const std::string& bytes) {
+        persist::KMeansFields f; std::string e;
+        if (!persist::from_bincode(bytes, f, e)) return error::Result<KMeans>::Err(error::Failed::input(e));
+        return error::Result<KMeans>::Ok(from_fields(f));
     }
 
     // PartialEq (kmeans.rs:85-107)

@@ -458,3 +458,67 @@ def test_config2_fit_parity_200k(ctx, O):
     x = cabi.blobs_host(0, n, d, k, 20260101)
     got = fit_gpu(ctx, x, k, 42)
     check_fit(O, x, k, 42, got)
+
+
+def test_serde_round_trip_reference_test(iris20):  # kmeans.rs:507-545: f32 model, serde_json round trip, PartialEq
+    x = sc.DenseMatrix.from_2d_array(iris20.astype(np.float32))
+    kmeans = sc.KMeans.fit(x, sc.KMeansParameters.default())
+    for back in (sc.KMeans.from_json(kmeans.to_json(), dtype=np.float32),
+                 sc.KMeans.from_bincode(kmeans.to_bincode(), dtype=np.float32)):
+        assert back == kmeans
+        assert np.array_equal(back._y, kmeans._y) and back._distortion == kmeans._distortion
+        assert np.array_equal(back.predict(x), kmeans.predict(x))      # a reloaded model predicts on the device
+
+
+# ---- cluster-quality scores (metrics/cluster_helpers.rs, cluster_hcv.rs): counting on the device --------------------
+def test_hcv_reference_known_answers():  # cluster_helpers.rs:117-147, cluster_hcv.rs:94-104
+    v1 = [0, 0, 1, 1, 2, 0, 4]
+    v2 = [1, 0, 0, 0, 0, 1, 0]
+    assert sc.contingency_matrix(v1, v2).tolist() == [[1, 2], [2, 0], [1, 0], [1, 0]]
+    assert abs(1.2770 - sc.entropy(v1)) < 1e-4
+    assert abs(0.3254 - sc.mutual_info_score(sc.contingency_matrix(v1, v2))) < 1e-4
+    s = sc.HCVScore.new().compute(v1, v2)
+    assert abs(0.2548 - s.homogeneity()) < 1e-4 and abs(0.5440 - s.completeness()) < 1e-4 and abs(0.3471 - s.v_measure()) < 1e-4
+
+
+@pytest.mark.parametrize("n,na,nb", [(1, 1, 1), (1000, 7, 5), (200000, 40, 33), (300000, 120, 100), (5000, 1, 9)])
+def test_hcv_matches_oracle(n, na, nb):
+    from oracle import metrics_oracle as M
+    rng = np.random.default_rng(n + na)
+    a = rng.integers(0, na, n) * 5 - 7                     # arbitrary (negative, sparse) label values
+    b = (a // 5 + rng.integers(0, nb, n) * (rng.random(n) < 0.4)) % nb
+    assert sc.contingency_matrix(a, b).tolist() == M.contingency_matrix(a, b)          # integer counts: exact
+    assert abs(sc.entropy(a) - M.entropy(a)) <= 1e-12 * max(1.0, M.entropy(a))
+    s = sc.HCVScore.new().compute(a, b)
+    for got, want in zip((s.homogeneity(), s.completeness(), s.v_measure()), M.hcv(a, b)):
+        if not np.isfinite(want):      # a single class: the reference divides a rounding-level MI by a zero entropy
+            assert not np.isfinite(got)
+        else:
+            assert abs(got - want) <= 1e-12 * max(1.0, abs(want))
+
+
+def test_contingency_of_resident_labels(ctx, O):
+    """After a fit the labels never leave the device: sckm_contingency counts them against the true classes there."""
+    from oracle import metrics_oracle as M
+    n, d, k = 20000, 16, 8
+    x = blobs(n, d, k, 3, spread=6.0)
+    truth = (np.arange(n) % k).astype(np.uint32)           # blobs(): point i belongs to centre i % k
+    ds = ctx.upload(x)
+    first, u = cluster.kmeanspp_draws(5, n, k)
+    ds.kmeanspp(k, first, u)
+    cent, _ = ds.init_centroids(k)
+    out = ds.lloyd_iterate(cent, 5)
+    table = ds.contingency(truth, k, k)
+    labels = ds.labels().astype(np.int64)
+    assert table.tolist() == M.contingency_matrix(truth, labels) or table.sum() == n
+    want = np.zeros((k, k), dtype=np.int64)
+    np.add.at(want, (truth, labels), 1)
+    assert np.array_equal(table, want)
+    s = sc.HCVScore.new().compute_from_table(table)
+    cols = table[:, table.sum(axis=0) > 0]                 # the reference only sees clusters that occur
+    for got, wantv in zip((s.homogeneity(), s.completeness(), s.v_measure()), M.hcv(truth, labels)):
+        assert abs(got - wantv) <= 1e-12
+    assert cols.shape[1] >= 1
+    with pytest.raises(cabi.SckmError):
+        ds.contingency(truth + 1, k, k)                    # class id k is outside [0, k)
+    ds.close()

@@ -21,7 +21,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libsmartcore_kmeans_cuda.so does not export %s" % name
     assert sorted(cabi.SYMBOLS) == declared
-    assert lib.sckm_abi_version() == 1
+    assert lib.sckm_abi_version() == int(re.search(r"#define SCKM_ABI_VERSION (\d+)", header).group(1)) == 2
 
 
 def test_no_cpu_fallback_when_device_missing():
@@ -109,3 +109,48 @@ def test_shard_range_partitions_rows():
                 assert a1 == b0 and a0 <= a1
             for lo, hi in spans[:-1]:
                 assert (hi - lo) % dist.SHARD_ALIGN == 0 or hi == n
+
+
+# ---- persistence: the serde images of the model (kmeans.rs:70-83; round-trip test kmeans.rs:538-544) --------------
+SERDE_JSON_GOLDEN = ('{"k":2,"_y":[0,1,1],"size":[1,2],"_distortion":0.5,"centroids":[[1.0,2.5],[3.0,-4.25]],'
+                     '"_phantom_tx":null,"_phantom_ty":null,"_phantom_x":null,"_phantom_y":null}')
+
+
+def test_model_serde_json_layout_and_round_trip():
+    """What serde_json writes for the derive on KMeans: declaration order, floats as floats, PhantomData as null."""
+    m = sc.KMeans.from_json(SERDE_JSON_GOLDEN)
+    assert m.k == 2 and m._y.tolist() == [0, 1, 1] and m.size.tolist() == [1, 2] and m._distortion == 0.5
+    assert m.centroids.tolist() == [[1.0, 2.5], [3.0, -4.25]]
+    assert m.to_json() == SERDE_JSON_GOLDEN                      # byte-identical image
+    assert sc.KMeans.from_json(m.to_json()) == m                # PartialEq (kmeans.rs:85-107)
+    # field order is free on input, unknown fields are skipped, shortest round-trip floats
+    shuffled = ('{"centroids":[[0.1,1e-7],[1e300,2]],"extra":{"a":[1,2,{"b":"x"}]},"size":[5,6],"k":2,"_y":[],'
+                '"_distortion":1.7976931348623157e308}')
+    m2 = sc.KMeans.from_json(shuffled)
+    assert m2.centroids.tolist() == [[0.1, 1e-7], [1e300, 2.0]] and m2._distortion == 1.7976931348623157e308
+    assert sc.KMeans.from_json(m2.to_json()) == m2 and m2 != m
+    import json
+    assert json.loads(m2.to_json())["centroids"] == [[0.1, 1e-7], [1e300, 2.0]]
+
+
+def test_model_serde_nan_centroids_and_errors():
+    # an empty initial cluster leaves 0/0 centroids (kmeans.rs:284-290); serde_json writes non-finite f64 as null
+    m = sc.KMeans.from_json('{"k":2,"_y":[0],"size":[1,0],"_distortion":0.0,"centroids":[[1.5],[null]]}')
+    assert np.isnan(m.centroids[1][0]) and '[null]' in m.to_json()
+    for bad in ('{"k":2', '{"k":"two","centroids":[]}', '{"_y":[1]}', '[1,2]'):
+        with pytest.raises(sc.Failed):
+            sc.KMeans.from_json(bad)
+
+
+def test_model_bincode_layout():
+    """bincode 1.3 default options: LE u64 for usize and lengths, raw f64, nothing for PhantomData."""
+    import struct
+    m = sc.KMeans.from_json(SERDE_JSON_GOLDEN, dtype=np.float32)
+    want = (struct.pack("<Q", 2) + struct.pack("<Q3Q", 3, 0, 1, 1) + struct.pack("<Q2Q", 2, 1, 2) + struct.pack("<d", 0.5)
+            + struct.pack("<Q", 2) + struct.pack("<Q2d", 2, 1.0, 2.5) + struct.pack("<Q2d", 2, 3.0, -4.25))
+    assert m.to_bincode() == want
+    back = sc.KMeans.from_bincode(want, dtype=np.float32)
+    assert back == m and back._y.tolist() == [0, 1, 1]
+    for bad in (want[:-1], want + b"\\0", struct.pack("<Q", 2) + struct.pack("<Q", 1 << 60)):
+        with pytest.raises(sc.Failed):
+            sc.KMeans.from_bincode(bad)

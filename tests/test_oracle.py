@@ -134,3 +134,29 @@ def test_kmeanspp_labels_are_nearest_seed(O, iris_f32):
         ds = [O.squared_distance(x[i], s) for s in seeds]
         assert dd[i] == min(ds)
         assert y[i] == int(np.argmin(ds))  # strict <: first minimum wins
+
+
+# ---- cluster-quality scores: the reference's own known answers pin the restatement ----------------------------
+def test_metrics_oracle_against_reference_kats():
+    from oracle import metrics_oracle as M
+    v1 = [0, 0, 1, 1, 2, 0, 4]
+    v2 = [1, 0, 0, 0, 0, 1, 0]
+    assert M.contingency_matrix(v1, v2) == [[1, 2], [2, 0], [1, 0], [1, 0]]   # cluster_helpers.rs:117-125
+    assert abs(1.2770 - M.entropy(v1)) < 1e-4                                  # cluster_helpers.rs:131-135
+    assert abs(0.3254 - M.mutual_info_score(M.contingency_matrix(v1, v2))) < 1e-4   # cluster_helpers.rs:141-147
+    h, c, v = M.hcv(v1, v2)                                                    # cluster_hcv.rs:94-104
+    assert abs(0.2548 - h) < 1e-4 and abs(0.5440 - c) < 1e-4 and abs(0.3471 - v) < 1e-4
+
+
+def test_metrics_oracle_against_sklearn():
+    """Second opinion: scikit-learn computes the same three scores (natural logs cancel in the ratios)."""
+    from oracle import metrics_oracle as M
+    from sklearn.metrics import homogeneity_completeness_v_measure, mutual_info_score
+    rng = np.random.default_rng(5)
+    for n, na, nb in ((50, 3, 4), (1000, 7, 5), (3000, 20, 31)):
+        a = rng.integers(0, na, n) * 3 - 4
+        b = (a // 3 + rng.integers(0, nb, n) * (rng.random(n) < 0.3)) % nb
+        h, c, v = M.hcv(a, b)
+        hs, cs, vs = homogeneity_completeness_v_measure(a, b)
+        assert abs(h - hs) < 1e-10 and abs(c - cs) < 1e-10 and abs(v - vs) < 1e-10
+        assert abs(M.mutual_info_score(M.contingency_matrix(a, b)) - mutual_info_score(a, b)) < 1e-10

@@ -75,7 +75,7 @@ void sckm_ctx_destroy(sckm_ctx* ctx) {
     ingest_destroy(ctx);
     cudaFree(ctx->d_centroids); cudaFree(ctx->d_cnorm); cudaFree(ctx->d_packed); cudaFree(ctx->d_partials);
     cudaFree(ctx->d_size); cudaFree(ctx->d_blocksum); cudaFree(ctx->d_totals); cudaFree(ctx->d_seedrow);
-    cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_flush); cudaFree(ctx->d_tc5);
+    cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_surv); cudaFree(ctx->d_kppctr); cudaFree(ctx->d_tshift); cudaFree(ctx->d_tshift_err); cudaFree(ctx->d_flush); cudaFree(ctx->d_tc5);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -199,11 +199,17 @@ int sckm_dataset_download_rows(sckm_dataset* ds, uint64_t local_row0, uint64_t n
 void sckm_dataset_destroy(sckm_dataset* ds) {
     if (!ds) return;
     if (ds->ctx) { cudaSetDevice(ds->ctx->device); cudaStreamSynchronize(ds->ctx->stream); }
-    cudaFree(ds->x); cudaFree(ds->labels); cudaFree(ds->mind); cudaFree(ds->labels64); cudaFree(ds->x32);
+    cudaFree(ds->x); cudaFree(ds->labels); cudaFree(ds->mind); cudaFree(ds->labels64); cudaFree(ds->x32); cudaFree(ds->kpp_shadow); cudaFree(ds->kpp_shadow_err);
     delete ds;
 }
 
 // ---- kmeans++ -----------------------------------------------------------------------------
+static void kpp_shadow_free(sckm_dataset* ds) {
+    if (ds->kpp_shadow) cudaFree(ds->kpp_shadow);
+    if (ds->kpp_shadow_err) cudaFree(ds->kpp_shadow_err);
+    ds->kpp_shadow = nullptr; ds->kpp_shadow_err = nullptr;
+}
+
 static int ensure_kpp(sckm_dataset* ds, uint64_t k) {
     sckm_ctx* ctx = ds->ctx;
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, 0));
@@ -213,6 +219,21 @@ static int ensure_kpp(sckm_dataset* ds, uint64_t k) {
         SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_blocksum, nb * sizeof(double)));
         ctx->cap_blocks = nb;
     }
+    if (ds->n > ctx->cap_surv && ds->n < 0xFFFFFFFFull) {
+        if (ctx->d_surv) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_surv); ctx->d_surv = nullptr; ctx->cap_surv = 0; }
+        SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_surv, ds->n * sizeof(uint32_t)));
+        ctx->cap_surv = ds->n;
+    }
+    if (!ctx->d_kppctr) {
+        SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_kppctr, 2 * sizeof(unsigned)));
+        SCKM_CUDA(ctx, cudaMemsetAsync(ctx->d_kppctr, 0, 2 * sizeof(unsigned), ctx->stream));
+    }
+    if (ds->d > ctx->cap_tshift) {
+        if (ctx->d_tshift) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_tshift); ctx->d_tshift = nullptr; }
+        SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_tshift, ds->d * sizeof(float)));
+        ctx->cap_tshift = ds->d;
+    }
+    if (!ctx->d_tshift_err) SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_tshift_err, sizeof(double)));
     const size_t tab_bytes = (size_t)k * ds->d * ds->elem();
     if (tab_bytes > ctx->cap_seedtab) {
         if (ctx->d_seedtab) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_seedtab); ctx->d_seedtab = nullptr; }
@@ -259,6 +280,16 @@ int sckm_kmeanspp(sckm_dataset* ds, uint64_t k, uint64_t first_index, const doub
     // Triangle-inequality pruning: a row whose D^2 to its nearest seed s is <= ||s_new - s||^2 / 4 cannot improve, so
     // it is neither read nor touched.  Exact (the skipped rows are exactly rows the reference would leave unchanged).
     const bool prune = getenv("SCKM_KPP_NOPRUNE") == nullptr && (size_t)k * sizeof(double) <= 64 * 1024;
+    // bf16 shadow for the screening test of the pruned passes (16-byte rows of 8 bf16, enough passes to repay the
+    // build, memory permitting): see kpp_prune_kernel.  Absent shadow = exact path only, same results.
+    kpp_shadow_free(ds);
+    if (prune && k >= 8 && ds->d % 8 == 0 && ds->n && ds->n < 0xFFFFFFFFull && !getenv("SCKM_KPP_NOSHADOW")) {
+        if (cudaMalloc((void**)&ds->kpp_shadow, ds->n * ds->d * sizeof(uint16_t)) != cudaSuccess ||
+            cudaMalloc((void**)&ds->kpp_shadow_err, ds->n * sizeof(float)) != cudaSuccess) {
+            cudaGetLastError();
+            kpp_shadow_free(ds);
+        }
+    }
     SCKM_TRY(launch_kpp_seedtab(ds, 0));
     for (uint64_t j = 1; j < k; j++) {
         SCKM_TRY(launch_kpp_refresh(ds, (uint32_t)(j - 1), j == 1, prune));
@@ -267,12 +298,13 @@ int sckm_kmeanspp(sckm_dataset* ds, uint64_t k, uint64_t first_index, const doub
         SCKM_TRY(nccl_allreduce_u64(ctx, (unsigned long long*)ctx->d_seedrow, seed_words));
         SCKM_TRY(launch_kpp_seedtab(ds, (uint32_t)j));
     }
-    SCKM_TRY(launch_kpp_refresh(ds, (uint32_t)(k - 1), k == 1, prune));  // final pass, label k-1 (kmeans.rs:399-410)
+    SCKM_TRY(launch_kpp_refresh(ds, (uint32_t)(k - 1), k == 1, prune, /*want_sums=*/false));  // final pass, label k-1 (kmeans.rs:399-410)
     if (seed_rows_out) {
         if (ctx->nranks > 1) SCKM_TRY(nccl_allreduce_u64(ctx, (unsigned long long*)ctx->d_seeds, k));
         SCKM_CUDA(ctx, cudaMemcpyAsync(seed_rows_out, ctx->d_seeds, k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
     SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    kpp_shadow_free(ds);
     ds->have_labels = true;
     return SCKM_OK;
 }

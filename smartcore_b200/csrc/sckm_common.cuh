@@ -48,6 +48,12 @@ struct sckm_ctx {
     void* d_seedtab = nullptr;       // [k][d] of TX: the chosen seed rows (kmeans++ pruning)
     double* d_skiptab = nullptr;     // [k] pruning thresholds of the current pass
     size_t cap_seedtab = 0, cap_skiptab = 0;
+    uint32_t* d_surv = nullptr;      // kmeans++: rows that survived the pruning test of the current pass
+    size_t cap_surv = 0;
+    unsigned* d_kppctr = nullptr;    // [0] survivor count, [1] block-sum CTAs finished
+    float* d_tshift = nullptr;       // kmeans++ screening: f32(new seed - seed 0) [d]
+    double* d_tshift_err = nullptr;  // ... and the length of what that rounding dropped
+    size_t cap_tshift = 0;
     unsigned long long* d_flags = nullptr;  // [0] rows marked as near-ties in the current step; rest: scratch
     bool cnorm_valid = false;        // d_cnorm matches d_centroids
     uint64_t ws_k = 0, ws_d = 0;     // shape the centroid workspaces currently hold
@@ -72,6 +78,8 @@ struct sckm_dataset {
     double* mind = nullptr;          // [n] kmeans++ D^2 / per-point min distance
     uint64_t* labels64 = nullptr;    // lazily allocated widening buffer for usize downloads
     float* x32 = nullptr;            // f32 shadow of an f64 X (tcgen05 ranking only; lazily built)
+    uint16_t* kpp_shadow = nullptr;  // kmeans++ only: bf16(x - seed 0) [n][d], built by the first pass, freed after the last
+    float* kpp_shadow_err = nullptr; // ... and ||(x - seed 0) - shadow row|| rounded up [n]
     bool have_labels = false;
     size_t elem() const { return dtype == SCKM_F32 ? 4 : 8; }
 };
@@ -113,7 +121,7 @@ int launch_blobs(sckm_ctx* ctx, void* x, int dtype, uint64_t row0, uint64_t nrow
                  uint64_t n_centers, uint64_t seed);
 // kmeans++ pass: D^2 refresh against the seed row in ctx->d_seedrow, label = `label` where improved;
 // writes per-1024-row block sums to ctx->d_blocksum and the rank total to ctx->d_totals[rank].
-int launch_kpp_refresh(sckm_dataset* ds, uint32_t label, bool first_pass, bool prune);
+int launch_kpp_refresh(sckm_dataset* ds, uint32_t label, bool first_pass, bool prune, bool want_sums = true);
 int launch_kpp_seedtab(sckm_dataset* ds, uint32_t slot);
 // pick the next seed: cutoff = u * sum(totals); the owning rank locates the row and publishes it
 // (row + global index) in ctx->d_seedrow; other ranks publish zeros (all-reduced by the caller).

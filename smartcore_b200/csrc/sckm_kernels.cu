@@ -11,6 +11,7 @@
 #include "sckm_blobs.cuh"
 #include <cfloat>
 #include <cstdarg>
+#include <cuda_bf16.h>
 
 namespace sckm {
 
@@ -225,13 +226,274 @@ kpp_refresh_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __r
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// kmeans++ pass, second generation (16-byte-aligned rows, n < 2^32): three streaming kernels whose cost is
+//   prune   : 12 B per row            (D^2 + label -> survivor list, one atomic per 4096-row CTA)
+//   compute : d*s + 12 B per SURVIVOR (dense warps over the compacted list, rows gathered with cp.async)
+//   sums    : 8 B per row             (per-1024-row block sums in an order that does not depend on the pruning
+//                                      pattern, total by the last CTA to finish)
+// instead of one kernel whose every 1024-row CTA paid three barriers and four dependent global round trips whether
+// or not any of its rows survived (~200 us per pass at 10M rows however few rows were left).
+// ------------------------------------------------------------------------------------------
+constexpr int KPPA_THREADS = 256, KPPA_ITERS = 16;              // 4096 rows per CTA, 512 per warp
+
+// Screening of a row that survived the triangle test, on a bf16 SHADOW of X (built by the first pass): with
+//   r = x - seed0 (exact), xs = bf16(r) stored, ex >= ||r - xs||, t = f32(seed - seed0), et >= ||(seed - seed0) - t||
+// the triangle inequality gives  ||x - seed|| >= ||xs - t|| - ex - et.  The f32 evaluation a of ||xs - t|| carries a
+// relative error < (d+2)*2^-24, covered by `shrink`.  If that lower bound, squared and reduced by `margin` (the
+// rounding of the reference's own TX-arithmetic distance), is still >= D^2[row], then `dist < d[i]` (kmeans.rs:375)
+// is false for the exact distance too and the 4x (f64) / 2x (f32) larger exact row is never read.  Rows it cannot
+// exclude -- the ones that do improve, and the borderline -- go to kpp_compute_kernel unchanged: results are
+// bit-identical with or without the shadow.
+template <int NV8>                                              // NV8 = d/8 when known at compile time (all loads in flight), 0 = loop
+__device__ __forceinline__ bool kpp_screen_excludes(const uint4* __restrict__ srow, uint32_t nv8, const float* __restrict__ t_s,
+                                                    float ex, double et, double old, float shrink, double margin) {
+    float a2 = 0.f;
+    auto eat = [&](const uint4& v, uint32_t q) {
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            const float lo = __uint_as_float(w[e] << 16), hi = __uint_as_float(w[e] & 0xffff0000u);   // bf16 -> f32
+            const float r0 = lo - t_s[q * 8 + 2 * e], r1 = hi - t_s[q * 8 + 2 * e + 1];
+            a2 = fmaf(r0, r0, a2);
+            a2 = fmaf(r1, r1, a2);
+        }
+    };
+    if (NV8 > 0) {
+        uint4 v[NV8 > 0 ? NV8 : 1];
+#pragma unroll
+        for (int q = 0; q < NV8; q++) v[q] = __ldg(srow + q);
+#pragma unroll
+        for (int q = 0; q < NV8; q++) eat(v[q], q);
+    } else {
+        for (uint32_t q = 0; q < nv8; q++) eat(__ldg(srow + q), q);
+    }
+    const double lb = (double)(sqrtf(a2) * shrink) - (double)ex - et;
+    return lb > 0.0 && lb * lb * (1.0 - margin) >= old;          // any NaN/inf on the way makes this false
+}
+
+template <int NV8>
+__global__ void __launch_bounds__(KPPA_THREADS)
+kpp_prune_kernel(const double* __restrict__ mind, const uint32_t* __restrict__ labels, uint64_t n,
+                 const double* __restrict__ skiptab, uint32_t ntab, uint32_t* __restrict__ surv,
+                 unsigned* __restrict__ counter, const uint16_t* __restrict__ shadow, const float* __restrict__ shadow_err,
+                 const float* __restrict__ tshift, const double* __restrict__ tshift_err, uint32_t d, double margin) {
+    extern __shared__ __align__(16) double tab_s[];             // [ntab] (1-margin)*||new seed - seed j||^2/4 | [d] f32 t
+    __shared__ uint32_t warp_cnt[KPPA_THREADS / 32];
+    __shared__ uint32_t cta_base;
+    __shared__ uint16_t list_s[KPPA_THREADS / 32][32 * KPPA_ITERS];   // per warp: rows that passed the triangle test
+    float* t_s = reinterpret_cast<float*>(tab_s + ntab);
+    for (uint32_t j = threadIdx.x; j < ntab; j += blockDim.x) tab_s[j] = skiptab[j];
+    if (shadow) for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) t_s[j] = tshift[j];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint64_t tile0 = ((uint64_t)blockIdx.x * (KPPA_THREADS / 32) + warp) * (32 * KPPA_ITERS);
+    uint16_t* list = list_s[warp];
+    // ---- phase 1: triangle test, coalesced over the warp's 512 rows; the rows it cannot exclude are compacted ----
+    uint32_t cnt = 0;
+#pragma unroll
+    for (int t = 0; t < KPPA_ITERS; t++) {
+        const uint64_t r = tile0 + (uint64_t)t * 32 + lane;
+        bool active = false;
+        if (r < n) active = !(mind[r] <= tab_s[labels[r]]);      // NaN D^2 stays active, like `dist < d[i]` would see it
+        const unsigned ball = __ballot_sync(0xffffffffu, active);
+        if (active) list[cnt + __popc(ball & ((1u << lane) - 1u))] = (uint16_t)(t * 32 + lane);
+        cnt += __popc(ball);
+    }
+    __syncwarp();
+    // ---- phase 2: dense warps over the compacted rows: screening on the bf16 shadow (every lane busy, all of a
+    // row's loads in flight at once) ----
+    unsigned pass[KPPA_ITERS];
+    uint32_t cnt2 = 0;
+    const double et = shadow ? *tshift_err : 0.0;
+    const float shrink = 1.0f - (float)(d + 2) * 1.2e-7f;       // > 2 x the f32 summation + sqrt error bound
+#pragma unroll
+    for (int t = 0; t < KPPA_ITERS; t++) {
+        bool keep = false;
+        if ((uint32_t)(t * 32) < cnt) {                          // warp-uniform
+            const uint32_t i = t * 32 + lane;
+            if (i < cnt) {
+                keep = true;
+                if (shadow) {
+                    const uint64_t r = tile0 + list[i];
+                    keep = !kpp_screen_excludes<NV8>(reinterpret_cast<const uint4*>(shadow + r * d), d / 8, t_s, shadow_err[r], et,
+                                                     mind[r], shrink, margin);
+                }
+            }
+        }
+        pass[t] = __ballot_sync(0xffffffffu, keep);
+        cnt2 += __popc(pass[t]);
+    }
+    if (lane == 0) warp_cnt[warp] = cnt2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t total = 0;
+        for (int w = 0; w < KPPA_THREADS / 32; w++) total += warp_cnt[w];
+        cta_base = total ? atomicAdd(counter, total) : 0u;
+    }
+    __syncthreads();
+    uint32_t base = cta_base;
+    for (int w = 0; w < warp; w++) base += warp_cnt[w];
+#pragma unroll
+    for (int t = 0; t < KPPA_ITERS; t++) {
+        if ((pass[t] >> lane) & 1u) surv[base + __popc(pass[t] & ((1u << lane) - 1u))] = (uint32_t)(tile0 + list[t * 32 + lane]);
+        base += __popc(pass[t]);
+    }
+}
+
+// D^2 of the listed rows (surv == nullptr: all rows) against the new seed; bit-identical arithmetic to
+// Euclidian::squared_distance (TX diff/square, sequential f64 sum) and the update rule of kmeans.rs:368-379
+template <typename T>
+__global__ void __launch_bounds__(KPP_WARPS * 32)
+kpp_compute_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __restrict__ seedrow, double* __restrict__ mind,
+                   uint32_t* __restrict__ labels, uint32_t label, int first_pass, const uint32_t* __restrict__ surv,
+                   const unsigned* __restrict__ counter, uint32_t pitch16, uint16_t* __restrict__ shadow,
+                   float* __restrict__ shadow_err) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    T* cent = reinterpret_cast<T*>(smem);
+    const uint32_t cent_bytes = (d * sizeof(T) + 15) / 16 * 16;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* slab = smem + cent_bytes + (size_t)warp * 32 * pitch16 * 16;
+    for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) cent[j] = seedrow[j];
+    __syncthreads();
+    const uint64_t total = surv ? (uint64_t)*counter : n;
+    const uint32_t cpr = d * sizeof(T) / 16;                    // 16-byte chunks per row
+    const uint32_t lane_e = lane / cpr, lane_q = lane % cpr, step_e = 32 / cpr, step_q = 32 % cpr;
+    using V = typename Vec16<T>::type;
+    const uint32_t nv = d / Vec16<T>::N;
+    for (uint64_t base = ((uint64_t)blockIdx.x * KPP_WARPS + warp) * 32; base < total; base += (uint64_t)gridDim.x * KPP_WARPS * 32) {
+        const uint32_t cnt = (uint32_t)min((uint64_t)32, total - base);
+        const uint64_t my_row = lane < cnt ? (surv ? (uint64_t)surv[base + lane] : base + lane) : 0;
+        {
+            uint32_t e = lane_e, q = lane_q;
+            const uint32_t nchunks = cnt * cpr;
+            for (uint32_t c0 = 0; c0 < nchunks; c0 += 32) {       // uniform trip count: every lane reaches the shuffle
+                const uint64_t r = __shfl_sync(0xffffffffu, my_row, (int)(e & 31u));
+                if (c0 + lane < nchunks)
+                    cp_async16(slab + ((size_t)e * pitch16 + q) * 16, reinterpret_cast<const unsigned char*>(x + r * d) + (size_t)q * 16);
+                e += step_e; q += step_q;
+                if (q >= cpr) { q -= cpr; e++; }
+            }
+            cp_async_wait_all();
+            __syncwarp();
+        }
+        if (lane < cnt) {
+            const V* xr = reinterpret_cast<const V*>(slab + (size_t)lane * pitch16 * 16);
+            const V* cr = reinterpret_cast<const V*>(cent);
+            double dist = 0.0;
+            for (uint32_t q = 0; q < nv; q++) {
+                V xv = xr[q], cv = cr[q];
+                const T* xe = reinterpret_cast<const T*>(&xv);
+                const T* ce = reinterpret_cast<const T*>(&cv);
+#pragma unroll
+                for (int e = 0; e < Vec16<T>::N; e++) dist = __dadd_rn(dist, sqdiff(xe[e], ce[e]));
+            }
+            if (first_pass) { labels[my_row] = 0; mind[my_row] = dist < DBL_MAX ? dist : DBL_MAX; }
+            else if (dist < mind[my_row]) { mind[my_row] = dist; labels[my_row] = label; }
+            if (first_pass && shadow) {
+                // bf16 shadow of (x - seed 0) and the exact length of what the rounding dropped (see kpp_prune_kernel);
+                // d % 8 == 0 here: eight elements -> one 16-byte store
+                uint4* srow = reinterpret_cast<uint4*>(shadow + my_row * d);
+                const T* xs = reinterpret_cast<const T*>(xr);
+                double e2 = 0.0;
+                for (uint32_t g8 = 0; g8 < d / 8; g8++) {
+                    uint32_t w[4];
+#pragma unroll
+                    for (int e = 0; e < 8; e += 2) {
+                        const uint32_t j = g8 * 8 + e;
+                        const double r0 = (double)xs[j] - (double)cent[j], r1 = (double)xs[j + 1] - (double)cent[j + 1];
+                        const __nv_bfloat16 b0 = __float2bfloat16_rn((float)r0), b1 = __float2bfloat16_rn((float)r1);
+                        const double q0 = r0 - (double)__bfloat162float(b0), q1 = r1 - (double)__bfloat162float(b1);
+                        e2 = fma(q0, q0, e2);
+                        e2 = fma(q1, q1, e2);
+                        w[e / 2] = (uint32_t)__bfloat16_as_ushort(b0) | ((uint32_t)__bfloat16_as_ushort(b1) << 16);
+                    }
+                    srow[g8] = make_uint4(w[0], w[1], w[2], w[3]);
+                }
+                shadow_err[my_row] = __double2float_ru(sqrt(e2) * (1.0 + 1e-9));
+            }
+        }
+        __syncwarp();
+    }
+}
+
+// block sums of D^2 (one warp per 1024-row block: lane-strided sequential sums, xor tree) and, by the last CTA to
+// finish, the rank total in the order of kpp_total_kernel -- both independent of which rows were pruned
+__global__ void __launch_bounds__(256)
+kpp_blocksum_kernel(const double* __restrict__ mind, uint64_t n, uint32_t nb, double* __restrict__ blocksum,
+                    double* __restrict__ totals, int rank, unsigned* __restrict__ done) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t b = blockIdx.x * 8 + warp;
+    if (b < nb) {
+        const uint64_t r0 = (uint64_t)b * kKppBlockRows;
+        double v[kKppBlockRows / 32];
+#pragma unroll
+        for (int i = 0; i < kKppBlockRows / 32; i++) {          // all loads in flight, then a fixed-order sum
+            const uint64_t r = r0 + (uint64_t)i * 32 + lane;
+            v[i] = r < n ? __ldcg(mind + r) : 0.0;
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int i = 0; i < kKppBlockRows / 32; i++) s = __dadd_rn(s, v[i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) s = __dadd_rn(s, __shfl_xor_sync(0xffffffffu, s, o));
+        if (lane == 0) blocksum[b] = s;
+    }
+    __shared__ bool is_last;
+    __shared__ double sh[256];
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = atomicAdd(done, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const uint32_t per = (nb + 255) / 256;
+    const uint32_t b0 = min(nb, threadIdx.x * per), b1 = min(nb, b0 + per);
+    double s = 0.0;
+    for (uint32_t i = b0; i < b1; i++) s = __dadd_rn(s, __ldcg(blocksum + i));
+    sh[threadIdx.x] = s;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        double t = 0.0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) t = __dadd_rn(t, sh[threadIdx.x * 8 + i]);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) t = __dadd_rn(t, __shfl_xor_sync(0xffffffffu, t, o));
+        if (threadIdx.x == 0) { totals[rank] = t; *done = 0u; }
+    }
+}
+
 // seedtab[slot] = the seed just published in seedrow; skiptab[j] = (1-margin) * ||seed_slot - seed_j||^2 / 4, j < slot
 template <typename T>
 __global__ void __launch_bounds__(256)
 kpp_seedtab_kernel(const T* __restrict__ seedrow, T* __restrict__ seedtab, uint32_t d, uint32_t slot,
-                   double* __restrict__ skiptab, double margin) {
+                   double* __restrict__ skiptab, double margin, float* __restrict__ tshift, double* __restrict__ tshift_err) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    if (blockIdx.x == 0) for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) seedtab[(size_t)slot * d + j] = seedrow[j];
+    if (blockIdx.x == 0) {
+        for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) seedtab[(size_t)slot * d + j] = seedrow[j];
+        if (tshift) {
+            // the new seed relative to seed 0 (the origin of the bf16 shadow), rounded to f32, and the length of what
+            // the rounding dropped -- both enter the screening bound of kpp_prune_kernel
+            __shared__ double part[8];
+            double e2 = 0.0;
+            for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) {
+                const double rd = slot ? (double)seedrow[j] - (double)seedtab[j] : 0.0;
+                const float tf = (float)rd;
+                tshift[j] = tf;
+                const double r = rd - (double)tf;
+                e2 = fma(r, r, e2);
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) e2 += __shfl_xor_sync(0xffffffffu, e2, o);
+            if (lane == 0) part[warp] = e2;
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                double t = 0.0;
+                for (int w = 0; w < 8; w++) t += part[w];
+                *tshift_err = sqrt(t) * (1.0 + 1e-9);
+            }
+        }
+    }
     const uint32_t j = blockIdx.x * 8 + warp;
     if (j >= slot) return;
     double s = 0.0;
@@ -278,7 +540,6 @@ kpp_select_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, uint64_t row_
                   const double* __restrict__ totals, int nranks, int rank, double u, long long inject_row,
                   unsigned char* __restrict__ seedbuf, uint32_t seed_words, long long* __restrict__ seeds,
                   uint32_t slot) {
-    __shared__ double sh[1024];
     __shared__ long long s_local;  // local row chosen on this rank, or -1
     unsigned long long* out = reinterpret_cast<unsigned long long*>(seedbuf);
     for (uint32_t w = threadIdx.x; w < seed_words; w += blockDim.x) out[w] = 0ull;
@@ -304,27 +565,49 @@ kpp_select_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, uint64_t row_
             // the last rank with any rows owns the clamp
         }
         if (owner == rank && n > 0) {
+            // first index whose running cost reaches the cutoff, at three granularities: 1024 thread chunks of block
+            // sums -> the blocks of one chunk -> the 1024 rows of one block.  The running cost of every candidate is a
+            // CTA-wide inclusive scan (fixed shape => deterministic), the pick the lowest index that reaches the cutoff.
+            __shared__ double s_warp[32];
+            __shared__ uint32_t s_first;
+            __shared__ uint32_t s_block;
+            __shared__ double s_cost;
+            auto first_reaching = [&](double v, bool valid, double cost0, double* excl_out) -> uint32_t {
+                // returns the lowest thread index t with cost0 + sum(v[0..t]) >= cutoff (1024 if none); every thread
+                // receives the result; *excl_out (thread-local) = running cost BEFORE this thread's own value
+                const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+                double inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const double up = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc = __dadd_rn(up, inc);
+                }
+                __syncthreads();
+                if (lane == 31) s_warp[warp] = inc;
+                if (threadIdx.x == 0) s_first = 1024u;
+                __syncthreads();
+                double wbase = cost0;
+                for (int w = 0; w < warp; w++) wbase = __dadd_rn(wbase, s_warp[w]);
+                const double incl = __dadd_rn(wbase, inc);
+                const double prev = __shfl_up_sync(0xffffffffu, inc, 1);
+                *excl_out = lane ? __dadd_rn(wbase, prev) : wbase;
+                if (valid && incl >= cutoff) atomicMin(&s_first, threadIdx.x);
+                __syncthreads();
+                return s_first;
+            };
             const uint32_t per = (nb + 1023) / 1024;
             const uint32_t b0 = min(nb, threadIdx.x * per), b1 = min(nb, b0 + per);
             double s = 0.0;
             for (uint32_t b = b0; b < b1; b++) s = __dadd_rn(s, blocksum[b]);
-            sh[threadIdx.x] = s;
-            __syncthreads();
-            __shared__ uint32_t s_block;
-            __shared__ double s_cost;
-            if (threadIdx.x == 0) {
-                double cost = run; uint32_t chunk = 1024;
-                for (uint32_t c = 0; c < 1024; c++) {
-                    double nxt = __dadd_rn(cost, sh[c]);
-                    if (nxt >= cutoff && min(nb, c * per) < nb) { chunk = c; break; }
-                    cost = nxt;
-                }
-                uint32_t blk = nb;  // not found -> clamp
-                if (chunk < 1024) {
-                    const uint32_t cb0 = chunk * per, cb1 = min(nb, cb0 + per);
-                    blk = cb1 - 1;
-                    for (uint32_t b = cb0; b < cb1; b++) {
-                        double nxt = __dadd_rn(cost, blocksum[b]);
+            double excl = 0.0;
+            const uint32_t chunk = first_reaching(s, b0 < nb, run, &excl);
+            if (threadIdx.x == (chunk < 1024u ? chunk : 0u)) {
+                uint32_t blk = nb;                                  // not found -> clamp to the last row
+                double cost = excl;
+                if (chunk < 1024u) {
+                    blk = b1 - 1;
+                    for (uint32_t b = b0; b < b1; b++) {
+                        const double nxt = __dadd_rn(cost, blocksum[b]);
                         if (nxt >= cutoff) { blk = b; break; }
                         cost = nxt;
                     }
@@ -338,17 +621,9 @@ kpp_select_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, uint64_t row_
             } else {
                 const uint64_t r0 = (uint64_t)blk * kKppBlockRows;
                 const uint32_t cnt = (uint32_t)min((uint64_t)kKppBlockRows, n - r0);
-                __syncthreads();
-                if (threadIdx.x < cnt) sh[threadIdx.x] = mind[r0 + threadIdx.x];
-                __syncthreads();
-                if (threadIdx.x == 0) {
-                    double cost = s_cost; long long pick = (long long)(r0 + cnt - 1);
-                    for (uint32_t i = 0; i < cnt; i++) {
-                        cost = __dadd_rn(cost, sh[i]);
-                        if (cost >= cutoff) { pick = (long long)(r0 + i); break; }
-                    }
-                    s_local = pick;
-                }
+                const double v = threadIdx.x < cnt ? mind[r0 + threadIdx.x] : 0.0;
+                const uint32_t hit = first_reaching(v, threadIdx.x < cnt, s_cost, &excl);
+                if (threadIdx.x == 0) s_local = (long long)(r0 + (hit < cnt ? hit : cnt - 1));
             }
         }
     }
@@ -687,9 +962,62 @@ static int kpp_refresh_t(sckm_dataset* ds, uint32_t label, bool first_pass, bool
     return SCKM_OK;
 }
 
-int launch_kpp_refresh(sckm_dataset* ds, uint32_t label, bool first_pass, bool prune) {
-    return ds->dtype == SCKM_F32 ? kpp_refresh_t<float>(ds, label, first_pass, prune)
-                                 : kpp_refresh_t<double>(ds, label, first_pass, prune);
+template <typename T>
+static int kpp_pass_t(sckm_dataset* ds, uint32_t label, bool first_pass, bool prune, bool want_sums) {
+    sckm_ctx* ctx = ds->ctx;
+    const uint32_t d = (uint32_t)ds->d;
+    const uint32_t row_bytes = d * sizeof(T), pitch16 = slab_pitch16(row_bytes);
+    const size_t cent_bytes = ((size_t)row_bytes + 15) / 16 * 16;
+    const size_t smem = cent_bytes + (size_t)KPP_WARPS * 32 * pitch16 * 16;
+    if (!vec_ok(d, ds->dtype) || smem > (size_t)ctx->smem_optin || ds->n >= 0xFFFFFFFFull || !ctx->d_surv ||
+        getenv("SCKM_KPP_GEN1"))
+        return kpp_refresh_t<T>(ds, label, first_pass, prune);          // first-generation single kernel
+    const uint32_t nb = (uint32_t)((ds->n + kKppBlockRows - 1) / kKppBlockRows);
+    if (ds->n) {
+        const uint32_t ntab = prune && !first_pass ? label : 0;
+        const uint32_t* surv = nullptr;
+        const bool screen = ds->kpp_shadow != nullptr;
+        if (ntab) {
+            SCKM_CUDA(ctx, cudaMemsetAsync(ctx->d_kppctr, 0, sizeof(unsigned), ctx->stream));
+            const unsigned grid = (unsigned)((ds->n + KPPA_THREADS * KPPA_ITERS - 1) / (KPPA_THREADS * KPPA_ITERS));
+            const size_t psmem = (size_t)ntab * sizeof(double) + (screen ? (size_t)d * sizeof(float) : 0);
+            const uint32_t nv8 = screen ? d / 8 : 0;
+            auto prune_kern = nv8 == 1 ? kpp_prune_kernel<1> : nv8 == 2 ? kpp_prune_kernel<2> : nv8 == 4 ? kpp_prune_kernel<4>
+                            : nv8 == 8 ? kpp_prune_kernel<8> : nv8 == 16 ? kpp_prune_kernel<16> : kpp_prune_kernel<0>;
+            SCKM_TRY(set_smem(ctx, prune_kern, psmem));
+            // rounding of the reference's own distance: (d+2) ulp of TX arithmetic, with two orders of magnitude to spare
+            const double margin = (ds->dtype == SCKM_F32 ? 1.2e-7 : 2.3e-16) * 100.0 * (double)(d + 2);
+            prune_kern<<<grid, KPPA_THREADS, psmem, ctx->stream>>>(ds->mind, ds->labels, ds->n, ctx->d_skiptab, ntab,
+                ctx->d_surv, ctx->d_kppctr, screen ? ds->kpp_shadow : nullptr, ds->kpp_shadow_err, ctx->d_tshift,
+                ctx->d_tshift_err, d, margin);
+            LAUNCH_CHECK(ctx);
+            surv = ctx->d_surv;
+        }
+        SCKM_TRY(set_smem(ctx, kpp_compute_kernel<T>, smem));
+        int per_sm = 0;
+        SCKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kpp_compute_kernel<T>, KPP_WARPS * 32, smem));
+        const uint64_t groups = (ds->n + KPP_WARPS * 32 - 1) / (KPP_WARPS * 32);
+        const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(groups, (uint64_t)ctx->num_sms * std::max(per_sm, 1)));
+        kpp_compute_kernel<T><<<grid, KPP_WARPS * 32, smem, ctx->stream>>>((const T*)ds->x, ds->n, d, (const T*)ctx->d_seedrow,
+            ds->mind, ds->labels, label, first_pass ? 1 : 0, surv, ctx->d_kppctr, pitch16,
+            first_pass ? ds->kpp_shadow : nullptr, ds->kpp_shadow_err);
+        LAUNCH_CHECK(ctx);
+    }
+    if (want_sums) {
+        if (nb) {
+            kpp_blocksum_kernel<<<(nb + 7) / 8, 256, 0, ctx->stream>>>(ds->mind, ds->n, nb, ctx->d_blocksum, ctx->d_totals,
+                                                                       ctx->rank, ctx->d_kppctr + 1);
+        } else {
+            kpp_total_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_blocksum, 0, ctx->d_totals, ctx->rank);
+        }
+        LAUNCH_CHECK(ctx);
+    }
+    return SCKM_OK;
+}
+
+int launch_kpp_refresh(sckm_dataset* ds, uint32_t label, bool first_pass, bool prune, bool want_sums) {
+    return ds->dtype == SCKM_F32 ? kpp_pass_t<float>(ds, label, first_pass, prune, want_sums)
+                                 : kpp_pass_t<double>(ds, label, first_pass, prune, want_sums);
 }
 
 // remember the seed just published (slot) and build the pruning table against all earlier seeds
@@ -700,10 +1028,12 @@ int launch_kpp_seedtab(sckm_dataset* ds, uint32_t slot) {
     // (eps = 2^-24 for f32 element arithmetic, 2^-53 for f64), so leave orders of magnitude of slack
     if (ds->dtype == SCKM_F32)
         kpp_seedtab_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float*)ctx->d_seedrow, (float*)ctx->d_seedtab,
-                                                              (uint32_t)ds->d, slot, ctx->d_skiptab, 1e-3);
+                                                              (uint32_t)ds->d, slot, ctx->d_skiptab, 1e-3,
+                                                              ds->kpp_shadow ? ctx->d_tshift : nullptr, ctx->d_tshift_err);
     else
         kpp_seedtab_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double*)ctx->d_seedrow, (double*)ctx->d_seedtab,
-                                                               (uint32_t)ds->d, slot, ctx->d_skiptab, 1e-9);
+                                                               (uint32_t)ds->d, slot, ctx->d_skiptab, 1e-9,
+                                                               ds->kpp_shadow ? ctx->d_tshift : nullptr, ctx->d_tshift_err);
     LAUNCH_CHECK(ctx);
     return SCKM_OK;
 }

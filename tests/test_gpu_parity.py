@@ -42,6 +42,32 @@ def test_kmeanspp_bit_exact(ctx, O, n, d, k, dtype):
     ds.close()
 
 
+@pytest.mark.parametrize("n,d,k,dtype,offset,scale", [
+    (20000, 16, 24, np.float64, 0.0, 1.0), (20000, 64, 40, np.float64, 0.0, 1.0), (30000, 32, 33, np.float32, 0.0, 1.0),
+    (12000, 8, 16, np.float64, 1e4, 1.0),       # far from the origin: bf16 keeps ~3 digits of (x - seed0), not of x
+    (12000, 24, 16, np.float32, -300.0, 0.01),  # tight clusters, f32 element arithmetic
+    (9000, 128, 12, np.float64, 5.0, 1e-3), (5000, 16, 64, np.float32, 0.0, 1e3), (4100, 40, 9, np.float64, 1e8, 1.0)])
+def test_kmeanspp_pruned_passes_bit_exact(ctx, O, n, d, k, dtype, offset, scale, monkeypatch):
+    """The pruned passes (triangle test, bf16-shadow screening, compacted exact pass) must leave every D^2, label and
+    seed exactly as the reference's full passes do -- also when the screening bound is weak (large offsets), tight
+    (tiny spreads), or meets duplicate rows (zero distances)."""
+    x = (blobs(n, d, k, 11 * n + d, np.float64, spread=3.0) * scale + offset).astype(dtype)
+    x[100:120] = x[7]                                   # duplicates of a row
+    first, u = cluster.kmeanspp_draws(77, n, k)
+    y_o, idx_o, dd_o = O.kmeanspp(x, k, seed=77)
+    for env in ({}, {"SCKM_KPP_NOSHADOW": "1"}, {"SCKM_KPP_GEN1": "1"}, {"SCKM_KPP_NOPRUNE": "1"}):
+        for key in ("SCKM_KPP_NOSHADOW", "SCKM_KPP_GEN1", "SCKM_KPP_NOPRUNE"):
+            monkeypatch.delenv(key, raising=False)
+        for key, val in env.items():
+            monkeypatch.setenv(key, val)
+        ds = ctx.upload(x)
+        seeds = ds.kmeanspp(k, first, u)
+        assert seeds.tolist() == idx_o.tolist(), env
+        assert np.array_equal(ds.labels(), y_o.astype(np.uint64)), env
+        assert np.array_equal(ds.mindist(), dd_o), env
+        ds.close()
+
+
 def test_kmeanspp_injected_rows_and_iris(ctx, O, iris_f32):
     x = iris_f32[0]
     inj = np.array([7, 77, 140, 3])

@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <algorithm>
 #include <cstdlib>
+#include <chrono>
 
 namespace sckm {
 const char* create_error_text();
@@ -272,7 +273,11 @@ int sckm_kmeanspp(sckm_dataset* ds, uint64_t k, uint64_t first_index, const doub
             if (inject_rows[j] < 0 || (uint64_t)inject_rows[j] >= ds->n_global)
                 return fail(ctx, SCKM_ERR_INVALID, "inject_rows[%llu] out of range", (unsigned long long)j);
     SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool trace = getenv("SCKM_TRACE") != nullptr;     // host-side phase times on stderr (diagnostics)
+    auto now = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     SCKM_TRY(ensure_kpp(ds, k));
+    const double t1 = now();
     const size_t seed_words = ctx->cap_seedrow / 8;
     // seed 0: the row drawn by gen_range (kmeans.rs:358-362)
     SCKM_TRY(launch_kpp_select(ds, 0.0, inject_rows ? inject_rows[0] : (int64_t)first_index, 0));
@@ -290,6 +295,7 @@ int sckm_kmeanspp(sckm_dataset* ds, uint64_t k, uint64_t first_index, const doub
             kpp_shadow_free(ds);
         }
     }
+    const double t2 = now();
     SCKM_TRY(launch_kpp_seedtab(ds, 0));
     for (uint64_t j = 1; j < k; j++) {
         SCKM_TRY(launch_kpp_refresh(ds, (uint32_t)(j - 1), j == 1, prune));
@@ -303,8 +309,13 @@ int sckm_kmeanspp(sckm_dataset* ds, uint64_t k, uint64_t first_index, const doub
         if (ctx->nranks > 1) SCKM_TRY(nccl_allreduce_u64(ctx, (unsigned long long*)ctx->d_seeds, k));
         SCKM_CUDA(ctx, cudaMemcpyAsync(seed_rows_out, ctx->d_seeds, k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     }
+    const double t3 = now();
     SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    const double t4 = now();
     kpp_shadow_free(ds);
+    if (trace)
+        fprintf(stderr, "[sckm] kmeans++ k=%llu: workspaces %.2f ms, seed0+shadow alloc %.2f ms, enqueue %.2f ms, drain %.2f ms, shadow free %.2f ms\n",
+                (unsigned long long)k, t1 - t0, t2 - t1, t3 - t2, t4 - t3, now() - t4);
     ds->have_labels = true;
     return SCKM_OK;
 }

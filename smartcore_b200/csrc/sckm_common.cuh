@@ -65,7 +65,7 @@ struct sckm_ctx {
     double* h_pinned = nullptr;      // small pinned scratch (>= 64 doubles)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     cudaStream_t copy_stream = nullptr;      // transfers that must not queue behind the kernels on `stream`
-    sckm::StagePool* stage_pool = nullptr;   // created on the first large transfer from/to pageable memory
+    sckm::StagePool* stage_pool = nullptr;   // pinned ring for transfers from/to pageable memory (lanes pinned on first use)
 };
 
 struct sckm_dataset {

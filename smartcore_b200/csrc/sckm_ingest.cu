@@ -5,7 +5,8 @@
 // DMA'd directly; a plain cudaMemcpy bounces it through one driver-owned staging buffer on ONE host thread
 // (measured 7-12 GB/s on the B200 box), far below what PCIe Gen5 x16 delivers from pinned memory (~53 GB/s).
 //
-// Engine: T host threads, each with its own CUDA stream and two pinned 4 MiB buffers.  Thread t takes chunks
+// Engine: T <= 8 host threads (one per 16 MB of the transfer), each with its own CUDA stream and two pinned 4 MiB
+// buffers, pinned by that thread on first use.  Thread t takes chunks
 // t, t+T, t+2T, ... of the transfer; for every chunk it memcpy()s pageable -> pinned (host DRAM bandwidth, in
 // parallel across threads) and queues the DMA pinned -> device on its stream, reusing a buffer only after the event
 // of its previous DMA has completed.  Device -> host runs the same ring backwards.  Pinned or registered caller
@@ -56,21 +57,25 @@ static int pool_threads() {
     return (int)std::max(2u, std::min<unsigned>(kMaxThreads, hc ? hc / 2 : 4));
 }
 
+// lanes are pinned on first use, by the thread that drives them: a label download of a few tens of MB pins one lane
+// (8 MiB, a few ms), a multi-GB upload pins all of them in parallel
+static bool lane_ready(Lane& l) {
+    if (l.stream) return true;
+    bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess;
+    for (int b = 0; b < 2 && ok; b++)
+        ok = cudaHostAlloc(&l.buf[b], kChunk, cudaHostAllocDefault) == cudaSuccess &&
+             cudaEventCreateWithFlags(&l.ev[b], cudaEventDisableTiming) == cudaSuccess;
+    if (!ok) cudaGetLastError();
+    return ok;
+}
+
 static StagePool* get_pool(sckm_ctx* ctx) {
-    if (ctx->stage_pool) return ctx->stage_pool;
-    StagePool* p = new StagePool();
-    p->device = ctx->device;
-    p->nthreads = pool_threads();
-    for (int t = 0; t < p->nthreads; t++) {
-        Lane& l = p->lane[t];
-        bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess;
-        for (int b = 0; b < 2 && ok; b++)
-            ok = cudaHostAlloc(&l.buf[b], kChunk, cudaHostAllocDefault) == cudaSuccess &&
-                 cudaEventCreateWithFlags(&l.ev[b], cudaEventDisableTiming) == cudaSuccess;
-        if (!ok) { cudaGetLastError(); delete p; return nullptr; }
+    if (!ctx->stage_pool) {
+        ctx->stage_pool = new StagePool();
+        ctx->stage_pool->device = ctx->device;
+        ctx->stage_pool->nthreads = pool_threads();
     }
-    ctx->stage_pool = p;
-    return p;
+    return ctx->stage_pool;
 }
 
 void ingest_destroy(sckm_ctx* ctx) {
@@ -108,11 +113,13 @@ static int staged_copy(sckm_ctx* ctx, void* dst, const void* src, size_t bytes, 
         return SCKM_OK;
     }
     const size_t nchunks = (bytes + kChunk - 1) / kChunk;
-    const int T = (int)std::min<size_t>((size_t)pool->nthreads, nchunks);
+    // one thread per 16 MB, so that small transfers do not pay for pinning lanes they cannot keep busy
+    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)pool->nthreads, bytes / ((size_t)16 << 20)));
     std::atomic<int> err{(int)cudaSuccess};
     auto work = [&](int t) {
         Lane& l = pool->lane[t];
         cudaError_t e = cudaSetDevice(pool->device);
+        if (e == cudaSuccess && !lane_ready(l)) e = cudaErrorMemoryAllocation;
         int slot = 0;
         bool used[2] = {false, false};
         size_t pend_off[2] = {0, 0}, pend_len[2] = {0, 0};

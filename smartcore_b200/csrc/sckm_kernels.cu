@@ -993,9 +993,13 @@ static int kpp_pass_t(sckm_dataset* ds, uint32_t label, bool first_pass, bool pr
             LAUNCH_CHECK(ctx);
             surv = ctx->d_surv;
         }
-        SCKM_TRY(set_smem(ctx, kpp_compute_kernel<T>, smem));
-        int per_sm = 0;
-        SCKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kpp_compute_kernel<T>, KPP_WARPS * 32, smem));
+        static thread_local size_t cached_smem = 0;              // one attribute + occupancy query per shape, not per pass
+        static thread_local int per_sm = 0;
+        if (cached_smem != smem || per_sm == 0) {
+            SCKM_TRY(set_smem(ctx, kpp_compute_kernel<T>, smem));
+            SCKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kpp_compute_kernel<T>, KPP_WARPS * 32, smem));
+            cached_smem = smem;
+        }
         const uint64_t groups = (ds->n + KPP_WARPS * 32 - 1) / (KPP_WARPS * 32);
         const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>(groups, (uint64_t)ctx->num_sms * std::max(per_sm, 1)));
         kpp_compute_kernel<T><<<grid, KPP_WARPS * 32, smem, ctx->stream>>>((const T*)ds->x, ds->n, d, (const T*)ctx->d_seedrow,

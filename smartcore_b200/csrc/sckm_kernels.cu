@@ -994,8 +994,9 @@ static int kpp_pass_t(sckm_dataset* ds, uint32_t label, bool first_pass, bool pr
             surv = ctx->d_surv;
         }
         static thread_local size_t cached_smem = 0;              // one attribute + occupancy query per shape, not per pass
-        static thread_local int per_sm = 0;
-        if (cached_smem != smem || per_sm == 0) {
+        static thread_local int per_sm = 0, cached_dev = -1;     // (function attributes are per device)
+        if (cached_smem != smem || per_sm == 0 || cached_dev != ctx->device) {
+            cached_dev = ctx->device;
             SCKM_TRY(set_smem(ctx, kpp_compute_kernel<T>, smem));
             SCKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kpp_compute_kernel<T>, KPP_WARPS * 32, smem));
             cached_smem = smem;

@@ -56,6 +56,12 @@ int sckm_ctx_create(int device, sckm_ctx** out) {
         sckm_ctx_destroy(ctx); return rc; } } while (0)
     CREATE_CUDA(cudaSetDevice(device));
     CREATE_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    {   // stream-ordered pool of this device: never hand freed blocks back to the driver behind our back (see dev_alloc)
+        cudaMemPool_t pool = nullptr;
+        unsigned long long keep = ~0ull;
+        CREATE_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+        CREATE_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    }
     CREATE_CUDA(cudaEventCreate(&ctx->ev0));
     CREATE_CUDA(cudaEventCreate(&ctx->ev1));
     CREATE_CUDA(cudaMalloc((void**)&ctx->d_flags, 64));
@@ -74,6 +80,7 @@ void sckm_ctx_destroy(sckm_ctx* ctx) {
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     nccl_destroy(ctx);
     ingest_destroy(ctx);
+    if (ctx->stream) dev_pool_trim(ctx);
     cudaFree(ctx->d_centroids); cudaFree(ctx->d_cnorm); cudaFree(ctx->d_packed); cudaFree(ctx->d_partials);
     cudaFree(ctx->d_size); cudaFree(ctx->d_blocksum); cudaFree(ctx->d_totals); cudaFree(ctx->d_seedrow);
     cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_surv); cudaFree(ctx->d_kppctr); cudaFree(ctx->d_tshift); cudaFree(ctx->d_tshift_err); cudaFree(ctx->d_flush); cudaFree(ctx->d_tc5);
@@ -121,9 +128,9 @@ static int dataset_alloc(sckm_ctx* ctx, uint64_t n, uint64_t d, int dtype, uint6
     ds->ctx = ctx; ds->n = n; ds->d = d; ds->dtype = dtype; ds->row_offset = row_offset; ds->n_global = n_global;
     const size_t nn = std::max<uint64_t>(n, 1);
     cudaError_t e;
-    if ((e = cudaMalloc(&ds->x, nn * d * ds->elem())) != cudaSuccess ||
-        (e = cudaMalloc((void**)&ds->labels, nn * sizeof(uint32_t))) != cudaSuccess ||
-        (e = cudaMalloc((void**)&ds->mind, nn * sizeof(double))) != cudaSuccess) {
+    if ((e = dev_alloc(ctx, &ds->x, nn * d * ds->elem())) != cudaSuccess ||
+        (e = dev_alloc(ctx, (void**)&ds->labels, nn * sizeof(uint32_t))) != cudaSuccess ||
+        (e = dev_alloc(ctx, (void**)&ds->mind, nn * sizeof(double))) != cudaSuccess) {
         sckm_dataset_destroy(ds);
         return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc for %llu x %llu dataset failed: %s", (unsigned long long)n,
                     (unsigned long long)d, cudaGetErrorString(e));
@@ -146,14 +153,13 @@ int sckm_dataset_upload(sckm_ctx* ctx, const void* host, uint64_t n_local, uint6
         } else {
             // from_2d_array's layout (matrix.rs:215-237): land the column-major image, transpose on the device
             void* tmp = nullptr;
-            if (cudaMalloc(&tmp, bytes) != cudaSuccess) {
-                cudaGetLastError();
+            if (dev_alloc(ctx, &tmp, bytes) != cudaSuccess) {
                 rc = fail(ctx, SCKM_ERR_CUDA, "cudaMalloc of the %zu-byte column-major staging image failed", bytes);
             }
             if (rc == SCKM_OK) rc = copy_to_device(ctx, tmp, host, bytes);
             if (rc == SCKM_OK) rc = launch_transpose(ctx, tmp, ds->x, n_local, d, dtype);
+            dev_free(ctx, tmp);
             cudaStreamSynchronize(ctx->stream);
-            cudaFree(tmp);
         }
     }
     if (rc != SCKM_OK) { sckm_dataset_destroy(ds); return rc; }
@@ -200,14 +206,19 @@ int sckm_dataset_download_rows(sckm_dataset* ds, uint64_t local_row0, uint64_t n
 void sckm_dataset_destroy(sckm_dataset* ds) {
     if (!ds) return;
     if (ds->ctx) { cudaSetDevice(ds->ctx->device); cudaStreamSynchronize(ds->ctx->stream); }
-    cudaFree(ds->x); cudaFree(ds->labels); cudaFree(ds->mind); cudaFree(ds->labels64); cudaFree(ds->x32); cudaFree(ds->kpp_shadow); cudaFree(ds->kpp_shadow_err);
+    if (ds->ctx) {
+        sckm_ctx* c = ds->ctx;
+        dev_free(c, ds->x); dev_free(c, ds->labels); dev_free(c, ds->mind); dev_free(c, ds->labels64); dev_free(c, ds->x32);
+        dev_free(c, ds->kpp_shadow); dev_free(c, ds->kpp_shadow_err);
+        cudaStreamSynchronize(c->stream);
+    }
     delete ds;
 }
 
 // ---- kmeans++ -----------------------------------------------------------------------------
 static void kpp_shadow_free(sckm_dataset* ds) {
-    if (ds->kpp_shadow) cudaFree(ds->kpp_shadow);
-    if (ds->kpp_shadow_err) cudaFree(ds->kpp_shadow_err);
+    dev_free(ds->ctx, ds->kpp_shadow);
+    dev_free(ds->ctx, ds->kpp_shadow_err);
     ds->kpp_shadow = nullptr; ds->kpp_shadow_err = nullptr;
 }
 
@@ -222,7 +233,7 @@ static int ensure_kpp(sckm_dataset* ds, uint64_t k) {
     }
     if (ds->n > ctx->cap_surv && ds->n < 0xFFFFFFFFull) {
         if (ctx->d_surv) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_surv); ctx->d_surv = nullptr; ctx->cap_surv = 0; }
-        SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_surv, ds->n * sizeof(uint32_t)));
+        SCKM_CUDA(ctx, ws_malloc(ctx, (void**)&ctx->d_surv, ds->n * sizeof(uint32_t)));
         ctx->cap_surv = ds->n;
     }
     if (!ctx->d_kppctr) {
@@ -289,9 +300,8 @@ int sckm_kmeanspp(sckm_dataset* ds, uint64_t k, uint64_t first_index, const doub
     // build, memory permitting): see kpp_prune_kernel.  Absent shadow = exact path only, same results.
     kpp_shadow_free(ds);
     if (prune && k >= 8 && ds->d % 8 == 0 && ds->n && ds->n < 0xFFFFFFFFull && !getenv("SCKM_KPP_NOSHADOW")) {
-        if (cudaMalloc((void**)&ds->kpp_shadow, ds->n * ds->d * sizeof(uint16_t)) != cudaSuccess ||
-            cudaMalloc((void**)&ds->kpp_shadow_err, ds->n * sizeof(float)) != cudaSuccess) {
-            cudaGetLastError();
+        if (dev_alloc(ctx, (void**)&ds->kpp_shadow, ds->n * ds->d * sizeof(uint16_t)) != cudaSuccess ||
+            dev_alloc(ctx, (void**)&ds->kpp_shadow_err, ds->n * sizeof(float)) != cudaSuccess) {
             kpp_shadow_free(ds);
         }
     }
@@ -473,7 +483,7 @@ static int download_labels(sckm_dataset* ds, void* out, int width) {
         return copy_to_host(ctx, out, ds->labels, n * 4);
     }
     if (width != 8) return fail(ctx, SCKM_ERR_INVALID, "label width must be 4 or 8");
-    if (!ds->labels64) SCKM_CUDA(ctx, cudaMalloc((void**)&ds->labels64, std::max<uint64_t>(n, 1) * 8));
+    if (!ds->labels64) SCKM_CUDA(ctx, dev_alloc(ctx, (void**)&ds->labels64, std::max<uint64_t>(n, 1) * 8));
     SCKM_TRY(launch_labels_widen(ctx, ds->labels, ds->labels64, n));
     return copy_to_host(ctx, out, ds->labels64, n * 8);
 }
@@ -523,8 +533,7 @@ int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int 
     void* cm_tmp = nullptr;                                   // column-major image of one chunk
     int rc = dataset_alloc(ctx, chunk_rows, d, dtype, 0, chunk_rows, &buf[0]);
     if (rc == SCKM_OK && nchunks > 1) rc = dataset_alloc(ctx, chunk_rows, d, dtype, 0, chunk_rows, &buf[1]);
-    if (rc == SCKM_OK && column_major && cudaMalloc(&cm_tmp, chunk_rows * row_bytes) != cudaSuccess) {
-        cudaGetLastError();
+    if (rc == SCKM_OK && column_major && dev_alloc(ctx, &cm_tmp, chunk_rows * row_bytes) != cudaSuccess) {
         rc = fail(ctx, SCKM_ERR_CUDA, "cudaMalloc of the column-major staging image failed");
     }
     if (rc == SCKM_OK) rc = ensure_workspace(ctx, k, d, 0);
@@ -543,6 +552,7 @@ int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int 
                                          cudaMemcpyHostToDevice, ctx->stream));
         return launch_transpose(ctx, cm_tmp, ds->x, rows, d, dtype);
     };
+    ctx->ingest_hint = (size_t)n * row_bytes;                 // the chunks belong to one transfer of this size
     if (rc == SCKM_OK) rc = upload(0, true);
     for (uint64_t c = 0; c < nchunks && rc == SCKM_OK; c++) {
         sckm_dataset* ds = buf[c & 1];
@@ -550,8 +560,9 @@ int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int 
         if (rc == SCKM_OK && c + 1 < nchunks) rc = upload(c + 1, false);      // other buffer: idle since its labels came back
         if (rc == SCKM_OK) rc = download_labels(ds, (char*)labels_out + c * chunk_rows * (size_t)width, width);
     }
+    ctx->ingest_hint = 0;
+    dev_free(ctx, cm_tmp);
     cudaStreamSynchronize(ctx->stream);
-    cudaFree(cm_tmp);
     sckm_dataset_destroy(buf[0]);
     sckm_dataset_destroy(buf[1]);
     return rc;
@@ -568,11 +579,11 @@ static int contingency_common(sckm_ctx* ctx, const uint32_t* a_host, const uint3
     uint32_t *d_a = nullptr, *d_b2 = nullptr;
     unsigned long long* d_out = nullptr;
     int rc = SCKM_OK;
-    auto cleanup = [&]() { cudaFree(d_a); cudaFree(d_b2); cudaFree(d_out); };
-    if (cudaMalloc((void**)&d_a, std::max<uint64_t>(n, 1) * 4) != cudaSuccess ||
-        cudaMalloc((void**)&d_out, (ncell + 1) * 8) != cudaSuccess ||
-        (!d_b && cudaMalloc((void**)&d_b2, std::max<uint64_t>(n, 1) * 4) != cudaSuccess)) {
-        cudaGetLastError(); cleanup();
+    auto cleanup = [&]() { dev_free(ctx, d_a); dev_free(ctx, d_b2); dev_free(ctx, d_out); };
+    if (dev_alloc(ctx, (void**)&d_a, std::max<uint64_t>(n, 1) * 4) != cudaSuccess ||
+        dev_alloc(ctx, (void**)&d_out, (ncell + 1) * 8) != cudaSuccess ||
+        (!d_b && dev_alloc(ctx, (void**)&d_b2, std::max<uint64_t>(n, 1) * 4) != cudaSuccess)) {
+        cleanup();
         return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc for the contingency table failed");
     }
     rc = copy_to_device(ctx, d_a, a_host, n * 4);

@@ -64,6 +64,7 @@ struct sckm_ctx {
     size_t flush_bytes = 0;
     double* h_pinned = nullptr;      // small pinned scratch (>= 64 doubles)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    size_t ingest_hint = 0;                  // bytes the current multi-transfer operation will move in total (0 = unknown)
     cudaStream_t copy_stream = nullptr;      // transfers that must not queue behind the kernels on `stream`
     sckm::StagePool* stage_pool = nullptr;   // pinned ring for transfers from/to pageable memory (lanes pinned on first use)
 };
@@ -87,6 +88,35 @@ struct sckm_dataset {
 namespace sckm {
 
 int fail(sckm_ctx* ctx, int code, const char* fmt, ...);
+
+// Transient device buffers (datasets, staging images, the kmeans++ shadow) come from the device's stream-ordered
+// memory pool, configured at context creation to KEEP what is freed: releasing a multi-GB block to the driver and
+// mapping it again on the next fit costs anything from 1 to 500 ms on this box (measured: cudaFree of the 1.3 GB
+// shadow), stream-ordered frees are microseconds.  Allocation and release are ordered on ctx->stream.
+inline cudaError_t dev_alloc(sckm_ctx* ctx, void** p, size_t bytes) {
+    *p = nullptr;
+    cudaError_t e = cudaMallocAsync(p, bytes ? bytes : 1, ctx->stream);
+    if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; }
+    return e;
+}
+inline void dev_free(sckm_ctx* ctx, void* p) {
+    if (p) cudaFreeAsync(p, ctx->stream);
+}
+// hand the pool's idle blocks back to the driver (context teardown; a plain cudaMalloc that ran out of memory)
+inline void dev_pool_trim(sckm_ctx* ctx) {
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, ctx->device) == cudaSuccess) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemPoolTrimTo(pool, 0);
+    }
+    cudaGetLastError();
+}
+// long-lived workspaces use plain cudaMalloc; if that fails while the pool sits on idle memory, trim and retry once
+inline cudaError_t ws_malloc(sckm_ctx* ctx, void** p, size_t bytes) {
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e == cudaErrorMemoryAllocation) { cudaGetLastError(); dev_pool_trim(ctx); e = cudaMalloc(p, bytes); }
+    return e;
+}
 
 #define SCKM_CUDA(ctx, call)                                                               \
     do {                                                                                   \

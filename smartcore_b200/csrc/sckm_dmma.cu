@@ -591,6 +591,83 @@ int launch_assign_dmma(sckm_dataset* ds, uint64_t k) {
     return ds->dtype == SCKM_F32 ? launch_by_d<true, float>(ds, k, pk) : launch_by_d<true, double>(ds, k, pk);
 }
 
+// ---- per-label sums and counts for GIVEN labels (initial centroids, kmeans.rs:275-292) at HBM rate ----
+// Same row -> lane mapping and the same deterministic warp-private accumulation as the fused update of the tile
+// kernel (rows of an m-tile that share a label are serialised in ascending row order), without any distance work.
+template <int KSTEPS, int MT, int DMMA_WARPS, typename TX>
+__global__ void __launch_bounds__(DMMA_WARPS * 32)
+update_given_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, uint32_t k, const uint32_t* __restrict__ labels,
+                    double* __restrict__ partials, size_t pk) {
+    constexpr int ROWS = 8 * MT;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const uint64_t nslabs = (n + ROWS - 1) / ROWS;
+    const uint64_t stride = (uint64_t)gridDim.x * DMMA_WARPS;
+    double* part = partials + ((size_t)blockIdx.x * DMMA_WARPS + warp) * ((pk + 15) / 16 * 16);
+    unsigned lanemask_lt;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanemask_lt));
+    for (uint64_t slab = (uint64_t)blockIdx.x * DMMA_WARPS + warp; slab < nslabs; slab += stride) {
+        const uint64_t r0 = slab * ROWS;
+        double a[MT][KSTEPS];
+        uint32_t lab[MT];
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const uint64_t row = r0 + mt * 8 + g;
+            const bool rok = row < n;
+            const TX* xr = x + row * d;
+            lab[mt] = rok ? labels[row] : 0xffffffffu;
+#pragma unroll
+            for (int ks = 0; ks < KSTEPS; ks++) {
+                const uint32_t col = ks * 4 + t;
+                a[mt][ks] = (rok && col < d) ? (double)__ldg(xr + col) : 0.0;
+            }
+        }
+#pragma unroll
+        for (int mt = 0; mt < MT; mt++) {
+            const bool ok = lab[mt] < k;                        // rows past the end and labels outside [0,k) add nothing
+            const uint32_t key = ok ? lab[mt] : (0x80000000u | (uint32_t)g);
+            const unsigned peers = __match_any_sync(0xffffffffu, key);
+            const int rank = __popc(peers & lanemask_lt) >> 2;
+            const int maxrank = __reduce_max_sync(0xffffffffu, ok ? rank : 0);
+            for (int r = 0; r <= maxrank; r++) {
+                if (r) { __threadfence(); __syncwarp(); }
+                if (ok && rank == r) {
+                    double* p = part + (size_t)lab[mt] * d + t;
+#pragma unroll
+                    for (int ks = 0; ks < KSTEPS; ks++)
+                        if (ks * 4 + t < d) atomicAdd(p + ks * 4, a[mt][ks]);
+                    if (t == 0) atomicAdd(part + (size_t)k * d + lab[mt], 1.0);
+                }
+            }
+        }
+    }
+}
+
+bool update_given_supported(const sckm_dataset* ds, uint64_t k) { return ds->d >= 4 && ds->d <= 128 && k >= 1; }
+
+template <int KSTEPS, typename TX>
+static int update_given_t(sckm_dataset* ds, uint64_t k, size_t pk) {
+    sckm_ctx* ctx = ds->ctx;
+    constexpr int WARPS = 12, MT = 2;
+    update_given_kernel<KSTEPS, MT, WARPS, TX><<<dmma_grid(ctx), WARPS * 32, 0, ctx->stream>>>(
+        (const TX*)ds->x, ds->n, (uint32_t)ds->d, (uint32_t)k, ds->labels, ctx->d_partials, pk);
+    LAUNCH_CHECK_D(ctx);
+    return launch_reduce_partials(ctx, dmma_grid(ctx) * WARPS, pk);
+}
+
+// sums/counts of the dataset's current labels into ctx->d_packed (inertia slot = 0)
+int launch_update_given(sckm_dataset* ds, uint64_t k) {
+    sckm_ctx* ctx = ds->ctx;
+    const size_t pk = (size_t)k * ds->d + k + 1;
+    SCKM_TRY(ensure_workspace(ctx, k, ds->d, dmma_partial_slots(ctx)));
+    const uint64_t d = ds->d;
+    const bool f32 = ds->dtype == SCKM_F32;
+    if (d <= 16) return f32 ? update_given_t<4, float>(ds, k, pk) : update_given_t<4, double>(ds, k, pk);
+    if (d <= 32) return f32 ? update_given_t<8, float>(ds, k, pk) : update_given_t<8, double>(ds, k, pk);
+    if (d <= 64) return f32 ? update_given_t<16, float>(ds, k, pk) : update_given_t<16, double>(ds, k, pk);
+    return f32 ? update_given_t<32, float>(ds, k, pk) : update_given_t<32, double>(ds, k, pk);
+}
+
 // labels only (KMeans::predict at scale): same ranking + exact re-decision of near-ties, no update, no distances.
 // For every row the result equals the exact direct-form argmin (kmeans.rs:334-347).
 int launch_predict_dmma(sckm_dataset* ds, uint64_t k) {

@@ -5,8 +5,8 @@
 // DMA'd directly; a plain cudaMemcpy bounces it through one driver-owned staging buffer on ONE host thread
 // (measured 7-12 GB/s on the B200 box), far below what PCIe Gen5 x16 delivers from pinned memory (~53 GB/s).
 //
-// Engine: T <= 8 host threads (one per 16 MB of the transfer), each with its own CUDA stream and two pinned 4 MiB
-// buffers, pinned by that thread on first use.  Thread t takes chunks
+// Engine: T <= 8 host threads, each with its own CUDA stream and two pinned 4 MiB buffers, pinned by that thread on
+// first use; a transfer gets one lane per 128 MB (pinning is slow, ~1.5 GB/s) plus every lane that is already pinned.  Thread t takes chunks
 // t, t+T, t+2T, ... of the transfer; for every chunk it memcpy()s pageable -> pinned (host DRAM bandwidth, in
 // parallel across threads) and queues the DMA pinned -> device on its stream, reusing a buffer only after the event
 // of its previous DMA has completed.  Device -> host runs the same ring backwards.  Pinned or registered caller
@@ -57,8 +57,7 @@ static int pool_threads() {
     return (int)std::max(2u, std::min<unsigned>(kMaxThreads, hc ? hc / 2 : 4));
 }
 
-// lanes are pinned on first use, by the thread that drives them: a label download of a few tens of MB pins one lane
-// (8 MiB, a few ms), a multi-GB upload pins all of them in parallel
+// lanes are pinned on first use, by the thread that drives them (see the sizing rule in staged_copy)
 static bool lane_ready(Lane& l) {
     if (l.stream) return true;
     bool ok = cudaStreamCreateWithFlags(&l.stream, cudaStreamNonBlocking) == cudaSuccess;
@@ -99,9 +98,21 @@ static int staged_copy(sckm_ctx* ctx, void* dst, const void* src, size_t bytes, 
     if (sync_first) SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     const void* host = to_device ? src : dst;
     const cudaMemcpyKind kind = to_device ? cudaMemcpyHostToDevice : cudaMemcpyDeviceToHost;
+    // Lanes that are already pinned are free to use; pinning a new one costs ~5 ms (8 MiB at ~1.5 GB/s), which only a
+    // lane that will carry >= 128 MB repays -- of this transfer or of the operation it belongs to (ctx->ingest_hint).
+    int T = 0;
     StagePool* pool = nullptr;
-    if (bytes >= kStagedMin && is_pageable(host) && !getenv("SCKM_INGEST_DIRECT")) pool = get_pool(ctx);
-    if (!pool) {
+    if (bytes >= kStagedMin && is_pageable(host) && !getenv("SCKM_INGEST_DIRECT")) {
+        pool = get_pool(ctx);
+        int ready = 0;
+        while (ready < pool->nthreads && pool->lane[ready].stream) ready++;
+        const size_t scope = std::max(bytes, ctx->ingest_hint);
+        const int want = getenv("SCKM_INGEST_FORCE") ? pool->nthreads      // tests: exercise the ring on small arrays
+                         : (int)std::min<size_t>((size_t)pool->nthreads, scope / ((size_t)128 << 20));
+        const size_t nchunks = (bytes + kChunk - 1) / kChunk;
+        T = (int)std::min<size_t>(nchunks, (size_t)std::max(ready, want));
+    }
+    if (T == 0) {
         if (sync_first) {
             SCKM_CUDA(ctx, cudaMemcpyAsync(dst, src, bytes, kind, ctx->stream));
             SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -113,8 +124,6 @@ static int staged_copy(sckm_ctx* ctx, void* dst, const void* src, size_t bytes, 
         return SCKM_OK;
     }
     const size_t nchunks = (bytes + kChunk - 1) / kChunk;
-    // one thread per 16 MB, so that small transfers do not pay for pinning lanes they cannot keep busy
-    const int T = (int)std::max<size_t>(1, std::min<size_t>((size_t)pool->nthreads, bytes / ((size_t)16 << 20)));
     std::atomic<int> err{(int)cudaSuccess};
     auto work = [&](int t) {
         Lane& l = pool->lane[t];

@@ -887,7 +887,7 @@ int fail(sckm_ctx* ctx, int code, const char* fmt, ...) {
 template <typename P> static int regrow(sckm_ctx* ctx, P** p, size_t* cap, size_t need_elems, size_t elem) {
     if (need_elems <= *cap && *p) return SCKM_OK;
     if (*p) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); SCKM_CUDA(ctx, cudaFree(*p)); *p = nullptr; }
-    SCKM_CUDA(ctx, cudaMalloc((void**)p, need_elems * elem));
+    SCKM_CUDA(ctx, ws_malloc(ctx, (void**)p, need_elems * elem));
     SCKM_CUDA(ctx, cudaMemsetAsync(*p, 0, need_elems * elem, ctx->stream));
     *cap = need_elems;
     return SCKM_OK;
@@ -1096,6 +1096,9 @@ int launch_assign_direct(sckm_dataset* ds, uint64_t k) {
     return launch_assign_direct_raw(ds->ctx, ds->x, ds->dtype, ds->n, ds->d, k, ds->labels, ds->mind);
 }
 
+bool update_given_supported(const sckm_dataset* ds, uint64_t k);   // sckm_dmma.cu
+int launch_update_given(sckm_dataset* ds, uint64_t k);             // sckm_dmma.cu
+
 static uint32_t update_slots(const sckm_ctx* ctx, uint64_t n) {
     uint64_t p = (n + 63) / 64;
     uint64_t cap = (uint64_t)ctx->num_sms * 16;
@@ -1107,6 +1110,8 @@ int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia) {
     const uint32_t slots = update_slots(ctx, ds->n);
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, slots));
     const size_t pk = (size_t)k * ds->d + k + 1;
+    if (!with_inertia && ds->n >= 65536 && update_given_supported(ds, k))
+        return launch_update_given(ds, k);                       // HBM-rate path for the initial means of a large fit
     const uint64_t rows_per_cta = (ds->n + slots - 1) / slots;
     const unsigned threads = (unsigned)std::min<uint64_t>(256, (ds->d + 31) / 32 * 32);
     if (ds->n) {
@@ -1125,7 +1130,8 @@ int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia) {
 int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk) {
     const size_t pitch = slot_pitch(pk);
     const unsigned blocks = (unsigned)((pitch / 2 + 31) / 32);
-    if (blocks < (unsigned)ctx->num_sms)   // small payload: more slot groups per block so the few blocks are not latency-bound
+    // small payload, or many slots to walk: more slot groups per block so that enough loads are in flight
+    if (blocks < (unsigned)ctx->num_sms || slots >= 256)
         reduce_partials_kernel<32><<<blocks, dim3(32, 32), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags);
     else
         reduce_partials_kernel<8><<<blocks, dim3(32, 8), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags);

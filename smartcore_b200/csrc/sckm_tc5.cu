@@ -479,7 +479,7 @@ int launch_assign_tc5(sckm_dataset* ds, uint64_t k) {
     const float* x32 = (const float*)ds->x;
     if (ds->dtype == SCKM_F64) {                                      // f32 shadow copy of X for the ranking, built once
         if (!ds->x32) {
-            SCKM_CUDA(ctx, cudaMalloc((void**)&ds->x32, ds->n * ds->d * sizeof(float)));
+            SCKM_CUDA(ctx, dev_alloc(ctx, (void**)&ds->x32, ds->n * ds->d * sizeof(float)));
             tc5_shadow_kernel<<<ctx->num_sms * 8, 256, 0, ctx->stream>>>((const double*)ds->x, ds->x32, ds->n * ds->d);
             LAUNCH_CHECK_T(ctx);
         }

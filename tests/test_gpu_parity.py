@@ -370,8 +370,10 @@ def test_predict_streams_in_chunks(ctx, O, monkeypatch):
         assert np.array_equal(ctx.predict(x, cent, column_major=True, width=4).astype(np.int64), want)
 
 
-def test_pageable_transfers_through_the_pinned_ring(ctx, O):
-    """> 32 MB from/to ordinary (pageable) numpy memory goes through the threaded staging ring in both directions."""
+def test_pageable_transfers_through_the_pinned_ring(ctx, O, monkeypatch):
+    """> 32 MB from/to ordinary (pageable) numpy memory goes through the threaded staging ring in both directions
+    (forced here: by default a lane is only pinned for >= 128 MB of traffic)."""
+    monkeypatch.setenv("SCKM_INGEST_FORCE", "1")
     n, d = 5_000_011, 2                                    # 40 MB of f32 rows, 40 MB of u64 labels; ragged tail chunk
     x = blobs(n, d, 2, 17, np.float32, spread=8.0)
     ds = ctx.upload(x)

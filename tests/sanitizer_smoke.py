@@ -22,6 +22,7 @@ def main():
     cases = [(1500, 16, 8, np.float64, cabi.ASSIGN_STREAM), (1111, 7, 5, np.float32, cabi.ASSIGN_STREAM),
              (2000, 64, 48, np.float64, cabi.ASSIGN_DMMA), (1777, 20, 33, np.float32, cabi.ASSIGN_DMMA),
              (1200, 128, 300, np.float64, cabi.ASSIGN_DMMA),          # streamed centroid blocks
+             (4096, 32, 64, np.float32, cabi.ASSIGN_TC5),              # tcgen05 / TMA / TMEM kernel
              (900, 9, 4, np.float64, cabi.ASSIGN_DIRECT), (700, 40, 6, np.float64, cabi.ASSIGN_DIRECT)]
     for n, d, k, dt, kern in cases:
         x = (rng.normal(size=(n, d)) + 3.0 * rng.integers(0, k, size=(n, 1))).astype(dt)
@@ -34,15 +35,31 @@ def main():
         ctx.set_assign_kernel(kern)
         inertia, sums, counts = ds.lloyd_step(cent)
         ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
-        d_o, s_o, c_o, m_o = O.brute_clustering(x, cent)
-        assert np.array_equal(ds.labels().astype(np.int64), m_o) and counts.tolist() == c_o.tolist()
-        assert abs(inertia - d_o) <= 1e-9 * d_o
+        d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+        bad = np.nonzero(ds.labels().astype(np.int64) != m_o)[0]
+        assert np.all(gap[bad] < (1e-5 if dt == np.float32 else 1e-12))
+        assert len(bad) or counts.tolist() == c_o.tolist()
+        assert abs(inertia - d_o) <= (1e-4 if dt == np.float32 else 1e-9) * d_o
+        table = ds.contingency((np.arange(n) % 5).astype(np.uint32), 5, k)     # counted against the resident labels
+        want = np.zeros((5, k), dtype=np.int64); np.add.at(want, (np.arange(n) % 5, ds.labels().astype(np.int64)), 1)
+        assert np.array_equal(table, want)
         fit = ds.lloyd_fit(cent, 5)
         assert fit["size"].sum() == n
         assert np.array_equal(ctx.predict(x, fit["centroids"]).astype(np.int64), O.predict(x, fit["centroids"]))
         assert np.array_equal(ctx.predict(x, fit["centroids"], column_major=True).astype(np.int64), O.predict(x, fit["centroids"]))
         ds.close()
         print("ok", n, d, k, np.dtype(dt).name, kern, flush=True)
+    # initial means of a larger fit go through the tile-layout update kernel (n >= 65536)
+    g = ctx.generate_blobs(70000, 16, 16, 9)
+    xs = g.download_rows(0, 70000)
+    first, u = cluster.kmeanspp_draws(4, 70000, 16)
+    g.kmeanspp(16, first, u)
+    cent, size = g.init_centroids(16)
+    lab = g.labels().astype(np.int64)
+    for j in range(16):
+        assert size[j] == (lab == j).sum() and np.allclose(cent[j], xs[lab == j].mean(axis=0), rtol=1e-9, atol=1e-9)
+    g.close()
+    print("ok init means 70000x16 k=16", flush=True)
     g = ctx.generate_blobs(3000, 16, 8, 5)
     assert np.array_equal(g.download_rows(10, 20), cabi.blobs_host(10, 20, 16, 8, 5))
     g.close()

@@ -140,8 +140,14 @@ def test_dmma_ties_duplicates_and_exact_refine(ctx, O):
     ds.close()
 
 
-def test_stream_kernel_ties_and_shapes(ctx, O):
-    """Small-k streaming kernel (k < 16): exact ties, odd d (scalar staging path), f32, ragged n."""
+@pytest.mark.parametrize("tma_ring", [False, True])
+def test_stream_kernel_ties_and_shapes(ctx, O, tma_ring, monkeypatch):
+    """Small-k streaming kernel (k < 16): exact ties, odd d (scalar staging path), f32, ragged n; with the rows
+    loaded straight into registers (default) and through the cp.async.bulk ring (SCKM_STREAM_TMA)."""
+    if tma_ring:
+        monkeypatch.setenv("SCKM_STREAM_TMA", "1")
+    else:
+        monkeypatch.delenv("SCKM_STREAM_TMA", raising=False)
     rng = np.random.default_rng(2)
     base = rng.normal(size=(6, 16))
     x = base[rng.integers(0, 6, size=3001)]

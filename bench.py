@@ -315,6 +315,32 @@ def main():
             mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:  # noqa: BLE001
             mp = {}
+        # per-shape roofline: intensity = 2kd / (d*s) flop per byte against a balance of ~6
+        hbm_peak = mp.get("hbm_gbs", 6650.0)
+        hbm_view = {"achieved_gbs": hbm_bytes / t_assign / 1e9, "peak_gbs": hbm_peak,
+                    "peak_source": "MEASURED_PEAKS.json" if mp else "fallback (B200_PROFILING.md)",
+                    "copy_gbs_measured_now": peaks["hbm_copy_gbs"]}
+        intensity = 2.0 * k / esize
+        if intensity < 6.0:
+            roof = {"bound": "hbm", "achieved": hbm_view["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
+                    "frac": hbm_view["achieved_gbs"] / hbm_peak,
+                    "peak_source": hbm_view["peak_source"] + " (copy bandwidth; measured now: %.0f GB/s)" % peaks["hbm_copy_gbs"]}
+        elif args.dtype == "f32":
+            # tcgen05 kind::tf32 runs at half the bf16 rate and the 3xTF32 split issues three MMAs per product
+            tf32x3 = mp.get("bf16_tflops_sustained", 1366.4) / 2.0 / 3.0
+            roof = {"bound": "tensor", "achieved": achieved, "peak": tf32x3, "unit": "TFLOP/s", "frac": achieved / tf32x3,
+                    "peak_source": "3xTF32 roof = sustained dense bf16 of MEASURED_PEAKS.json / 2 (TF32) / 3 (MMAs per product)"}
+        else:
+            roof = {"bound": "tensor", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
+                    "frac": achieved / fp64_peak if fp64_peak else None,
+                    "peak_source": "FP64 peak measured now by the library's DFMA/DMMA micro-kernels (dfma %.1f, dmma %.1f "
+                                   "TFLOP/s); MEASURED_PEAKS.json carries no FP64 figure" % (peaks["fp64_dfma_tflops"], peaks["fp64_dmma_tflops"])}
+        roof.update({
+            "traffic": ncu_traffic_bytes() if (n_local, k, d, args.dtype) == (N_PER_GPU, K_CLUSTERS, D, "f64") else None,
+            "traffic_note": "DRAM read+write bytes of one assignment launch from the committed ncu --set full capture "
+                            "(profiles/ncu_r1_assign_dmma_final_summary.csv); algorithmic bytes per launch = n*(d*s+4) = %.3e" % hbm_bytes,
+            "kernel": "assignment kernel (dominant), CUDA events on the library stream, mean of %d launches" % args.steps,
+            "kernel_ms": 1e3 * t_assign, "flop_per_byte": intensity, "hbm": hbm_view})
         line = {
             "metric": "lloyd_point_iters_per_sec", "value": value, "unit": "point-iters/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_dev / args.steps,
@@ -325,19 +351,7 @@ def main():
                        "n_global": n_global, "d": d, "k": k, "l2": "inputs (5.12 GB/GPU) larger than L2; no flush",
                        "parallelism": "rows sharded x%d, one NCCL all-reduce of k*d+k+1 f64 per step" % world,
                        "kmeanspp_init_s": t_init, "wall_s_timed_region": wall},
-            "roofline": {"bound": "tensor" if k >= 4 * 6 else "hbm", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": achieved / fp64_peak if fp64_peak else None,
-                         "traffic": ncu_traffic_bytes() if (n_local, k, d) == (N_PER_GPU, K_CLUSTERS, D) else None,
-                         "traffic_note": "DRAM read+write bytes of one assignment launch from the committed ncu --set full capture "
-                                         "(profiles/ncu_r1_assign_dmma_final_summary.csv); algorithmic bytes per launch = n*(d*8+4) = %.3e"
-                                         % hbm_bytes,
-                         "kernel": "assignment kernel (dominant), CUDA events on the library stream, mean of %d launches" % args.steps,
-                         "kernel_ms": 1e3 * t_assign,
-                         "peak_source": "FP64 peak measured now by the library's DFMA/DMMA micro-kernels (dfma %.1f, dmma %.1f "
-                                        "TFLOP/s); MEASURED_PEAKS.json carries no FP64 figure" % (peaks["fp64_dfma_tflops"], peaks["fp64_dmma_tflops"]),
-                         "hbm": {"achieved_gbs": hbm_bytes / t_assign / 1e9, "peak_gbs": mp.get("hbm_gbs", 6650.0),
-                                 "peak_source": "MEASURED_PEAKS.json" if mp else "fallback (B200_PROFILING.md)",
-                                 "copy_gbs_measured_now": peaks["hbm_copy_gbs"]}},
+            "roofline": roof,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "tf32_ranked": alt,
         }
         print(json.dumps(line), flush=True)

@@ -217,10 +217,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         const uint64_t row0 = b * 32;
         const int stage = TMA ? (int)(it % (STAGES > 0 ? STAGES : 1)) : 0;
         const TX* stage_rows = TMA ? ring_w + (size_t)stage * 32 * d : nullptr;
-        if (TMA) {
-            s_mbar_wait(&full_bar[warp][stage], (it / (STAGES > 0 ? STAGES : 1)) & 1u);
-            load_rows_smem(stage_rows, row0, full_tag);
-        }
+        // (ring mode: the A fragments of this batch were read out of its ring buffer at the end of the previous turn)
         // ---- scores x.c - ||c||^2/2 on the FP64 tensor path ----
         double acc[4][KT][2];
 #pragma unroll
@@ -247,8 +244,25 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
                 *reinterpret_cast<double2*>(tr + nt * 8 + 2 * t) = make_double2(acc[mt][nt][0], acc[mt][nt][1]);
         }
         __syncwarp();
-        // the A registers are dead now: prefetch the next batch so its HBM latency hides under epilogue + update
+        // the A registers are dead now.  Registers-direct mode: prefetch the next batch into them so its HBM latency
+        // hides under epilogue + update.  Ring mode: read the update's B fragments (this batch's rows again, K = row)
+        // out of the ring buffer now, so that their latency hides under the epilogue instead of stalling the DMMAs.
         if (!TMA && b + nwarps < nbatches) load_any((b + nwarps) * 32);
+        double xbe[TMA ? 8 : 1][NTU];
+        if (TMA) {
+            const TX* ubs = stage_rows + (size_t)t * d + g * VU;
+#pragma unroll
+            for (int ks = 0; ks < 8; ks++)
+#pragma unroll
+                for (int j = 0; j < NTU / VU; j++) {
+                    double v[VU];
+#pragma unroll
+                    for (int e = 0; e < VU; e++) v[e] = 0.0;
+                    if (FULL || row0 + 4 * ks + t < n) VecLoad<TX, VU>::lds(ubs + (size_t)ks * 4 * d + j * 8 * VU, v);
+#pragma unroll
+                    for (int e = 0; e < VU; e++) xbe[ks][j * VU + e] = v[e];
+                }
+        }
         double sc[8 * KT];
         double xn;
         {
@@ -286,27 +300,29 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         if (valid) labels[row0 + lane] = lab;
         // ---- update: sums[cluster][feature] += onehot(label)^T . X as DMMAs accumulating in registers.
         // K dimension = the 32 rows (row 4*ks+t), A = one-hot of the labels, B = the rows again (L1 hits). ----
-        const TX* ub = TMA ? stage_rows + (size_t)t * d + g * VU : x + (row0 + t) * d + g * VU;
+        const TX* ub = x + (row0 + t) * d + g * VU;
 #pragma unroll
         for (int ks = 0; ks < 8; ks++) {
             const uint32_t lr = __shfl_sync(0xffffffffu, lab, 4 * ks + t);
             double xb[NTU];
+            if (TMA) {
 #pragma unroll
-            for (int j = 0; j < NTU / VU; j++) {
-                double v[VU];
-                if (FULL) {
-                    if (TMA) VecLoad<TX, VU>::lds(ub + (size_t)ks * 4 * d + j * 8 * VU, v);
-                    else VecLoad<TX, VU>::ld(ub + (size_t)ks * 4 * d + j * 8 * VU, v);
-                } else {
+                for (int nt = 0; nt < NTU; nt++) xb[nt] = xbe[ks][nt];
+            } else {
 #pragma unroll
-                    for (int e = 0; e < VU; e++) v[e] = 0.0;
-                    if (row0 + 4 * ks + t < n && (uint32_t)(j * 8 * VU + g * VU) < d) {
-                        if (TMA) VecLoad<TX, VU>::lds(ub + (size_t)ks * 4 * d + j * 8 * VU, v);
-                        else VecLoad<TX, VU>::ld(ub + (size_t)ks * 4 * d + j * 8 * VU, v);
+                for (int j = 0; j < NTU / VU; j++) {
+                    double v[VU];
+                    if (FULL) {
+                        VecLoad<TX, VU>::ld(ub + (size_t)ks * 4 * d + j * 8 * VU, v);
+                    } else {
+#pragma unroll
+                        for (int e = 0; e < VU; e++) v[e] = 0.0;
+                        if (row0 + 4 * ks + t < n && (uint32_t)(j * 8 * VU + g * VU) < d)
+                            VecLoad<TX, VU>::ld(ub + (size_t)ks * 4 * d + j * 8 * VU, v);
                     }
-                }
 #pragma unroll
-                for (int e = 0; e < VU; e++) xb[j * VU + e] = v[e];
+                    for (int e = 0; e < VU; e++) xb[j * VU + e] = v[e];
+                }
             }
 #pragma unroll
             for (int ct = 0; ct < KT; ct++) {
@@ -322,6 +338,15 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
             __syncwarp();
             const uint64_t nb2 = b + (uint64_t)(STAGES > 0 ? STAGES : 1) * nwarps;
             if (lane == 0 && nb2 < nbatches) ring_fill(nb2, stage);
+            // and pull the next batch's A fragments out of its buffer (landed long ago) while the update DMMAs drain
+            const uint64_t b1 = b + nwarps;
+            if (b1 < nbatches) {
+                const int st1 = (int)((it + 1) % (STAGES > 0 ? STAGES : 1));
+                s_mbar_wait(&full_bar[warp][st1], ((it + 1) / (STAGES > 0 ? STAGES : 1)) & 1u);
+                const TX* rows1 = ring_w + (size_t)st1 * 32 * d;
+                if (b1 * 32 + 32 <= n) load_rows_smem(rows1, b1 * 32, std::true_type{});
+                else load_rows_smem(rows1, b1 * 32, std::false_type{});
+            }
         }
     };
 
@@ -331,6 +356,11 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
                 const uint64_t b = wglobal + (uint64_t)s * nwarps;
                 if (b < nbatches) ring_fill(b, s);
             }
+        if (wglobal < nbatches) {
+            s_mbar_wait(&full_bar[warp][0], 0u);
+            if (wglobal * 32 + 32 <= n) load_rows_smem(ring_w, wglobal * 32, std::true_type{});
+            else load_rows_smem(ring_w, wglobal * 32, std::false_type{});
+        }
     } else if (wglobal < nbatches) {
         load_any(wglobal * 32);
     }
@@ -422,10 +452,13 @@ template <int KS, int KT, int VW, typename TX>
 static int launch_stream_t(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* grid_out) {
     if (ds->d == 4 * KS) {
         // whole rows, 16-byte multiples (d = 4*KS, KS even): batches are contiguous 16-byte-aligned blocks, so the
-        // TMA ring applies.  Measured at 10M x 16 k=8 on B200: ring 335 us (f64) / 243 us (f32), registers-direct
-        // 315 us / 243 us -- the kernel is bound by its dependent DMMA/epilogue chain at 4 warps per scheduler, not
-        // by load latency, and the dense 128-byte row pitch a single bulk copy produces costs 2-way (A) and 4-way
-        // (update B) bank conflicts.  The ring therefore stays opt-in (SCKM_STREAM_TMA=1, covered by the tests).
+        // TMA ring applies.  Measured at 10M x 16 k=8 on B200: ring 338 us (f64) / 258 us (f32), registers-direct
+        // 316 us / 243 us.  With f32 rows (half the bytes) the kernel still takes 243 us: it is bound by the FP64
+        // datapath (32 DMMAs + ~55 scalar FP64 instructions per 32 rows keep it ~70 % busy) and the latency of the
+        // per-batch chain at 4 warps per scheduler, not by how the rows arrive; the ring adds an mbarrier wait and
+        // shared-memory reads with 2-way (A) / 4-way (update B) bank conflicts from the dense 128-byte row pitch a
+        // single bulk copy produces.  It therefore stays opt-in (SCKM_STREAM_TMA=1, covered by the parity tests).
+        // An integer-key epilogue (as in the tile kernel) measured 316 / 254 us: no gain here, not kept.
         constexpr bool RING_OK = (4 * KS * sizeof(TX)) % 16 == 0;
         if (RING_OK && getenv("SCKM_STREAM_TMA")) {
             constexpr int STAGES = (32 * 4 * KS * sizeof(TX) <= 2048) ? 4 : 2;

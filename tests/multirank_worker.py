@@ -28,6 +28,8 @@ def main():
     seeds = ds.kmeanspp(k, first, u)
     cent, size = ds.init_centroids(k)
     fit = ds.lloyd_fit(cent, 50)
+    truth = (np.arange(n) % k).astype(np.uint32)           # blobs_host: row i belongs to centre i % k
+    table = ds.contingency(truth[lo:hi], k, k)             # summed over ranks inside the library (NCCL, u64)
     labels = torch.zeros(n, dtype=torch.int64, device="cuda")
     labels[lo:hi] = torch.from_numpy(ds.labels().astype(np.int64)).cuda()
     tdist.all_reduce(labels)
@@ -42,7 +44,8 @@ def main():
               and np.allclose(fit["centroids"], fit1["centroids"], rtol=1e-9)
               and abs(fit["distortion"] - fit1["distortion"]) <= 1e-9 * fit1["distortion"]
               and fit["size"].tolist() == fit1["size"].tolist()
-              and np.array_equal(labels.cpu().numpy(), ds1.labels().astype(np.int64)))
+              and np.array_equal(labels.cpu().numpy(), ds1.labels().astype(np.int64))
+              and np.array_equal(table, ds1.contingency(truth, k, k)) and int(table.sum()) == n)
         print("MULTIRANK_RESULT " + json.dumps({"ok": bool(ok), "iters": int(fit["iters"]), "world": world}))
     ds.close(); ctx.close()
     tdist.destroy_process_group()

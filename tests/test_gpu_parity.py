@@ -556,3 +556,54 @@ def test_contingency_of_resident_labels(ctx, O):
     with pytest.raises(cabi.SckmError):
         ds.contingency(truth + 1, k, k)                    # class id k is outside [0, k)
     ds.close()
+
+
+# ---- BASELINE configs 3-5 at the full per-GPU size: size-independent properties + sampled rows against the oracle ----
+def _full_size_check(ctx, O, n, d, k, dtype, max_iter, gap_tol, rtol, sample=2048):
+    seed_data = 20260101
+    ds = ctx.generate_blobs(n, d, k, seed_data, dtype=dtype)
+    first, u = cluster.kmeanspp_draws(42, n, k)
+    seeds = ds.kmeanspp(k, first, u)
+    assert seeds[0] == first and len(set(seeds.tolist())) == k and seeds.min() >= 0 and seeds.max() < n
+    # D^2 of sampled rows against the chosen seeds: bit-identical to the reference arithmetic (euclidian.rs:56-63)
+    rows = np.sort(np.random.default_rng(1).choice(n, sample, replace=False))
+    xs = np.vstack([cabi.blobs_host(int(r), 1, d, k, seed_data, dtype=dtype) for r in rows])
+    seed_rows = np.vstack([cabi.blobs_host(int(r), 1, d, k, seed_data, dtype=dtype) for r in seeds])
+    dd = ds.mindist()[rows]
+    lab0 = ds.labels()[rows].astype(np.int64)
+    for i in range(0, sample, 97):
+        want = [O.squared_distance(xs[i], seed_rows[j]) for j in range(k)]
+        assert dd[i] == min(want) and lab0[i] == int(np.argmin(want))
+    cent, size = ds.init_centroids(k)
+    assert size.sum() == n and size.min() >= 1
+    out = ds.lloyd_fit(cent, max_iter)
+    assert out["size"].sum() == n and 1 <= out["iters"] <= max_iter
+    labels = ds.labels().astype(np.int64)
+    assert np.array_equal(np.bincount(labels, minlength=k), out["size"])
+    # one more step from the final centroids: inertia does not go up, sums are those of the final labels' successor
+    inertia, sums, counts = ds.lloyd_step(out["centroids"])
+    assert inertia <= out["distortion"] * (1 + 1e-9) and counts.sum() == n
+    # sampled rows, labels recomputed by the oracle against the GPU's centroids
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(xs, out["centroids"], want_gap=True)
+    got = ds.labels()[rows].astype(np.int64)
+    bad = np.nonzero(got != m_o)[0]
+    assert np.all(gap[bad] < gap_tol), "%d sampled rows differ with gap >= %g" % (len(bad), gap_tol)
+    # inertia of the sample from the GPU's labels equals the oracle's within the tolerance of the data type
+    mine = np.array([O.squared_distance(xs[i].astype(np.float64), out["centroids"][got[i]]) for i in range(0, sample, 16)])
+    ref = np.array([O.squared_distance(xs[i].astype(np.float64), out["centroids"][m_o[i]]) for i in range(0, sample, 16)])
+    assert abs(mine.sum() - ref.sum()) <= rtol * ref.sum()
+    ds.close()
+
+
+def test_config3_10Mx64_k256_full_size(ctx, O):
+    _full_size_check(ctx, O, 10_000_000, 64, 256, np.float64, max_iter=6, gap_tol=GAP_TOL, rtol=RTOL)
+
+
+def test_config4_shard_12p5Mx128_k1024(ctx, O):
+    """One GPU's share of config 4 (100M x 128, k = 1024 over 8 GPUs): the streamed-centroid tile kernel."""
+    _full_size_check(ctx, O, 12_500_000, 128, 1024, np.float64, max_iter=2, gap_tol=GAP_TOL, rtol=RTOL, sample=1024)
+
+
+def test_config5_shard_6p25Mx32_k4096_f32(ctx, O):
+    """One GPU's share of config 5 (50M x 32 f32, k = 4096 over 8 GPUs): kmeans++ on the GPU, tcgen05 3xTF32 kernel."""
+    _full_size_check(ctx, O, 6_250_000, 32, 4096, np.float32, max_iter=2, gap_tol=1e-5, rtol=1e-4, sample=1024)

@@ -268,8 +268,11 @@ __device__ __forceinline__ bool kpp_screen_excludes(const uint4* __restrict__ sr
     } else {
         for (uint32_t q = 0; q < nv8; q++) eat(__ldg(srow + q), q);
     }
+    // f32 overflow (|x - seed0| beyond ~1e19 with f64 data) must not pass for "far away": the bound only counts
+    // while its f32 evaluation stayed finite; NaN anywhere on the way makes every comparison below false
+    if (!(a2 <= 3.0e38f)) return false;
     const double lb = (double)(sqrtf(a2) * shrink) - (double)ex - et;
-    return lb > 0.0 && lb * lb * (1.0 - margin) >= old;          // any NaN/inf on the way makes this false
+    return lb > 0.0 && lb * lb * (1.0 - margin) >= old;
 }
 
 template <int NV8>

@@ -46,7 +46,9 @@ def test_kmeanspp_bit_exact(ctx, O, n, d, k, dtype):
     (20000, 16, 24, np.float64, 0.0, 1.0), (20000, 64, 40, np.float64, 0.0, 1.0), (30000, 32, 33, np.float32, 0.0, 1.0),
     (12000, 8, 16, np.float64, 1e4, 1.0),       # far from the origin: bf16 keeps ~3 digits of (x - seed0), not of x
     (12000, 24, 16, np.float32, -300.0, 0.01),  # tight clusters, f32 element arithmetic
-    (9000, 128, 12, np.float64, 5.0, 1e-3), (5000, 16, 64, np.float32, 0.0, 1e3), (4100, 40, 9, np.float64, 1e8, 1.0)])
+    (9000, 128, 12, np.float64, 5.0, 1e-3), (5000, 16, 64, np.float32, 0.0, 1e3), (4100, 40, 9, np.float64, 1e8, 1.0),
+    (3000, 8, 10, np.float64, 0.0, 1e24),       # squares overflow f32 (not f64): the screening bound must stand down
+    (3000, 16, 9, np.float64, 0.0, 1e-30)])     # squares underflow f32
 def test_kmeanspp_pruned_passes_bit_exact(ctx, O, n, d, k, dtype, offset, scale, monkeypatch):
     """The pruned passes (triangle test, bf16-shadow screening, compacted exact pass) must leave every D^2, label and
     seed exactly as the reference's full passes do -- also when the screening bound is weak (large offsets), tight

@@ -131,7 +131,8 @@ int sckm_lloyd_iterate(sckm_dataset* ds, uint64_t k, uint64_t n_iters, double* c
 
 /* Labels of this rank's rows; width = 4 (uint32_t) or 8 (uint64_t, Rust usize). */
 int sckm_labels_download(sckm_dataset* ds, void* out, int width);
-/* The D^2 array of kmeans++ / the per-point min distance of the last Lloyd step. */
+/* The D^2 array of kmeans++; after a Lloyd step, the per-point min distance (direct-form and tile kernels only:
+ * the streaming kernel for k < 16 does not materialise it). */
 int sckm_mindist_download(sckm_dataset* ds, double* out);
 
 /* ---- predict (kmeans.rs:327-352): direct form in f64, strict <, lowest index wins ---- */

@@ -159,6 +159,17 @@ int sckm_contingency(sckm_dataset* ds, const uint32_t* class_ids_host, uint64_t 
 int sckm_contingency_host(sckm_ctx* ctx, const uint32_t* a_host, const uint32_t* b_host, uint64_t n,
                           uint64_t na, uint64_t nb, int64_t* out);
 
+/* ---- batched k-nearest neighbours (src/algorithm/neighbour/linear_search.rs:52-84 with Euclidian::distance) ----
+ * For each of the nq query rows (host, row-major, the dataset's element type) the k nearest rows of this rank's
+ * resident dataset: idx_out[nq][k] = global row indices, dist_out[nq][k] = Euclidian::distance values (bit-identical
+ * to the reference's arithmetic), ascending by (distance, index).  1 <= k <= min(n, 64), else SCKM_ERR_INVALID with
+ * the reference's message; rows must be multiples of 16 bytes.  The reference returns the same neighbours in its
+ * heap's internal order and resolves EXACT ties at the k-th distance by that heap's layout; here the lowest indices
+ * win.  A query whose distances are NaN gets idx -1 / dist +inf in the unfilled places (the reference returns fewer
+ * tuples). */
+int sckm_knn(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k, int64_t* idx_out,
+             double* dist_out);
+
 /* ---- measurement helpers ------------------------------------------------------- */
 /* out[0] = HBM copy GB/s (read+write), out[1] = FP64 DFMA TFLOP/s, out[2] = FP64 DMMA TFLOP/s,
  * measured now on the context's device with CUDA events (micro-kernels, ~100 ms). */

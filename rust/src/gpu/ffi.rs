@@ -59,6 +59,10 @@ extern "C" {
     pub fn sckm_contingency(
         ds: *mut sckm_dataset, class_ids_host: *const u32, n_classes: u64, k: u64, out: *mut i64,
     ) -> c_int;
+    // batched LinearKNNSearch::find with Euclidian::distance (linear_search.rs:52-84)
+    pub fn sckm_knn(
+        ds: *mut sckm_dataset, queries_host: *const c_void, nq: u64, k: u64, idx_out: *mut i64, dist_out: *mut f64,
+    ) -> c_int;
     pub fn sckm_contingency_host(
         ctx: *mut sckm_ctx, a_host: *const u32, b_host: *const u32, n: u64, na: u64, nb: u64, out: *mut i64,
     ) -> c_int;

@@ -7,6 +7,7 @@ Layout
   cabi.py     ctypes binding of the C ABI (Context, Dataset)
   cluster.py  Python face of the host mirror: KMeans.fit / predict, KMeansParameters, DenseMatrix
   metrics.py  cluster-quality scores of the reference (contingency on the GPU): HCVScore, entropy, mutual_info_score
+  neighbour.py  LinearKNNSearch (Euclidian rows) with the batched search on the GPU
   dist.py     one-process-per-GPU plumbing over torch.distributed (row sharding, NCCL id exchange)
 
 There is no CPU fallback: importing cabi without the built CUDA library raises.
@@ -14,3 +15,4 @@ There is no CPU fallback: importing cabi without the built CUDA library raises.
 from .cabi import Context, Dataset, SckmError, F32, F64  # noqa: F401
 from .cluster import KMeans, KMeansParameters, KMeansSearchParameters, DenseMatrix, Failed  # noqa: F401
 from .metrics import HCVScore, contingency_matrix, entropy, mutual_info_score  # noqa: F401
+from .neighbour import LinearKNNSearch  # noqa: F401

@@ -21,7 +21,7 @@ SYMBOLS = [
     "sckm_dataset_generate_blobs", "sckm_blobs_fill_host", "sckm_dataset_download_rows", "sckm_dataset_destroy",
     "sckm_kmeanspp", "sckm_init_centroids", "sckm_lloyd_step", "sckm_lloyd_fit", "sckm_lloyd_iterate",
     "sckm_labels_download", "sckm_mindist_download", "sckm_predict", "sckm_kmeans_fit", "sckm_device_peaks",
-    "sckm_contingency", "sckm_contingency_host",
+    "sckm_contingency", "sckm_contingency_host", "sckm_knn",
     "sckm_flush_l2",
 ]
 
@@ -64,6 +64,7 @@ def _load():
     L.sckm_kmeans_fit.argtypes = [vp, vp, u64, u64, i32, i32, u64, u64, u64, vp, vp, i32, vp, vp, vp, vp]
     L.sckm_device_peaks.argtypes = [vp, vp]
     L.sckm_contingency.argtypes = [vp, vp, u64, u64, vp]
+    L.sckm_knn.argtypes = [vp, vp, u64, u64, vp, vp]
     L.sckm_contingency_host.argtypes = [vp, vp, vp, u64, u64, u64, vp]
     L.sckm_flush_l2.argtypes = [vp]
     return L
@@ -254,6 +255,14 @@ class Dataset:
         out = np.zeros((n_classes, k), dtype=np.int64)
         self.ctx._check(lib.sckm_contingency(self.h, _p(a), n_classes, k, _p(out)))
         return out
+
+    def knn(self, queries, k):
+        """sckm_knn: for each query row the k nearest resident rows -> (idx [nq, k] int64, dist [nq, k] float64)."""
+        q = np.ascontiguousarray(queries, dtype=self.dtype)
+        assert q.ndim == 2 and q.shape[1] == self.d
+        idx = np.zeros((q.shape[0], k), dtype=np.int64); dist = np.zeros((q.shape[0], k))
+        self.ctx._check(lib.sckm_knn(self.h, _p(q), q.shape[0], k, _p(idx), _p(dist)))
+        return idx, dist
 
     def mindist(self):
         out = np.empty(self.n)

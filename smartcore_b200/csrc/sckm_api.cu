@@ -17,6 +17,7 @@ int launch_assign_dmma(sckm_dataset* ds, uint64_t k);         // sckm_dmma.cu
 bool dmma_supported(const sckm_dataset* ds, uint64_t k);      // sckm_dmma.cu
 uint32_t dmma_partial_slots(const sckm_ctx* ctx);             // sckm_dmma.cu
 int launch_predict_dmma(sckm_dataset* ds, uint64_t k);        // sckm_dmma.cu
+int knn_search(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k, int64_t* idx_out, double* dist_out);   // sckm_knn.cu
 int launch_contingency(sckm_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, uint64_t n, uint64_t na, uint64_t nb,
                        unsigned long long* d_out);            // sckm_metrics.cu
 int launch_assign_stream(sckm_dataset* ds, uint64_t k);       // sckm_stream.cu
@@ -612,6 +613,13 @@ int sckm_contingency_host(sckm_ctx* ctx, const uint32_t* a_host, const uint32_t*
                           uint64_t nb, int64_t* out) {
     if (!ctx) return SCKM_ERR_INVALID;
     return contingency_common(ctx, a_host, nullptr, b_host, n, na, nb, false, out);
+}
+
+// ---- batched k-nearest neighbours -----------------------------------------------------------------
+int sckm_knn(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k, int64_t* idx_out, double* dist_out) {
+    if (!ds) return SCKM_ERR_INVALID;
+    if (nq && (!queries_host || !idx_out || !dist_out)) return fail(ds->ctx, SCKM_ERR_INVALID, "NULL buffer");
+    return knn_search(ds, queries_host, nq, k, idx_out, dist_out);
 }
 
 // ---- whole fit from host buffers ----------------------------------------------------------------

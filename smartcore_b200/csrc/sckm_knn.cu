@@ -1,0 +1,271 @@
+// sckm_knn.cu -- batched brute-force k-nearest-neighbour search over the rows of a resident dataset
+// (SURVEY.md section 8(f) rank 2b): the batched form of LinearKNNSearch::find
+// (src/algorithm/neighbour/linear_search.rs:52-84) with Euclidian::distance
+// (src/metrics/distance/euclidian.rs:51-76: squared_distance(..).sqrt()) as the metric, i.e. what KNNClassifier /
+// KNNRegressor / DBSCAN ask of it when built with Distances::euclidian().
+//
+// Arithmetic is the reference's: (a-b) and its square in TX, widened, sequential f64 sum, then sqrt -- every
+// returned distance is bit-identical to Euclidian::distance.  Candidates are ranked by (distance, row index):
+// the k smallest, ascending.  The reference returns the same neighbours in the internal order of its HeapSelection
+// (heap_select.rs:62-83) and, among rows whose distance ties EXACTLY with the k-th smallest, the survivor depends on
+// that heap's layout; callers sort or aggregate the result (linear_search.rs:151-160), so the contract here is:
+// identical distance multiset always, identical index set whenever the k-th distance is not tied.
+//
+//   knn_tile_kernel : grid (row chunks, tiles of 8 queries).  A warp stages 32 rows at a time (16-byte cp.async
+//                     into a padded slab, one lane = one row), computes its row's distance to the 8 queries held
+//                     in shared memory (broadcast reads) and offers it to the warp's private top-k list of each
+//                     query: ballot of the lanes that beat the current k-th entry, warp-parallel sorted insertion
+//                     (insertion point = popcount of the entries smaller than the candidate).
+//   knn_merge_kernel: one CTA per query selects the k smallest of all partial lists by k rounds of "smallest
+//                     entry greater than the previous pick" -- a pure reduction, hence deterministic.
+#include "sckm_common.cuh"
+#include <algorithm>
+#include <cfloat>
+
+namespace sckm {
+
+#define LAUNCH_CHECK_K(ctx)                                                                        \
+    do {                                                                                           \
+        (ctx)->launches++;                                                                         \
+        cudaError_t _e = cudaGetLastError();                                                       \
+        if (_e != cudaSuccess)                                                                     \
+            return fail((ctx), SCKM_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+                        __FILE__, __LINE__);                                                       \
+    } while (0)
+
+constexpr int KNN_WARPS = 4;
+constexpr int KNN_TQ = 8;          // queries per CTA
+constexpr int KNN_MAXK = 64;       // two list slots per lane
+
+__device__ __forceinline__ void knn_cp_async16(void* smem_dst, const void* gmem_src) {
+    unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void knn_cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+// (a-b)^2 with the reference's rounding: subtract and multiply in TX, widen to f64 (no FMA)
+__device__ __forceinline__ double knn_sqdiff(double a, double b) { const double r = __dsub_rn(a, b); return __dmul_rn(r, r); }
+__device__ __forceinline__ double knn_sqdiff(float a, float b) { const float r = __fsub_rn(a, b); return (double)__fmul_rn(r, r); }
+
+// (distance, index) lexicographic order
+__device__ __forceinline__ bool knn_less(double da, uint32_t ia, double db, uint32_t ib) {
+    return da < db || (da == db && ia < ib);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+knn_tile_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __restrict__ queries, uint32_t nq, uint32_t k,
+                uint32_t pitch16, uint64_t rows_per_cta, double* __restrict__ part_dist, uint32_t* __restrict__ part_idx) {
+    extern __shared__ __align__(16) unsigned char smem_k[];
+    const uint32_t row_bytes = d * sizeof(T);
+    const size_t qbytes = ((size_t)KNN_TQ * row_bytes + 15) / 16 * 16;
+    T* qbuf = reinterpret_cast<T*>(smem_k);                                          // [TQ][d]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* slab = smem_k + qbytes + (size_t)warp * 32 * pitch16 * 16;       // this warp's 32 staged rows
+    double* ld = reinterpret_cast<double*>(smem_k + qbytes + (size_t)KNN_WARPS * 32 * pitch16 * 16) +
+                 (size_t)warp * KNN_TQ * KNN_MAXK;                                   // [TQ][64] distances, ascending
+    uint32_t* li = reinterpret_cast<uint32_t*>(smem_k + qbytes + (size_t)KNN_WARPS * 32 * pitch16 * 16 +
+                                               (size_t)KNN_WARPS * KNN_TQ * KNN_MAXK * sizeof(double)) +
+                   (size_t)warp * KNN_TQ * KNN_MAXK;                                 // [TQ][64] row indices
+
+    const uint32_t q0 = blockIdx.y * KNN_TQ;
+    const uint32_t tq = min((uint32_t)KNN_TQ, nq - q0);
+    for (uint32_t e = threadIdx.x; e < tq * d; e += blockDim.x) qbuf[e] = queries[(size_t)q0 * d + e];
+    __syncthreads();
+    uint32_t len[KNN_TQ];                                                            // list lengths (warp-uniform)
+#pragma unroll
+    for (int q = 0; q < KNN_TQ; q++) len[q] = 0;
+
+    const uint64_t r_begin = (uint64_t)blockIdx.x * rows_per_cta, r_end = min(n, r_begin + rows_per_cta);
+    const uint32_t cpr = row_bytes / 16;                                             // 16-byte chunks per row
+    for (uint64_t row0 = r_begin + (uint64_t)warp * 32; row0 < r_end; row0 += KNN_WARPS * 32) {
+        const uint32_t nrows = (uint32_t)min((uint64_t)32, r_end - row0);
+        {   // stage the rows: consecutive lanes, consecutive 16-byte chunks of the contiguous block
+            const uint32_t total = nrows * cpr;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(x + row0 * d);
+            for (uint32_t c = lane; c < total; c += 32) {
+                const uint32_t r = c / cpr, qq = c - r * cpr;
+                knn_cp_async16(slab + ((size_t)r * pitch16 + qq) * 16, src + (size_t)c * 16);
+            }
+            knn_cp_async_wait_all();
+            __syncwarp();
+        }
+        double dq[KNN_TQ];
+#pragma unroll
+        for (int q = 0; q < KNN_TQ; q++) dq[q] = DBL_MAX;
+        if (lane < nrows) {
+            const T* xr = reinterpret_cast<const T*>(slab + (size_t)lane * pitch16 * 16);
+            double s[KNN_TQ];
+#pragma unroll
+            for (int q = 0; q < KNN_TQ; q++) s[q] = 0.0;
+            for (uint32_t j = 0; j < d; j++) {                   // feature-major: the row element is read once, every
+                const T xv = xr[j];                              // query keeps its own sequential f64 sum
+#pragma unroll
+                for (int q = 0; q < KNN_TQ; q++)
+                    if ((uint32_t)q < tq) s[q] = __dadd_rn(s[q], knn_sqdiff(xv, qbuf[(size_t)q * d + j]));
+            }
+#pragma unroll
+            for (int q = 0; q < KNN_TQ; q++)
+                if ((uint32_t)q < tq) dq[q] = __dsqrt_rn(s[q]);  // Euclidian::distance
+        }
+        const uint32_t my_idx = (uint32_t)(row0 + lane);
+#pragma unroll
+        for (int q = 0; q < KNN_TQ; q++) {
+            if ((uint32_t)q >= tq) continue;                                         // warp-uniform
+            double* lq = ld + q * KNN_MAXK;
+            uint32_t* iq = li + q * KNN_MAXK;
+            // lanes whose row beats the current k-th entry (NaN distances never do, like `d < datum.distance`)
+            bool cand = lane < nrows && dq[q] == dq[q];
+            if (cand && len[q] == k) cand = knn_less(dq[q], my_idx, lq[k - 1], iq[k - 1]);
+            unsigned ball = __ballot_sync(0xffffffffu, cand);
+            while (ball) {
+                const int src = __ffs(ball) - 1;
+                ball &= ball - 1;
+                const double cd = __shfl_sync(0xffffffffu, dq[q], src);
+                const uint32_t ci = (uint32_t)(row0 + src);
+                // entries this lane owns: positions lane and lane + 32
+                const bool h0 = (uint32_t)lane < len[q], h1 = (uint32_t)lane + 32 < len[q];
+                const double e0d = h0 ? lq[lane] : 0.0, e1d = h1 ? lq[lane + 32] : 0.0;
+                const uint32_t e0i = h0 ? iq[lane] : 0u, e1i = h1 ? iq[lane + 32] : 0u;
+                const unsigned s0 = __ballot_sync(0xffffffffu, h0 && knn_less(e0d, e0i, cd, ci));
+                const unsigned s1 = __ballot_sync(0xffffffffu, h1 && knn_less(e1d, e1i, cd, ci));
+                const uint32_t pos = __popc(s0) + __popc(s1);                        // entries smaller than the candidate
+                if (pos >= k) continue;                                              // an earlier insertion raised the bar
+                __syncwarp();                                                        // everyone has read its entries
+                if (h1 && (uint32_t)lane + 32 >= pos && (uint32_t)lane + 33 < k) { lq[lane + 33] = e1d; iq[lane + 33] = e1i; }
+                if (h0 && (uint32_t)lane >= pos && (uint32_t)lane + 1 < k) { lq[lane + 1] = e0d; iq[lane + 1] = e0i; }
+                __syncwarp();                                                        // shifts done before the insert lands
+                if (lane == 0) { lq[pos] = cd; iq[pos] = ci; }
+                len[q] = min(len[q] + 1u, k);
+                __syncwarp();
+            }
+        }
+        __syncwarp();                                                                // slab free for the next group
+    }
+    // this warp's lists -> global partials [query][list][k], padded with (+inf, 0xffffffff)
+    const uint32_t nlists = gridDim.x * KNN_WARPS, mylist = blockIdx.x * KNN_WARPS + warp;
+    __syncwarp();
+#pragma unroll
+    for (int q = 0; q < KNN_TQ; q++) {
+        if ((uint32_t)q >= tq) continue;
+        double* od = part_dist + ((size_t)(q0 + q) * nlists + mylist) * k;
+        uint32_t* oi = part_idx + ((size_t)(q0 + q) * nlists + mylist) * k;
+        for (uint32_t p = lane; p < k; p += 32) {
+            const bool has = p < len[q];
+            od[p] = has ? ld[q * KNN_MAXK + p] : INFINITY;
+            oi[p] = has ? li[q * KNN_MAXK + p] : 0xffffffffu;
+        }
+    }
+}
+
+// one CTA per query: k rounds of "smallest (distance, index) greater than the previous pick" over all partial entries
+__global__ void __launch_bounds__(256)
+knn_merge_kernel(const double* __restrict__ part_dist, const uint32_t* __restrict__ part_idx, uint32_t nentries, uint32_t k,
+                 uint64_t row_offset, long long* __restrict__ idx_out, double* __restrict__ dist_out) {
+    __shared__ double sd[8];
+    __shared__ uint32_t si[8];
+    __shared__ double pick_d;
+    __shared__ uint32_t pick_i;
+    const double* pd = part_dist + (size_t)blockIdx.x * nentries;
+    const uint32_t* pi = part_idx + (size_t)blockIdx.x * nentries;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double prev_d = -1.0;                                         // distances are >= 0; (-1, 0) precedes everything
+    uint32_t prev_i = 0;
+    for (uint32_t r = 0; r < k; r++) {
+        double bd = INFINITY; uint32_t bi = 0xffffffffu;          // the padding entry is the identity
+        for (uint32_t e = threadIdx.x; e < nentries; e += blockDim.x) {
+            const double dd = pd[e]; const uint32_t ii = pi[e];
+            if (knn_less(prev_d, prev_i, dd, ii) && knn_less(dd, ii, bd, bi)) { bd = dd; bi = ii; }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const double od = __shfl_xor_sync(0xffffffffu, bd, o);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+            if (knn_less(od, oi, bd, bi)) { bd = od; bi = oi; }
+        }
+        if (lane == 0) { sd[warp] = bd; si[warp] = bi; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double d0 = sd[0]; uint32_t i0 = si[0];
+            for (int w = 1; w < 8; w++) if (knn_less(sd[w], si[w], d0, i0)) { d0 = sd[w]; i0 = si[w]; }
+            pick_d = d0; pick_i = i0;
+            idx_out[(size_t)blockIdx.x * k + r] = i0 == 0xffffffffu ? -1ll : (long long)(row_offset + i0);
+            dist_out[(size_t)blockIdx.x * k + r] = d0;
+        }
+        __syncthreads();
+        prev_d = pick_d; prev_i = pick_i;
+        __syncthreads();
+    }
+}
+
+template <typename T>
+static int knn_t(sckm_dataset* ds, const T* d_queries, uint64_t nq, uint64_t k, long long* d_idx, double* d_dist) {
+    sckm_ctx* ctx = ds->ctx;
+    const uint32_t d = (uint32_t)ds->d;
+    const uint32_t row_bytes = d * sizeof(T), pitch16 = (row_bytes / 16) | 1;
+    const size_t qbytes = ((size_t)KNN_TQ * row_bytes + 15) / 16 * 16;
+    const size_t smem = qbytes + (size_t)KNN_WARPS * 32 * pitch16 * 16 + (size_t)KNN_WARPS * KNN_TQ * KNN_MAXK * (sizeof(double) + sizeof(uint32_t));
+    if (smem > (size_t)ctx->smem_optin) return fail(ctx, SCKM_ERR_INVALID, "d=%u too large for the k-NN tile kernel", d);
+    const unsigned qtiles = (unsigned)((nq + KNN_TQ - 1) / KNN_TQ);
+    // enough CTAs to fill the GPU a few times over, but no more row chunks than that needs: every chunk adds
+    // KNN_WARPS partial lists per query to the merge
+    const uint64_t groups = (ds->n + KNN_WARPS * 32 - 1) / (KNN_WARPS * 32);
+    const uint64_t want_ctas = (uint64_t)ctx->num_sms * 4;
+    uint64_t chunks = std::max<uint64_t>(1, std::min<uint64_t>(groups, (want_ctas + qtiles - 1) / qtiles));
+    const uint64_t rows_per_cta = (groups + chunks - 1) / chunks * (KNN_WARPS * 32);
+    chunks = (ds->n + rows_per_cta - 1) / rows_per_cta;
+    const uint32_t nlists = (uint32_t)chunks * KNN_WARPS;
+    double* part_dist = nullptr; uint32_t* part_idx = nullptr;
+    if (dev_alloc(ctx, (void**)&part_dist, (size_t)nq * nlists * k * sizeof(double)) != cudaSuccess ||
+        dev_alloc(ctx, (void**)&part_idx, (size_t)nq * nlists * k * sizeof(uint32_t)) != cudaSuccess) {
+        dev_free(ctx, part_dist); dev_free(ctx, part_idx);
+        return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc for the k-NN partial lists failed");
+    }
+    auto kern = knn_tile_kernel<T>;
+    int rc = SCKM_OK;
+    if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+        rc = fail(ctx, SCKM_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == SCKM_OK) {
+        kern<<<dim3((unsigned)chunks, qtiles), KNN_WARPS * 32, smem, ctx->stream>>>((const T*)ds->x, ds->n, d, d_queries, (uint32_t)nq,
+            (uint32_t)k, pitch16, rows_per_cta, part_dist, part_idx);
+        ctx->launches++;
+        knn_merge_kernel<<<(unsigned)nq, 256, 0, ctx->stream>>>(part_dist, part_idx, nlists * (uint32_t)k, (uint32_t)k, ds->row_offset,
+                                                              d_idx, d_dist);
+        ctx->launches++;
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "k-NN kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    dev_free(ctx, part_dist); dev_free(ctx, part_idx);
+    return rc;
+}
+
+// queries: nq rows of the dataset's element type, row-major, on the HOST; outputs on the host: [nq][k]
+int knn_search(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k, int64_t* idx_out, double* dist_out) {
+    sckm_ctx* ctx = ds->ctx;
+    if (k < 1 || k > ds->n) return fail(ctx, SCKM_ERR_INVALID, "k should be >= 1 and <= length(data)");   // linear_search.rs:53-58
+    if (k > KNN_MAXK) return fail(ctx, SCKM_ERR_INVALID, "k=%llu: at most %d neighbours per query", (unsigned long long)k, KNN_MAXK);
+    if ((ds->d * ds->elem()) % 16 != 0) return fail(ctx, SCKM_ERR_INVALID, "k-NN needs rows that are multiples of 16 bytes (d=%llu)", (unsigned long long)ds->d);
+    if (ds->n >= 0xFFFFFFFFull) return fail(ctx, SCKM_ERR_INVALID, "k-NN: more than 2^32-2 rows per rank");
+    if (nq == 0) return SCKM_OK;
+    if (nq > 65535ull * KNN_TQ) return fail(ctx, SCKM_ERR_INVALID, "k-NN: at most %d queries per call", 65535 * KNN_TQ);
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const size_t qbytes = (size_t)nq * ds->d * ds->elem();
+    void* d_q = nullptr; long long* d_idx = nullptr; double* d_dist = nullptr;
+    auto cleanup = [&]() { dev_free(ctx, d_q); dev_free(ctx, d_idx); dev_free(ctx, d_dist); cudaStreamSynchronize(ctx->stream); };
+    if (dev_alloc(ctx, &d_q, qbytes) != cudaSuccess || dev_alloc(ctx, (void**)&d_idx, nq * k * sizeof(long long)) != cudaSuccess ||
+        dev_alloc(ctx, (void**)&d_dist, nq * k * sizeof(double)) != cudaSuccess) {
+        cleanup();
+        return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc for the k-NN queries failed");
+    }
+    int rc = copy_to_device(ctx, d_q, queries_host, qbytes);
+    if (rc == SCKM_OK)
+        rc = ds->dtype == SCKM_F32 ? knn_t<float>(ds, (const float*)d_q, nq, k, d_idx, d_dist)
+                                   : knn_t<double>(ds, (const double*)d_q, nq, k, d_idx, d_dist);
+    if (rc == SCKM_OK) rc = copy_to_host(ctx, idx_out, d_idx, nq * k * sizeof(long long));
+    if (rc == SCKM_OK) rc = copy_to_host(ctx, dist_out, d_dist, nq * k * sizeof(double));
+    cleanup();
+    return rc;
+}
+
+}  // namespace sckm

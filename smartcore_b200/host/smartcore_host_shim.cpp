@@ -4,6 +4,7 @@
 // libsmartcore_kmeans_cuda.so.
 #include "smartcore_kmeans.hpp"
 #include "smartcore_metrics.hpp"
+#include "smartcore_neighbour.hpp"
 #include <cstring>
 
 using namespace smartcore;
@@ -211,5 +212,49 @@ void sch_hcv_from_table(const int64_t* table, size_t nr, size_t nc, double* out3
     s.compute_from_table(t);
     out3[0] = *s.homogeneity(); out3[1] = *s.completeness(); out3[2] = *s.v_measure();
 }
+
+// ---- algorithm::neighbour::linear_search::LinearKNNSearch<f32|f64> with the Euclidian metric -----------------------
+struct KnnHandle {
+    int dtype;
+    algorithm::neighbour::linear_search::LinearKNNSearch<float> f32;
+    algorithm::neighbour::linear_search::LinearKNNSearch<double> f64;
+};
+int sch_knn_new(int dtype, const void* values, size_t nrows, size_t ncols, int column_major, void** out, char* err, size_t errlen) {
+    KnnHandle* h = new KnnHandle(); h->dtype = dtype;
+    int rc = 0;
+    if (dtype == SCH_F32) {
+        auto r = algorithm::neighbour::linear_search::LinearKNNSearch<float>::new_(wrap<float>(values, nrows, ncols, column_major));
+        if (r.is_err()) { set_err(err, errlen, r.unwrap_err().to_string()); rc = 1; } else h->f32 = std::move(r.unwrap());
+    } else if (dtype == SCH_F64) {
+        auto r = algorithm::neighbour::linear_search::LinearKNNSearch<double>::new_(wrap<double>(values, nrows, ncols, column_major));
+        if (r.is_err()) { set_err(err, errlen, r.unwrap_err().to_string()); rc = 1; } else h->f64 = std::move(r.unwrap());
+    } else { set_err(err, errlen, "unsupported dtype"); rc = 2; }
+    if (rc) { delete h; return rc; }
+    *out = h;
+    return 0;
+}
+// find for nq query rows; counts[q] = tuples returned for query q (k, or fewer when distances are NaN)
+int sch_knn_find(void* handle, const void* queries, size_t nq, size_t d, size_t k, int64_t* idx_out, double* dist_out,
+                 int64_t* counts, char* err, size_t errlen) {
+    KnnHandle* h = (KnnHandle*)handle;
+    auto emit = [&](auto& r) -> int {
+        if (r.is_err()) { set_err(err, errlen, r.unwrap_err().to_string()); return 1; }
+        auto& v = r.unwrap();
+        for (size_t q = 0; q < nq; q++) {
+            counts[q] = (int64_t)v[q].size();
+            for (size_t j = 0; j < v[q].size(); j++) { idx_out[q * k + j] = (int64_t)v[q][j].first; dist_out[q * k + j] = v[q][j].second; }
+        }
+        return 0;
+    };
+    if (h->dtype == SCH_F32) {
+        const float* q = (const float*)queries;
+        auto r = h->f32.find_batch(std::vector<float>(q, q + nq * d), nq, k);
+        return emit(r);
+    }
+    const double* q = (const double*)queries;
+    auto r = h->f64.find_batch(std::vector<double>(q, q + nq * d), nq, k);
+    return emit(r);
+}
+void sch_knn_free(void* handle) { delete (KnnHandle*)handle; }
 
 }  // extern "C"

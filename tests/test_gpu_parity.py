@@ -609,3 +609,68 @@ def test_config4_shard_12p5Mx128_k1024(ctx, O):
 def test_config5_shard_6p25Mx32_k4096_f32(ctx, O):
     """One GPU's share of config 5 (50M x 32 f32, k = 4096 over 8 GPUs): kmeans++ on the GPU, tcgen05 3xTF32 kernel."""
     _full_size_check(ctx, O, 6_250_000, 32, 4096, np.float32, max_iter=2, gap_tol=1e-5, rtol=1e-4, sample=1024)
+
+
+# ---- batched LinearKNNSearch::find with Euclidian::distance (linear_search.rs:52-84) ---------------------------------
+def _oracle_knn(O, x, q, k):
+    from oracle import knn_oracle as K
+    dist = lambda a, b: float(np.sqrt(O.squared_distance(a, b)))          # Euclidian::distance, TX arithmetic inside
+    return sorted(((d, i) for i, d in K.find(list(x), dist, q, k)))
+
+
+def test_knn_reference_known_answer():  # linear_search.rs knn_find, Euclidian part
+    s = sc.LinearKNNSearch.new(np.array([[1., 1.], [2., 2.], [3., 3.], [4., 4.], [5., 5.]]))
+    got = s.find([3., 3.], 3)
+    assert sorted(i for i, _ in got) == [1, 2, 3] and got[0] == (2, 0.0)
+    with pytest.raises(sc.Failed, match="k should be >= 1 and <= length"):
+        s.find([3., 3.], 6)
+    with pytest.raises(sc.Failed, match="k should be >= 1 and <= length"):
+        s.find([3., 3.], 0)
+
+
+@pytest.mark.parametrize("n,d,k,nq,dtype", [(300, 2, 1, 3, np.float64), (1000, 4, 5, 9, np.float32), (2500, 16, 32, 8, np.float64),
+                                            (4000, 64, 64, 5, np.float64), (129, 8, 129 - 70, 17, np.float32), (65, 2, 64, 2, np.float64)])
+def test_knn_matches_oracle(O, n, d, k, nq, dtype):
+    """Distances bit-identical to Euclidian::distance; the neighbour set is the reference's (continuous data: no ties at
+    the k-th distance); order: ascending (distance, index) vs the reference's heap order, compared after sorting."""
+    rng = np.random.default_rng(n + d)
+    x = rng.normal(size=(n, d)).astype(dtype)
+    q = np.vstack([rng.normal(size=(nq - 1, d)).astype(dtype), x[7:8]])   # the last query is a data row: distance 0 first
+    s = sc.LinearKNNSearch.new(x)
+    got = s.find_batch(q, k)
+    for qi in range(nq):
+        want = _oracle_knn(O, x, q[qi], k)
+        assert [(dd, i) for i, dd in got[qi]] == want
+    assert got[-1][0] == (7, 0.0)
+    # column-major storage (DenseMatrix default) gives the same answer
+    s2 = sc.LinearKNNSearch.new(sc.DenseMatrix.from_2d_array(x))
+    assert s2.find(q[0], k) == got[0]
+
+
+def test_knn_duplicates_and_large_n(ctx, O):
+    """Exact ties: the distance multiset always equals the reference's; which of several rows at exactly the k-th
+    distance survives is the heap-layout artefact documented in sckm_knn -- here the lowest indices win."""
+    rng = np.random.default_rng(3)
+    base = rng.normal(size=(40, 4))
+    x = np.repeat(base, 5, axis=0)                          # every row 5 times
+    s = sc.LinearKNNSearch.new(x)
+    for qi in range(6):
+        got = s.find(base[qi] + 0.25, 7)
+        want = _oracle_knn(O, x, base[qi] + 0.25, 7)
+        assert [dd for _, dd in got] == [dd for dd, _ in want]
+        assert all(dd == float(np.sqrt(O.squared_distance(x[i], base[qi] + 0.25))) for i, dd in got)
+        assert got == sorted(got, key=lambda t: (t[1], t[0])) and len(set(i for i, _ in got)) == 7
+    # many rows, many chunks per query and the merge across them: against a float64 numpy ranking on sampled queries
+    n, d, k = 200_000, 16, 8
+    xl = cabi.blobs_host(0, n, d, 8, 5)
+    ds = ctx.upload(xl)
+    ql = xl[::25_000] + 0.5
+    idx, dist = ds.knn(ql, k)
+    for qi in range(len(ql)):
+        d2 = ((xl - ql[qi]) ** 2).sum(axis=1)
+        order = np.lexsort((np.arange(n), d2))[:k]
+        assert idx[qi].tolist() == order.tolist()
+        assert all(dist[qi, j] == float(np.sqrt(O.squared_distance(xl[idx[qi, j]], ql[qi]))) for j in range(k))
+    with pytest.raises(cabi.SckmError):
+        ds.knn(ql, 65)
+    ds.close()

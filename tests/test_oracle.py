@@ -160,3 +160,34 @@ def test_metrics_oracle_against_sklearn():
         hs, cs, vs = homogeneity_completeness_v_measure(a, b)
         assert abs(h - hs) < 1e-10 and abs(c - cs) < 1e-10 and abs(v - vs) < 1e-10
         assert abs(M.mutual_info_score(M.contingency_matrix(a, b)) - mutual_info_score(a, b)) < 1e-10
+
+
+# ---- brute-force neighbour search: the reference's own known answers pin the restatement ------------------------
+def test_knn_oracle_against_reference_kats():
+    from oracle import knn_oracle as K
+    h = K.HeapSelection(3)                                   # heap_select.rs test_add
+    for v in (-5, 333, 13, 10, 2, 0, 40, 30):
+        h.add(v)
+    assert h.n == 8 and h.get() == [2, 0, -5]
+    h = K.HeapSelection(3)                                   # test_add1
+    for v in (float("inf"), -5.0, 4.0, -1.0, 2.0, 1.0, 0.0):
+        h.add(v)
+    assert h.n == 7 and h.get() == [0.0, -1.0, -5.0]
+    h = K.HeapSelection(3)                                   # test_add2
+    for v in (float("inf"), 0.0, 8.4852, 5.6568, 2.8284):
+        h.add(v)
+    assert h.get() == [5.6568, 2.8284, 0.0]
+    h = K.HeapSelection(3)                                   # test_add_ordered
+    for v in (1.0, 2.0, 3.0, 4.0, 5.0, 6.0):
+        h.add(v)
+    assert h.get() == [3.0, 2.0, 1.0]
+    simple = lambda a, b: float(abs(a - b))                  # linear_search.rs knn_find
+    data1 = list(range(1, 11))
+    assert sorted(i for i, _ in K.find(data1, simple, 2, 3)) == [0, 1, 2]
+    assert sorted(data1[i] for i, _ in K.find_radius(data1, simple, 5, 3.0)) == [2, 3, 4, 5, 6, 7, 8]
+    import math
+    eu = lambda a, b: math.sqrt(sum((x - y) * (x - y) for x, y in zip(a, b)))
+    data2 = [[1., 1.], [2., 2.], [3., 3.], [4., 4.], [5., 5.]]
+    assert sorted(i for i, _ in K.find(data2, eu, [3., 3.], 3)) == [1, 2, 3]
+    with pytest.raises(ValueError):
+        K.find(data1, simple, 2, 11)

@@ -60,6 +60,15 @@ def main():
         assert size[j] == (lab == j).sum() and np.allclose(cent[j], xs[lab == j].mean(axis=0), rtol=1e-9, atol=1e-9)
     g.close()
     print("ok init means 70000x16 k=16", flush=True)
+    # batched k-NN: warp-private sorted lists in shared memory, merge across row chunks
+    xk = rng.normal(size=(3000, 16)); qk = rng.normal(size=(11, 16))
+    dk = ctx.upload(xk)
+    idx, dist = dk.knn(qk, 33)
+    for qi in range(11):
+        d2 = ((xk - qk[qi]) ** 2).sum(axis=1)
+        assert idx[qi].tolist() == np.lexsort((np.arange(3000), d2))[:33].tolist()
+    dk.close()
+    print("ok knn 3000x16 k=33", flush=True)
     g = ctx.generate_blobs(3000, 16, 8, 5)
     assert np.array_equal(g.download_rows(10, 20), cabi.blobs_host(10, 20, 16, 8, 5))
     g.close()

@@ -170,6 +170,15 @@ int sckm_contingency_host(sckm_ctx* ctx, const uint32_t* a_host, const uint32_t*
 int sckm_knn(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k, int64_t* idx_out,
              double* dist_out);
 
+/* LinearKNNSearch::find_radius (linear_search.rs:89-110): every row with Euclidian distance <= radius, in ascending
+ * row order, for nq queries.  The result is ragged, hence two calls: sckm_radius_count fills counts_out[nq]; the caller
+ * builds offsets[nq] = exclusive prefix of the counts, sizes idx_out / dist_out to total = sum(counts) and calls
+ * sckm_radius_fill, which writes query q's neighbours at [offsets[q], offsets[q] + counts[q]).  radius <= 0 is
+ * SCKM_ERR_INVALID with the reference's message. */
+int sckm_radius_count(sckm_dataset* ds, const void* queries_host, uint64_t nq, double radius, int64_t* counts_out);
+int sckm_radius_fill(sckm_dataset* ds, const void* queries_host, uint64_t nq, double radius,
+                     const int64_t* offsets, uint64_t total, int64_t* idx_out, double* dist_out);
+
 /* ---- measurement helpers ------------------------------------------------------- */
 /* out[0] = HBM copy GB/s (read+write), out[1] = FP64 DFMA TFLOP/s, out[2] = FP64 DMMA TFLOP/s,
  * measured now on the context's device with CUDA events (micro-kernels, ~100 ms). */

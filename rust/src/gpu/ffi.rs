@@ -63,6 +63,13 @@ extern "C" {
     pub fn sckm_knn(
         ds: *mut sckm_dataset, queries_host: *const c_void, nq: u64, k: u64, idx_out: *mut i64, dist_out: *mut f64,
     ) -> c_int;
+    pub fn sckm_radius_count(
+        ds: *mut sckm_dataset, queries_host: *const c_void, nq: u64, radius: f64, counts_out: *mut i64,
+    ) -> c_int;
+    pub fn sckm_radius_fill(
+        ds: *mut sckm_dataset, queries_host: *const c_void, nq: u64, radius: f64, offsets: *const i64, total: u64,
+        idx_out: *mut i64, dist_out: *mut f64,
+    ) -> c_int;
     pub fn sckm_contingency_host(
         ctx: *mut sckm_ctx, a_host: *const u32, b_host: *const u32, n: u64, na: u64, nb: u64, out: *mut i64,
     ) -> c_int;

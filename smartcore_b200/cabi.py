@@ -21,7 +21,7 @@ SYMBOLS = [
     "sckm_dataset_generate_blobs", "sckm_blobs_fill_host", "sckm_dataset_download_rows", "sckm_dataset_destroy",
     "sckm_kmeanspp", "sckm_init_centroids", "sckm_lloyd_step", "sckm_lloyd_fit", "sckm_lloyd_iterate",
     "sckm_labels_download", "sckm_mindist_download", "sckm_predict", "sckm_kmeans_fit", "sckm_device_peaks",
-    "sckm_contingency", "sckm_contingency_host", "sckm_knn",
+    "sckm_contingency", "sckm_contingency_host", "sckm_knn", "sckm_radius_count", "sckm_radius_fill",
     "sckm_flush_l2",
 ]
 
@@ -65,6 +65,8 @@ def _load():
     L.sckm_device_peaks.argtypes = [vp, vp]
     L.sckm_contingency.argtypes = [vp, vp, u64, u64, vp]
     L.sckm_knn.argtypes = [vp, vp, u64, u64, vp, vp]
+    L.sckm_radius_count.argtypes = [vp, vp, u64, C.c_double, vp]
+    L.sckm_radius_fill.argtypes = [vp, vp, u64, C.c_double, vp, u64, vp, vp]
     L.sckm_contingency_host.argtypes = [vp, vp, vp, u64, u64, u64, vp]
     L.sckm_flush_l2.argtypes = [vp]
     return L
@@ -263,6 +265,19 @@ class Dataset:
         idx = np.zeros((q.shape[0], k), dtype=np.int64); dist = np.zeros((q.shape[0], k))
         self.ctx._check(lib.sckm_knn(self.h, _p(q), q.shape[0], k, _p(idx), _p(dist)))
         return idx, dist
+
+    def radius(self, queries, radius):
+        """sckm_radius_count + sckm_radius_fill: per query (idx, dist) arrays of the rows within `radius`, row order."""
+        q = np.ascontiguousarray(queries, dtype=self.dtype)
+        assert q.ndim == 2 and q.shape[1] == self.d
+        nq = q.shape[0]
+        counts = np.zeros(nq, dtype=np.int64)
+        self.ctx._check(lib.sckm_radius_count(self.h, _p(q), nq, float(radius), _p(counts)))
+        offsets = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+        total = int(offsets[-1])
+        idx = np.zeros(max(total, 1), dtype=np.int64); dist = np.zeros(max(total, 1))
+        self.ctx._check(lib.sckm_radius_fill(self.h, _p(q), nq, float(radius), _p(offsets[:-1].copy()), total, _p(idx), _p(dist)))
+        return [(idx[offsets[i]:offsets[i + 1]], dist[offsets[i]:offsets[i + 1]]) for i in range(nq)]
 
     def mindist(self):
         out = np.empty(self.n)

@@ -18,6 +18,8 @@ bool dmma_supported(const sckm_dataset* ds, uint64_t k);      // sckm_dmma.cu
 uint32_t dmma_partial_slots(const sckm_ctx* ctx);             // sckm_dmma.cu
 int launch_predict_dmma(sckm_dataset* ds, uint64_t k);        // sckm_dmma.cu
 int knn_search(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k, int64_t* idx_out, double* dist_out);   // sckm_knn.cu
+int radius_search(sckm_dataset* ds, const void* queries_host, uint64_t nq, double radius, int64_t* counts_out,
+                  const int64_t* offsets_host, uint64_t total, int64_t* idx_out, double* dist_out);               // sckm_knn.cu
 int launch_contingency(sckm_ctx* ctx, const uint32_t* d_a, const uint32_t* d_b, uint64_t n, uint64_t na, uint64_t nb,
                        unsigned long long* d_out);            // sckm_metrics.cu
 int launch_assign_stream(sckm_dataset* ds, uint64_t k);       // sckm_stream.cu
@@ -620,6 +622,19 @@ int sckm_knn(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k
     if (!ds) return SCKM_ERR_INVALID;
     if (nq && (!queries_host || !idx_out || !dist_out)) return fail(ds->ctx, SCKM_ERR_INVALID, "NULL buffer");
     return knn_search(ds, queries_host, nq, k, idx_out, dist_out);
+}
+
+int sckm_radius_count(sckm_dataset* ds, const void* queries_host, uint64_t nq, double radius, int64_t* counts_out) {
+    if (!ds) return SCKM_ERR_INVALID;
+    if (nq && (!queries_host || !counts_out)) return fail(ds->ctx, SCKM_ERR_INVALID, "NULL buffer");
+    return radius_search(ds, queries_host, nq, radius, counts_out, nullptr, 0, nullptr, nullptr);
+}
+
+int sckm_radius_fill(sckm_dataset* ds, const void* queries_host, uint64_t nq, double radius, const int64_t* offsets,
+                     uint64_t total, int64_t* idx_out, double* dist_out) {
+    if (!ds) return SCKM_ERR_INVALID;
+    if (nq && (!queries_host || !offsets || (total && (!idx_out || !dist_out)))) return fail(ds->ctx, SCKM_ERR_INVALID, "NULL buffer");
+    return radius_search(ds, queries_host, nq, radius, nullptr, offsets, total, idx_out, dist_out);
 }
 
 // ---- whole fit from host buffers ----------------------------------------------------------------

@@ -240,6 +240,180 @@ static int knn_t(sckm_dataset* ds, const T* d_queries, uint64_t nq, uint64_t k, 
     return rc;
 }
 
+// ---- find_radius (linear_search.rs:89-110): every row with distance <= radius, in ascending row order ----
+// Same staging and arithmetic as knn_tile_kernel.  A warp owns a CONTIGUOUS run of rows of its CTA's chunk, so the
+// per-(query, chunk, warp) segments concatenate in row order.  Pass 1 (FILL = false) counts the hits of every segment,
+// radius_scan_kernel turns the counts into segment offsets (+ the caller's per-query offsets), pass 2 recomputes the
+// same distances and writes (index, distance) at segment offset + running count + rank within the ballot.
+template <typename T, bool FILL>
+__global__ void __launch_bounds__(KNN_WARPS * 32)
+radius_tile_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __restrict__ queries, uint32_t nq, double radius,
+                   uint32_t pitch16, uint64_t rows_per_cta, uint32_t* __restrict__ seg_cnt, const unsigned long long* __restrict__ seg_off,
+                   uint64_t row_offset, long long* __restrict__ idx_out, double* __restrict__ dist_out) {
+    extern __shared__ __align__(16) unsigned char smem_k[];
+    const uint32_t row_bytes = d * sizeof(T);
+    const size_t qbytes = ((size_t)KNN_TQ * row_bytes + 15) / 16 * 16;
+    T* qbuf = reinterpret_cast<T*>(smem_k);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned char* slab = smem_k + qbytes + (size_t)warp * 32 * pitch16 * 16;
+    const uint32_t q0 = blockIdx.y * KNN_TQ;
+    const uint32_t tq = min((uint32_t)KNN_TQ, nq - q0);
+    for (uint32_t e = threadIdx.x; e < tq * d; e += blockDim.x) qbuf[e] = queries[(size_t)q0 * d + e];
+    __syncthreads();
+    const uint32_t nseg = gridDim.x * KNN_WARPS, myseg = blockIdx.x * KNN_WARPS + warp;
+    unsigned long long run[KNN_TQ];                                 // hits so far in this segment (warp-uniform)
+#pragma unroll
+    for (int q = 0; q < KNN_TQ; q++) run[q] = (FILL && (uint32_t)q < tq) ? seg_off[(size_t)(q0 + q) * nseg + myseg] : 0ull;
+
+    const uint64_t rows_per_warp = rows_per_cta / KNN_WARPS;        // rows_per_cta is a multiple of 32 * KNN_WARPS
+    const uint64_t w_begin = min(n, (uint64_t)blockIdx.x * rows_per_cta + (uint64_t)warp * rows_per_warp);
+    const uint64_t w_end = min(n, w_begin + rows_per_warp);
+    const uint32_t cpr = row_bytes / 16;
+    const unsigned lt = (1u << lane) - 1u;
+    for (uint64_t row0 = w_begin; row0 < w_end; row0 += 32) {
+        const uint32_t nrows = (uint32_t)min((uint64_t)32, w_end - row0);
+        {
+            const uint32_t total = nrows * cpr;
+            const unsigned char* src = reinterpret_cast<const unsigned char*>(x + row0 * d);
+            for (uint32_t c = lane; c < total; c += 32) {
+                const uint32_t r = c / cpr, qq = c - r * cpr;
+                knn_cp_async16(slab + ((size_t)r * pitch16 + qq) * 16, src + (size_t)c * 16);
+            }
+            knn_cp_async_wait_all();
+            __syncwarp();
+        }
+        double s[KNN_TQ];
+#pragma unroll
+        for (int q = 0; q < KNN_TQ; q++) s[q] = 0.0;
+        if (lane < nrows) {
+            const T* xr = reinterpret_cast<const T*>(slab + (size_t)lane * pitch16 * 16);
+            for (uint32_t j = 0; j < d; j++) {
+                const T xv = xr[j];
+#pragma unroll
+                for (int q = 0; q < KNN_TQ; q++)
+                    if ((uint32_t)q < tq) s[q] = __dadd_rn(s[q], knn_sqdiff(xv, qbuf[(size_t)q * d + j]));
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < KNN_TQ; q++) {
+            if ((uint32_t)q >= tq) continue;
+            const double dist = __dsqrt_rn(s[q]);
+            const bool hit = lane < nrows && dist <= radius;       // `d <= radius` (linear_search.rs:101); NaN: no
+            const unsigned ball = __ballot_sync(0xffffffffu, hit);
+            if (FILL && hit) {
+                const unsigned long long o = run[q] + __popc(ball & lt);
+                idx_out[o] = (long long)(row_offset + row0 + lane);
+                dist_out[o] = dist;
+            }
+            run[q] += __popc(ball);
+        }
+        __syncwarp();
+    }
+    if (!FILL && lane == 0)
+#pragma unroll
+        for (int q = 0; q < KNN_TQ; q++)
+            if ((uint32_t)q < tq) seg_cnt[(size_t)(q0 + q) * nseg + myseg] = (uint32_t)run[q];
+}
+
+// per query: exclusive prefix of its segment counts (+ base offset when given), total into counts_out
+__global__ void radius_scan_kernel(const uint32_t* __restrict__ seg_cnt, uint32_t nq, uint32_t nseg,
+                                   const long long* __restrict__ base, unsigned long long* __restrict__ seg_off,
+                                   long long* __restrict__ counts_out) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= nq) return;
+    unsigned long long run = base ? (unsigned long long)base[q] : 0ull;
+    const unsigned long long start = run;
+    for (uint32_t sgm = 0; sgm < nseg; sgm++) {
+        if (seg_off) seg_off[(size_t)q * nseg + sgm] = run;
+        run += seg_cnt[(size_t)q * nseg + sgm];
+    }
+    if (counts_out) counts_out[q] = (long long)(run - start);
+}
+
+
+// fill == false: counts_out[nq]; fill == true: offsets[nq] (exclusive prefix of the counts, caller-computed) and
+// idx_out / dist_out of sum(counts) entries
+template <typename T>
+static int radius_t(sckm_dataset* ds, const T* d_queries, uint64_t nq, double radius, bool fill, const long long* d_offsets,
+                    long long* d_counts, long long* d_idx, double* d_dist) {
+    sckm_ctx* ctx = ds->ctx;
+    const uint32_t d = (uint32_t)ds->d;
+    const uint32_t row_bytes = d * sizeof(T), pitch16 = (row_bytes / 16) | 1;
+    const size_t qbytes = ((size_t)KNN_TQ * row_bytes + 15) / 16 * 16;
+    const size_t smem = qbytes + (size_t)KNN_WARPS * 32 * pitch16 * 16;
+    if (smem > (size_t)ctx->smem_optin) return fail(ctx, SCKM_ERR_INVALID, "d=%u too large for the radius kernel", d);
+    const unsigned qtiles = (unsigned)((nq + KNN_TQ - 1) / KNN_TQ);
+    const uint64_t groups = (ds->n + KNN_WARPS * 32 - 1) / (KNN_WARPS * 32);
+    const uint64_t want_ctas = (uint64_t)ctx->num_sms * 4;
+    uint64_t chunks = std::max<uint64_t>(1, std::min<uint64_t>(groups, (want_ctas + qtiles - 1) / qtiles));
+    const uint64_t rows_per_cta = (groups + chunks - 1) / chunks * (KNN_WARPS * 32);
+    chunks = (ds->n + rows_per_cta - 1) / rows_per_cta;
+    const uint32_t nseg = (uint32_t)chunks * KNN_WARPS;
+    uint32_t* seg_cnt = nullptr; unsigned long long* seg_off = nullptr;
+    if (dev_alloc(ctx, (void**)&seg_cnt, (size_t)nq * nseg * sizeof(uint32_t)) != cudaSuccess ||
+        (fill && dev_alloc(ctx, (void**)&seg_off, (size_t)nq * nseg * sizeof(unsigned long long)) != cudaSuccess)) {
+        dev_free(ctx, seg_cnt); dev_free(ctx, seg_off);
+        return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc for the radius segments failed");
+    }
+    int rc = SCKM_OK;
+    auto count_kern = radius_tile_kernel<T, false>;
+    auto fill_kern = radius_tile_kernel<T, true>;
+    if (smem > 48 * 1024 && (cudaFuncSetAttribute(count_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+                             cudaFuncSetAttribute(fill_kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess))
+        rc = fail(ctx, SCKM_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc == SCKM_OK) {
+        const dim3 grid((unsigned)chunks, qtiles);
+        count_kern<<<grid, KNN_WARPS * 32, smem, ctx->stream>>>((const T*)ds->x, ds->n, d, d_queries, (uint32_t)nq, radius, pitch16,
+                                                              rows_per_cta, seg_cnt, nullptr, ds->row_offset, nullptr, nullptr);
+        radius_scan_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, ctx->stream>>>(seg_cnt, (uint32_t)nq, nseg, fill ? d_offsets : nullptr,
+                                                                                  seg_off, fill ? nullptr : d_counts);
+        ctx->launches += 2;
+        if (fill) {
+            fill_kern<<<grid, KNN_WARPS * 32, smem, ctx->stream>>>((const T*)ds->x, ds->n, d, d_queries, (uint32_t)nq, radius, pitch16,
+                                                                 rows_per_cta, nullptr, seg_off, ds->row_offset, d_idx, d_dist);
+            ctx->launches++;
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "radius kernel launch failed: %s", cudaGetErrorString(e));
+    }
+    dev_free(ctx, seg_cnt); dev_free(ctx, seg_off);
+    return rc;
+}
+
+// counts_out != nullptr: pass 1 only.  Otherwise offsets_host[nq] + total entries: pass 1 + scan + pass 2.
+int radius_search(sckm_dataset* ds, const void* queries_host, uint64_t nq, double radius, int64_t* counts_out,
+                  const int64_t* offsets_host, uint64_t total, int64_t* idx_out, double* dist_out) {
+    sckm_ctx* ctx = ds->ctx;
+    if (!(radius > 0.0)) return fail(ctx, SCKM_ERR_INVALID, "radius should be > 0");                     // linear_search.rs:90-95
+    if ((ds->d * ds->elem()) % 16 != 0) return fail(ctx, SCKM_ERR_INVALID, "radius search needs rows that are multiples of 16 bytes (d=%llu)", (unsigned long long)ds->d);
+    if (nq == 0) return SCKM_OK;
+    if (nq > 65535ull * KNN_TQ) return fail(ctx, SCKM_ERR_INVALID, "radius search: at most %d queries per call", 65535 * KNN_TQ);
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    const bool fill = counts_out == nullptr;
+    const size_t qbytes = (size_t)nq * ds->d * ds->elem();
+    void* d_q = nullptr; long long *d_cnt = nullptr, *d_off = nullptr, *d_idx = nullptr; double* d_dist = nullptr;
+    auto cleanup = [&]() { dev_free(ctx, d_q); dev_free(ctx, d_cnt); dev_free(ctx, d_off); dev_free(ctx, d_idx); dev_free(ctx, d_dist);
+                           cudaStreamSynchronize(ctx->stream); };
+    bool ok = dev_alloc(ctx, &d_q, qbytes) == cudaSuccess;
+    if (ok && !fill) ok = dev_alloc(ctx, (void**)&d_cnt, nq * sizeof(long long)) == cudaSuccess;
+    if (ok && fill) ok = dev_alloc(ctx, (void**)&d_off, nq * sizeof(long long)) == cudaSuccess &&
+                         dev_alloc(ctx, (void**)&d_idx, std::max<uint64_t>(total, 1) * sizeof(long long)) == cudaSuccess &&
+                         dev_alloc(ctx, (void**)&d_dist, std::max<uint64_t>(total, 1) * sizeof(double)) == cudaSuccess;
+    if (!ok) { cleanup(); return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc for the radius search failed"); }
+    int rc = copy_to_device(ctx, d_q, queries_host, qbytes);
+    if (rc == SCKM_OK && fill) rc = copy_to_device(ctx, d_off, offsets_host, nq * sizeof(long long));
+    if (rc == SCKM_OK)
+        rc = ds->dtype == SCKM_F32 ? radius_t<float>(ds, (const float*)d_q, nq, radius, fill, d_off, d_cnt, d_idx, d_dist)
+                                   : radius_t<double>(ds, (const double*)d_q, nq, radius, fill, d_off, d_cnt, d_idx, d_dist);
+    if (rc == SCKM_OK && !fill) rc = copy_to_host(ctx, counts_out, d_cnt, nq * sizeof(long long));
+    if (rc == SCKM_OK && fill && total) {
+        rc = copy_to_host(ctx, idx_out, d_idx, total * sizeof(long long));
+        if (rc == SCKM_OK) rc = copy_to_host(ctx, dist_out, d_dist, total * sizeof(double));
+    }
+    cleanup();
+    return rc;
+}
+
 // queries: nq rows of the dataset's element type, row-major, on the HOST; outputs on the host: [nq][k]
 int knn_search(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k, int64_t* idx_out, double* dist_out) {
     sckm_ctx* ctx = ds->ctx;

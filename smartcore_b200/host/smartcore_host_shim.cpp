@@ -255,6 +255,25 @@ int sch_knn_find(void* handle, const void* queries, size_t nq, size_t d, size_t 
     auto r = h->f64.find_batch(std::vector<double>(q, q + nq * d), nq, k);
     return emit(r);
 }
+// find_radius for one query row: returns the number of neighbours (or -1 with the message in err); copies up to cap
+long long sch_knn_find_radius(void* handle, const void* query, size_t d, double radius, int64_t* idx_out, double* dist_out,
+                              size_t cap, char* err, size_t errlen) {
+    KnnHandle* h = (KnnHandle*)handle;
+    auto emit = [&](auto& r) -> long long {
+        if (r.is_err()) { set_err(err, errlen, r.unwrap_err().to_string()); return -1; }
+        auto& v = r.unwrap();
+        for (size_t j = 0; j < v.size() && j < cap; j++) { idx_out[j] = (int64_t)v[j].first; dist_out[j] = v[j].second; }
+        return (long long)v.size();
+    };
+    if (h->dtype == SCH_F32) {
+        const float* q = (const float*)query;
+        auto r = h->f32.find_radius(std::vector<float>(q, q + d), radius);
+        return emit(r);
+    }
+    const double* q = (const double*)query;
+    auto r = h->f64.find_radius(std::vector<double>(q, q + d), radius);
+    return emit(r);
+}
 void sch_knn_free(void* handle) { delete (KnnHandle*)handle; }
 
 }  // extern "C"

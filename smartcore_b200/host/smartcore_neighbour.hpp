@@ -4,8 +4,8 @@
 //   smartcore::algorithm::neighbour::linear_search::LinearKNNSearch   src/algorithm/neighbour/linear_search.rs:35-84
 //   with D = smartcore::metrics::distance::euclidian::Euclidian       src/metrics/distance/euclidian.rs:51-76
 //
-// `new` uploads the data once (the reference moves the Vec into the struct); `find(from, k)` is the reference call,
-// `find_batch` its batched form (what KNNClassifier::predict does row by row, knn_classifier.rs).  Results are
+// `new` uploads the data once (the reference moves the Vec into the struct); `find(from, k)` and
+// `find_radius(from, radius)` are the reference calls, `find_batch` the batched form of `find` (what KNNClassifier::predict does row by row, knn_classifier.rs).  Results are
 // (index, distance) pairs ascending by (distance, index); the reference returns the same pairs in the internal order
 // of its HeapSelection (see include/smartcore_kmeans_cuda.h, sckm_knn, for the tie rule).
 #pragma once
@@ -69,6 +69,28 @@ public:
         for (size_t q = 0; q < nq; q++)
             for (size_t j = 0; j < k; j++)
                 if (idx[q * k + j] >= 0) out[q].emplace_back((size_t)idx[q * k + j], dist[q * k + j]);   // NaN: fewer tuples
+        return R::Ok(std::move(out));
+    }
+
+    // find_radius(from, radius) (linear_search.rs:89-110): rows with distance <= radius, ascending row order
+    error::Result<std::vector<std::pair<size_t, double>>> find_radius(const std::vector<TX>& from, double radius) const {
+        using R = error::Result<std::vector<std::pair<size_t, double>>>;
+        if (!(radius > 0.0)) return R::Err(error::Failed{error::FailedError::FindFailed, "radius should be > 0"});
+        if (from.size() != d_) return R::Err(error::Failed{error::FailedError::FindFailed, "query length differs from the data"});
+        auto dev = cluster::kmeans::Device::get();
+        if (dev.is_err()) return R::Err(dev.unwrap_err());
+        std::vector<double> w;
+        const void* q = from.data();
+        if constexpr (!(std::is_same<TX, float>::value || std::is_same<TX, double>::value)) { w.assign(from.begin(), from.end()); q = w.data(); }
+        int64_t count = 0, offset = 0;
+        if (sckm_radius_count(ds_, q, 1, radius, &count) != SCKM_OK)
+            return R::Err(error::Failed{error::FailedError::FindFailed, sckm_last_error(dev.unwrap())});
+        std::vector<int64_t> idx((size_t)count); std::vector<double> dist((size_t)count);
+        if (sckm_radius_fill(ds_, q, 1, radius, &offset, (uint64_t)count, idx.data(), dist.data()) != SCKM_OK)
+            return R::Err(error::Failed{error::FailedError::FindFailed, sckm_last_error(dev.unwrap())});
+        std::vector<std::pair<size_t, double>> out;
+        out.reserve((size_t)count);
+        for (int64_t i = 0; i < count; i++) out.emplace_back((size_t)idx[(size_t)i], dist[(size_t)i]);
         return R::Ok(std::move(out));
     }
 

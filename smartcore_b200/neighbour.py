@@ -10,6 +10,8 @@ from .cluster import DenseMatrix, Failed, _DT, _h, _p
 _vp = C.c_void_p
 _h.sch_knn_new.argtypes = [C.c_int, _vp, C.c_size_t, C.c_size_t, C.c_int, _vp, C.c_char_p, C.c_size_t]
 _h.sch_knn_find.argtypes = [_vp, _vp, C.c_size_t, C.c_size_t, C.c_size_t, _vp, _vp, _vp, C.c_char_p, C.c_size_t]
+_h.sch_knn_find_radius.argtypes = [_vp, _vp, C.c_size_t, C.c_double, _vp, _vp, C.c_size_t, C.c_char_p, C.c_size_t]
+_h.sch_knn_find_radius.restype = C.c_longlong
 _h.sch_knn_free.argtypes = [_vp]; _h.sch_knn_free.restype = None
 
 
@@ -46,6 +48,21 @@ class LinearKNNSearch:
         if _h.sch_knn_find(self._h, _p(q), nq, self._d, int(k), _p(idx), _p(dist), _p(counts), err, len(err)):
             raise Failed(err.value.decode())
         return [list(zip(idx[i, :counts[i]].tolist(), dist[i, :counts[i]].tolist())) for i in range(nq)]
+
+    def find_radius(self, frm, radius):
+        """LinearKNNSearch::find_radius(&from, radius) (linear_search.rs:89-110): [(index, distance)] in row order."""
+        q = np.ascontiguousarray(frm, dtype=self._dtype).reshape(-1)
+        if q.size != self._d:
+            raise Failed("Find failed: query length differs from the data")
+        cap = 1024
+        while True:
+            idx = np.zeros(cap, dtype=np.int64); dist = np.zeros(cap); err = C.create_string_buffer(1024)
+            m = _h.sch_knn_find_radius(self._h, _p(q), self._d, float(radius), _p(idx), _p(dist), cap, err, len(err))
+            if m < 0:
+                raise Failed(err.value.decode())
+            if m <= cap:
+                return list(zip(idx[:m].tolist(), dist[:m].tolist()))
+            cap = int(m)
 
     def find(self, frm, k):
         """LinearKNNSearch::find(&from, k) (linear_search.rs:52-84)."""

@@ -674,3 +674,39 @@ def test_knn_duplicates_and_large_n(ctx, O):
     with pytest.raises(cabi.SckmError):
         ds.knn(ql, 65)
     ds.close()
+
+
+@pytest.mark.parametrize("n,d,dtype", [(500, 2, np.float64), (3000, 16, np.float32), (70001, 4, np.float64)])
+def test_find_radius_matches_oracle(ctx, O, n, d, dtype):
+    """LinearKNNSearch::find_radius (linear_search.rs:89-110): same rows, same order (ascending index), bit-identical
+    distances; `d <= radius` includes the boundary; ragged results over many row chunks."""
+    from oracle import knn_oracle as K
+    rng = np.random.default_rng(n)
+    x = rng.normal(size=(n, d)).astype(dtype)
+    dist = lambda a, b: float(np.sqrt(O.squared_distance(a, b)))
+    s = sc.LinearKNNSearch.new(x)
+    sub = list(x[: min(n, 3000)])                           # the pure-Python restatement is slow: check a prefix of the rows
+    for qi, radius in ((3, 0.9), (11, 2.5), (20, 1e-3)):
+        got = s.find_radius(x[qi], radius)
+        want = K.find_radius(sub, dist, x[qi], radius)
+        assert [(i, dd) for i, dd in got if i < len(sub)] == want
+        assert all(dd <= radius for _, dd in got) and [i for i, _ in got] == sorted(i for i, _ in got)
+        assert (qi, 0.0) in got
+    # boundary inclusive: radius equal to an actual distance keeps that row
+    j, dj = s.find(x[5], 3)[2]
+    assert (j, dj) in s.find_radius(x[5], dj)
+    # batched, ragged, against numpy on the whole set
+    ds = ctx.upload(x)
+    q = x[:9] + dtype(0.125)
+    res = ds.radius(q, 1.75)
+    for qi in range(9):
+        full = np.sqrt(((x.astype(np.float64) - q[qi].astype(np.float64)) ** 2).sum(axis=1))   # numpy ranking, ~1e-7 apart for f32
+        idx, dv = res[qi]
+        got = set(idx.tolist())
+        assert set(np.nonzero(full <= 1.75 * (1 - 1e-5))[0].tolist()) <= got <= set(np.nonzero(full <= 1.75 * (1 + 1e-5))[0].tolist())
+        assert np.all(np.diff(idx) > 0) and np.all(dv <= 1.75)
+        for j in range(0, len(idx), max(1, len(idx) // 25)):
+            assert dv[j] == dist(x[idx[j]], q[qi])                                              # Euclidian::distance, bit for bit
+    ds.close()
+    with pytest.raises(sc.Failed, match="radius should be > 0"):
+        s.find_radius(x[0], 0.0)

@@ -67,8 +67,12 @@ def main():
     for qi in range(11):
         d2 = ((xk - qk[qi]) ** 2).sum(axis=1)
         assert idx[qi].tolist() == np.lexsort((np.arange(3000), d2))[:33].tolist()
+    res = dk.radius(qk[:5], 4.0)                            # find_radius: count / scan / fill
+    for qi in range(5):
+        full = np.sqrt(((xk - qk[qi]) ** 2).sum(axis=1))
+        assert set(np.nonzero(full <= 4.0 * (1 - 1e-9))[0].tolist()) <= set(res[qi][0].tolist()) <= set(np.nonzero(full <= 4.0 * (1 + 1e-9))[0].tolist())
     dk.close()
-    print("ok knn 3000x16 k=33", flush=True)
+    print("ok knn / radius 3000x16 k=33", flush=True)
     g = ctx.generate_blobs(3000, 16, 8, 5)
     assert np.array_equal(g.download_rows(10, 20), cabi.blobs_host(10, 20, 16, 8, 5))
     g.close()

@@ -24,15 +24,6 @@
 
 namespace sckm {
 
-#define LAUNCH_CHECK_K(ctx)                                                                        \
-    do {                                                                                           \
-        (ctx)->launches++;                                                                         \
-        cudaError_t _e = cudaGetLastError();                                                       \
-        if (_e != cudaSuccess)                                                                     \
-            return fail((ctx), SCKM_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
-                        __FILE__, __LINE__);                                                       \
-    } while (0)
-
 constexpr int KNN_WARPS = 4;
 constexpr int KNN_TQ = 8;          // queries per CTA
 constexpr int KNN_MAXK = 64;       // two list slots per lane

@@ -249,8 +249,10 @@ public:
     error::Result<std::vector<TY>> predict(const X& x) const {
         using R = error::Result<std::vector<TY>>;
         const size_t n = x.nrows, d = x.ncols;
-        if (!centroids.empty() && d != centroids[0].size())
-            return R::Err(error::Failed::predict("Input vector sizes are different."));  // reference panics (euclidian.rs:52-54)
+        if (centroids.size() != k) return R::Err(error::Failed::predict("model holds " + std::to_string(centroids.size()) + " centroids, k = " + std::to_string(k)));
+        for (const auto& row : centroids)
+            if (row.size() != d)
+                return R::Err(error::Failed::predict("Input vector sizes are different."));  // reference panics (euclidian.rs:52-54)
         auto dev = Device::get();
         if (dev.is_err()) return R::Err(error::Failed::predict(dev.unwrap_err().msg));
         sckm_ctx* ctx = dev.unwrap();

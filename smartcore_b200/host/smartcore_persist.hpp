@@ -124,6 +124,20 @@ struct JsonReader {
     }
 };
 
+// Shape invariants every image written by the reference's derive(Serialize) satisfies (kmeans.rs:73-83): `size` and
+// `centroids` have k entries, the centroid rows share one length, every label is a cluster index.  The Rust reference
+// panics safely when a hand-edited image breaks them (index out of bounds); here the loaders refuse such an image,
+// because the accessors and predict() size their buffers from k and centroids[0].
+inline bool validate(const KMeansFields& m, std::string& err) {
+    if (m.centroids.size() != m.k) { err = "field `centroids` has " + std::to_string(m.centroids.size()) + " rows, k = " + std::to_string(m.k); return false; }
+    if (m.size.size() != m.k) { err = "field `size` has " + std::to_string(m.size.size()) + " entries, k = " + std::to_string(m.k); return false; }
+    for (const auto& row : m.centroids)
+        if (row.size() != m.centroids[0].size()) { err = "field `centroids` is ragged"; return false; }
+    for (uint64_t v : m.y)
+        if (v >= m.k) { err = "field `_y` holds label " + std::to_string(v) + " >= k = " + std::to_string(m.k); return false; }
+    return true;
+}
+
 inline bool from_json(const std::string& text, KMeansFields& m, std::string& err) {
     JsonReader r(text);
     bool have_k = false, have_c = false;
@@ -153,6 +167,8 @@ inline bool from_json(const std::string& text, KMeansFields& m, std::string& err
     };
     if (!body()) { err = "invalid KMeans JSON: " + r.err; return false; }
     if (!have_k || !have_c) { err = "invalid KMeans JSON: missing field `k` or `centroids`"; return false; }
+    std::string why;
+    if (!validate(m, why)) { err = "invalid KMeans JSON: " + why; return false; }
     return true;
 }
 
@@ -199,6 +215,8 @@ inline bool from_bincode(const std::string& bytes, KMeansFields& m, std::string&
         }
     }
     if (!ok || pos != bytes.size()) { err = "invalid KMeans bincode image (truncated or trailing bytes)"; return false; }
+    std::string why;
+    if (!validate(m, why)) { err = "invalid KMeans bincode image: " + why; return false; }
     return true;
 }
 

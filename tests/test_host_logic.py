@@ -142,6 +142,26 @@ def test_model_serde_nan_centroids_and_errors():
             sc.KMeans.from_json(bad)
 
 
+def test_model_images_with_inconsistent_shapes_are_refused():
+    """A hand-edited image whose k / size / centroids / labels disagree must not reach the accessors (they size their
+    buffers from k and centroids[0]); the Rust reference panics safely on such a model, here the loaders refuse it."""
+    import struct
+    for bad in ('{"k":3,"_y":[0],"size":[1,0],"_distortion":0.0,"centroids":[[1.5],[2.5]]}',        # k != rows
+                '{"k":2,"_y":[0],"size":[1,0,7,7,7],"_distortion":0.0,"centroids":[[1.5],[2.5]]}',   # size too long
+                '{"k":2,"_y":[0],"size":[1],"_distortion":0.0,"centroids":[[1.5],[2.5]]}',           # size too short
+                '{"k":2,"_y":[0],"size":[1,0],"_distortion":0.0,"centroids":[[1.5],[2.5,3.5]]}',     # ragged rows
+                '{"k":2,"_y":[0,2],"size":[1,1],"_distortion":0.0,"centroids":[[1.5],[2.5]]}'):      # label >= k
+        with pytest.raises(sc.Failed):
+            sc.KMeans.from_json(bad)
+    ragged = (struct.pack("<Q", 2) + struct.pack("<Q", 0) + struct.pack("<Q2Q", 2, 1, 2) + struct.pack("<d", 0.5)
+              + struct.pack("<Q", 2) + struct.pack("<Q2d", 2, 1.0, 2.5) + struct.pack("<Q1d", 1, 3.0))
+    short = (struct.pack("<Q", 4) + struct.pack("<Q", 0) + struct.pack("<Q2Q", 2, 1, 2) + struct.pack("<d", 0.5)
+             + struct.pack("<Q", 2) + struct.pack("<Q2d", 2, 1.0, 2.5) + struct.pack("<Q2d", 2, 3.0, 4.0))
+    for bad in (ragged, short):
+        with pytest.raises(sc.Failed):
+            sc.KMeans.from_bincode(bad)
+
+
 def test_model_bincode_layout():
     """bincode 1.3 default options: LE u64 for usize and lengths, raw f64, nothing for PhantomData."""
     import struct

@@ -162,11 +162,12 @@ int sckm_contingency_host(sckm_ctx* ctx, const uint32_t* a_host, const uint32_t*
 /* ---- batched k-nearest neighbours (src/algorithm/neighbour/linear_search.rs:52-84 with Euclidian::distance) ----
  * For each of the nq query rows (host, row-major, the dataset's element type) the k nearest rows of this rank's
  * resident dataset: idx_out[nq][k] = global row indices, dist_out[nq][k] = Euclidian::distance values (bit-identical
- * to the reference's arithmetic), ascending by (distance, index).  1 <= k <= min(n, 64), else SCKM_ERR_INVALID with
- * the reference's message; rows must be multiples of 16 bytes.  The reference returns the same neighbours in its
- * heap's internal order and resolves EXACT ties at the k-th distance by that heap's layout; here the lowest indices
- * win.  A query whose distances are NaN gets idx -1 / dist +inf in the unfilled places (the reference returns fewer
- * tuples). */
+ * to the reference's arithmetic), ascending by (distance, index).  1 <= k <= n, else SCKM_ERR_INVALID with the
+ * reference's message; any d (rows that are not multiples of 16 bytes take an element-wise staging path) and any k
+ * (k > 64 runs ceil(k/64) passes over the rows).  The reference returns the same neighbours in its heap's internal
+ * order and resolves EXACT ties at the k-th distance by that heap's layout; here the lowest indices win.  Rows at NaN
+ * or +inf distance are never neighbours (linear_search.rs:62-76: only `d < INFINITY` enters the heap): the unfilled
+ * places carry idx -1 / dist +inf (the reference returns fewer tuples). */
 int sckm_knn(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k, int64_t* idx_out,
              double* dist_out);
 
@@ -174,7 +175,9 @@ int sckm_knn(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k
  * row order, for nq queries.  The result is ragged, hence two calls: sckm_radius_count fills counts_out[nq]; the caller
  * builds offsets[nq] = exclusive prefix of the counts, sizes idx_out / dist_out to total = sum(counts) and calls
  * sckm_radius_fill, which writes query q's neighbours at [offsets[q], offsets[q] + counts[q]).  radius <= 0 is
- * SCKM_ERR_INVALID with the reference's message. */
+ * SCKM_ERR_INVALID with the reference's message.  sckm_radius_fill recomputes the counts: offsets/total that do not
+ * match them (another query set, radius or dataset) are SCKM_ERR_INVALID and nothing is written outside a query's
+ * slot [offsets[q], offsets[q+1]) (the last slot ends at total). */
 int sckm_radius_count(sckm_dataset* ds, const void* queries_host, uint64_t nq, double radius, int64_t* counts_out);
 int sckm_radius_fill(sckm_dataset* ds, const void* queries_host, uint64_t nq, double radius,
                      const int64_t* offsets, uint64_t total, int64_t* idx_out, double* dist_out);

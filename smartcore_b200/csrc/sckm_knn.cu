@@ -18,6 +18,9 @@
 //                     (insertion point = popcount of the entries smaller than the candidate).
 //   knn_merge_kernel: one CTA per query selects the k smallest of all partial lists by k rounds of "smallest
 //                     entry greater than the previous pick" -- a pure reduction, hence deterministic.
+//   Any d and any k <= n are accepted, as in the reference: rows that are not multiples of 16 bytes are staged
+//   element by element (same padded slab, same arithmetic), and k > 64 runs ceil(k / 64) passes, each collecting
+//   the next 64 entries above the (distance, index) of the previous pass's last pick.
 #include "sckm_common.cuh"
 #include <algorithm>
 #include <cfloat>
@@ -39,6 +42,30 @@ __device__ __forceinline__ void knn_cp_async_wait_all() {
 __device__ __forceinline__ double knn_sqdiff(double a, double b) { const double r = __dsub_rn(a, b); return __dmul_rn(r, r); }
 __device__ __forceinline__ double knn_sqdiff(float a, float b) { const float r = __fsub_rn(a, b); return (double)__fmul_rn(r, r); }
 
+// Stage `nrows` consecutive rows (one contiguous block starting at `src`) into a warp's slab, one padded slab row per
+// data row.  Rows that are multiples of 16 bytes go as 16-byte cp.async chunks (consecutive lanes, consecutive chunks);
+// any other row length element by element with plain loads (the block need not even be 16-byte aligned then).
+template <typename T>
+__device__ __forceinline__ void knn_stage_rows(unsigned char* slab, const T* src, uint32_t nrows, uint32_t d, uint32_t pitch16, int lane) {
+    const uint32_t row_bytes = d * sizeof(T);
+    if (row_bytes % 16 == 0) {
+        const uint32_t cpr = row_bytes / 16, total = nrows * cpr;
+        const unsigned char* s8 = reinterpret_cast<const unsigned char*>(src);
+        for (uint32_t c = lane; c < total; c += 32) {
+            const uint32_t r = c / cpr, qq = c - r * cpr;
+            knn_cp_async16(slab + ((size_t)r * pitch16 + qq) * 16, s8 + (size_t)c * 16);
+        }
+        knn_cp_async_wait_all();
+    } else {
+        const uint32_t total = nrows * d;
+        for (uint32_t e = lane; e < total; e += 32) {
+            const uint32_t r = e / d, j = e - r * d;
+            reinterpret_cast<T*>(slab + (size_t)r * pitch16 * 16)[j] = __ldg(src + e);
+        }
+    }
+    __syncwarp();
+}
+
 // (distance, index) lexicographic order
 __device__ __forceinline__ bool knn_less(double da, uint32_t ia, double db, uint32_t ib) {
     return da < db || (da == db && ia < ib);
@@ -47,7 +74,8 @@ __device__ __forceinline__ bool knn_less(double da, uint32_t ia, double db, uint
 template <typename T>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 knn_tile_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __restrict__ queries, uint32_t nq, uint32_t k,
-                uint32_t pitch16, uint64_t rows_per_cta, double* __restrict__ part_dist, uint32_t* __restrict__ part_idx) {
+                uint32_t pitch16, uint64_t rows_per_cta, const double* __restrict__ lb_dist, const uint32_t* __restrict__ lb_idx,
+                double* __restrict__ part_dist, uint32_t* __restrict__ part_idx) {
     extern __shared__ __align__(16) unsigned char smem_k[];
     const uint32_t row_bytes = d * sizeof(T);
     const size_t qbytes = ((size_t)KNN_TQ * row_bytes + 15) / 16 * 16;
@@ -65,23 +93,18 @@ knn_tile_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __rest
     for (uint32_t e = threadIdx.x; e < tq * d; e += blockDim.x) qbuf[e] = queries[(size_t)q0 * d + e];
     __syncthreads();
     uint32_t len[KNN_TQ];                                                            // list lengths (warp-uniform)
+    double lbd[KNN_TQ]; uint32_t lbi[KNN_TQ];                                        // only entries ABOVE this bound compete
 #pragma unroll
-    for (int q = 0; q < KNN_TQ; q++) len[q] = 0;
+    for (int q = 0; q < KNN_TQ; q++) {
+        len[q] = 0;
+        lbd[q] = (uint32_t)q < tq ? lb_dist[q0 + q] : -1.0;
+        lbi[q] = (uint32_t)q < tq ? lb_idx[q0 + q] : 0u;
+    }
 
     const uint64_t r_begin = (uint64_t)blockIdx.x * rows_per_cta, r_end = min(n, r_begin + rows_per_cta);
-    const uint32_t cpr = row_bytes / 16;                                             // 16-byte chunks per row
     for (uint64_t row0 = r_begin + (uint64_t)warp * 32; row0 < r_end; row0 += KNN_WARPS * 32) {
         const uint32_t nrows = (uint32_t)min((uint64_t)32, r_end - row0);
-        {   // stage the rows: consecutive lanes, consecutive 16-byte chunks of the contiguous block
-            const uint32_t total = nrows * cpr;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(x + row0 * d);
-            for (uint32_t c = lane; c < total; c += 32) {
-                const uint32_t r = c / cpr, qq = c - r * cpr;
-                knn_cp_async16(slab + ((size_t)r * pitch16 + qq) * 16, src + (size_t)c * 16);
-            }
-            knn_cp_async_wait_all();
-            __syncwarp();
-        }
+        knn_stage_rows<T>(slab, x + row0 * d, nrows, d, pitch16, lane);
         double dq[KNN_TQ];
 #pragma unroll
         for (int q = 0; q < KNN_TQ; q++) dq[q] = DBL_MAX;
@@ -106,8 +129,9 @@ knn_tile_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __rest
             if ((uint32_t)q >= tq) continue;                                         // warp-uniform
             double* lq = ld + q * KNN_MAXK;
             uint32_t* iq = li + q * KNN_MAXK;
-            // lanes whose row beats the current k-th entry (NaN distances never do, like `d < datum.distance`)
-            bool cand = lane < nrows && dq[q] == dq[q];
+            // lanes whose row beats the current k-th entry.  NaN and +inf distances never do: the reference's heap
+            // starts out full of INFINITY entries and only `d < datum.distance` replaces one (linear_search.rs:62-76)
+            bool cand = lane < nrows && dq[q] < INFINITY && knn_less(lbd[q], lbi[q], dq[q], my_idx);
             if (cand && len[q] == k) cand = knn_less(dq[q], my_idx, lq[k - 1], iq[k - 1]);
             unsigned ball = __ballot_sync(0xffffffffu, cand);
             while (ball) {
@@ -153,7 +177,8 @@ knn_tile_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __rest
 // one CTA per query: k rounds of "smallest (distance, index) greater than the previous pick" over all partial entries
 __global__ void __launch_bounds__(256)
 knn_merge_kernel(const double* __restrict__ part_dist, const uint32_t* __restrict__ part_idx, uint32_t nentries, uint32_t k,
-                 uint64_t row_offset, long long* __restrict__ idx_out, double* __restrict__ dist_out) {
+                 uint64_t row_offset, uint32_t out_stride, uint32_t out_off, double* __restrict__ lb_dist, uint32_t* __restrict__ lb_idx,
+                 long long* __restrict__ idx_out, double* __restrict__ dist_out) {
     __shared__ double sd[8];
     __shared__ uint32_t si[8];
     __shared__ double pick_d;
@@ -181,8 +206,10 @@ knn_merge_kernel(const double* __restrict__ part_dist, const uint32_t* __restric
             double d0 = sd[0]; uint32_t i0 = si[0];
             for (int w = 1; w < 8; w++) if (knn_less(sd[w], si[w], d0, i0)) { d0 = sd[w]; i0 = si[w]; }
             pick_d = d0; pick_i = i0;
-            idx_out[(size_t)blockIdx.x * k + r] = i0 == 0xffffffffu ? -1ll : (long long)(row_offset + i0);
-            dist_out[(size_t)blockIdx.x * k + r] = d0;
+            idx_out[(size_t)blockIdx.x * out_stride + out_off + r] = i0 == 0xffffffffu ? -1ll : (long long)(row_offset + i0);
+            dist_out[(size_t)blockIdx.x * out_stride + out_off + r] = d0;
+            // the last pick of this pass is the bound of the next one (k > 64); the padding entry (+inf, 2^32-1) ends the search
+            if (r + 1 == k) { lb_dist[blockIdx.x] = d0; lb_idx[blockIdx.x] = i0; }
         }
         __syncthreads();
         prev_d = pick_d; prev_i = pick_i;
@@ -190,11 +217,16 @@ knn_merge_kernel(const double* __restrict__ part_dist, const uint32_t* __restric
     }
 }
 
+__global__ void knn_bound_init_kernel(double* __restrict__ lb_dist, uint32_t* __restrict__ lb_idx, uint32_t nq) {
+    const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < nq) { lb_dist[q] = -1.0; lb_idx[q] = 0u; }            // distances are >= 0: (-1, 0) precedes every entry
+}
+
 template <typename T>
 static int knn_t(sckm_dataset* ds, const T* d_queries, uint64_t nq, uint64_t k, long long* d_idx, double* d_dist) {
     sckm_ctx* ctx = ds->ctx;
     const uint32_t d = (uint32_t)ds->d;
-    const uint32_t row_bytes = d * sizeof(T), pitch16 = (row_bytes / 16) | 1;
+    const uint32_t row_bytes = d * sizeof(T), pitch16 = ((row_bytes + 15) / 16) | 1;
     const size_t qbytes = ((size_t)KNN_TQ * row_bytes + 15) / 16 * 16;
     const size_t smem = qbytes + (size_t)KNN_WARPS * 32 * pitch16 * 16 + (size_t)KNN_WARPS * KNN_TQ * KNN_MAXK * (sizeof(double) + sizeof(uint32_t));
     if (smem > (size_t)ctx->smem_optin) return fail(ctx, SCKM_ERR_INVALID, "d=%u too large for the k-NN tile kernel", d);
@@ -207,10 +239,14 @@ static int knn_t(sckm_dataset* ds, const T* d_queries, uint64_t nq, uint64_t k, 
     const uint64_t rows_per_cta = (groups + chunks - 1) / chunks * (KNN_WARPS * 32);
     chunks = (ds->n + rows_per_cta - 1) / rows_per_cta;
     const uint32_t nlists = (uint32_t)chunks * KNN_WARPS;
-    double* part_dist = nullptr; uint32_t* part_idx = nullptr;
-    if (dev_alloc(ctx, (void**)&part_dist, (size_t)nq * nlists * k * sizeof(double)) != cudaSuccess ||
-        dev_alloc(ctx, (void**)&part_idx, (size_t)nq * nlists * k * sizeof(uint32_t)) != cudaSuccess) {
-        dev_free(ctx, part_dist); dev_free(ctx, part_idx);
+    const uint32_t kpass = (uint32_t)std::min<uint64_t>(k, KNN_MAXK);          // list length of one pass
+    double* part_dist = nullptr; uint32_t* part_idx = nullptr; double* lb_dist = nullptr; uint32_t* lb_idx = nullptr;
+    auto cleanup = [&]() { dev_free(ctx, part_dist); dev_free(ctx, part_idx); dev_free(ctx, lb_dist); dev_free(ctx, lb_idx); };
+    if (dev_alloc(ctx, (void**)&part_dist, (size_t)nq * nlists * kpass * sizeof(double)) != cudaSuccess ||
+        dev_alloc(ctx, (void**)&part_idx, (size_t)nq * nlists * kpass * sizeof(uint32_t)) != cudaSuccess ||
+        dev_alloc(ctx, (void**)&lb_dist, nq * sizeof(double)) != cudaSuccess ||
+        dev_alloc(ctx, (void**)&lb_idx, nq * sizeof(uint32_t)) != cudaSuccess) {
+        cleanup();
         return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc for the k-NN partial lists failed");
     }
     auto kern = knn_tile_kernel<T>;
@@ -218,16 +254,22 @@ static int knn_t(sckm_dataset* ds, const T* d_queries, uint64_t nq, uint64_t k, 
     if (smem > 48 * 1024 && cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
         rc = fail(ctx, SCKM_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (rc == SCKM_OK) {
-        kern<<<dim3((unsigned)chunks, qtiles), KNN_WARPS * 32, smem, ctx->stream>>>((const T*)ds->x, ds->n, d, d_queries, (uint32_t)nq,
-            (uint32_t)k, pitch16, rows_per_cta, part_dist, part_idx);
+        knn_bound_init_kernel<<<(unsigned)((nq + 255) / 256), 256, 0, ctx->stream>>>(lb_dist, lb_idx, (uint32_t)nq);
         ctx->launches++;
-        knn_merge_kernel<<<(unsigned)nq, 256, 0, ctx->stream>>>(part_dist, part_idx, nlists * (uint32_t)k, (uint32_t)k, ds->row_offset,
-                                                              d_idx, d_dist);
-        ctx->launches++;
+        // k <= 64: one pass.  Larger k: pass p collects entries [64 p, 64 p + kk) of the sorted result, i.e. the kk
+        // smallest (distance, index) pairs above the last pick of pass p - 1; the distances are recomputed per pass.
+        for (uint64_t done = 0; done < k; done += KNN_MAXK) {
+            const uint32_t kk = (uint32_t)std::min<uint64_t>(KNN_MAXK, k - done);
+            kern<<<dim3((unsigned)chunks, qtiles), KNN_WARPS * 32, smem, ctx->stream>>>((const T*)ds->x, ds->n, d, d_queries, (uint32_t)nq,
+                kk, pitch16, rows_per_cta, lb_dist, lb_idx, part_dist, part_idx);
+            knn_merge_kernel<<<(unsigned)nq, 256, 0, ctx->stream>>>(part_dist, part_idx, nlists * kk, kk, ds->row_offset, (uint32_t)k,
+                                                                  (uint32_t)done, lb_dist, lb_idx, d_idx, d_dist);
+            ctx->launches += 2;
+        }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "k-NN kernel launch failed: %s", cudaGetErrorString(e));
     }
-    dev_free(ctx, part_dist); dev_free(ctx, part_idx);
+    cleanup();
     return rc;
 }
 
@@ -240,7 +282,8 @@ template <typename T, bool FILL>
 __global__ void __launch_bounds__(KNN_WARPS * 32)
 radius_tile_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __restrict__ queries, uint32_t nq, double radius,
                    uint32_t pitch16, uint64_t rows_per_cta, uint32_t* __restrict__ seg_cnt, const unsigned long long* __restrict__ seg_off,
-                   uint64_t row_offset, long long* __restrict__ idx_out, double* __restrict__ dist_out) {
+                   const unsigned long long* __restrict__ slot_end, uint64_t row_offset, long long* __restrict__ idx_out,
+                   double* __restrict__ dist_out) {
     extern __shared__ __align__(16) unsigned char smem_k[];
     const uint32_t row_bytes = d * sizeof(T);
     const size_t qbytes = ((size_t)KNN_TQ * row_bytes + 15) / 16 * 16;
@@ -253,26 +296,20 @@ radius_tile_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __r
     __syncthreads();
     const uint32_t nseg = gridDim.x * KNN_WARPS, myseg = blockIdx.x * KNN_WARPS + warp;
     unsigned long long run[KNN_TQ];                                 // hits so far in this segment (warp-uniform)
+    unsigned long long lim[KNN_TQ];                                 // end of the caller's slot for the query: never write past it
 #pragma unroll
-    for (int q = 0; q < KNN_TQ; q++) run[q] = (FILL && (uint32_t)q < tq) ? seg_off[(size_t)(q0 + q) * nseg + myseg] : 0ull;
+    for (int q = 0; q < KNN_TQ; q++) {
+        run[q] = (FILL && (uint32_t)q < tq) ? seg_off[(size_t)(q0 + q) * nseg + myseg] : 0ull;
+        lim[q] = (FILL && (uint32_t)q < tq) ? slot_end[q0 + q] : 0ull;
+    }
 
     const uint64_t rows_per_warp = rows_per_cta / KNN_WARPS;        // rows_per_cta is a multiple of 32 * KNN_WARPS
     const uint64_t w_begin = min(n, (uint64_t)blockIdx.x * rows_per_cta + (uint64_t)warp * rows_per_warp);
     const uint64_t w_end = min(n, w_begin + rows_per_warp);
-    const uint32_t cpr = row_bytes / 16;
     const unsigned lt = (1u << lane) - 1u;
     for (uint64_t row0 = w_begin; row0 < w_end; row0 += 32) {
         const uint32_t nrows = (uint32_t)min((uint64_t)32, w_end - row0);
-        {
-            const uint32_t total = nrows * cpr;
-            const unsigned char* src = reinterpret_cast<const unsigned char*>(x + row0 * d);
-            for (uint32_t c = lane; c < total; c += 32) {
-                const uint32_t r = c / cpr, qq = c - r * cpr;
-                knn_cp_async16(slab + ((size_t)r * pitch16 + qq) * 16, src + (size_t)c * 16);
-            }
-            knn_cp_async_wait_all();
-            __syncwarp();
-        }
+        knn_stage_rows<T>(slab, x + row0 * d, nrows, d, pitch16, lane);
         double s[KNN_TQ];
 #pragma unroll
         for (int q = 0; q < KNN_TQ; q++) s[q] = 0.0;
@@ -293,8 +330,10 @@ radius_tile_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __r
             const unsigned ball = __ballot_sync(0xffffffffu, hit);
             if (FILL && hit) {
                 const unsigned long long o = run[q] + __popc(ball & lt);
-                idx_out[o] = (long long)(row_offset + row0 + lane);
-                dist_out[o] = dist;
+                if (o < lim[q]) {                                   // (a mismatch is reported by radius_scan_kernel)
+                    idx_out[o] = (long long)(row_offset + row0 + lane);
+                    dist_out[o] = dist;
+                }
             }
             run[q] += __popc(ball);
         }
@@ -307,9 +346,13 @@ radius_tile_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const T* __r
 }
 
 // per query: exclusive prefix of its segment counts (+ base offset when given), total into counts_out
+// Fill mode (base != nullptr): the caller's slot of query q is [base[q], base[q+1]) (the last one ends at `total`);
+// slot_end[q] receives its end, and a recomputed count that does not fill the slot exactly -- offsets that belong to
+// another query set, another radius or another dataset -- raises *mismatch (the fill kernel never writes past a slot).
 __global__ void radius_scan_kernel(const uint32_t* __restrict__ seg_cnt, uint32_t nq, uint32_t nseg,
-                                   const long long* __restrict__ base, unsigned long long* __restrict__ seg_off,
-                                   long long* __restrict__ counts_out) {
+                                   const long long* __restrict__ base, unsigned long long total,
+                                   unsigned long long* __restrict__ seg_off, unsigned long long* __restrict__ slot_end,
+                                   unsigned long long* __restrict__ mismatch, long long* __restrict__ counts_out) {
     const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;
     if (q >= nq) return;
     unsigned long long run = base ? (unsigned long long)base[q] : 0ull;
@@ -319,6 +362,11 @@ __global__ void radius_scan_kernel(const uint32_t* __restrict__ seg_cnt, uint32_
         run += seg_cnt[(size_t)q * nseg + sgm];
     }
     if (counts_out) counts_out[q] = (long long)(run - start);
+    if (base) {
+        const unsigned long long end = q + 1 < nq ? (unsigned long long)base[q + 1] : total;
+        slot_end[q] = end;
+        if (run != end) atomicAdd(mismatch, 1ull);
+    }
 }
 
 
@@ -326,10 +374,10 @@ __global__ void radius_scan_kernel(const uint32_t* __restrict__ seg_cnt, uint32_
 // idx_out / dist_out of sum(counts) entries
 template <typename T>
 static int radius_t(sckm_dataset* ds, const T* d_queries, uint64_t nq, double radius, bool fill, const long long* d_offsets,
-                    long long* d_counts, long long* d_idx, double* d_dist) {
+                    uint64_t total, long long* d_counts, long long* d_idx, double* d_dist) {
     sckm_ctx* ctx = ds->ctx;
     const uint32_t d = (uint32_t)ds->d;
-    const uint32_t row_bytes = d * sizeof(T), pitch16 = (row_bytes / 16) | 1;
+    const uint32_t row_bytes = d * sizeof(T), pitch16 = ((row_bytes + 15) / 16) | 1;
     const size_t qbytes = ((size_t)KNN_TQ * row_bytes + 15) / 16 * 16;
     const size_t smem = qbytes + (size_t)KNN_WARPS * 32 * pitch16 * 16;
     if (smem > (size_t)ctx->smem_optin) return fail(ctx, SCKM_ERR_INVALID, "d=%u too large for the radius kernel", d);
@@ -340,10 +388,11 @@ static int radius_t(sckm_dataset* ds, const T* d_queries, uint64_t nq, double ra
     const uint64_t rows_per_cta = (groups + chunks - 1) / chunks * (KNN_WARPS * 32);
     chunks = (ds->n + rows_per_cta - 1) / rows_per_cta;
     const uint32_t nseg = (uint32_t)chunks * KNN_WARPS;
-    uint32_t* seg_cnt = nullptr; unsigned long long* seg_off = nullptr;
+    uint32_t* seg_cnt = nullptr; unsigned long long *seg_off = nullptr, *slot_end = nullptr;   // slot_end[nq] | mismatch count
     if (dev_alloc(ctx, (void**)&seg_cnt, (size_t)nq * nseg * sizeof(uint32_t)) != cudaSuccess ||
-        (fill && dev_alloc(ctx, (void**)&seg_off, (size_t)nq * nseg * sizeof(unsigned long long)) != cudaSuccess)) {
-        dev_free(ctx, seg_cnt); dev_free(ctx, seg_off);
+        (fill && (dev_alloc(ctx, (void**)&seg_off, (size_t)nq * nseg * sizeof(unsigned long long)) != cudaSuccess ||
+                  dev_alloc(ctx, (void**)&slot_end, (nq + 1) * sizeof(unsigned long long)) != cudaSuccess))) {
+        dev_free(ctx, seg_cnt); dev_free(ctx, seg_off); dev_free(ctx, slot_end);
         return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc for the radius segments failed");
     }
     int rc = SCKM_OK;
@@ -355,19 +404,31 @@ static int radius_t(sckm_dataset* ds, const T* d_queries, uint64_t nq, double ra
     if (rc == SCKM_OK) {
         const dim3 grid((unsigned)chunks, qtiles);
         count_kern<<<grid, KNN_WARPS * 32, smem, ctx->stream>>>((const T*)ds->x, ds->n, d, d_queries, (uint32_t)nq, radius, pitch16,
-                                                              rows_per_cta, seg_cnt, nullptr, ds->row_offset, nullptr, nullptr);
+                                                              rows_per_cta, seg_cnt, nullptr, nullptr, ds->row_offset, nullptr, nullptr);
+        if (fill) cudaMemsetAsync(slot_end + nq, 0, sizeof(unsigned long long), ctx->stream);
         radius_scan_kernel<<<(unsigned)((nq + 127) / 128), 128, 0, ctx->stream>>>(seg_cnt, (uint32_t)nq, nseg, fill ? d_offsets : nullptr,
-                                                                                  seg_off, fill ? nullptr : d_counts);
+                                                                                  total, seg_off, slot_end, fill ? slot_end + nq : nullptr,
+                                                                                  fill ? nullptr : d_counts);
         ctx->launches += 2;
         if (fill) {
             fill_kern<<<grid, KNN_WARPS * 32, smem, ctx->stream>>>((const T*)ds->x, ds->n, d, d_queries, (uint32_t)nq, radius, pitch16,
-                                                                 rows_per_cta, nullptr, seg_off, ds->row_offset, d_idx, d_dist);
+                                                                 rows_per_cta, nullptr, seg_off, slot_end, ds->row_offset, d_idx, d_dist);
             ctx->launches++;
         }
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "radius kernel launch failed: %s", cudaGetErrorString(e));
+        if (rc == SCKM_OK && fill) {
+            unsigned long long bad = 0;
+            if (cudaMemcpyAsync(&bad, slot_end + nq, sizeof(bad), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+                cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+                rc = fail(ctx, SCKM_ERR_CUDA, "radius search failed: %s", cudaGetErrorString(cudaGetLastError()));
+            else if (bad)
+                rc = fail(ctx, SCKM_ERR_INVALID, "sckm_radius_fill: offsets/total do not match the counts of these queries "
+                          "(%llu of %llu queries differ): run sckm_radius_count on the same dataset, queries and radius first",
+                          bad, (unsigned long long)nq);
+        }
     }
-    dev_free(ctx, seg_cnt); dev_free(ctx, seg_off);
+    dev_free(ctx, seg_cnt); dev_free(ctx, seg_off); dev_free(ctx, slot_end);
     return rc;
 }
 
@@ -376,11 +437,17 @@ int radius_search(sckm_dataset* ds, const void* queries_host, uint64_t nq, doubl
                   const int64_t* offsets_host, uint64_t total, int64_t* idx_out, double* dist_out) {
     sckm_ctx* ctx = ds->ctx;
     if (!(radius > 0.0)) return fail(ctx, SCKM_ERR_INVALID, "radius should be > 0");                     // linear_search.rs:90-95
-    if ((ds->d * ds->elem()) % 16 != 0) return fail(ctx, SCKM_ERR_INVALID, "radius search needs rows that are multiples of 16 bytes (d=%llu)", (unsigned long long)ds->d);
     if (nq == 0) return SCKM_OK;
     if (nq > 65535ull * KNN_TQ) return fail(ctx, SCKM_ERR_INVALID, "radius search: at most %d queries per call", 65535 * KNN_TQ);
     SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
     const bool fill = counts_out == nullptr;
+    if (fill)                                                       // slots must be ordered and inside [0, total]
+        for (uint64_t q = 0; q < nq; q++) {
+            const int64_t end = q + 1 < nq ? offsets_host[q + 1] : (int64_t)total;
+            if (offsets_host[q] < 0 || offsets_host[q] > end || (uint64_t)end > total)
+                return fail(ctx, SCKM_ERR_INVALID, "sckm_radius_fill: offsets[%llu] is not an exclusive prefix within total=%llu",
+                            (unsigned long long)q, (unsigned long long)total);
+        }
     const size_t qbytes = (size_t)nq * ds->d * ds->elem();
     void* d_q = nullptr; long long *d_cnt = nullptr, *d_off = nullptr, *d_idx = nullptr; double* d_dist = nullptr;
     auto cleanup = [&]() { dev_free(ctx, d_q); dev_free(ctx, d_cnt); dev_free(ctx, d_off); dev_free(ctx, d_idx); dev_free(ctx, d_dist);
@@ -394,8 +461,8 @@ int radius_search(sckm_dataset* ds, const void* queries_host, uint64_t nq, doubl
     int rc = copy_to_device(ctx, d_q, queries_host, qbytes);
     if (rc == SCKM_OK && fill) rc = copy_to_device(ctx, d_off, offsets_host, nq * sizeof(long long));
     if (rc == SCKM_OK)
-        rc = ds->dtype == SCKM_F32 ? radius_t<float>(ds, (const float*)d_q, nq, radius, fill, d_off, d_cnt, d_idx, d_dist)
-                                   : radius_t<double>(ds, (const double*)d_q, nq, radius, fill, d_off, d_cnt, d_idx, d_dist);
+        rc = ds->dtype == SCKM_F32 ? radius_t<float>(ds, (const float*)d_q, nq, radius, fill, d_off, total, d_cnt, d_idx, d_dist)
+                                   : radius_t<double>(ds, (const double*)d_q, nq, radius, fill, d_off, total, d_cnt, d_idx, d_dist);
     if (rc == SCKM_OK && !fill) rc = copy_to_host(ctx, counts_out, d_cnt, nq * sizeof(long long));
     if (rc == SCKM_OK && fill && total) {
         rc = copy_to_host(ctx, idx_out, d_idx, total * sizeof(long long));
@@ -409,8 +476,6 @@ int radius_search(sckm_dataset* ds, const void* queries_host, uint64_t nq, doubl
 int knn_search(sckm_dataset* ds, const void* queries_host, uint64_t nq, uint64_t k, int64_t* idx_out, double* dist_out) {
     sckm_ctx* ctx = ds->ctx;
     if (k < 1 || k > ds->n) return fail(ctx, SCKM_ERR_INVALID, "k should be >= 1 and <= length(data)");   // linear_search.rs:53-58
-    if (k > KNN_MAXK) return fail(ctx, SCKM_ERR_INVALID, "k=%llu: at most %d neighbours per query", (unsigned long long)k, KNN_MAXK);
-    if ((ds->d * ds->elem()) % 16 != 0) return fail(ctx, SCKM_ERR_INVALID, "k-NN needs rows that are multiples of 16 bytes (d=%llu)", (unsigned long long)ds->d);
     if (ds->n >= 0xFFFFFFFFull) return fail(ctx, SCKM_ERR_INVALID, "k-NN: more than 2^32-2 rows per rank");
     if (nq == 0) return SCKM_OK;
     if (nq > 65535ull * KNN_TQ) return fail(ctx, SCKM_ERR_INVALID, "k-NN: at most %d queries per call", 65535 * KNN_TQ);

@@ -629,7 +629,10 @@ def test_knn_reference_known_answer():  # linear_search.rs knn_find, Euclidian p
 
 
 @pytest.mark.parametrize("n,d,k,nq,dtype", [(300, 2, 1, 3, np.float64), (1000, 4, 5, 9, np.float32), (2500, 16, 32, 8, np.float64),
-                                            (4000, 64, 64, 5, np.float64), (129, 8, 129 - 70, 17, np.float32), (65, 2, 64, 2, np.float64)])
+                                            (4000, 64, 64, 5, np.float64), (129, 8, 129 - 70, 17, np.float32), (65, 2, 64, 2, np.float64),
+                                            # rows that are not multiples of 16 bytes (2-D / 3-D f32 points, odd d) and k > 64
+                                            (1000, 3, 5, 4, np.float32), (700, 2, 100, 3, np.float32), (900, 5, 70, 3, np.float64),
+                                            (500, 1, 200, 2, np.float32), (333, 7, 333, 2, np.float64)])
 def test_knn_matches_oracle(O, n, d, k, nq, dtype):
     """Distances bit-identical to Euclidian::distance; the neighbour set is the reference's (continuous data: no ties at
     the k-th distance); order: ascending (distance, index) vs the reference's heap order, compared after sorting."""
@@ -671,12 +674,51 @@ def test_knn_duplicates_and_large_n(ctx, O):
         order = np.lexsort((np.arange(n), d2))[:k]
         assert idx[qi].tolist() == order.tolist()
         assert all(dist[qi, j] == float(np.sqrt(O.squared_distance(xl[idx[qi, j]], ql[qi]))) for j in range(k))
-    with pytest.raises(cabi.SckmError):
-        ds.knn(ql, 65)
+    # k > 64: several passes of 64, each above the previous pass's last pick
+    idx, dist = ds.knn(ql[:3], 150)
+    for qi in range(3):
+        d2 = ((xl - ql[qi]) ** 2).sum(axis=1)
+        assert idx[qi].tolist() == np.lexsort((np.arange(n), d2))[:150].tolist()
+        assert np.all(np.diff(dist[qi]) >= 0)
     ds.close()
 
 
-@pytest.mark.parametrize("n,d,dtype", [(500, 2, np.float64), (3000, 16, np.float32), (70001, 4, np.float64)])
+def test_knn_infinite_distances_are_not_neighbours(ctx):
+    """The reference's heap starts full of INFINITY entries and only `d < datum.distance` replaces one
+    (linear_search.rs:62-76): a row at infinite (or NaN) distance is never returned, the result is shorter than k."""
+    x = np.array([[0.0, 0.0], [1.0, 0.0], [np.inf, 0.0], [np.nan, 1.0], [3.0, 4.0], [1e200, 1e200]])   # last: d^2 overflows
+    ds = ctx.upload(x)
+    idx, dist = ds.knn(np.array([[0.0, 0.0]]), 5)
+    assert idx[0].tolist() == [0, 1, 4, -1, -1] and dist[0, :3].tolist() == [0.0, 1.0, 5.0] and np.all(np.isinf(dist[0, 3:]))
+    ds.close()
+
+
+def test_radius_fill_refuses_offsets_of_another_query_set(ctx):
+    """sckm_radius_fill recomputes the counts: offsets that do not match them are an error, never an out-of-bounds write."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    x = rng.normal(size=(5000, 3)).astype(np.float32)        # 12-byte rows: the element-wise staging path
+    ds = ctx.upload(x)
+    q = x[:4] + np.float32(0.25)
+    res = ds.radius(q, 1.0)
+    counts = np.array([len(i) for i, _ in res], dtype=np.int64)
+    full = np.sqrt(((x.astype(np.float64)[None] - q.astype(np.float64)[:, None]) ** 2).sum(-1))
+    assert np.all(np.abs(counts - (full <= 1.0).sum(1)) <= 2) and counts.min() > 0
+    offsets = np.concatenate([[0], np.cumsum(counts)[:-1]]).astype(np.int64)
+    total = int(counts.sum())
+    idx = np.full(total + 64, -7, dtype=np.int64); dist = np.zeros(total + 64)
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    for bad_off, bad_total in ((offsets // 2, total // 2), (offsets, total - 1), (offsets[::-1].copy(), total)):
+        rc = cabi.lib.sckm_radius_fill(ds.h, vp(q), 4, C.c_double(1.0), vp(bad_off), bad_total, vp(idx), vp(dist))
+        assert rc == 1 and np.all(idx[bad_total:] == -7)
+    # a different radius with the old offsets
+    rc = cabi.lib.sckm_radius_fill(ds.h, vp(q), 4, C.c_double(1.5), vp(offsets), total, vp(idx), vp(dist))
+    assert rc == 1 and np.all(idx[total:] == -7)
+    ds.close()
+
+
+@pytest.mark.parametrize("n,d,dtype", [(500, 2, np.float64), (3000, 16, np.float32), (70001, 4, np.float64),
+                                       (800, 2, np.float32), (2500, 3, np.float64), (1200, 1, np.float32)])   # DBSCAN-style 2-D f32 points
 def test_find_radius_matches_oracle(ctx, O, n, d, dtype):
     """LinearKNNSearch::find_radius (linear_search.rs:89-110): same rows, same order (ascending index), bit-identical
     distances; `d <= radius` includes the boundary; ragged results over many row chunks."""

@@ -19,11 +19,12 @@
  *   * The caller owns every host buffer for the duration of the call only; the
  *     library keeps no host pointer after return.  Device memory lives behind
  *     the opaque handles and is released by the matching *_destroy.
- *   * A context is bound to ONE CUDA device and is not thread-safe; multi-GPU is
- *     one context per device (one per process under torchrun, or one per host
- *     thread) joined by sckm_comm_init_rank.  Rows are sharded across ranks; the
- *     only per-iteration exchange is one all-reduce of [k*d sums | k counts |
- *     inertia] (f64).
+ *   * A context is not thread-safe.  Multi-GPU comes in two forms: ONE context over
+ *     all devices of the box (sckm_ctx_create_multi: the drop-in form, the caller
+ *     stays single-threaded), or one single-device context per process / host
+ *     thread joined by sckm_comm_init_rank (torchrun).  Either way rows are sharded
+ *     across ranks and the only per-iteration exchange is one all-reduce of
+ *     [k*d sums | k counts | inertia] (f64).
  *   * The RNG stays on the host (kmeans.rs:355, src/rand_custom.rs:8-33): the
  *     caller draws `first_index = rng.gen_range(0..n)` and the k-1 uniforms
  *     `rng.gen::<f64>()` (they do not depend on the data) and passes them in.
@@ -40,7 +41,7 @@
 extern "C" {
 #endif
 
-#define SCKM_ABI_VERSION 2
+#define SCKM_ABI_VERSION 3
 
 typedef struct sckm_ctx sckm_ctx;         /* device + stream + workspaces (+ NCCL communicator) */
 typedef struct sckm_dataset sckm_dataset; /* this rank's rows of X, labels y and D^2 array, on device */
@@ -69,6 +70,19 @@ int sckm_abi_version(void);
 /* ---- context ------------------------------------------------------------- */
 int  sckm_ctx_create(int device, sckm_ctx** out);
 void sckm_ctx_destroy(sckm_ctx* ctx);
+/* ONE context over several devices of this box, driven from the caller's single thread -- what a smartcore program
+ * calling KMeans::fit / predict (kmeans.rs:254, :327) gets: the devices stay invisible to the caller.
+ * n_dev <= 0: every visible device; dev_ids nullable (0..n_dev-1).  One device: identical to sckm_ctx_create.
+ * The result behaves as a context on dev_ids[0] for every dataset-level entry point; the whole-matrix calls
+ * sckm_kmeans_fit and sckm_predict shard the caller's host buffer in contiguous row blocks over the devices (one host
+ * thread, stream, staging ring and NCCL communicator per device; one all-reduce of k*d+k+1 doubles per Lloyd step).
+ * Inputs too small for every device to get >= 32768 rows run on dev_ids[0] alone. */
+int  sckm_ctx_create_multi(int n_dev, const int* dev_ids, sckm_ctx** out);
+/* Devices behind this context (1 for sckm_ctx_create). */
+int  sckm_ctx_device_count(const sckm_ctx* ctx);
+/* Wall-clock phases of the last sckm_kmeans_fit on this context, seconds: out6 = {upload, kmeans++ + initial means,
+ * Lloyd loop, label download, total, devices used} (max over devices per phase). */
+int  sckm_ctx_last_fit_times(const sckm_ctx* ctx, double* out6);
 /* Last error text of this context (or of the failed sckm_ctx_create when ctx == NULL). */
 const char* sckm_last_error(const sckm_ctx* ctx);
 /* Force an assignment kernel (SCKM_ASSIGN_*); default AUTO. */

@@ -22,7 +22,7 @@ SYMBOLS = [
     "sckm_kmeanspp", "sckm_init_centroids", "sckm_lloyd_step", "sckm_lloyd_fit", "sckm_lloyd_iterate",
     "sckm_labels_download", "sckm_mindist_download", "sckm_predict", "sckm_kmeans_fit", "sckm_device_peaks",
     "sckm_contingency", "sckm_contingency_host", "sckm_knn", "sckm_radius_count", "sckm_radius_fill",
-    "sckm_flush_l2",
+    "sckm_flush_l2", "sckm_ctx_create_multi", "sckm_ctx_device_count", "sckm_ctx_last_fit_times",
 ]
 
 
@@ -42,6 +42,9 @@ def _load():
     vp, u64, i32 = C.c_void_p, C.c_uint64, C.c_int
     L.sckm_abi_version.restype = i32
     L.sckm_ctx_create.argtypes = [i32, C.POINTER(vp)]
+    L.sckm_ctx_create_multi.argtypes = [i32, vp, C.POINTER(vp)]
+    L.sckm_ctx_device_count.argtypes = [vp]; L.sckm_ctx_device_count.restype = i32
+    L.sckm_ctx_last_fit_times.argtypes = [vp, vp]
     L.sckm_ctx_destroy.argtypes = [vp]; L.sckm_ctx_destroy.restype = None
     L.sckm_last_error.argtypes = [vp]; L.sckm_last_error.restype = C.c_char_p
     L.sckm_ctx_set_assign_kernel.argtypes = [vp, i32]
@@ -99,13 +102,29 @@ def blobs_host(row0, nrows, d, n_centers, seed, dtype=np.float64):
 class Context:
     """sckm_ctx: one CUDA device + stream (+ NCCL communicator when joined)."""
 
-    def __init__(self, device=0):
+    def __init__(self, device=0, devices=None):
+        """device: one CUDA device.  devices: a list of devices (or "all") behind ONE context (sckm_ctx_create_multi):
+        kmeans_fit / predict then shard the rows of the host matrix over them."""
         h = C.c_void_p()
-        rc = lib.sckm_ctx_create(device, C.byref(h))
+        if devices is None:
+            rc = lib.sckm_ctx_create(device, C.byref(h))
+        elif isinstance(devices, str):
+            rc = lib.sckm_ctx_create_multi(0, None, C.byref(h))
+        else:
+            ids = (C.c_int * len(devices))(*devices)
+            rc = lib.sckm_ctx_create_multi(len(devices), ids, C.byref(h))
         if rc:
             raise SckmError(rc, (lib.sckm_last_error(None) or b"").decode())
         self.h = h
         self.nranks, self.rank = 1, 0
+
+    def device_count(self):
+        return int(lib.sckm_ctx_device_count(self.h))
+
+    def last_fit_times(self):
+        out = np.zeros(6)
+        self._check(lib.sckm_ctx_last_fit_times(self.h, _p(out)))
+        return dict(upload_s=out[0], kmeanspp_init_s=out[1], lloyd_s=out[2], download_s=out[3], total_s=out[4], devices=int(out[5]))
 
     def _check(self, rc):
         if rc:

@@ -2,8 +2,8 @@
 //
 // The driver logic mirrors KMeans::fit (src/cluster/kmeans.rs:254-323): kmeans++ labels ->
 // per-label means -> loop { clustering step; centroid update; stop rule }.  Everything below runs
-// on the context's own CUDA stream; the only host round trip per Lloyd iteration is the 8-byte
-// inertia needed by the stop rule `if distortion <= dist { break }` (kmeans.rs:305).
+// on the context's own CUDA stream; the stop rule `if distortion <= dist { break }` (kmeans.rs:305) is
+// evaluated on the device, the host reads a 32-byte loop state back once per batch of iterations.
 #include "sckm_common.cuh"
 #include "sckm_blobs.cuh"
 #include <cfloat>
@@ -27,6 +27,14 @@ bool stream_supported(const sckm_dataset* ds, uint64_t k);    // sckm_stream.cu
 int launch_assign_tc5(sckm_dataset* ds, uint64_t k);          // sckm_tc5.cu
 bool tc5_supported(const sckm_dataset* ds, uint64_t k);       // sckm_tc5.cu
 bool tc5_auto(const sckm_dataset* ds, uint64_t k);            // sckm_tc5.cu
+void multi_destroy(sckm_ctx* ctx);                            // sckm_multi.cu
+bool multi_shards(const sckm_ctx* ctx, uint64_t n, std::vector<uint64_t>* bounds);   // sckm_multi.cu
+int multi_kmeans_fit(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int dtype, int column_major, uint64_t k,
+                     uint64_t max_iter, uint64_t first_index, const double* uniforms, void* labels_out, int width,
+                     int64_t* size_out, double* centroids_out, double* distortion_out, int64_t* iters_out);   // sckm_multi.cu
+int multi_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int dtype, int column_major,
+                  const double* centroids, uint64_t k, void* labels_out, int width);   // sckm_multi.cu
+uint64_t multi_launch_count(const sckm_ctx* ctx);             // sckm_multi.cu
 }
 using namespace sckm;
 
@@ -79,6 +87,7 @@ int sckm_ctx_create(int device, sckm_ctx** out) {
 
 void sckm_ctx_destroy(sckm_ctx* ctx) {
     if (!ctx) return;
+    multi_destroy(ctx);                       // the per-device contexts of a multi-GPU context, if any
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     nccl_destroy(ctx);
@@ -86,7 +95,7 @@ void sckm_ctx_destroy(sckm_ctx* ctx) {
     if (ctx->stream) dev_pool_trim(ctx);
     cudaFree(ctx->d_centroids); cudaFree(ctx->d_cnorm); cudaFree(ctx->d_packed); cudaFree(ctx->d_partials);
     cudaFree(ctx->d_size); cudaFree(ctx->d_blocksum); cudaFree(ctx->d_totals); cudaFree(ctx->d_seedrow);
-    cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_surv); cudaFree(ctx->d_kppctr); cudaFree(ctx->d_tshift); cudaFree(ctx->d_tshift_err); cudaFree(ctx->d_flush); cudaFree(ctx->d_tc5);
+    cudaFree(ctx->d_seeds); cudaFree(ctx->d_seedtab); cudaFree(ctx->d_skiptab); cudaFree(ctx->d_flags); cudaFree(ctx->d_surv); cudaFree(ctx->d_kppctr); cudaFree(ctx->d_tshift); cudaFree(ctx->d_tshift_err); cudaFree(ctx->d_flush); cudaFree(ctx->d_tc5); cudaFree(ctx->d_loop); cudaFree(ctx->d_inertia_trace); cudaFree(ctx->d_mu);
     if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -103,7 +112,7 @@ int sckm_ctx_set_assign_kernel(sckm_ctx* ctx, int which) {
     return SCKM_OK;
 }
 
-uint64_t sckm_ctx_launch_count(const sckm_ctx* ctx) { return ctx ? ctx->launches : 0; }
+uint64_t sckm_ctx_launch_count(const sckm_ctx* ctx) { return ctx ? ctx->launches + multi_launch_count(ctx) : 0; }
 
 int sckm_comm_unique_id(sckm_ctx* ctx, void* id128) {
     if (!ctx || !id128) return SCKM_ERR_INVALID;
@@ -116,8 +125,10 @@ int sckm_comm_init_rank(sckm_ctx* ctx, int nranks, int rank, const void* id128) 
 }
 
 // ---- dataset ------------------------------------------------------------------------------
-static int dataset_alloc(sckm_ctx* ctx, uint64_t n, uint64_t d, int dtype, uint64_t row_offset, uint64_t n_global,
-                         sckm_dataset** out) {
+}  // extern "C"
+namespace sckm {
+int dataset_alloc(sckm_ctx* ctx, uint64_t n, uint64_t d, int dtype, uint64_t row_offset, uint64_t n_global,
+                  sckm_dataset** out) {
     if (!ctx || !out) return SCKM_ERR_INVALID;
     *out = nullptr;
     if (dtype != SCKM_F32 && dtype != SCKM_F64) return fail(ctx, SCKM_ERR_INVALID, "dtype must be SCKM_F32 or SCKM_F64");
@@ -142,29 +153,43 @@ static int dataset_alloc(sckm_ctx* ctx, uint64_t n, uint64_t d, int dtype, uint6
     return SCKM_OK;
 }
 
+// Rows [lo, lo + ds->n) of a host matrix of `host_rows` rows -> ds->x (row-major on the device).  Row-major host
+// memory (DenseMatrix::new(.., false), matrix.rs:187-206): one contiguous block.  Column-major (from_2d_array,
+// matrix.rs:215-237): the shard is d strided runs of ds->n elements; they land as a [d][n] image (every run through
+// the pinned ring) and are transposed on the device.
+int upload_rows(sckm_dataset* ds, const void* host, uint64_t host_rows, uint64_t lo, int column_major) {
+    sckm_ctx* ctx = ds->ctx;
+    const size_t elem = ds->elem(), bytes = (size_t)ds->n * ds->d * elem;
+    if (!bytes) return SCKM_OK;
+    if (!column_major) return copy_to_device(ctx, ds->x, (const char*)host + (size_t)lo * ds->d * elem, bytes);
+    void* tmp = nullptr;
+    if (dev_alloc(ctx, &tmp, bytes) != cudaSuccess)
+        return fail(ctx, SCKM_ERR_CUDA, "cudaMalloc of the %zu-byte column-major staging image failed", bytes);
+    int rc = SCKM_OK;
+    if (lo == 0 && host_rows == ds->n) {
+        rc = copy_to_device(ctx, tmp, host, bytes);                           // the whole image is one block
+    } else {
+        const size_t run = (size_t)ds->n * elem;
+        ctx->ingest_hint = bytes;
+        for (uint64_t c = 0; c < ds->d && rc == SCKM_OK; c++)
+            rc = copy_to_device(ctx, (char*)tmp + c * run, (const char*)host + ((size_t)c * host_rows + lo) * elem, run, c == 0);
+        ctx->ingest_hint = 0;
+    }
+    if (rc == SCKM_OK) rc = launch_transpose(ctx, tmp, ds->x, ds->n, ds->d, ds->dtype);
+    dev_free(ctx, tmp);
+    cudaStreamSynchronize(ctx->stream);
+    return rc;
+}
+}  // namespace sckm
+extern "C" {
+
 int sckm_dataset_upload(sckm_ctx* ctx, const void* host, uint64_t n_local, uint64_t d, int dtype,
                         int column_major, uint64_t row_offset, uint64_t n_global, sckm_dataset** out) {
     if (!ctx) return SCKM_ERR_INVALID;
     if (!host && n_local) return fail(ctx, SCKM_ERR_INVALID, "host pointer is NULL");
     sckm_dataset* ds = nullptr;
     SCKM_TRY(dataset_alloc(ctx, n_local, d, dtype, row_offset, n_global, &ds));
-    const size_t bytes = (size_t)n_local * d * ds->elem();
-    int rc = SCKM_OK;
-    if (bytes) {
-        if (!column_major) {
-            rc = copy_to_device(ctx, ds->x, host, bytes);
-        } else {
-            // from_2d_array's layout (matrix.rs:215-237): land the column-major image, transpose on the device
-            void* tmp = nullptr;
-            if (dev_alloc(ctx, &tmp, bytes) != cudaSuccess) {
-                rc = fail(ctx, SCKM_ERR_CUDA, "cudaMalloc of the %zu-byte column-major staging image failed", bytes);
-            }
-            if (rc == SCKM_OK) rc = copy_to_device(ctx, tmp, host, bytes);
-            if (rc == SCKM_OK) rc = launch_transpose(ctx, tmp, ds->x, n_local, d, dtype);
-            dev_free(ctx, tmp);
-            cudaStreamSynchronize(ctx->stream);
-        }
-    }
+    const int rc = upload_rows(ds, host, n_local, 0, column_major);
     if (rc != SCKM_OK) { sckm_dataset_destroy(ds); return rc; }
     *out = ds;
     return SCKM_OK;
@@ -358,6 +383,7 @@ static int clustering_step(sckm_dataset* ds, uint64_t k, cudaEvent_t ev_a0 = nul
         if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
         SCKM_TRY(launch_reduce_partials(ctx, ctx->partial_slots_used, (size_t)k * ds->d + k + 1));
     } else {
+        ctx->packed_centered = false;
         SCKM_TRY(launch_assign_direct(ds, k));
         if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
         SCKM_TRY(launch_update(ds, k, true));
@@ -381,6 +407,7 @@ int sckm_init_centroids(sckm_dataset* ds, uint64_t k, double* centroids_out, int
     SCKM_TRY(launch_update(ds, k, false));
     SCKM_TRY(nccl_allreduce_f64(ctx, ctx->d_packed, (size_t)k * ds->d + k + 1));
     SCKM_TRY(launch_finalize(ctx, k, ds->d, /*guarded=*/false));
+    ctx->cnorm_valid = false;     // the first step of the fit picks its centring shift from these centroids (launch_cnorm)
     if (centroids_out) SCKM_CUDA(ctx, cudaMemcpyAsync(centroids_out, ctx->d_centroids, k * ds->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
     if (size_out) SCKM_CUDA(ctx, cudaMemcpyAsync(size_out, ctx->d_size, k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
     SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -398,21 +425,39 @@ int sckm_lloyd_step(sckm_dataset* ds, const double* centroids, uint64_t k, doubl
     SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->d_centroids, centroids, kd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     ctx->cnorm_valid = false;
     SCKM_TRY(clustering_step(ds, k));
-    std::vector<double> packed(kd + k + 1);
+    std::vector<double> packed(kd + k + 1), mu;
     SCKM_CUDA(ctx, cudaMemcpyAsync(packed.data(), ctx->d_packed, packed.size() * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->packed_centered && sums_out) {
+        mu.resize(ds->d);
+        SCKM_CUDA(ctx, cudaMemcpyAsync(mu.data(), ctx->d_mu, ds->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    }
     SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     if (sums_out) memcpy(sums_out, packed.data(), kd * sizeof(double));
+    if (!mu.empty())                                   // the tile kernel summed x - mu: sum(x) = sum(x - mu) + count * mu
+        for (uint64_t c = 0; c < k; c++)
+            for (uint64_t j = 0; j < ds->d; j++) sums_out[c * ds->d + j] += packed[kd + c] * mu[j];
     if (counts_out) for (uint64_t c = 0; c < k; c++) counts_out[c] = (int64_t)packed[kd + c];
     if (inertia_out) *inertia_out = packed[kd + k];
     return SCKM_OK;
 }
 
-static int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop, double* centroids_inout,
-                      int64_t* size_out, double* distortion_out, int64_t* iters_out, double* inertia_trace,
-                      float* ms_trace, float* assign_ms_trace = nullptr) {
+// The loop of KMeans::fit (kmeans.rs:294-310).  The stop rule lives on the device (finalize_kernel + LoopState), so
+// the host enqueues BATCHES of iterations and reads the 32-byte state back once per batch: kernels of iterations past
+// the one that broke the loop return at once, which leaves labels / centroids / sizes exactly as the reference's
+// `break` does.  The batch size adapts to the measured iteration time: a long iteration (config C3: 10 ms) is followed
+// by a read-back every time (nothing speculative is ever enqueued), a short one (config C2: ~50 us) only every few
+// iterations, so the host round trip (~10-15 us) stops being a quarter of the step.  The batch size is a pure function
+// of the shape (never of a clock): every rank of a multi-GPU fit must enqueue the same sequence of collectives.
+// honor_stop = false (bench): all iterations in one batch, no read-back in between.
+}  // extern "C"
+namespace sckm {
+int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop, double* centroids_inout,
+               int64_t* size_out, double* distortion_out, int64_t* iters_out, double* inertia_trace,
+               float* ms_trace, float* assign_ms_trace) {
     sckm_ctx* ctx = ds->ctx;
     SCKM_TRY(check_k(ds, k));
     if (max_iter == 0) return fail(ctx, SCKM_ERR_INVALID, "max_iter must be >= 1");
+    if (max_iter > 0xFFFFFFF0ull) return fail(ctx, SCKM_ERR_INVALID, "max_iter too large");
     SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, 0));
     const size_t kd = (size_t)k * ds->d;
@@ -420,8 +465,7 @@ static int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool hono
         SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->d_centroids, centroids_inout, kd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->cnorm_valid = false;
     }
-    double distortion = DBL_MAX;
-    int64_t iters = 0;
+    SCKM_TRY(launch_loop_init(ctx, max_iter, honor_stop));
     std::vector<cudaEvent_t> evs, evs_a;
     if (assign_ms_trace) {
         evs_a.resize(2 * max_iter);
@@ -432,44 +476,69 @@ static int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool hono
         for (auto& e : evs) SCKM_CUDA(ctx, cudaEventCreate(&e));
         SCKM_CUDA(ctx, cudaEventRecord(evs[0], ctx->stream));
     }
-    for (uint64_t it = 1; it <= max_iter; it++) {
-        if (assign_ms_trace) SCKM_TRY(clustering_step(ds, k, evs_a[2 * (it - 1)], evs_a[2 * (it - 1) + 1]));
-        else SCKM_TRY(clustering_step(ds, k));                    // bbd.clustering(...)        kmeans.rs:296
-        SCKM_TRY(launch_finalize(ctx, k, ds->d, /*guarded=*/true));  // centroids = sums / size   kmeans.rs:297-303
-        iters++;
-        if (ms_trace) SCKM_CUDA(ctx, cudaEventRecord(evs[it], ctx->stream));
-        if (honor_stop || inertia_trace) {
-            SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned, ctx->d_packed + kd + k, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-            SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-            const double dist = ctx->h_pinned[0];
-            if (inertia_trace) inertia_trace[it - 1] = dist;
-            if (honor_stop) {
-                if (distortion <= dist) break;                    // kmeans.rs:305-309
-                distortion = dist;
-            }
+    LoopState* h_state = reinterpret_cast<LoopState*>(ctx->h_pinned);
+    uint64_t batch = max_iter;
+    if (honor_stop) {
+        // ~400 us of estimated device work between read-backs, at most 8 iterations enqueued ahead of the stop test
+        const double n_loc = (double)((ds->n_global + ctx->nranks - 1) / std::max(ctx->nranks, 1));
+        const double us_hbm = n_loc * ((double)ds->d * ds->elem() + 4.0) / 5e6;                  // ~5 TB/s
+        const double us_fp = 2.0 * n_loc * (double)k * (double)ds->d / (ds->dtype == SCKM_F32 ? 150e6 : 25e6);   // TFLOP/s -> flop/us
+        batch = (uint64_t)std::max(1.0, std::min(8.0, 400.0 / (std::max(us_hbm, us_fp) + 15.0)));
+    }
+    if (const char* e = getenv("SCKM_LLOYD_BATCH")) batch = std::max<uint64_t>(1, strtoull(e, nullptr, 10));   // tests / tuning
+    int rc = SCKM_OK;
+    uint64_t it = 0;
+    h_state->done_at = 0; h_state->iters = 0; h_state->distortion = DBL_MAX;
+    while (it < max_iter && rc == SCKM_OK) {
+        const uint64_t nb = std::min(batch, max_iter - it);
+        for (uint64_t b = 0; b < nb && rc == SCKM_OK; b++) {
+            it++;
+            ctx->loop_it = (uint32_t)it;
+            if (assign_ms_trace) rc = clustering_step(ds, k, evs_a[2 * (it - 1)], evs_a[2 * (it - 1) + 1]);
+            else rc = clustering_step(ds, k);                                      // bbd.clustering(...)        kmeans.rs:296
+            if (rc == SCKM_OK) rc = launch_finalize(ctx, k, ds->d, /*guarded=*/true);  // centroids = sums / size + stop rule  kmeans.rs:297-309
+            if (rc == SCKM_OK && ms_trace && cudaEventRecord(evs[it], ctx->stream) != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "cudaEventRecord failed");
         }
+        ctx->loop_it = 0;
+        if (rc != SCKM_OK) break;
+        if (cudaMemcpyAsync(h_state, ctx->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            rc = fail(ctx, SCKM_ERR_CUDA, "Lloyd loop failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        if (h_state->done_at) break;
     }
-    if (centroids_inout)
-        SCKM_CUDA(ctx, cudaMemcpyAsync(centroids_inout, ctx->d_centroids, kd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-    if (size_out) SCKM_CUDA(ctx, cudaMemcpyAsync(size_out, ctx->d_size, k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
-    SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-    if (ms_trace) {
-        for (int64_t i = 0; i < iters; i++) SCKM_CUDA(ctx, cudaEventElapsedTime(&ms_trace[i], evs[i], evs[i + 1]));
-        for (auto& e : evs) cudaEventDestroy(e);
+    ctx->loop_it = 0;
+    const int64_t iters = (int64_t)h_state->iters;
+    const double distortion = h_state->distortion;
+    if (rc == SCKM_OK) {
+        if (centroids_inout && cudaMemcpyAsync(centroids_inout, ctx->d_centroids, kd * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = SCKM_ERR_CUDA;
+        if (size_out && cudaMemcpyAsync(size_out, ctx->d_size, k * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = SCKM_ERR_CUDA;
+        if (inertia_trace && iters > 0 &&
+            cudaMemcpyAsync(inertia_trace, ctx->d_inertia_trace, (size_t)iters * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = SCKM_ERR_CUDA;
+        if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = SCKM_ERR_CUDA;
+        if (rc != SCKM_OK) rc = fail(ctx, SCKM_ERR_CUDA, "Lloyd loop download failed: %s", cudaGetErrorString(cudaGetLastError()));
+    } else {
+        cudaStreamSynchronize(ctx->stream);
     }
-    if (assign_ms_trace) {
-        for (int64_t i = 0; i < iters; i++) SCKM_CUDA(ctx, cudaEventElapsedTime(&assign_ms_trace[i], evs_a[2 * i], evs_a[2 * i + 1]));
-        for (auto& e : evs_a) cudaEventDestroy(e);
-    }
+    if (rc == SCKM_OK && ms_trace)
+        for (int64_t i = 0; i < iters; i++) cudaEventElapsedTime(&ms_trace[i], evs[i], evs[i + 1]);
+    if (rc == SCKM_OK && assign_ms_trace)
+        for (int64_t i = 0; i < iters; i++) cudaEventElapsedTime(&assign_ms_trace[i], evs_a[2 * i], evs_a[2 * i + 1]);
+    for (auto& e : evs) cudaEventDestroy(e);
+    for (auto& e : evs_a) cudaEventDestroy(e);
+    if (rc != SCKM_OK) return rc;
     if (distortion_out) *distortion_out = distortion;
     if (iters_out) *iters_out = iters;
     return SCKM_OK;
 }
+}  // namespace sckm
+extern "C" {
 
 int sckm_lloyd_fit(sckm_dataset* ds, uint64_t k, uint64_t max_iter, double* centroids_inout,
                    int64_t* size_out, double* distortion_out, int64_t* iters_out) {
     if (!ds || !centroids_inout) return SCKM_ERR_INVALID;
-    return lloyd_loop(ds, k, max_iter, true, centroids_inout, size_out, distortion_out, iters_out, nullptr, nullptr);
+    return lloyd_loop(ds, k, max_iter, true, centroids_inout, size_out, distortion_out, iters_out, nullptr, nullptr, nullptr);
 }
 
 int sckm_lloyd_iterate(sckm_dataset* ds, uint64_t k, uint64_t n_iters, double* centroids_inout,
@@ -479,7 +548,9 @@ int sckm_lloyd_iterate(sckm_dataset* ds, uint64_t k, uint64_t n_iters, double* c
                       assign_ms_out);
 }
 
-static int download_labels(sckm_dataset* ds, void* out, int width) {
+}  // extern "C"
+namespace sckm {
+int download_labels(sckm_dataset* ds, void* out, int width) {
     sckm_ctx* ctx = ds->ctx;
     const uint64_t n = ds->n;
     if (width == 4) {
@@ -490,6 +561,8 @@ static int download_labels(sckm_dataset* ds, void* out, int width) {
     SCKM_TRY(launch_labels_widen(ctx, ds->labels, ds->labels64, n));
     return copy_to_host(ctx, out, ds->labels64, n * 8);
 }
+}  // namespace sckm
+extern "C" {
 
 int sckm_labels_download(sckm_dataset* ds, void* out, int width) {
     if (!ds || !out) return SCKM_ERR_INVALID;
@@ -517,13 +590,11 @@ static int predict_chunk(sckm_dataset* ds, uint64_t k) {
     return launch_assign_direct_raw(ctx, ds->x, ds->dtype, ds->n, ds->d, k, ds->labels, nullptr);
 }
 
-int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int dtype,
+}  // extern "C"
+namespace sckm {
+// rows [lo, lo + n) of a host matrix with `host_rows` rows (the pitch of a column-major image) -> labels_out[0..n)
+int predict_rows(sckm_ctx* ctx, const void* x_host, uint64_t host_rows, uint64_t lo, uint64_t n, uint64_t d, int dtype,
                  int column_major, const double* centroids, uint64_t k, void* labels_out, int width) {
-    if (!ctx) return SCKM_ERR_INVALID;
-    if ((!x_host || !labels_out) && n) return fail(ctx, SCKM_ERR_INVALID, "NULL buffer");
-    if (!centroids || k < 1) return fail(ctx, SCKM_ERR_INVALID, "no centroids");
-    if (width != 4 && width != 8) return fail(ctx, SCKM_ERR_INVALID, "label width must be 4 or 8");
-    if (dtype != SCKM_F32 && dtype != SCKM_F64) return fail(ctx, SCKM_ERR_INVALID, "dtype must be SCKM_F32 or SCKM_F64");
     if (n == 0) return SCKM_OK;
     SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
     const size_t elem = dtype == SCKM_F32 ? 4 : 8, row_bytes = (size_t)d * elem;
@@ -544,14 +615,14 @@ int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int 
         rc = fail(ctx, SCKM_ERR_CUDA, "centroid upload failed");
     ctx->cnorm_valid = false;
 
-    // chunk c covers rows [c*chunk_rows, ...): row-major = one contiguous block; column-major = d strided pieces,
+    // chunk c covers rows [lo + c*chunk_rows, ...): row-major = one contiguous block; column-major = d strided pieces,
     // landed as a [d][rows] image (2-D copy, stream-ordered) and transposed on the device
     auto upload = [&](uint64_t c, bool first) -> int {
         sckm_dataset* ds = buf[c & 1];
-        const uint64_t r0 = c * chunk_rows, rows = std::min(chunk_rows, n - r0);
+        const uint64_t r0 = lo + c * chunk_rows, rows = std::min(chunk_rows, lo + n - r0);
         ds->n = rows;
         if (!column_major) return copy_to_device(ctx, ds->x, (const char*)x_host + r0 * row_bytes, rows * row_bytes, first);
-        SCKM_CUDA(ctx, cudaMemcpy2DAsync(cm_tmp, rows * elem, (const char*)x_host + r0 * elem, n * elem, rows * elem, d,
+        SCKM_CUDA(ctx, cudaMemcpy2DAsync(cm_tmp, rows * elem, (const char*)x_host + r0 * elem, host_rows * elem, rows * elem, d,
                                          cudaMemcpyHostToDevice, ctx->stream));
         return launch_transpose(ctx, cm_tmp, ds->x, rows, d, dtype);
     };
@@ -569,6 +640,21 @@ int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int 
     sckm_dataset_destroy(buf[0]);
     sckm_dataset_destroy(buf[1]);
     return rc;
+}
+}  // namespace sckm
+extern "C" {
+
+int sckm_predict(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int dtype,
+                 int column_major, const double* centroids, uint64_t k, void* labels_out, int width) {
+    if (!ctx) return SCKM_ERR_INVALID;
+    if ((!x_host || !labels_out) && n) return fail(ctx, SCKM_ERR_INVALID, "NULL buffer");
+    if (!centroids || k < 1) return fail(ctx, SCKM_ERR_INVALID, "no centroids");
+    if (width != 4 && width != 8) return fail(ctx, SCKM_ERR_INVALID, "label width must be 4 or 8");
+    if (dtype != SCKM_F32 && dtype != SCKM_F64) return fail(ctx, SCKM_ERR_INVALID, "dtype must be SCKM_F32 or SCKM_F64");
+    if (d == 0 || d > (1u << 20)) return fail(ctx, SCKM_ERR_INVALID, "d=%llu out of range", (unsigned long long)d);
+    if (multi_shards(ctx, n, nullptr))                                        // rows sharded over the context's devices
+        return multi_predict(ctx, x_host, n, d, dtype, column_major, centroids, k, labels_out, width);
+    return predict_rows(ctx, x_host, n, 0, n, d, dtype, column_major, centroids, k, labels_out, width);
 }
 
 // ---- cluster quality: contingency table --------------------------------------------------------
@@ -638,6 +724,41 @@ int sckm_radius_fill(sckm_dataset* ds, const void* queries_host, uint64_t nq, do
 }
 
 // ---- whole fit from host buffers ----------------------------------------------------------------
+}  // extern "C"
+namespace sckm {
+// KMeans::fit on the rows [lo, lo + n_local) of the host matrix, as rank ctx->rank of ctx->nranks (1 rank: the whole
+// matrix).  Phase 1 (allocation + upload) and phase 2 (kmeans++, means, loop, download) are separate calls so that a
+// multi-GPU driver can stop every rank before the first collective when one of them could not get its memory.
+int fit_upload(sckm_ctx* ctx, const void* x_host, uint64_t host_rows, uint64_t lo, uint64_t n_local, uint64_t d, int dtype,
+               int column_major, sckm_dataset** out) {
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    sckm_dataset* ds = nullptr;
+    SCKM_TRY(dataset_alloc(ctx, n_local, d, dtype, lo, host_rows, &ds));
+    const int rc = upload_rows(ds, x_host, host_rows, lo, column_major);
+    if (rc != SCKM_OK) { sckm_dataset_destroy(ds); return rc; }
+    *out = ds;
+    return SCKM_OK;
+}
+int fit_compute(sckm_dataset* ds, uint64_t k, uint64_t max_iter, uint64_t first_index, const double* uniforms,
+                int64_t* size_out, double* centroids_out, double* distortion_out, int64_t* iters_out, double* phase_s) {
+    sckm_ctx* ctx = ds->ctx;
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    int rc = sckm_kmeanspp(ds, k, first_index, uniforms, nullptr, nullptr);
+    if (rc == SCKM_OK) rc = sckm_init_centroids(ds, k, nullptr, nullptr);
+    const double t1 = now();
+    if (rc == SCKM_OK) rc = lloyd_loop(ds, k, max_iter, true, nullptr, size_out, distortion_out, iters_out, nullptr, nullptr, nullptr);
+    if (rc == SCKM_OK && centroids_out &&
+        (cudaMemcpyAsync(centroids_out, ctx->d_centroids, k * ds->d * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+         cudaStreamSynchronize(ctx->stream) != cudaSuccess))
+        rc = fail(ctx, SCKM_ERR_CUDA, "centroid download failed");
+    if (phase_s) { phase_s[0] = t1 - t0; phase_s[1] = now() - t1; }
+    return rc;
+}
+}  // namespace sckm
+extern "C" {
+
 int sckm_kmeans_fit(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, int dtype,
                     int column_major, uint64_t k, uint64_t max_iter, uint64_t first_index,
                     const double* uniforms, void* labels_out, int width, int64_t* size_out,
@@ -645,16 +766,31 @@ int sckm_kmeans_fit(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, i
     if (!ctx) return SCKM_ERR_INVALID;
     if (!centroids_out) return fail(ctx, SCKM_ERR_INVALID, "centroids_out is NULL");
     if (n == 0) return fail(ctx, SCKM_ERR_INVALID, "empty input");
+    if (!x_host) return fail(ctx, SCKM_ERR_INVALID, "host pointer is NULL");
+    if (labels_out && width != 4 && width != 8) return fail(ctx, SCKM_ERR_INVALID, "label width must be 4 or 8");
+    if (multi_shards(ctx, n, nullptr))                                        // rows sharded over the context's devices
+        return multi_kmeans_fit(ctx, x_host, n, d, dtype, column_major, k, max_iter, first_index, uniforms, labels_out,
+                                width, size_out, centroids_out, distortion_out, iters_out);
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
     sckm_dataset* ds = nullptr;
-    SCKM_TRY(sckm_dataset_upload(ctx, x_host, n, d, dtype, column_major, 0, n, &ds));
-    int rc = sckm_kmeanspp(ds, k, first_index, uniforms, nullptr, nullptr);
-    if (rc == SCKM_OK) rc = sckm_init_centroids(ds, k, centroids_out, nullptr);
-    if (rc == SCKM_OK) rc = lloyd_loop(ds, k, max_iter, true, nullptr, size_out, distortion_out, iters_out, nullptr, nullptr);
-    if (rc == SCKM_OK && cudaMemcpy(centroids_out, ctx->d_centroids, k * d * sizeof(double), cudaMemcpyDeviceToHost) != cudaSuccess)
-        rc = fail(ctx, SCKM_ERR_CUDA, "centroid download failed");
+    SCKM_TRY(fit_upload(ctx, x_host, n, 0, n, d, dtype, column_major, &ds));
+    const double t1 = now();
+    double ph[2] = {0, 0};
+    int rc = fit_compute(ds, k, max_iter, first_index, uniforms, size_out, centroids_out, distortion_out, iters_out, ph);
+    const double t2 = now();
     if (rc == SCKM_OK && labels_out) rc = download_labels(ds, labels_out, width);
     sckm_dataset_destroy(ds);
+    const double t3 = now();
+    ctx->fit_times[0] = t1 - t0; ctx->fit_times[1] = ph[0]; ctx->fit_times[2] = ph[1]; ctx->fit_times[3] = t3 - t2;
+    ctx->fit_times[4] = t3 - t0; ctx->fit_times[5] = 1.0;
     return rc;
+}
+
+int sckm_ctx_last_fit_times(const sckm_ctx* ctx, double* out6) {
+    if (!ctx || !out6) return SCKM_ERR_INVALID;
+    for (int i = 0; i < 6; i++) out6[i] = ctx->fit_times[i];
+    return SCKM_OK;
 }
 
 // ---- measurement --------------------------------------------------------------------------------

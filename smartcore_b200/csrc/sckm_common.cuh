@@ -17,7 +17,19 @@ constexpr int kKppBlockRows = 1024;   // fixed summation unit of the kmeans++ D^
 // pitch (in doubles) of one partial slot [k*d sums | k counts | inertia]: 128-byte aligned rows
 inline size_t slot_pitch(size_t pk) { return (pk + 15) / 16 * 16; }
 
+struct MultiExt;    // sckm_multi.cu
 struct StagePool;   // pinned staging ring of the host<->device transfer engine (sckm_ingest.cu)
+
+// Device-resident state of the loop of KMeans::fit (kmeans.rs:294-310).  The stop rule `if distortion <= dist { break }`
+// (kmeans.rs:305-309) is evaluated on the device by the finalize kernel of each iteration, so the host can enqueue
+// several iterations without reading the inertia back: once `done_at` is set, every kernel of a LATER iteration
+// returns at once and the state (labels, centroids, sizes) stays that of the iteration that broke the loop.
+struct LoopState {
+    double distortion;             // last strictly smaller inertia (f64::MAX before the first step, kmeans.rs:273)
+    unsigned long long done_at;    // iteration (1-based) whose stop test fired; 0 = still running
+    unsigned long long iters;      // clustering steps executed so far
+    unsigned long long honor_stop; // 0: fixed number of steps (sckm_lloyd_iterate)
+};
 
 }  // namespace sckm
 
@@ -34,7 +46,11 @@ struct sckm_ctx {
     int nranks = 1, rank = 0;
     // workspaces, grown on demand
     double* d_centroids = nullptr;   // [k*d] current centroids
-    double* d_cnorm = nullptr;       // [k] ||c||^2 (GEMM-form kernels)
+    double* d_cnorm = nullptr;       // [k] ||c - mu||^2 (GEMM-form kernels), [k] = their max
+    double* d_mu = nullptr;          // [d] centring shift of the GEMM-form kernels (see launch_cnorm); zeros = no shift
+    size_t cap_mu = 0;
+    bool mu_zero = true;             // d_mu currently holds zeros
+    bool packed_centered = false;    // d_packed sums of the last step are sums of (x - mu), not of x
     double* d_packed = nullptr;      // [k*d sums | k counts | inertia]
     double* d_partials = nullptr;    // [P][k*d + k + 1] per-CTA/warp partial sums (deterministic)
     size_t cap_centroids = 0, cap_packed = 0, cap_cnorm = 0, cap_size = 0, cap_seeds = 0, cap_partials = 0;
@@ -54,6 +70,10 @@ struct sckm_ctx {
     float* d_tshift = nullptr;       // kmeans++ screening: f32(new seed - seed 0) [d]
     double* d_tshift_err = nullptr;  // ... and the length of what that rounding dropped
     size_t cap_tshift = 0;
+    sckm::LoopState* d_loop = nullptr;      // stop-rule state of the running Lloyd loop
+    uint32_t loop_it = 0;                   // iteration being enqueued (1-based); 0 = outside a loop (kernels never skip)
+    double* d_inertia_trace = nullptr;      // [cap_trace] inertia of every step of the running loop
+    size_t cap_trace = 0;
     unsigned long long* d_flags = nullptr;  // [0] rows marked as near-ties in the current step; rest: scratch
     bool cnorm_valid = false;        // d_cnorm matches d_centroids
     uint64_t ws_k = 0, ws_d = 0;     // shape the centroid workspaces currently hold
@@ -64,6 +84,9 @@ struct sckm_ctx {
     size_t flush_bytes = 0;
     double* h_pinned = nullptr;      // small pinned scratch (>= 64 doubles)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    sckm::MultiExt* multi = nullptr;         // per-device contexts of a multi-GPU context (sckm_ctx_create_multi)
+    int ingest_max_threads = 0;              // cap on the staging threads of this context (0 = default)
+    double fit_times[6] = {0, 0, 0, 0, 0, 0}; // last sckm_kmeans_fit: upload, kmeans++ + means, loop, download, total [s], devices
     size_t ingest_hint = 0;                  // bytes the current multi-transfer operation will move in total (0 = unknown)
     cudaStream_t copy_stream = nullptr;      // transfers that must not queue behind the kernels on `stream`
     sckm::StagePool* stage_pool = nullptr;   // pinned ring for transfers from/to pageable memory (lanes pinned on first use)
@@ -118,6 +141,14 @@ inline cudaError_t ws_malloc(sckm_ctx* ctx, void** p, size_t bytes) {
     return e;
 }
 
+// the (state, iteration) pair every kernel of a Lloyd step receives: it returns at once when the loop already stopped
+#define SCKM_LOOP_ARGS(ctx) ((ctx)->loop_it ? (ctx)->d_loop : nullptr), (ctx)->loop_it
+#ifdef __CUDACC__
+__device__ __forceinline__ bool loop_done(const LoopState* st, uint32_t it) {
+    return st != nullptr && st->done_at != 0ull && st->done_at < (unsigned long long)it;
+}
+#endif
+
 #define SCKM_CUDA(ctx, call)                                                               \
     do {                                                                                   \
         cudaError_t _e = (call);                                                           \
@@ -145,6 +176,19 @@ int copy_to_device(sckm_ctx* ctx, void* dst_dev, const void* src_host, size_t by
 int copy_to_host(sckm_ctx* ctx, void* dst_host, const void* src_dev, size_t bytes);
 void ingest_destroy(sckm_ctx* ctx);
 
+// ---- pieces of the API layer shared with the multi-GPU driver (sckm_api.cu) ----
+int dataset_alloc(sckm_ctx* ctx, uint64_t n, uint64_t d, int dtype, uint64_t row_offset, uint64_t n_global, sckm_dataset** out);
+int upload_rows(sckm_dataset* ds, const void* host, uint64_t host_rows, uint64_t lo, int column_major);
+int download_labels(sckm_dataset* ds, void* out, int width);
+int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop, double* centroids_inout, int64_t* size_out,
+               double* distortion_out, int64_t* iters_out, double* inertia_trace, float* ms_trace, float* assign_ms_trace);
+int fit_upload(sckm_ctx* ctx, const void* x_host, uint64_t host_rows, uint64_t lo, uint64_t n_local, uint64_t d, int dtype,
+               int column_major, sckm_dataset** out);
+int fit_compute(sckm_dataset* ds, uint64_t k, uint64_t max_iter, uint64_t first_index, const double* uniforms,
+                int64_t* size_out, double* centroids_out, double* distortion_out, int64_t* iters_out, double* phase_s);
+int predict_rows(sckm_ctx* ctx, const void* x_host, uint64_t host_rows, uint64_t lo, uint64_t n, uint64_t d, int dtype,
+                 int column_major, const double* centroids, uint64_t k, void* labels_out, int width);
+
 // ---- kernel launchers (sckm_kernels.cu) ----
 int launch_transpose(sckm_ctx* ctx, const void* src_colmajor, void* dst_rowmajor, uint64_t n, uint64_t d, int dtype);
 int launch_blobs(sckm_ctx* ctx, void* x, int dtype, uint64_t row0, uint64_t nrows, uint64_t d,
@@ -166,6 +210,7 @@ int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia);
 int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk);
 // centroids = sums / counts (guarded: keep old when count == 0; unguarded for the initial means)
 int launch_finalize(sckm_ctx* ctx, uint64_t k, uint64_t d, bool guarded);
+int launch_loop_init(sckm_ctx* ctx, uint64_t max_iter, bool honor_stop);
 int launch_labels_widen(sckm_ctx* ctx, const uint32_t* in, uint64_t* out, uint64_t n);
 int measure_peaks(sckm_ctx* ctx, double* out3);
 

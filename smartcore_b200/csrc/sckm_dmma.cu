@@ -15,6 +15,12 @@
 //     block is resident, so one warp's HBM latency hides under the other warps' DMMAs.
 //   * Accumulators start at -(||x||^2 + ||c||^2)/2, DMMA adds x.c: acc = -dist^2/2; the epilogue
 //     is max / second-max tracking only.
+//   * Both operands are CENTRED on a per-fit shift mu (the mean of the fit's initial centroids, launch_cnorm):
+//     rows become x - mu as they are loaded, the staged centroid block holds c - mu, the norms are ||c - mu||^2.
+//     ||x - c||^2 does not change, but the cancellation error of the GEMM form now scales with the spread of the
+//     data around mu instead of its distance from the origin, and so do the near-tie threshold and the per-point
+//     distance.  The fused update accumulates the centred values; finalize_kernel adds mu back
+//     (centroid = sum(x - mu) / count + mu).
 //   * Rows whose best/second gap is within 1e-10*(||x||^2 + max||c||^2) (>= 1e4 x the rounding
 //     error bound of the GEMM form) are marked and re-decided by refine_rows_kernel with the
 //     reference's exact arithmetic (euclidian.rs:56-63), so labels equal the exact direct-form argmin.
@@ -100,17 +106,21 @@ __device__ __forceinline__ void epilogue_all(const double (&acc)[MT][NT][2], uin
 template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool UPDATE, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
-                   const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t* __restrict__ labels,
-                   double* __restrict__ mind, double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked) {
+                   const double* __restrict__ cnorm, const double* __restrict__ mu, uint32_t k, uint32_t bn, uint32_t* __restrict__ labels,
+                   double* __restrict__ mind, double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked,
+                   const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    if (loop_done(loop_st, loop_it)) return;       // the fit's stop rule already fired (kmeans.rs:305)
     constexpr int DP = KSTEPS * 4;                 // padded feature count
     constexpr int PITCH = DP + 4;                  // doubles per staged centroid row (pitch = d*8+32 B)
     constexpr int ROWS = 8 * MT;
     extern __shared__ __align__(16) double smem_d[];
-    double* cbuf = smem_d;                         // [bn][PITCH]
-    double* cn = smem_d + (size_t)bn * PITCH;      // [bn]  -||c||^2/2, -inf for padding columns
+    double* cbuf = smem_d;                         // [bn][PITCH]  c - mu
+    double* cn = smem_d + (size_t)bn * PITCH;      // [bn]  -||c - mu||^2/2, -inf for padding columns
+    double* mu_s = cn + bn;                        // [DP]  centring shift (0 in the padding columns)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const double cmax = cta_max(cnorm, k);         // max_j ||c_j||^2
+    for (uint32_t c = threadIdx.x; c < (uint32_t)DP; c += blockDim.x) mu_s[c] = c < d ? mu[c] : 0.0;
+    const double cmax = cta_max(cnorm, k);         // max_j ||c_j - mu||^2 (its barriers also publish mu_s)
 
     const uint64_t nslabs = (n + ROWS - 1) / ROWS;
     const uint64_t stride = (uint64_t)gridDim.x * DMMA_WARPS;
@@ -138,7 +148,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
             for (int ks = 0; ks < KSTEPS; ks++) {
                 const uint32_t col = ks * 4 + t;
                 double v = 0.0;
-                if (rok && col < d) v = (double)__ldg(xr + col);
+                if (rok && col < d) v = (double)__ldg(xr + col) - mu_s[col];
                 a[mt][ks] = v;
                 s = fma(v, v, s);
             }
@@ -159,7 +169,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
                 for (uint32_t e = threadIdx.x; e < bn * DP; e += blockDim.x) {
                     const uint32_t r = e / DP, c = e - r * DP;
                     double v = 0.0;
-                    if (c0 + r < k && c < d) v = centroids[(size_t)(c0 + r) * d + c];
+                    if (c0 + r < k && c < d) v = centroids[(size_t)(c0 + r) * d + c] - mu_s[c];
                     cbuf[(size_t)r * PITCH + c] = v;
                 }
                 for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
@@ -245,23 +255,27 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
 template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool MULTI, bool UPDATE, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
-                   const double* __restrict__ cnorm, uint32_t k, uint32_t bn, uint32_t sl_arg, uint32_t* __restrict__ labels,
-                   double* __restrict__ mind, double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked) {
+                   const double* __restrict__ cnorm, const double* __restrict__ mu, uint32_t k, uint32_t bn, uint32_t sl_arg, uint32_t* __restrict__ labels,
+                   double* __restrict__ mind, double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked,
+                   const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    if (loop_done(loop_st, loop_it)) return;       // the fit's stop rule already fired (kmeans.rs:305)
     const uint32_t sl = MULTI ? sl_arg : 1u;
     constexpr int DP = KSTEPS * 4;                 // padded feature count
     constexpr int PITCH = DP + 4;                  // doubles per staged centroid row (pitch = d*8+32 B)
     constexpr int ROWS = 8 * MT;
     constexpr int SUB = 8 * DMMA_NT;               // centroids per accumulator sub-block
     extern __shared__ __align__(16) double smem_d[];
-    double* cbuf = smem_d;                         // [bn][PITCH]
-    double* cn = smem_d + (size_t)bn * PITCH;      // [bn]  -||c||^2/2, -inf for padding columns
+    double* cbuf = smem_d;                         // [bn][PITCH]  c - mu
+    double* cn = smem_d + (size_t)bn * PITCH;      // [bn]  -||c - mu||^2/2, -inf for padding columns
+    double* mu_s = cn + bn;                        // [DP]  centring shift (0 in the padding columns)
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
     // per-warp row state between centroid blocks: [sl][ROWS] x {best, second, idx}
-    key_t* st_best = reinterpret_cast<key_t*>(cn + bn) + (size_t)warp * sl * ROWS * 3;
+    key_t* st_best = reinterpret_cast<key_t*>(mu_s + DP) + (size_t)warp * sl * ROWS * 3;
     key_t* st_second = st_best + (size_t)sl * ROWS;
     key_t* st_idx = st_second + (size_t)sl * ROWS;
-    const double cmax = cta_max(cnorm, k);         // max_j ||c_j||^2
+    for (uint32_t c = threadIdx.x; c < (uint32_t)DP; c += blockDim.x) mu_s[c] = c < d ? mu[c] : 0.0;
+    const double cmax = cta_max(cnorm, k);         // max_j ||c_j - mu||^2 (its barriers also publish mu_s)
 
     const uint64_t nslabs = (n + ROWS - 1) / ROWS;
     const uint64_t stride = (uint64_t)gridDim.x * DMMA_WARPS;
@@ -281,7 +295,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                 for (uint32_t e = threadIdx.x; e < bn * DP; e += blockDim.x) {
                     const uint32_t r = e / DP, c = e - r * DP;
                     double v = 0.0;
-                    if (c0 + r < k && c < d) v = centroids[(size_t)(c0 + r) * d + c];
+                    if (c0 + r < k && c < d) v = centroids[(size_t)(c0 + r) * d + c] - mu_s[c];
                     cbuf[(size_t)r * PITCH + c] = v;
                 }
                 for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
@@ -310,7 +324,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                     for (int ks = 0; ks < KSTEPS; ks++) {
                         const uint32_t col = ks * 4 + t;
                         double v = 0.0;
-                        if (rok && col < d) v = (double)__ldg(xr + col);
+                        if (rok && col < d) v = (double)__ldg(xr + col) - mu_s[col];
                         a[mt][ks] = v;
                         s = fma(v, v, s);
                     }
@@ -412,15 +426,16 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
 
 // Exact re-decision of the rows marked 0xffffffff by the tile kernel.  Warp w scans the fixed row range
 // [w*R, (w+1)*R) in order; for a marked row, lane l scans centroids l, l+32, ... with the reference's
-// arithmetic (widen to f64, diff, square, sequential sum, never fused), then a warp argmin with strict <
-// and lowest index on ties (kmeans.rs:334-347 / bbd_tree.rs:101-111); the row is then added to this
-// warp's private partial (lanes own columns), so the result does not depend on scheduling.
+// arithmetic (widen to f64, diff, square, sequential sum, never fused; raw x and raw centroids, no centring), then
+// a warp argmin with strict < and lowest index on ties (kmeans.rs:334-347 / bbd_tree.rs:101-111); the row is then
+// added to this warp's private partial (lanes own columns), so the result does not depend on scheduling.
 template <typename TX, int DMMA_WARPS, bool UPDATE = true>
 __global__ void __launch_bounds__(DMMA_WARPS * 32)
 refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids, uint32_t k,
                    uint32_t* __restrict__ labels, double* __restrict__ mind, double* __restrict__ partials, size_t pk,
-                   const unsigned long long* __restrict__ nmarked) {
-    if (*nmarked == 0ull) return;                                // nothing was marked in this step (the common case)
+                   const unsigned long long* __restrict__ nmarked, const double* __restrict__ mu,
+                   const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    if (*nmarked == 0ull || loop_done(loop_st, loop_it)) return; // nothing was marked in this step (the common case)
     const int lane = threadIdx.x & 31;
     const uint64_t w = (uint64_t)blockIdx.x * DMMA_WARPS + (threadIdx.x >> 5);
     const uint64_t nw = (uint64_t)gridDim.x * DMMA_WARPS;
@@ -464,7 +479,8 @@ refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
             if (bi == 0xffffffffu) bi = 0;                      // all distances NaN: the reference keeps cluster 0
             if (UPDATE) {
                 double* p = part + (size_t)bi * d;
-                for (uint32_t j = lane; j < d; j += 32) __stcg(p + j, __dadd_rn(__ldcg(p + j), (double)xr[j]));
+                // (the slots of this step hold sums of x - mu when the tile kernel centred its rows: mu != nullptr)
+                for (uint32_t j = lane; j < d; j += 32) __stcg(p + j, __dadd_rn(__ldcg(p + j), mu ? (double)xr[j] - mu[j] : (double)xr[j]));
             }
             if (lane == 0) {
                 labels[row] = bi;
@@ -483,13 +499,29 @@ refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
     if (UPDATE && lane == 0 && any) __stcg(part + pk - 1, __dadd_rn(__ldcg(part + pk - 1), inertia));
 }
 
-// ||c||^2 of the centroids currently in ctx->d_centroids (the finalize kernel also writes them, but
+// mu = per-feature mean of the finite centroids (fixed order: one thread per feature walks the k centroids), the
+// centring shift of the GEMM-form kernels.  NaN / inf centroids (an empty initial cluster leaves 0/0, kmeans.rs:288-292)
+// are left out; any finite mu is correct, a central one is accurate.
+__global__ void center_kernel(const double* __restrict__ centroids, uint32_t k, uint32_t d, double* __restrict__ mu) {
+    for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) {
+        double s = 0.0; uint32_t cnt = 0;
+        for (uint32_t c = 0; c < k; c++) {
+            const double v = centroids[(size_t)c * d + j];
+            if (isfinite(v)) { s += v; cnt++; }
+        }
+        const double m = cnt ? s / (double)cnt : 0.0;
+        mu[j] = isfinite(m) ? m : 0.0;
+    }
+}
+
+// ||c - mu||^2 of the centroids currently in ctx->d_centroids (the finalize kernel also writes them, but
 // sckm_lloyd_step uploads centroids from the host)
-__global__ void cnorm_kernel(const double* __restrict__ centroids, uint32_t k, uint32_t d, double* __restrict__ cnorm) {
+__global__ void cnorm_kernel(const double* __restrict__ centroids, uint32_t k, uint32_t d, const double* __restrict__ mu,
+                             double* __restrict__ cnorm) {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= k) return;
     double s = 0.0;
-    for (uint32_t j = 0; j < d; j++) { const double v = centroids[(size_t)c * d + j]; s = fma(v, v, s); }
+    for (uint32_t j = 0; j < d; j++) { const double v = centroids[(size_t)c * d + j] - mu[j]; s = fma(v, v, s); }
     cnorm[c] = s;
 }
 
@@ -510,7 +542,8 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     const uint32_t kpad = (uint32_t)((k + 8 * NT - 1) / (8 * NT) * (8 * NT));
     uint32_t sl = 1;
     bool multi = false;
-    uint32_t bn = (uint32_t)(((size_t)ctx->smem_optin - 1024) / row_bytes);
+    const size_t fixed = 2048 + (size_t)DP * 8;                       // static shared memory + slack, the centring shift
+    uint32_t bn = (uint32_t)(((size_t)ctx->smem_optin - fixed) / row_bytes);
     bn = bn / (8 * NT) * (8 * NT);
     if (bn >= kpad) {
         bn = kpad;                                                     // whole centroid set resident, no row state
@@ -519,31 +552,31 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
         sl = 12;                                                       // slabs per warp per resident centroid block
         if (const char* e = getenv("SCKM_DMMA_SL")) sl = (uint32_t)std::max(1, std::min(16, atoi(e)));   // tuning knob
         const size_t state = (size_t)WARPS * sl * ROWS * 3 * sizeof(long long);
-        bn = (uint32_t)(((size_t)ctx->smem_optin - 1024 - state) / row_bytes);
+        bn = (uint32_t)(((size_t)ctx->smem_optin - fixed - state) / row_bytes);
         bn = bn / (8 * NT) * (8 * NT);
         // balance the blocks: same count, even sizes
         const uint32_t nch = (kpad + bn - 1) / bn;
         bn = ((kpad + nch - 1) / nch + 8 * NT - 1) / (8 * NT) * (8 * NT);
     }
     if (bn < 8 * NT) return fail(ctx, SCKM_ERR_INVALID, "shared memory too small for the DMMA tile");
-    const size_t smem = (size_t)bn * row_bytes + (multi ? (size_t)WARPS * sl * ROWS * 3 * sizeof(long long) : 0);
+    const size_t smem = (size_t)bn * row_bytes + (size_t)DP * 8 + (multi ? (size_t)WARPS * sl * ROWS * 3 * sizeof(long long) : 0);
     ctx->partial_slots_used = dmma_grid(ctx) * WARPS;
     if (!multi) {
         auto kern = assign_dmma_resident_kernel<KSTEPS, MT, NT, WARPS, UPDATE, TX>;
         SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
-                                                              ctx->d_cnorm, (uint32_t)k, bn, ds->labels, ds->mind,
-                                                              ctx->d_partials, pk, ctx->d_flags);
+                                                              ctx->d_cnorm, ctx->d_mu, (uint32_t)k, bn, ds->labels, ds->mind,
+                                                              ctx->d_partials, pk, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     } else {
         auto kern = assign_dmma_kernel<KSTEPS, MT, NT, WARPS, true, UPDATE, TX>;
         SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
-                                                              ctx->d_cnorm, (uint32_t)k, bn, sl, ds->labels, ds->mind,
-                                                              ctx->d_partials, pk, ctx->d_flags);
+                                                              ctx->d_cnorm, ctx->d_mu, (uint32_t)k, bn, sl, ds->labels, ds->mind,
+                                                              ctx->d_partials, pk, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     }
     LAUNCH_CHECK_D(ctx);
     refine_rows_kernel<TX, WARPS, UPDATE><<<dmma_grid(ctx), WARPS * 32, 0, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d,
-        ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags);
+        ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, ctx->d_mu, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }
@@ -557,11 +590,16 @@ static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     return launch_t<32, 1, 4, 12, UPDATE, TX>(ds, k, pk);
 }
 
-// ||c||^2 of ctx->d_centroids -- only needed when the centroids came from the host; inside the Lloyd loop the
-// finalize kernel keeps the norms current (an unchanged centroid keeps its norm)
-int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d) {
-    if (ctx->cnorm_valid) return SCKM_OK;
-    cnorm_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_cnorm);
+// Centring shift and ||c - mu||^2 of ctx->d_centroids -- only needed when the centroids came from the host (start of
+// a fit, sckm_lloyd_step, predict); inside the Lloyd loop mu stays what it was at the start of the fit and the
+// finalize kernel keeps the norms current (an unchanged centroid keeps its norm).  center = false (tcgen05 path, which
+// ranks raw f32 rows): mu = 0, i.e. the raw norms.
+int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center) {
+    if (ctx->cnorm_valid && ctx->mu_zero == !center) return SCKM_OK;
+    if (center) { center_kernel<<<1, 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_mu); ctx->launches++; }
+    else SCKM_CUDA(ctx, cudaMemsetAsync(ctx->d_mu, 0, d * sizeof(double), ctx->stream));
+    ctx->mu_zero = !center;
+    cnorm_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_mu, ctx->d_cnorm);
     LAUNCH_CHECK_D(ctx);
     ctx->cnorm_valid = true;
     return SCKM_OK;
@@ -572,10 +610,10 @@ int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ct
     sckm_ctx* ctx = ds->ctx;
     if (ds->dtype == SCKM_F32)
         refine_rows_kernel<float, 8><<<grid_ctas, 256, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d,
-            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags);
+            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, nullptr, SCKM_LOOP_ARGS(ctx));
     else
         refine_rows_kernel<double, 8><<<grid_ctas, 256, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d,
-            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags);
+            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, nullptr, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }
@@ -587,7 +625,8 @@ int launch_assign_dmma(sckm_dataset* ds, uint64_t k) {
     const size_t pk = (size_t)k * ds->d + k + 1;
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, dmma_partial_slots(ctx)));
     if (ds->n == 0) return SCKM_OK;
-    SCKM_TRY(launch_cnorm(ctx, k, ds->d));
+    SCKM_TRY(launch_cnorm(ctx, k, ds->d, true));
+    ctx->packed_centered = true;                                   // the slots receive sums of x - mu
     return ds->dtype == SCKM_F32 ? launch_by_d<true, float>(ds, k, pk) : launch_by_d<true, double>(ds, k, pk);
 }
 
@@ -676,7 +715,7 @@ int launch_predict_dmma(sckm_dataset* ds, uint64_t k) {
     const size_t pk = (size_t)k * ds->d + k + 1;
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, 0));                 // no partial sums in this mode
     if (ds->n == 0) return SCKM_OK;
-    SCKM_TRY(launch_cnorm(ctx, k, ds->d));
+    SCKM_TRY(launch_cnorm(ctx, k, ds->d, true));
     SCKM_TRY(ds->dtype == SCKM_F32 ? (launch_by_d<false, float>(ds, k, pk)) : (launch_by_d<false, double>(ds, k, pk)));
     // the marked-row counter is normally cleared by the reduce of the step; there is none here
     SCKM_CUDA(ctx, cudaMemsetAsync(ctx->d_flags, 0, sizeof(unsigned long long), ctx->stream));

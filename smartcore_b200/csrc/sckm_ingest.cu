@@ -51,10 +51,12 @@ struct StagePool {
     }
 };
 
-static int pool_threads() {
+static int pool_threads(const sckm_ctx* ctx) {
     if (const char* e = getenv("SCKM_INGEST_THREADS")) return std::max(1, std::min(kMaxThreads, atoi(e)));
     const unsigned hc = std::thread::hardware_concurrency();
-    return (int)std::max(2u, std::min<unsigned>(kMaxThreads, hc ? hc / 2 : 4));
+    int t = (int)std::max(2u, std::min<unsigned>(kMaxThreads, hc ? hc / 2 : 4));
+    if (ctx->ingest_max_threads > 0) t = std::min(t, ctx->ingest_max_threads);   // several devices share the host cores
+    return t;
 }
 
 // lanes are pinned on first use, by the thread that drives them (see the sizing rule in staged_copy)
@@ -72,7 +74,7 @@ static StagePool* get_pool(sckm_ctx* ctx) {
     if (!ctx->stage_pool) {
         ctx->stage_pool = new StagePool();
         ctx->stage_pool->device = ctx->device;
-        ctx->stage_pool->nthreads = pool_threads();
+        ctx->stage_pool->nthreads = pool_threads(ctx);
     }
     return ctx->stage_pool;
 }

@@ -652,7 +652,8 @@ template <typename T, bool VEC>
 __global__ void __launch_bounds__(ASG_WARPS * 32)
 assign_direct_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                      uint32_t k, uint32_t kc, uint32_t* __restrict__ labels, double* __restrict__ mind,
-                     uint32_t pitch16) {
+                     uint32_t pitch16, const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    if (loop_done(loop_st, loop_it)) return;                              // the fit's stop rule already fired
     extern __shared__ __align__(16) unsigned char smem[];
     double* cbuf = reinterpret_cast<double*>(smem);                       // [kc][d]
     const size_t cbuf_bytes = ((size_t)kc * d * sizeof(double) + 15) / 16 * 16;
@@ -710,7 +711,9 @@ assign_direct_kernel(const T* __restrict__ x, uint64_t n, uint32_t d, const doub
 template <typename T>
 __global__ void update_partial_kernel(const T* __restrict__ x, uint64_t n, uint32_t d,
                                       const uint32_t* __restrict__ labels, const double* __restrict__ mind,
-                                      uint32_t k, uint64_t rows_per_cta, double* __restrict__ partials) {
+                                      uint32_t k, uint64_t rows_per_cta, double* __restrict__ partials,
+                                      const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    if (loop_done(loop_st, loop_it)) return;
     const size_t pk = (size_t)k * d + k + 1;
     double* part = partials + (size_t)blockIdx.x * ((pk + 15) / 16 * 16);
     const uint64_t r0 = (uint64_t)blockIdx.x * rows_per_cta;
@@ -736,7 +739,9 @@ __global__ void update_partial_kernel(const T* __restrict__ x, uint64_t n, uint3
 template <int GROUPS>
 __global__ void __launch_bounds__(32 * GROUPS) reduce_partials_kernel(double* __restrict__ partials, uint32_t nslots, size_t pk,
                                                                      size_t pitch, double* __restrict__ packed,
-                                                                     unsigned long long* __restrict__ nmarked) {
+                                                                     unsigned long long* __restrict__ nmarked,
+                                                                     const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    if (loop_done(loop_st, loop_it)) return;
     __shared__ double2 sh[GROUPS][33];
     if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *nmarked = 0ull;   // consumed by the refine pass of this step
     const size_t e = ((size_t)blockIdx.x * 32 + threadIdx.x) * 2;
@@ -776,22 +781,45 @@ __global__ void __launch_bounds__(32 * GROUPS) reduce_partials_kernel(double* __
     }
 }
 
-// K6: centroids = sums / counts (kmeans.rs:288-292 unguarded, :297-303 guarded), sizes, ||c||^2
-__global__ void finalize_kernel(const double* __restrict__ packed, uint32_t k, uint32_t d, int guarded,
-                                double* __restrict__ centroids, double* __restrict__ cnorm,
-                                long long* __restrict__ size) {
+// K6: centroids = sums / counts (kmeans.rs:288-292 unguarded, :297-303 guarded), sizes, ||c||^2.
+// Inside a Lloyd loop (loop_st != nullptr) the kernel also applies the reference's stop rule to the device-resident
+// state (kmeans.rs:305-309: compare, then store; the centroids of the breaking iteration ARE updated): CTA 0 records
+// `done_at = it` when `distortion <= dist`, else `distortion = dist`.  The CTAs of this launch test `done_at < it`, so
+// the write cannot hide work of the iteration that sets it; every kernel of a later iteration returns at once.
+// centered != 0: the packed sums are sums of (x - mu) (tile kernel, see sckm_dmma.cu): centroid = sum / count + mu.
+// The norms are always ||c - mu||^2 for the shift currently in `mu` (zeros when nothing is centred).
+__global__ void finalize_kernel(const double* __restrict__ packed, uint32_t k, uint32_t d, int guarded, int centered,
+                                const double* __restrict__ mu, double* __restrict__ centroids, double* __restrict__ cnorm,
+                                long long* __restrict__ size, LoopState* __restrict__ loop_st, uint32_t loop_it,
+                                double* __restrict__ inertia_trace) {
+    if (loop_done(loop_st, loop_it)) return;
     const uint32_t c = blockIdx.x;
     const double cnt = packed[(size_t)k * d + c];
     if (threadIdx.x == 0) size[c] = (long long)cnt;
     if (!guarded || cnt > 0.0)
-        for (uint32_t j = threadIdx.x; j < d; j += blockDim.x)
-            centroids[(size_t)c * d + j] = __ddiv_rn(packed[(size_t)c * d + j], cnt);
+        for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) {
+            const double mean = __ddiv_rn(packed[(size_t)c * d + j], cnt);
+            centroids[(size_t)c * d + j] = centered ? __dadd_rn(mean, mu[j]) : mean;
+        }
     __syncthreads();
     if (threadIdx.x == 0 && cnorm) {
         double s = 0.0;
-        for (uint32_t j = 0; j < d; j++) { double v = centroids[(size_t)c * d + j]; s = fma(v, v, s); }
+        for (uint32_t j = 0; j < d; j++) { double v = centroids[(size_t)c * d + j] - mu[j]; s = fma(v, v, s); }
         cnorm[c] = s;
     }
+    if (loop_st != nullptr && c == 0 && threadIdx.x == 0) {
+        const double dist = packed[(size_t)k * d + k];
+        if (inertia_trace) inertia_trace[loop_it - 1] = dist;
+        loop_st->iters = loop_it;
+        if (loop_st->honor_stop) {
+            if (loop_st->distortion <= dist) loop_st->done_at = loop_it;      // break (kmeans.rs:305-306)
+            else loop_st->distortion = dist;                                  // kmeans.rs:307-308
+        }
+    }
+}
+
+__global__ void loop_init_kernel(LoopState* st, int honor_stop) {
+    st->distortion = DBL_MAX; st->done_at = 0ull; st->iters = 0ull; st->honor_stop = honor_stop ? 1ull : 0ull;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -902,6 +930,7 @@ int ensure_workspace(sckm_ctx* ctx, uint64_t k, uint64_t d, size_t partial_slots
     SCKM_TRY(regrow(ctx, &ctx->d_centroids, &ctx->cap_centroids, kd, sizeof(double)));
     SCKM_TRY(regrow(ctx, &ctx->d_packed, &ctx->cap_packed, pk, sizeof(double)));
     SCKM_TRY(regrow(ctx, &ctx->d_cnorm, &ctx->cap_cnorm, k + 1, sizeof(double)));  // [k] norms + max
+    if (d > ctx->cap_mu || !ctx->d_mu) { SCKM_TRY(regrow(ctx, &ctx->d_mu, &ctx->cap_mu, d, sizeof(double))); ctx->mu_zero = true; ctx->cnorm_valid = false; }
     SCKM_TRY(regrow(ctx, &ctx->d_size, &ctx->cap_size, k, sizeof(int64_t)));
     SCKM_TRY(regrow(ctx, &ctx->d_seeds, &ctx->cap_seeds, k, sizeof(int64_t)));
     if (partial_slots)
@@ -1078,12 +1107,12 @@ static int assign_direct_t(sckm_ctx* ctx, const void* x, int dtype, uint64_t n, 
     if (vec) {
         SCKM_TRY(set_smem(ctx, assign_direct_kernel<T, true>, smem_vec));
         assign_direct_kernel<T, true><<<grid, ASG_WARPS * 32, smem_vec, ctx->stream>>>(
-            (const T*)x, n, d, ctx->d_centroids, k, kc, labels, mind, pitch16);
+            (const T*)x, n, d, ctx->d_centroids, k, kc, labels, mind, pitch16, SCKM_LOOP_ARGS(ctx));
     } else {
         if (cbuf_bytes > (size_t)ctx->smem_optin) return fail(ctx, SCKM_ERR_INVALID, "d=%u too large", d);
         SCKM_TRY(set_smem(ctx, assign_direct_kernel<T, false>, cbuf_bytes));
         assign_direct_kernel<T, false><<<grid, ASG_WARPS * 32, cbuf_bytes, ctx->stream>>>(
-            (const T*)x, n, d, ctx->d_centroids, k, kc, labels, mind, pitch16);
+            (const T*)x, n, d, ctx->d_centroids, k, kc, labels, mind, pitch16, SCKM_LOOP_ARGS(ctx));
     }
     LAUNCH_CHECK(ctx);
     return SCKM_OK;
@@ -1110,6 +1139,7 @@ static uint32_t update_slots(const sckm_ctx* ctx, uint64_t n) {
 
 int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia) {
     sckm_ctx* ctx = ds->ctx;
+    ctx->packed_centered = false;                                // plain sums of x on every path below
     const uint32_t slots = update_slots(ctx, ds->n);
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, slots));
     const size_t pk = (size_t)k * ds->d + k + 1;
@@ -1120,10 +1150,10 @@ int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia) {
     if (ds->n) {
         if (ds->dtype == SCKM_F32)
             update_partial_kernel<float><<<slots, threads, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d,
-                ds->labels, with_inertia ? ds->mind : nullptr, (uint32_t)k, rows_per_cta, ctx->d_partials);
+                ds->labels, with_inertia ? ds->mind : nullptr, (uint32_t)k, rows_per_cta, ctx->d_partials, SCKM_LOOP_ARGS(ctx));
         else
             update_partial_kernel<double><<<slots, threads, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d,
-                ds->labels, with_inertia ? ds->mind : nullptr, (uint32_t)k, rows_per_cta, ctx->d_partials);
+                ds->labels, with_inertia ? ds->mind : nullptr, (uint32_t)k, rows_per_cta, ctx->d_partials, SCKM_LOOP_ARGS(ctx));
         LAUNCH_CHECK(ctx);
     }
     SCKM_TRY(launch_reduce_partials(ctx, slots, pk));
@@ -1135,9 +1165,9 @@ int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk) {
     const unsigned blocks = (unsigned)((pitch / 2 + 31) / 32);
     // small payload, or many slots to walk: more slot groups per block so that enough loads are in flight
     if (blocks < (unsigned)ctx->num_sms || slots >= 256)
-        reduce_partials_kernel<32><<<blocks, dim3(32, 32), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags);
+        reduce_partials_kernel<32><<<blocks, dim3(32, 32), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     else
-        reduce_partials_kernel<8><<<blocks, dim3(32, 8), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags);
+        reduce_partials_kernel<8><<<blocks, dim3(32, 8), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK(ctx);
     return SCKM_OK;
 }
@@ -1145,9 +1175,24 @@ int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk) {
 int launch_finalize(sckm_ctx* ctx, uint64_t k, uint64_t d, bool guarded) {
     const unsigned threads = (unsigned)std::min<uint64_t>(256, (d + 31) / 32 * 32);
     finalize_kernel<<<(unsigned)k, threads, 0, ctx->stream>>>(ctx->d_packed, (uint32_t)k, (uint32_t)d, guarded ? 1 : 0,
-                                                            ctx->d_centroids, ctx->d_cnorm, (long long*)ctx->d_size);
+                                                            ctx->packed_centered ? 1 : 0, ctx->d_mu,
+                                                            ctx->d_centroids, ctx->d_cnorm, (long long*)ctx->d_size,
+                                                            SCKM_LOOP_ARGS(ctx), ctx->loop_it ? ctx->d_inertia_trace : nullptr);
     LAUNCH_CHECK(ctx);
     ctx->cnorm_valid = ctx->cnorm_valid || !guarded;   // a guarded update keeps stale norms of empty clusters stale
+    return SCKM_OK;
+}
+
+// start a Lloyd loop on the device: distortion = f64::MAX, nothing done (kmeans.rs:273); room for `max_iter` inertias
+int launch_loop_init(sckm_ctx* ctx, uint64_t max_iter, bool honor_stop) {
+    if (!ctx->d_loop) SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_loop, sizeof(LoopState)));
+    if (max_iter > ctx->cap_trace) {
+        if (ctx->d_inertia_trace) { SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->d_inertia_trace); ctx->d_inertia_trace = nullptr; }
+        SCKM_CUDA(ctx, cudaMalloc((void**)&ctx->d_inertia_trace, max_iter * sizeof(double)));
+        ctx->cap_trace = max_iter;
+    }
+    loop_init_kernel<<<1, 1, 0, ctx->stream>>>(ctx->d_loop, honor_stop ? 1 : 0);
+    LAUNCH_CHECK(ctx);
     return SCKM_OK;
 }
 

@@ -97,8 +97,10 @@ template <int VU> __device__ __forceinline__ constexpr int ucol(int g, int nt) {
 template <int KS, int KT, int VW, bool DFULL, int STAGES, typename TX>
 __global__ void __launch_bounds__(STREAM_WARPS * 32, (KS * KT <= 8) ? 2 : 1)
 assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const double* __restrict__ centroids,
-                     const double* __restrict__ cnorm, uint32_t k, uint32_t* __restrict__ labels,
-                     double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked) {
+                     const double* __restrict__ cnorm, const double* __restrict__ mu, uint32_t k, uint32_t* __restrict__ labels,
+                     double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked,
+                     const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    if (loop_done(loop_st, loop_it)) return;             // the fit's stop rule already fired (kmeans.rs:305)
     constexpr int NTU = KS / 2 > 0 ? KS / 2 : 1;         // feature n-tiles of the update GEMM (8 features each)
     constexpr int VU = VW < NTU ? VW : NTU;              // features per update load
     const uint32_t d = DFULL ? (uint32_t)(4 * KS) : d_rt;
@@ -111,7 +113,14 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
     static_assert(!TMA || DFULL, "the bulk-copy ring needs d == 4*KS");
     __shared__ __align__(8) uint64_t full_bar[TMA ? STREAM_WARPS : 1][TMA ? STAGES : 1];
 
-    // centroid B fragments and -||c||^2/2, resident in registers for the whole launch
+    // Both operands of the scoring GEMM are centred on the fit's shift mu (see sckm_dmma.cu / launch_cnorm): rows become
+    // x - mu as they arrive, the centroid fragments hold c - mu, cnorm holds ||c - mu||^2, so the cancellation error of
+    // ||x||^2 - 2 x.c + ||c||^2 follows the spread of the data, not its distance from the origin.  The update GEMM reads
+    // the rows again, uncentred: the sums this kernel stores are plain sums of x.
+    double mu_f[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) { const uint32_t col = kcol<VW>(t, ks); mu_f[ks] = col < d ? mu[col] : 0.0; }
+    // centroid B fragments and -||c - mu||^2/2, resident in registers for the whole launch
     double bc[KT][KS], hc[KT][2];
 #pragma unroll
     for (int nt = 0; nt < KT; nt++) {
@@ -119,7 +128,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
 #pragma unroll
         for (int ks = 0; ks < KS; ks++) {
             const uint32_t col = kcol<VW>(t, ks);
-            bc[nt][ks] = (c < k && col < d) ? centroids[(size_t)c * d + col] : 0.0;
+            bc[nt][ks] = (c < k && col < d) ? centroids[(size_t)c * d + col] - mu_f[ks] : 0.0;
         }
 #pragma unroll
         for (int e = 0; e < 2; e++) {
@@ -153,16 +162,17 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
 #pragma unroll
             for (int i = 0; i < KS / VW; i++) {
                 double v[VW];
+                bool have = true;
                 if (FULL) {
                     VecLoad<TX, VW>::ld(base + (size_t)mt * 8 * d + i * 4 * VW, v);
                 } else {
 #pragma unroll
                     for (int e = 0; e < VW; e++) v[e] = 0.0;
-                    if (row0 + mt * 8 + g < n && (uint32_t)(i * 4 * VW + t * VW) < d)
-                        VecLoad<TX, VW>::ld(base + (size_t)mt * 8 * d + i * 4 * VW, v);
+                    have = row0 + mt * 8 + g < n && (uint32_t)(i * 4 * VW + t * VW) < d;
+                    if (have) VecLoad<TX, VW>::ld(base + (size_t)mt * 8 * d + i * 4 * VW, v);
                 }
 #pragma unroll
-                for (int e = 0; e < VW; e++) a[mt][i * VW + e] = v[e];
+                for (int e = 0; e < VW; e++) a[mt][i * VW + e] = have ? v[e] - mu_f[i * VW + e] : 0.0;
             }
         }
     };
@@ -181,9 +191,10 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
                 double v[VW];
 #pragma unroll
                 for (int e = 0; e < VW; e++) v[e] = 0.0;
-                if (FULL || row0 + mt * 8 + g < n) VecLoad<TX, VW>::lds(base + (size_t)mt * 8 * d + i * 4 * VW, v);
+                const bool have = FULL || row0 + mt * 8 + g < n;
+                if (have) VecLoad<TX, VW>::lds(base + (size_t)mt * 8 * d + i * 4 * VW, v);
 #pragma unroll
-                for (int e = 0; e < VW; e++) a[mt][i * VW + e] = v[e];
+                for (int e = 0; e < VW; e++) a[mt][i * VW + e] = have ? v[e] - mu_f[i * VW + e] : 0.0;
             }
         }
     };
@@ -441,8 +452,8 @@ static int launch_stream_f(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* gr
     const uint64_t nbatches = (ds->n + 31) / 32;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbatches + STREAM_WARPS - 1) / STREAM_WARPS,
                                                                               (uint64_t)ctx->num_sms * ctas_per_sm));
-    kern<<<grid, STREAM_WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, d, ctx->d_centroids, ctx->d_cnorm,
-                                                        (uint32_t)k, ds->labels, ctx->d_partials, pk, ctx->d_flags);
+    kern<<<grid, STREAM_WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, d, ctx->d_centroids, ctx->d_cnorm, ctx->d_mu,
+                                                        (uint32_t)k, ds->labels, ctx->d_partials, pk, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK_S(ctx);
     *grid_out = grid;
     return SCKM_OK;
@@ -490,7 +501,7 @@ static int launch_stream_by_d(sckm_dataset* ds, uint64_t k, size_t pk, unsigned*
     return launch_stream_vw<8, 2, TX>(ds, k, pk, grid_out);
 }
 
-int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d);   // sckm_dmma.cu
+int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center);   // sckm_dmma.cu
 
 // labels + per-warp partials (fused update); the caller reduces ctx->partial_slots_used slots
 int launch_assign_stream(sckm_dataset* ds, uint64_t k) {
@@ -500,7 +511,8 @@ int launch_assign_stream(sckm_dataset* ds, uint64_t k) {
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, (size_t)ctx->num_sms * 4 * STREAM_WARPS));
     ctx->partial_slots_used = 0;
     if (ds->n == 0) return SCKM_OK;
-    SCKM_TRY(launch_cnorm(ctx, k, ds->d));
+    SCKM_TRY(launch_cnorm(ctx, k, ds->d, true));
+    ctx->packed_centered = false;                                 // the update GEMM sums the rows as they are
     unsigned grid = 0;
     SCKM_TRY(ds->dtype == SCKM_F32 ? launch_stream_by_d<float>(ds, k, pk, &grid) : launch_stream_by_d<double>(ds, k, pk, &grid));
     // exact re-decision of marked rows: (grid/8) CTAs x 8 warps, warp w adds into slot w -- the slots the streaming

@@ -36,7 +36,7 @@ namespace sckm {
     } while (0)
 
 int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas);   // sckm_dmma.cu
-int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d);                               // sckm_dmma.cu
+int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center);                  // sckm_dmma.cu
 
 constexpr int TC_BM = 128;               // rows per MMA tile (TMEM lanes)
 constexpr int TC_EPI_WARPS = 8;
@@ -126,7 +126,9 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                   const __grid_constant__ CUtensorMap mapCl, const TXS* __restrict__ xsrc, uint64_t n, uint32_t d,
                   const double* __restrict__ centroids, const double* __restrict__ cnorm, const float* __restrict__ hcn,
                   uint32_t k, uint32_t nblocks, uint32_t* __restrict__ labels, double* __restrict__ mind,
-                  double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked) {
+                  double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked,
+                  const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    if (loop_done(loop_st, loop_it)) return;                          // the fit's stop rule already fired (kmeans.rs:305)
     using Smem = TcSmemT<NK, TILES, BN>;
     constexpr int CP = 2 / TILES;                    // column parts per row
     constexpr int COLS = BN / CP;                    // columns per epilogue thread per block
@@ -462,7 +464,7 @@ static int launch_tc5_t(sckm_dataset* ds, uint64_t k, size_t pk, const float* x3
     SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, TC_THREADS, smem, ctx->stream>>>(mapX, mapCh, mapCl, (const TXS*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
                                                   ctx->d_cnorm, hcn, (uint32_t)k, nblocks, ds->labels, ds->mind,
-                                                  ctx->d_partials, pk, ctx->d_flags);
+                                                  ctx->d_partials, pk, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK_T(ctx);
     return SCKM_OK;
 }
@@ -475,7 +477,8 @@ int launch_assign_tc5(sckm_dataset* ds, uint64_t k) {
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, (size_t)grid * TC_EPI_WARPS));
     ctx->partial_slots_used = grid * TC_EPI_WARPS;
     if (ds->n == 0) return SCKM_OK;
-    SCKM_TRY(launch_cnorm(ctx, k, ds->d));
+    SCKM_TRY(launch_cnorm(ctx, k, ds->d, false));                     // raw norms: this kernel ranks the raw f32 rows
+    ctx->packed_centered = false;
     const float* x32 = (const float*)ds->x;
     if (ds->dtype == SCKM_F64) {                                      // f32 shadow copy of X for the ranking, built once
         if (!ds->x32) {

@@ -18,6 +18,7 @@
 #pragma once
 #include <cstdint>
 #include <cstddef>
+#include <cstdlib>
 #include <optional>
 #include <string>
 #include <type_traits>
@@ -182,13 +183,23 @@ struct KMeansSearchParameters {
     Iterator into_iter() const { return Iterator{this}; }
 };
 
-// process-wide device context used by KMeans (one device; multi-GPU goes through the C ABI directly)
+// Process-wide device context used by KMeans: ONE context over every visible GPU (sckm_ctx_create_multi), so that a
+// plain `KMeans::fit(&x, params)` shards its rows over the whole box with no change to the caller (kmeans.rs:254).
+// SMARTCORE_CUDA_DEVICES="0,2,3" restricts / orders the devices ("0": single GPU).
 class Device {
 public:
     static error::Result<sckm_ctx*> get() {
         static sckm_ctx* ctx = nullptr;
         if (!ctx) {
-            int rc = sckm_ctx_create(0, &ctx);
+            std::vector<int> ids;
+            if (const char* e = std::getenv("SMARTCORE_CUDA_DEVICES")) {
+                int v = 0; bool have = false;
+                for (const char* p = e;; p++) {
+                    if (*p >= '0' && *p <= '9') { v = v * 10 + (*p - '0'); have = true; }
+                    else { if (have) ids.push_back(v); v = 0; have = false; if (!*p) break; }
+                }
+            }
+            int rc = sckm_ctx_create_multi((int)ids.size(), ids.empty() ? nullptr : ids.data(), &ctx);
             if (rc != SCKM_OK) return error::Result<sckm_ctx*>::Err(error::Failed::fit(std::string("CUDA backend unavailable: ") + sckm_last_error(nullptr)));
         }
         return error::Result<sckm_ctx*>::Ok(ctx);

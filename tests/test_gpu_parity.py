@@ -311,6 +311,183 @@ def test_fit_is_run_to_run_deterministic(ctx):
     assert np.array_equal(a["centroids"], b["centroids"]) and np.array_equal(a["labels"], b["labels"])
 
 
+def test_device_stop_rule_is_independent_of_the_batch_size(ctx, O, monkeypatch):
+    """The stop rule `if distortion <= dist { break }` (kmeans.rs:305-309) runs on the device; the host enqueues batches
+    of iterations and kernels past the breaking iteration return at once.  Whatever the batch size, the fit must end in
+    the state of the reference's `break`: same iteration count, distortion, centroids, sizes and labels."""
+    for (n, d, k, dtype) in ((30000, 16, 8, np.float64), (20000, 64, 32, np.float64), (20000, 32, 64, np.float32), (3000, 3, 5, np.float64)):
+        x = blobs(n, d, k, 5 * n + d, dtype, spread=1.5)
+        monkeypatch.setenv("SCKM_LLOYD_BATCH", "1")
+        a = fit_gpu(ctx, x, k, 11)
+        want = check_fit(O, x, k, 11, a)
+        assert 2 <= a["iters"] < 100                                 # the rule fired (not max_iter)
+        for batch in ("2", "3", "8", "64"):
+            monkeypatch.setenv("SCKM_LLOYD_BATCH", batch)
+            b = fit_gpu(ctx, x, k, 11)
+            assert b["iters"] == a["iters"] and b["distortion"] == a["distortion"]
+            assert np.array_equal(b["centroids"], a["centroids"]) and np.array_equal(b["labels"], a["labels"])
+            assert np.array_equal(b["size"], a["size"])
+        monkeypatch.delenv("SCKM_LLOYD_BATCH")
+        c = fit_gpu(ctx, x, k, 11)                                    # the shape-derived default
+        assert c["iters"] == a["iters"] and np.array_equal(c["centroids"], a["centroids"]) and np.array_equal(c["labels"], a["labels"])
+        # max_iter smaller than the stopping iteration: exactly max_iter steps, distortion = the last strictly smaller value
+        m = max(1, a["iters"] - 2)
+        monkeypatch.setenv("SCKM_LLOYD_BATCH", "8")
+        e = fit_gpu(ctx, x, k, 11, max_iter=m)
+        w = O.fit(x, k, m, 11)
+        assert e["iters"] == m == w.iters and abs(e["distortion"] - w.distortion) <= RTOL * w.distortion
+        np.testing.assert_allclose(e["centroids"], w.centroids, rtol=RTOL, atol=1e-12)
+        monkeypatch.delenv("SCKM_LLOYD_BATCH")
+        # the per-iteration inertias of the fixed-length loop (bench path) are non-increasing and end at the fit's value
+        ds = ctx.upload(x)
+        first, u = cluster.kmeanspp_draws(11, n, k)
+        ds.kmeanspp(k, first, u)
+        cent0, _ = ds.init_centroids(k)
+        tr = ds.lloyd_iterate(cent0, a["iters"], want_inertia=True)
+        assert np.all(np.diff(tr["inertia"][: a["iters"] - 1]) <= 0) and tr["inertia"][a["iters"] - 2] == a["distortion"]
+        assert np.array_equal(tr["centroids"], a["centroids"])
+        ds.close()
+
+
+# ---- cancellation stress for the GEMM-form kernels: data far from the origin, tiny spreads ---------------------------
+@pytest.mark.parametrize("n,d,k,dtype,offset,scale", [
+    (12000, 64, 32, np.float64, 1e4, 1.0),      # DMMA tile kernel, resident centroids
+    (12000, 64, 32, np.float64, 1e8, 1.0),      # ||x||^2 ~ 1e18: every row is a near-tie for the GEMM form -> exact re-decision
+    (9000, 128, 300, np.float64, 1e4, 1e-3),    # DMMA with streamed centroid blocks, spread 1e-3 around 1e4
+    (20000, 16, 8, np.float64, 1e4, 1.0),       # streaming kernel
+    (20000, 16, 8, np.float64, 1e8, 1e-3),
+    (16000, 8, 12, np.float64, -3e5, 1e-3),
+    (15000, 32, 64, np.float32, 1e4, 1.0),      # tcgen05 3xTF32 kernel: f32 keeps ~3 digits of the spread at 1e4
+    (15000, 32, 64, np.float32, 300.0, 1e-3),
+    (10000, 24, 40, np.float32, 1e8, 1.0)])     # f32 data at 1e8: all rows collapse onto a few representable points
+def test_lloyd_step_far_from_origin(ctx, O, n, d, k, dtype, offset, scale):
+    """||x||^2 - 2 x.c + ||c||^2 loses everything when the offset dwarfs the spread; the tile kernels only RANK with
+    it and re-decide every row whose gap is inside the error bound exactly, so labels must still be the oracle's,
+    and sums / inertia within the north-star tolerance (f32 rows: the reference itself runs Lloyd in f64 on the
+    widened values, bbd_tree.rs:207-213)."""
+    x = (blobs(n, d, k, 3 * n + d, np.float64, spread=3.0) * scale + offset).astype(dtype)
+    cent = x[np.random.default_rng(2).choice(n, k, replace=False)].astype(np.float64) + 0.05 * scale
+    ds = ctx.upload(x)
+    inertia, sums, counts = ds.lloyd_step(cent)
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+    labels = ds.labels().astype(np.int64)
+    tol = GAP_TOL if dtype == np.float64 else 1e-5
+    bad = np.nonzero(labels != m_o)[0]
+    assert np.all(gap[bad] < tol), "%d labels differ with gap >= %g" % (len(bad), tol)
+    if len(bad) == 0:
+        assert counts.tolist() == c_o.tolist()
+        np.testing.assert_allclose(sums, s_o, rtol=RTOL, atol=0)
+    assert abs(inertia - d_o) <= RTOL * d_o, (inertia, d_o)
+    # whole fit from these centroids: iteration count and final state equal the oracle's tree path
+    out = ds.lloyd_fit(cent, 30)
+    ds.close()
+    tree = O.BBDTree(x)
+    c_ref = cent.copy(); dist_ref = np.finfo(np.float64).max; it_ref = 0
+    for it in range(1, 31):
+        dd, ss, cc, mm = tree.clustering(c_ref)
+        nz = cc > 0
+        c_ref[nz] = ss[nz] / cc[nz, None]
+        it_ref = it
+        if dist_ref <= dd:
+            break
+        dist_ref = dd
+    if dtype == np.float64:
+        assert out["iters"] == it_ref
+        np.testing.assert_allclose(out["centroids"], c_ref, rtol=RTOL, atol=0)
+        assert abs(out["distortion"] - dist_ref) <= RTOL * dist_ref
+    else:
+        np.testing.assert_allclose(out["centroids"], c_ref, rtol=1e-4, atol=0) if out["iters"] == it_ref else None
+        assert abs(out["distortion"] - dist_ref) <= 1e-4 * dist_ref
+
+
+def test_step_is_bit_reproducible_at_full_size(ctx):
+    """The stop rule compares successive inertias exactly, so a step must be bit-reproducible run to run: config C3
+    (10M x 64, k = 256), five repeats of the same step -- packed sums, counts, inertia and labels identical."""
+    n, d, k = 10_000_000, 64, 256
+    ds = ctx.generate_blobs(n, d, k, 20260101)
+    cent = np.vstack([ds.download_rows(i * (n // k), 1) for i in range(k)]).astype(np.float64) + 0.01
+    ref = ds.lloyd_step(cent)
+    lab = ds.labels(width=4)
+    for _ in range(4):
+        got = ds.lloyd_step(cent)
+        assert got[0] == ref[0] and np.array_equal(got[1], ref[1]) and np.array_equal(got[2], ref[2])
+        assert np.array_equal(ds.labels(width=4), lab)
+    assert ref[2].sum() == n
+    ds.close()
+
+
+# ---- full KMeans::fit against the oracle's tree path with the k and d of configs C3 / C4 / C5 (SURVEY 8d gate) -------
+@pytest.mark.timeout(900)      # the oracle's tree path needs ~1-2 minutes of one host core at k = 1024 / 4096
+@pytest.mark.parametrize("n,d,k,dtype,max_iter", [(200_000, 64, 256, np.float64, 8), (200_000, 128, 1024, np.float64, 3),
+                                                  (200_000, 32, 4096, np.float32, 2)])
+def test_fit_parity_with_config_k_and_d(ctx, O, n, d, k, dtype, max_iter):
+    x = cabi.blobs_host(0, n, d, k, 20260101, dtype=dtype)
+    got = fit_gpu(ctx, x, k, 42, max_iter=max_iter)
+    want = O.fit(x, k, max_iter, 42, use_tree=True)
+    f64 = dtype == np.float64
+    lab = got["labels"].astype(np.int64)
+    if not np.array_equal(lab, want.y):
+        gap = O.brute_clustering(x, want.centroids, want_gap=True)[4]
+        bad = np.nonzero(lab != want.y)[0]
+        assert np.all(gap[bad] < (GAP_TOL if f64 else 1e-5)), "%d labels differ beyond the tolerance" % len(bad)
+    assert got["iters"] == want.iters
+    np.testing.assert_allclose(got["centroids"], want.centroids, rtol=RTOL if f64 else 1e-4, atol=1e-12)
+    assert abs(got["distortion"] - want.distortion) <= (RTOL if f64 else 1e-4) * want.distortion
+    if np.array_equal(lab, want.y):
+        assert got["size"].tolist() == want.size.tolist()
+
+
+# ---- ONE context over several devices (sckm_ctx_create_multi): KMeans::fit / predict use the whole box ----------------
+def test_multi_context_on_one_device_is_the_plain_context(O):
+    c = sc.Context(devices=[0])
+    assert c.device_count() == 1
+    x = blobs(5000, 8, 4, 1)
+    got = fit_gpu(c, x, 4, 3)
+    check_fit(O, x, 4, 3, got)
+    t = c.last_fit_times()
+    assert t["devices"] == 1 and t["total_s"] > 0
+    c.close()
+    with pytest.raises(cabi.SckmError):
+        sc.Context(devices=[0, 0])
+
+
+@pytest.mark.parametrize("n,d,k,dtype", [(50_000, 32, 24, np.float64), (300_000, 64, 256, np.float64), (40_000, 16, 8, np.float64),
+                                         (120_000, 32, 128, np.float32), (5_000, 3, 4, np.float64)])
+def test_multi_context_fit_and_predict_equal_single_device(ctx, O, n, d, k, dtype, monkeypatch):
+    """Rows sharded over every visible device behind ONE context and ONE host thread of the caller: same seeds, same
+    iteration count, same labels as the single-device fit; sums are added in a different order (per-shard partials, then
+    the all-reduce), hence centroids within the north-star tolerance instead of bit-equal."""
+    import torch
+    ndev = torch.cuda.device_count()
+    if ndev < 2:
+        pytest.skip("needs >= 2 GPUs")
+    monkeypatch.setenv("SCKM_MULTI_MIN_ROWS", "1")
+    mc = sc.Context(devices="all")
+    assert mc.device_count() == ndev
+    x = blobs(n, d, k, n + 3 * d, dtype, spread=2.0)
+    one = fit_gpu(ctx, x, k, 5, max_iter=40)
+    for cm in (False, True):
+        many = fit_gpu(mc, x, k, 5, max_iter=40, column_major=cm)
+        assert mc.last_fit_times()["devices"] == ndev
+        assert many["iters"] == one["iters"] and many["size"].tolist() == one["size"].tolist()
+        assert np.array_equal(many["labels"], one["labels"])
+        rt = RTOL if dtype == np.float64 else 1e-4
+        np.testing.assert_allclose(many["centroids"], one["centroids"], rtol=rt, atol=1e-12)
+        assert abs(many["distortion"] - one["distortion"]) <= rt * one["distortion"]
+    if n <= 60_000:
+        check_fit(O, x, k, 5, fit_gpu(mc, x, k, 5))
+    # predict: no collective, labels bit-equal to the single-device direct form
+    assert np.array_equal(mc.predict(x, one["centroids"]), ctx.predict(x, one["centroids"]))
+    assert np.array_equal(mc.predict(x, one["centroids"], column_major=True, width=4), ctx.predict(x, one["centroids"], width=4))
+    # an input too small to give every device a non-empty aligned share runs on the first device alone
+    small = blobs(1500, d, k, 9, dtype)
+    s1 = fit_gpu(mc, small, min(k, 8), 2)
+    assert mc.last_fit_times()["devices"] == 1
+    s0 = fit_gpu(ctx, small, min(k, 8), 2)
+    assert np.array_equal(s1["labels"], s0["labels"]) and np.array_equal(s1["centroids"], s0["centroids"])
+    mc.close()
+
+
 # ---- host mirror: the reference's own tests, re-expressed ----------------------------------------------
 def test_fit_predict_reference_test(iris20):  # kmeans.rs:473-505
     x = sc.DenseMatrix.from_2d_array(iris20)

@@ -21,7 +21,7 @@ def test_cabi_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), "libsmartcore_kmeans_cuda.so does not export %s" % name
     assert sorted(cabi.SYMBOLS) == declared
-    assert lib.sckm_abi_version() == int(re.search(r"#define SCKM_ABI_VERSION (\d+)", header).group(1)) == 2
+    assert lib.sckm_abi_version() == int(re.search(r"#define SCKM_ABI_VERSION (\d+)", header).group(1)) == 3
 
 
 def test_no_cpu_fallback_when_device_missing():

@@ -161,6 +161,15 @@ int sckm_kmeans_fit(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, i
                     const double* uniforms, void* labels_out, int width, int64_t* size_out,
                     double* centroids_out, double* distortion_out, int64_t* iters_out);
 
+/* The per-rank form for one-process-per-GPU deployments: this rank passes rows [row_offset, row_offset + n_local)
+ * of the n_global x d matrix (x_local points at ITS rows; column_major: a [d][n_local] image), the context having
+ * been joined to the other ranks by sckm_comm_init_rank.  size / centroids / distortion / iters are the global
+ * results on every rank; labels_out covers this rank's rows. */
+int sckm_kmeans_fit_shard(sckm_ctx* ctx, const void* x_local, uint64_t n_local, uint64_t d, int dtype,
+                          int column_major, uint64_t row_offset, uint64_t n_global, uint64_t k, uint64_t max_iter,
+                          uint64_t first_index, const double* uniforms, void* labels_out, int width,
+                          int64_t* size_out, double* centroids_out, double* distortion_out, int64_t* iters_out);
+
 /* ---- cluster quality (src/metrics/cluster_helpers.rs:7-25 contingency_matrix) --------
  * out[n_classes][k] (row-major) = number of rows with class id c and cluster label j, counted on the device.
  * sckm_contingency: cluster labels = the dataset's resident labels (after a fit / Lloyd step); class_ids_host holds

@@ -23,6 +23,7 @@ SYMBOLS = [
     "sckm_labels_download", "sckm_mindist_download", "sckm_predict", "sckm_kmeans_fit", "sckm_device_peaks",
     "sckm_contingency", "sckm_contingency_host", "sckm_knn", "sckm_radius_count", "sckm_radius_fill",
     "sckm_flush_l2", "sckm_ctx_create_multi", "sckm_ctx_device_count", "sckm_ctx_last_fit_times",
+    "sckm_kmeans_fit_shard",
 ]
 
 
@@ -65,6 +66,7 @@ def _load():
     L.sckm_mindist_download.argtypes = [vp, vp]
     L.sckm_predict.argtypes = [vp, vp, u64, u64, i32, i32, vp, u64, vp, i32]
     L.sckm_kmeans_fit.argtypes = [vp, vp, u64, u64, i32, i32, u64, u64, u64, vp, vp, i32, vp, vp, vp, vp]
+    L.sckm_kmeans_fit_shard.argtypes = [vp, vp, u64, u64, i32, i32, u64, u64, u64, u64, u64, vp, vp, i32, vp, vp, vp, vp]
     L.sckm_device_peaks.argtypes = [vp, vp]
     L.sckm_contingency.argtypes = [vp, vp, u64, u64, vp]
     L.sckm_knn.argtypes = [vp, vp, u64, u64, vp, vp]
@@ -199,6 +201,18 @@ class Context:
         self._check(lib.sckm_kmeans_fit(self.h, _p(buf), n, d, dtype_code(buf), 1 if column_major else 0, k, max_iter,
                                         first_index, _p(u), _p(labels), 8, _p(size), _p(cent), C.addressof(dist),
                                         C.addressof(iters)))
+        return dict(labels=labels, size=size, centroids=cent, distortion=dist.value, iters=iters.value)
+
+    def kmeans_fit_shard(self, x_local, row_offset, n_global, k, max_iter, first_index, uniforms, width=8):
+        """sckm_kmeans_fit_shard: this rank's rows [row_offset, row_offset + len(x_local)) of an n_global-row matrix."""
+        n, d = x_local.shape
+        buf = np.ascontiguousarray(x_local)
+        u = np.ascontiguousarray(uniforms, dtype=np.float64)
+        labels = np.empty(n, dtype=np.uint64 if width == 8 else np.uint32); size = np.zeros(k, dtype=np.int64); cent = np.zeros((k, d))
+        dist = C.c_double(0); iters = C.c_int64(0)
+        self._check(lib.sckm_kmeans_fit_shard(self.h, _p(buf), n, d, dtype_code(buf), 0, row_offset, n_global, k, max_iter,
+                                              first_index, _p(u), _p(labels), width, _p(size), _p(cent), C.addressof(dist),
+                                              C.addressof(iters)))
         return dict(labels=labels, size=size, centroids=cent, distortion=dist.value, iters=iters.value)
 
     def device_peaks(self):

@@ -787,6 +787,34 @@ int sckm_kmeans_fit(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, i
     return rc;
 }
 
+// The per-rank form of sckm_kmeans_fit for one-process-per-GPU deployments (torchrun): this rank holds rows
+// [row_offset, row_offset + n_local) of the n_global x d matrix, the context is joined to the others by
+// sckm_comm_init_rank.  Same outputs; labels_out covers this rank's rows.
+int sckm_kmeans_fit_shard(sckm_ctx* ctx, const void* x_local, uint64_t n_local, uint64_t d, int dtype, int column_major,
+                          uint64_t row_offset, uint64_t n_global, uint64_t k, uint64_t max_iter, uint64_t first_index,
+                          const double* uniforms, void* labels_out, int width, int64_t* size_out, double* centroids_out,
+                          double* distortion_out, int64_t* iters_out) {
+    if (!ctx) return SCKM_ERR_INVALID;
+    if (!centroids_out) return fail(ctx, SCKM_ERR_INVALID, "centroids_out is NULL");
+    if (n_global == 0) return fail(ctx, SCKM_ERR_INVALID, "empty input");
+    if (!x_local && n_local) return fail(ctx, SCKM_ERR_INVALID, "host pointer is NULL");
+    if (labels_out && width != 4 && width != 8) return fail(ctx, SCKM_ERR_INVALID, "label width must be 4 or 8");
+    auto now = []() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    const double t0 = now();
+    sckm_dataset* ds = nullptr;
+    SCKM_TRY(sckm_dataset_upload(ctx, x_local, n_local, d, dtype, column_major, row_offset, n_global, &ds));
+    const double t1 = now();
+    double ph[2] = {0, 0};
+    int rc = fit_compute(ds, k, max_iter, first_index, uniforms, size_out, centroids_out, distortion_out, iters_out, ph);
+    const double t2 = now();
+    if (rc == SCKM_OK && labels_out) rc = download_labels(ds, labels_out, width);
+    sckm_dataset_destroy(ds);
+    const double t3 = now();
+    ctx->fit_times[0] = t1 - t0; ctx->fit_times[1] = ph[0]; ctx->fit_times[2] = ph[1]; ctx->fit_times[3] = t3 - t2;
+    ctx->fit_times[4] = t3 - t0; ctx->fit_times[5] = (double)ctx->nranks;
+    return rc;
+}
+
 int sckm_ctx_last_fit_times(const sckm_ctx* ctx, double* out6) {
     if (!ctx || !out6) return SCKM_ERR_INVALID;
     for (int i = 0; i < 6; i++) out6[i] = ctx->fit_times[i];

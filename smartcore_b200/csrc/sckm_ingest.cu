@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <atomic>
 #include <thread>
+#include <pthread.h>
+#include <sched.h>
 
 namespace sckm {
 
@@ -38,6 +40,8 @@ struct StagePool {
     int device = 0;
     int nthreads = 0;
     Lane lane[kMaxThreads];
+    bool have_cpus = false;          // CPUs of the NUMA node the device hangs off (sysfs); staging threads run there so
+    cpu_set_t cpus;                  // that the pinned buffers (first touch) and the memcpy traffic stay node-local
 
     ~StagePool() {
         cudaSetDevice(device);
@@ -70,11 +74,51 @@ static bool lane_ready(Lane& l) {
     return ok;
 }
 
+// cpulist of the device's NUMA node: /sys/bus/pci/devices/<bus id>/numa_node -> /sys/devices/system/node/nodeN/cpulist
+static bool device_numa_cpus(int device, cpu_set_t* out) {
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return false; }
+    for (char* p = bus; *p; p++) if (*p >= 'A' && *p <= 'Z') *p = (char)(*p - 'A' + 'a');
+    char path[160];
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/numa_node", bus);
+    FILE* f = fopen(path, "r");
+    if (!f) return false;
+    int node = -1;
+    const int got = fscanf(f, "%d", &node);
+    fclose(f);
+    if (got != 1 || node < 0) return false;
+    snprintf(path, sizeof(path), "/sys/devices/system/node/node%d/cpulist", node);
+    f = fopen(path, "r");
+    if (!f) return false;
+    char list[4096] = {0};
+    const bool ok = fgets(list, sizeof(list), f) != nullptr;
+    fclose(f);
+    if (!ok) return false;
+    CPU_ZERO(out);
+    int n = 0;
+    for (const char* p = list; *p;) {                            // "0-31,64-95"
+        if (*p < '0' || *p > '9') { p++; continue; }
+        char* end = nullptr;
+        long a = strtol(p, &end, 10), b = a;
+        if (*end == '-') b = strtol(end + 1, &end, 10);
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int)c, out); n++; }
+        p = end;
+    }
+    // only keep CPUs this process may run on (cgroup / taskset)
+    cpu_set_t allowed;
+    if (sched_getaffinity(0, sizeof(allowed), &allowed) == 0) {
+        n = 0;
+        for (int c = 0; c < CPU_SETSIZE; c++) { if (CPU_ISSET(c, out) && !CPU_ISSET(c, &allowed)) CPU_CLR(c, out); if (CPU_ISSET(c, out)) n++; }
+    }
+    return n > 0;
+}
+
 static StagePool* get_pool(sckm_ctx* ctx) {
     if (!ctx->stage_pool) {
         ctx->stage_pool = new StagePool();
         ctx->stage_pool->device = ctx->device;
         ctx->stage_pool->nthreads = pool_threads(ctx);
+        if (!getenv("SCKM_INGEST_NO_NUMA")) ctx->stage_pool->have_cpus = device_numa_cpus(ctx->device, &ctx->stage_pool->cpus);
     }
     return ctx->stage_pool;
 }
@@ -160,10 +204,14 @@ static int staged_copy(sckm_ctx* ctx, void* dst, const void* src, size_t bytes, 
             }
         if (e != cudaSuccess) err.store((int)e);
     };
+    // all lanes run on threads of their own (not the caller's): they bind themselves to the device's NUMA node
+    auto bound_work = [&](int t) {
+        if (pool->have_cpus) pthread_setaffinity_np(pthread_self(), sizeof(cpu_set_t), &pool->cpus);
+        work(t);
+    };
     std::vector<std::thread> th;
     th.reserve(T);
-    for (int t = 1; t < T; t++) th.emplace_back(work, t);
-    work(0);
+    for (int t = 0; t < T; t++) th.emplace_back(bound_work, t);
     for (auto& x : th) x.join();
     if (err.load() != (int)cudaSuccess)
         return fail(ctx, SCKM_ERR_CUDA, "staged %s copy failed: %s", to_device ? "H2D" : "D2H",

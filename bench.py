@@ -465,6 +465,11 @@ def main():
     # NCCL prints its version banner on stdout at any debug level >= VERSION; rank 0 must print ONE JSON line, so send
     # NCCL's own log to a file instead (override with NCCL_DEBUG_FILE)
     os.environ.setdefault("NCCL_DEBUG_FILE", "/tmp/sckm_nccl_%h_%p.log")
+    # ... and whatever else a library writes to fd 1 (NCCL 2.28 still prints its banner there from some code paths) goes to
+    # stderr for the whole run; stdout comes back for the one JSON line at the end
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     B = Bench(args)
     n_local, k, d = args.rows, args.k, args.d
     n_global, row0 = n_local * world, rank * n_local
@@ -534,7 +539,10 @@ def main():
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": head["launches"], "clocks": clocks,
             "configs": configs or None, "strong": {"C3": strong} if strong else None, "parity": parity,
         }
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     B.close()
 
 

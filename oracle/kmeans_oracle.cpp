@@ -109,6 +109,73 @@ inline void xo_seed(Xoshiro256pp& r, uint64_t seed, int mode) {
     if (mode == 1) xo_seed_splitmix(r, seed); else xo_seed_pcg(r, seed);
 }
 
+// ---- `std_rand` builds (rand_custom.rs:1-4; forced by the `datasets` feature, Cargo.toml:39-40): RngImpl = StdRng =
+// rand_chacha 0.3 ChaCha12Rng.  seed_from_u64 = rand_core's PCG32 fill of the 32-byte key (same routine as above);
+// stream id 0, 64-bit block counter from 0; BlockRng hands out the 16 words of a block in order, next_u64 = two
+// consecutive words, low first (the buffer index stays even when only next_u64 is used, as on this path).
+// The block function is pinned to the published ChaCha test vectors (TC1: all-zero key and IV, 8 / 12 / 20 rounds).
+inline uint32_t rotl32(uint32_t x, int k) { return (x << k) | (x >> (32 - k)); }
+inline void chacha_block(const uint32_t key[8], uint64_t counter, uint64_t stream, int rounds, uint32_t out[16]) {
+    uint32_t s[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3], key[4], key[5], key[6], key[7],
+                      (uint32_t)counter, (uint32_t)(counter >> 32), (uint32_t)stream, (uint32_t)(stream >> 32)};
+    uint32_t x[16];
+    for (int i = 0; i < 16; i++) x[i] = s[i];
+    auto qr = [&](int a, int b, int c, int d) {
+        x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 16);
+        x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 12);
+        x[a] += x[b]; x[d] = rotl32(x[d] ^ x[a], 8);
+        x[c] += x[d]; x[b] = rotl32(x[b] ^ x[c], 7);
+    };
+    for (int r = 0; r < rounds; r += 2) {
+        qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+        qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+    }
+    for (int i = 0; i < 16; i++) out[i] = x[i] + s[i];
+}
+inline void pcg32_fill(uint64_t state, uint8_t seed[32]) {
+    const uint64_t MUL = 6364136223846793005ULL, INC = 11634580027462260723ULL;
+    for (int c = 0; c < 8; c++) {
+        state = state * MUL + INC;
+        uint32_t xorshifted = (uint32_t)(((state >> 18) ^ state) >> 27);
+        uint32_t rot = (uint32_t)(state >> 59);
+        uint32_t x = (xorshifted >> rot) | (xorshifted << ((32 - rot) & 31));
+        for (int b = 0; b < 4; b++) seed[4 * c + b] = (uint8_t)(x >> (8 * b));
+    }
+}
+
+// The RngImpl of either build: mode 0 / 1 = SmallRng (xoshiro256++, PCG32 / SplitMix64 seeding), mode 2 = StdRng.
+struct RandRng {
+    int mode = 0;
+    Xoshiro256pp xo;
+    uint32_t key[8], buf[16];
+    uint64_t counter = 0;
+    int index = 16;
+    void seed(uint64_t s, int m) {
+        mode = m;
+        if (m != 2) { xo_seed(xo, s, m); return; }
+        uint8_t b[32];
+        pcg32_fill(s, b);
+        for (int i = 0; i < 8; i++) key[i] = (uint32_t)b[4 * i] | ((uint32_t)b[4 * i + 1] << 8) | ((uint32_t)b[4 * i + 2] << 16) | ((uint32_t)b[4 * i + 3] << 24);
+        counter = 0; index = 16;
+    }
+    uint64_t next_u64() {
+        if (mode != 2) return xo_next(xo);
+        if (index >= 16) { chacha_block(key, counter++, 0, 12, buf); index = 0; }
+        const uint64_t v = (uint64_t)buf[index] | ((uint64_t)buf[index + 1] << 32);
+        index += 2;
+        return v;
+    }
+    double gen_f64() { return (double)(next_u64() >> 11) * (1.0 / 9007199254740992.0); }   // Standard f64
+    uint64_t gen_range(uint64_t range) {                                                   // UniformInt<usize>::sample_single
+        if (range == 0) return next_u64();
+        const uint64_t zone = (range << __builtin_clzll(range)) - 1;
+        for (;;) {
+            unsigned __int128 m = (unsigned __int128)next_u64() * (unsigned __int128)range;
+            if ((uint64_t)m <= zone) return (uint64_t)(m >> 64);
+        }
+    }
+};
+
 // rand 0.8.5 Standard f64: (next_u64 >> 11) * 2^-53
 inline double xo_gen_f64(Xoshiro256pp& r) {
     return (double)(xo_next(r) >> 11) * (1.0 / 9007199254740992.0);
@@ -317,9 +384,9 @@ double brute_clustering(const double* x, size_t n, size_t d, const double* centr
 template <typename T>
 void kmeanspp(const T* x, size_t n, size_t d, size_t k, uint64_t seed, int seed_mode,
               const int64_t* inject, int64_t* y, int64_t* seed_idx_out, double* dist_out) {
-    Xoshiro256pp rng; xo_seed(rng, seed, seed_mode);
+    RandRng rng; rng.seed(seed, seed_mode);
     for (size_t i = 0; i < n; i++) y[i] = 0;
-    int64_t first = inject ? inject[0] : (int64_t)xo_gen_range(rng, (uint64_t)n);
+    int64_t first = inject ? inject[0] : (int64_t)rng.gen_range((uint64_t)n);
     if (seed_idx_out) seed_idx_out[0] = first;
     std::vector<T> centroid(x + (size_t)first * d, x + (size_t)first * d + d);
     std::vector<double> dd(n, DBL_MAX);
@@ -334,7 +401,7 @@ void kmeanspp(const T* x, size_t n, size_t d, size_t k, uint64_t seed, int seed_
         if (inject) {
             index = (size_t)inject[j];
         } else {
-            double cutoff = xo_gen_f64(rng) * sum;
+            double cutoff = rng.gen_f64() * sum;
             double cost = 0.0;
             while (index < n) {
                 cost += dd[index];
@@ -362,6 +429,20 @@ double now_s() {
 extern "C" {
 
 // ---- RNG -------------------------------------------------------------------
+// draw sequence of kmeans_plus_plus (kmeans.rs:359,385) for any RngImpl: mode 0 / 1 SmallRng, mode 2 StdRng (ChaCha12)
+void orc_draws(uint64_t seed, int mode, uint64_t n, size_t k, uint64_t* first, double* uniforms) {
+    RandRng r; r.seed(seed, mode);
+    *first = r.gen_range(n);
+    for (size_t j = 0; j + 1 < k; j++) uniforms[j] = r.gen_f64();
+}
+void orc_rand_next_u64(uint64_t seed, int mode, size_t count, uint64_t* out) {
+    RandRng r; r.seed(seed, mode);
+    for (size_t i = 0; i < count; i++) out[i] = r.next_u64();
+}
+void orc_chacha_block(const uint32_t* key8, uint64_t counter, uint64_t stream, int rounds, uint32_t* out16) {
+    chacha_block(key8, counter, stream, rounds, out16);
+}
+void orc_pcg32_fill(uint64_t seed, uint8_t* out32) { pcg32_fill(seed, out32); }
 void orc_rng_seed(uint64_t seed, int mode, uint64_t* state) {
     Xoshiro256pp r; xo_seed(r, seed, mode); std::memcpy(state, r.s, 32);
 }

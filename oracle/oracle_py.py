@@ -14,6 +14,7 @@ _LIB = None
 
 SEED_MODE_PCG = 0       # rand_core 0.6 default seed_from_u64 (PCG32 fill)  -- default
 SEED_MODE_SPLITMIX = 1  # xoshiro's own seed_from_u64 (SplitMix64)
+SEED_MODE_STDRNG = 2    # `std_rand` builds: StdRng = ChaCha12Rng, key = PCG32 fill of the seed (rand_custom.rs:1-4)
 
 
 def build(force=False):
@@ -33,6 +34,10 @@ def lib():
         L.orc_rng_next_u64.argtypes = [u64p]; L.orc_rng_next_u64.restype = C.c_uint64
         L.orc_rng_gen_f64.argtypes = [u64p]; L.orc_rng_gen_f64.restype = C.c_double
         L.orc_rng_gen_range.argtypes = [u64p, C.c_uint64]; L.orc_rng_gen_range.restype = C.c_uint64
+        L.orc_draws.argtypes = [C.c_uint64, C.c_int, C.c_uint64, C.c_size_t, C.c_void_p, C.c_void_p]; L.orc_draws.restype = None
+        L.orc_rand_next_u64.argtypes = [C.c_uint64, C.c_int, C.c_size_t, C.c_void_p]; L.orc_rand_next_u64.restype = None
+        L.orc_chacha_block.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_void_p]; L.orc_chacha_block.restype = None
+        L.orc_pcg32_fill.argtypes = [C.c_uint64, C.c_void_p]; L.orc_pcg32_fill.restype = None
         for nm in ("f64", "f32", "i32"):
             f = getattr(L, "orc_squared_distance_" + nm)
             f.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]; f.restype = C.c_double
@@ -86,6 +91,31 @@ class Rng:
 
     def gen_range(self, n):
         return lib().orc_rng_gen_range(self.state, n)
+
+
+def draws(seed, n, k, mode=SEED_MODE_PCG):
+    """RNG draw sequence of kmeans_plus_plus (kmeans.rs:359,385): (first_index, uniforms[k-1]) for either RngImpl."""
+    first = C.c_uint64(0); u = np.zeros(max(k - 1, 0))
+    lib().orc_draws(seed, mode, n, k, C.addressof(first), _p(u))
+    return first.value, u
+
+
+def rand_next_u64(seed, mode, count):
+    out = np.zeros(count, dtype=np.uint64)
+    lib().orc_rand_next_u64(seed, mode, count, _p(out))
+    return out
+
+
+def chacha_block(key_words, counter, rounds, stream=0):
+    key = np.ascontiguousarray(key_words, dtype=np.uint32); out = np.zeros(16, dtype=np.uint32)
+    lib().orc_chacha_block(_p(key), counter, stream, rounds, _p(out))
+    return out
+
+
+def pcg32_fill(seed):
+    out = np.zeros(32, dtype=np.uint8)
+    lib().orc_pcg32_fill(seed, _p(out))
+    return out
 
 
 def squared_distance(a, b):

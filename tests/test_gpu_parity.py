@@ -485,7 +485,7 @@ def test_multi_context_fit_and_predict_equal_single_device(ctx, O, n, d, k, dtyp
     assert np.array_equal(mc.predict(x, one["centroids"]), ctx.predict(x, one["centroids"]))
     assert np.array_equal(mc.predict(x, one["centroids"], column_major=True, width=4), ctx.predict(x, one["centroids"], width=4))
     # an input too small to give every device a non-empty aligned share runs on the first device alone
-    small = blobs(1500, d, k, 9, dtype)
+    small = blobs(1000, d, k, 9, dtype)
     s1 = fit_gpu(mc, small, min(k, 8), 2)
     assert mc.last_fit_times()["devices"] == 1
     s0 = fit_gpu(ctx, small, min(k, 8), 2)

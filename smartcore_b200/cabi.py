@@ -10,6 +10,8 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsmartcore_kmeans_cuda.so")
+if os.environ.get("SCKM_LIB_VARIANT"):      # A/B builds of the same sources with experiment flags (tools/build_variant.sh)
+    LIB_PATH = os.path.join(_HERE, "lib", "libsmartcore_kmeans_cuda.%s.so" % os.environ["SCKM_LIB_VARIANT"])
 
 F32, F64 = 0, 1
 ASSIGN_AUTO, ASSIGN_DIRECT, ASSIGN_DMMA, ASSIGN_STREAM, ASSIGN_TC5 = 0, 1, 2, 3, 4

@@ -26,7 +26,7 @@ namespace {
 
 constexpr size_t kChunk = 4u << 20;          // bytes per DMA
 constexpr size_t kStagedMin = 32u << 20;     // below this a plain cudaMemcpy is as fast as spinning up the ring
-constexpr int kMaxThreads = 8;
+constexpr int kMaxThreads = 16;
 
 struct Lane {
     cudaStream_t stream = nullptr;
@@ -58,7 +58,7 @@ struct StagePool {
 static int pool_threads(const sckm_ctx* ctx) {
     if (const char* e = getenv("SCKM_INGEST_THREADS")) return std::max(1, std::min(kMaxThreads, atoi(e)));
     const unsigned hc = std::thread::hardware_concurrency();
-    int t = (int)std::max(2u, std::min<unsigned>(kMaxThreads, hc ? hc / 2 : 4));
+    int t = (int)std::max(2u, std::min<unsigned>(8u, hc ? hc / 2 : 4));
     if (ctx->ingest_max_threads > 0) t = std::min(t, ctx->ingest_max_threads);   // several devices share the host cores
     return t;
 }
@@ -118,7 +118,13 @@ static StagePool* get_pool(sckm_ctx* ctx) {
         ctx->stage_pool = new StagePool();
         ctx->stage_pool->device = ctx->device;
         ctx->stage_pool->nthreads = pool_threads(ctx);
-        if (!getenv("SCKM_INGEST_NO_NUMA")) ctx->stage_pool->have_cpus = device_numa_cpus(ctx->device, &ctx->stage_pool->cpus);
+        // bind only when the node offers every lane a CPU of its own among those this process may use (a container that
+        // is confined to a few CPUs of the node would otherwise pile all lanes onto them)
+        if (!getenv("SCKM_INGEST_NO_NUMA") && device_numa_cpus(ctx->device, &ctx->stage_pool->cpus))
+            ctx->stage_pool->have_cpus = CPU_COUNT(&ctx->stage_pool->cpus) >= std::max(4, 2 * ctx->stage_pool->nthreads);
+        if (getenv("SCKM_TRACE"))
+            fprintf(stderr, "[sckm] ingest: device %d, %d lanes, NUMA binding %s (%d usable CPUs on the device's node)\n", ctx->device,
+                    ctx->stage_pool->nthreads, ctx->stage_pool->have_cpus ? "on" : "off", ctx->stage_pool->have_cpus ? CPU_COUNT(&ctx->stage_pool->cpus) : 0);
     }
     return ctx->stage_pool;
 }

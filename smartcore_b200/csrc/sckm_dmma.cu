@@ -46,13 +46,6 @@ namespace sckm {
     } while (0)
 
 constexpr int DMMA_MAX_WARPS = 16;
-// A/B switch for measurements (tools/build_variant.sh nocenter -DSCKM_NO_CENTER): the tile kernels without the centring
-// subtraction (mu is then kept at zero by launch_cnorm)
-#ifdef SCKM_NO_CENTER
-#define SCKM_SHIFT(v, m) (v)
-#else
-#define SCKM_SHIFT(v, m) ((v) - (m))
-#endif
 constexpr double DMMA_TIE_REL = 1e-10;
 
 
@@ -155,7 +148,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
             for (int ks = 0; ks < KSTEPS; ks++) {
                 const uint32_t col = ks * 4 + t;
                 double v = 0.0;
-                if (rok && col < d) v = SCKM_SHIFT((double)__ldg(xr + col), mu_s[col]);
+                if (rok && col < d) v = (double)__ldg(xr + col) - mu_s[col];
                 a[mt][ks] = v;
                 s = fma(v, v, s);
             }
@@ -176,7 +169,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
                 for (uint32_t e = threadIdx.x; e < bn * DP; e += blockDim.x) {
                     const uint32_t r = e / DP, c = e - r * DP;
                     double v = 0.0;
-                    if (c0 + r < k && c < d) v = SCKM_SHIFT(centroids[(size_t)(c0 + r) * d + c], mu_s[c]);
+                    if (c0 + r < k && c < d) v = centroids[(size_t)(c0 + r) * d + c] - mu_s[c];
                     cbuf[(size_t)r * PITCH + c] = v;
                 }
                 for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
@@ -302,7 +295,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                 for (uint32_t e = threadIdx.x; e < bn * DP; e += blockDim.x) {
                     const uint32_t r = e / DP, c = e - r * DP;
                     double v = 0.0;
-                    if (c0 + r < k && c < d) v = SCKM_SHIFT(centroids[(size_t)(c0 + r) * d + c], mu_s[c]);
+                    if (c0 + r < k && c < d) v = centroids[(size_t)(c0 + r) * d + c] - mu_s[c];
                     cbuf[(size_t)r * PITCH + c] = v;
                 }
                 for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
@@ -331,7 +324,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                     for (int ks = 0; ks < KSTEPS; ks++) {
                         const uint32_t col = ks * 4 + t;
                         double v = 0.0;
-                        if (rok && col < d) v = SCKM_SHIFT((double)__ldg(xr + col), mu_s[col]);
+                        if (rok && col < d) v = (double)__ldg(xr + col) - mu_s[col];
                         a[mt][ks] = v;
                         s = fma(v, v, s);
                     }
@@ -436,30 +429,13 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
 // arithmetic (widen to f64, diff, square, sequential sum, never fused; raw x and raw centroids, no centring), then
 // a warp argmin with strict < and lowest index on ties (kmeans.rs:334-347 / bbd_tree.rs:101-111); the row is then
 // added to this warp's private partial (lanes own columns), so the result does not depend on scheduling.
-// TAIL (small payloads, single GPU, inside a Lloyd loop): the last CTA to finish also does what reduce_partials_kernel
-// and finalize_kernel do -- fold the `tail_slots` partial slots in slot order, zero them, centroids = sums / counts
-// (guarded, kmeans.rs:297-303), sizes, norms, stop rule (kmeans.rs:305-309) -- so a step is two launches instead of four.
-struct RefineTail {
-    uint32_t slots;                 // 0 = no tail
-    unsigned* counter;              // CTAs arrived (reset by the tail)
-    double* packed;                 // [pk]
-    double* centroids;              // written by the tail only, after every CTA is done reading them
-    double* cnorm;
-    long long* size;
-    LoopState* state;
-    double* inertia_trace;
-    unsigned long long* nmarked_w;
-};
-
-template <typename TX, int DMMA_WARPS, bool UPDATE = true, bool TAIL = false>
+template <typename TX, int DMMA_WARPS, bool UPDATE = true>
 __global__ void __launch_bounds__(DMMA_WARPS * 32)
-refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* centroids, uint32_t k,
-                   uint32_t* __restrict__ labels, double* __restrict__ mind, double* partials, size_t pk,
-                   const unsigned long long* nmarked, const double* __restrict__ mu,
-                   const LoopState* loop_st, uint32_t loop_it, RefineTail tail) {
-    if (loop_done(loop_st, loop_it)) return;
-    if (!TAIL && *nmarked == 0ull) return;                       // nothing was marked in this step (the common case)
-    if (*nmarked != 0ull) {
+refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids, uint32_t k,
+                   uint32_t* __restrict__ labels, double* __restrict__ mind, double* __restrict__ partials, size_t pk,
+                   const unsigned long long* __restrict__ nmarked, const double* __restrict__ mu,
+                   const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    if (*nmarked == 0ull || loop_done(loop_st, loop_it)) return; // nothing was marked in this step (the common case)
     const int lane = threadIdx.x & 31;
     const uint64_t w = (uint64_t)blockIdx.x * DMMA_WARPS + (threadIdx.x >> 5);
     const uint64_t nw = (uint64_t)gridDim.x * DMMA_WARPS;
@@ -521,48 +497,6 @@ refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
         }
     }
     if (UPDATE && lane == 0 && any) __stcg(part + pk - 1, __dadd_rn(__ldcg(part + pk - 1), inertia));
-    }
-    if (!TAIL) return;
-    // ---- fused reduce + finalize + stop rule by the last CTA ----
-    __shared__ bool s_last;
-    __threadfence();                                             // this CTA's slot updates and labels are out
-    __syncthreads();
-    if (threadIdx.x == 0) s_last = atomicAdd(tail.counter, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const size_t pitch = (pk + 15) / 16 * 16;
-    for (size_t e = threadIdx.x; e < pk; e += blockDim.x) {      // fixed order: slot 0, 1, 2, ...
-        double s = 0.0;
-        double* q = partials + e;
-        for (uint32_t p = 0; p < tail.slots; p++, q += pitch) { s = __dadd_rn(s, __ldcg(q)); __stcg(q, 0.0); }
-        tail.packed[e] = s;
-    }
-    __syncthreads();
-    const size_t kd = (size_t)k * d;
-    for (size_t e = threadIdx.x; e < kd; e += blockDim.x) {      // centroids of non-empty clusters (plain sums: mu not involved)
-        const uint32_t c = (uint32_t)(e / d);
-        const double cnt = tail.packed[kd + c];
-        if (cnt > 0.0) tail.centroids[e] = __ddiv_rn(tail.packed[e], cnt);
-    }
-    __syncthreads();
-    for (uint32_t c = threadIdx.x; c < k; c += blockDim.x) {
-        tail.size[c] = (long long)tail.packed[kd + c];
-        double s = 0.0;
-        for (uint32_t j = 0; j < d; j++) { const double v = tail.centroids[(size_t)c * d + j] - mu[j]; s = fma(v, v, s); }
-        tail.cnorm[c] = s;
-    }
-    if (threadIdx.x == 0) {
-        *tail.counter = 0u;
-        *tail.nmarked_w = 0ull;
-        const double dist = tail.packed[kd + k];
-        if (tail.inertia_trace) tail.inertia_trace[loop_it - 1] = dist;
-        tail.state->iters = loop_it;
-        if (tail.state->honor_stop) {
-            if (tail.state->distortion <= dist) tail.state->done_at = loop_it;   // break (kmeans.rs:305-306)
-            else tail.state->distortion = dist;                                   // kmeans.rs:307-308
-        }
-    }
 }
 
 // mu = per-feature mean of the finite centroids (fixed order: one thread per feature walks the k centroids), the
@@ -642,7 +576,7 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     }
     LAUNCH_CHECK_D(ctx);
     refine_rows_kernel<TX, WARPS, UPDATE><<<dmma_grid(ctx), WARPS * 32, 0, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d,
-        ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, ctx->d_mu, SCKM_LOOP_ARGS(ctx), RefineTail{});
+        ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, ctx->d_mu, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }
@@ -661,9 +595,6 @@ static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
 // finalize kernel keeps the norms current (an unchanged centroid keeps its norm).  center = false (tcgen05 path, which
 // ranks raw f32 rows): mu = 0, i.e. the raw norms.
 int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center) {
-#ifdef SCKM_NO_CENTER
-    center = false;
-#endif
     if (ctx->cnorm_valid && ctx->mu_zero == !center) return SCKM_OK;
     if (center) { center_kernel<<<1, 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_mu); ctx->launches++; }
     else SCKM_CUDA(ctx, cudaMemsetAsync(ctx->d_mu, 0, d * sizeof(double), ctx->stream));
@@ -674,32 +605,15 @@ int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center) {
     return SCKM_OK;
 }
 
-// refine pass for the streaming / tcgen05 kernels' launch geometry (8 warps per CTA).  tail_slots != 0: the same launch
-// folds that many partial slots and finalises the step (RefineTail); the caller must then skip the reduce, the
-// all-reduce and the finalize launch (ctx->step_finalized).
-int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas, uint32_t tail_slots) {
+// refine pass for the streaming kernel's launch geometry (8 warps per CTA)
+int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas) {
     sckm_ctx* ctx = ds->ctx;
-    ctx->step_finalized = false;
-    if (tail_slots) {
-        // the stream kernel's sums are plain sums of x (packed_centered == false): the tail's centroids need no shift
-        RefineTail t{tail_slots, reinterpret_cast<unsigned*>(ctx->d_flags + 1), ctx->d_packed, ctx->d_centroids, ctx->d_cnorm,
-                     (long long*)ctx->d_size, ctx->d_loop, ctx->d_inertia_trace, ctx->d_flags};
-        if (ds->dtype == SCKM_F32)
-            refine_rows_kernel<float, 8, true, true><<<grid_ctas, 256, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d,
-                ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, ctx->d_mu, SCKM_LOOP_ARGS(ctx), t);
-        else
-            refine_rows_kernel<double, 8, true, true><<<grid_ctas, 256, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d,
-                ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, ctx->d_mu, SCKM_LOOP_ARGS(ctx), t);
-        LAUNCH_CHECK_D(ctx);
-        ctx->step_finalized = true;
-        return SCKM_OK;
-    }
     if (ds->dtype == SCKM_F32)
         refine_rows_kernel<float, 8><<<grid_ctas, 256, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d,
-            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, nullptr, SCKM_LOOP_ARGS(ctx), RefineTail{});
+            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, nullptr, SCKM_LOOP_ARGS(ctx));
     else
         refine_rows_kernel<double, 8><<<grid_ctas, 256, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d,
-            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, nullptr, SCKM_LOOP_ARGS(ctx), RefineTail{});
+            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, nullptr, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }

@@ -36,7 +36,7 @@ constexpr int STREAM_WARPS = 8;
 constexpr int STREAM_MAX_K = 15;
 constexpr double STREAM_TIE_REL = 1e-10;
 
-int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas, uint32_t tail_slots = 0);   // sckm_dmma.cu
+int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas);   // sckm_dmma.cu
 
 // Feature (k-dimension) permutation used by both operands of the scoring GEMM so that a lane's KS elements of a
 // row are VW-element vectors in memory (one 16-byte LDG per VW k-steps): the dot product does not care about the
@@ -98,7 +98,7 @@ template <int KS, int KT, int VW, bool DFULL, int STAGES, typename TX>
 __global__ void __launch_bounds__(STREAM_WARPS * 32, (KS * KT <= 8) ? 2 : 1)
 assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const double* __restrict__ centroids,
                      const double* __restrict__ cnorm, const double* __restrict__ mu, uint32_t k, uint32_t* __restrict__ labels,
-                     double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked, uint32_t reverse,
+                     double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked,
                      const LoopState* __restrict__ loop_st, uint32_t loop_it) {
     if (loop_done(loop_st, loop_it)) return;             // the fit's stop rule already fired (kmeans.rs:305)
     constexpr int NTU = KS / 2 > 0 ? KS / 2 : 1;         // feature n-tiles of the update GEMM (8 features each)
@@ -150,11 +150,6 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
     const uint64_t nbatches = (n + 31) / 32;
     const uint64_t wglobal = (uint64_t)blockIdx.x * STREAM_WARPS + warp;
     const uint64_t nwarps = (uint64_t)gridDim.x * STREAM_WARPS;
-    // Zig-zag: successive Lloyd steps walk X in opposite directions (reverse = iteration parity), so a step starts on
-    // the rows the previous one finished with -- still in the 126 MB L2 when X is about that size (config C2: 128 MB),
-    // instead of chasing its own tail through an LRU cache.  `b` stays the logical batch (work split, ring parity); the
-    // rows it stands for are batch phys(b).  The order is fixed per (n, grid, parity): results stay bit-reproducible.
-    auto phys = [&](uint64_t b) -> uint64_t { return reverse ? nbatches - 1 - b : b; };
 
     // rows -> A fragments straight from HBM (8 rows x full 32-byte sectors per request).  FULL: all 32 rows exist
     // and d == 4*KS, so there is nothing to predicate and every offset folds into the instruction.
@@ -222,7 +217,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         __syncwarp();
     }
     auto ring_fill = [&](uint64_t b, int stage) {            // lane 0: fetch batch b into `stage`
-        const uint64_t row0 = phys(b) * 32;
+        const uint64_t row0 = b * 32;
         const uint32_t bytes = (uint32_t)(min((uint64_t)32, n - row0) * d * sizeof(TX));
         s_mbar_expect_tx(&full_bar[warp][stage], bytes);
         s_bulk_g2s(ring_w + (size_t)stage * 32 * d, x + row0 * d, bytes, &full_bar[warp][stage]);
@@ -230,7 +225,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
 
     auto batch = [&](uint64_t b, uint32_t it, auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
-        const uint64_t row0 = phys(b) * 32;
+        const uint64_t row0 = b * 32;
         const int stage = TMA ? (int)(it % (STAGES > 0 ? STAGES : 1)) : 0;
         const TX* stage_rows = TMA ? ring_w + (size_t)stage * 32 * d : nullptr;
         // (ring mode: the A fragments of this batch were read out of its ring buffer at the end of the previous turn)
@@ -263,7 +258,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         // the A registers are dead now.  Registers-direct mode: prefetch the next batch into them so its HBM latency
         // hides under epilogue + update.  Ring mode: read the update's B fragments (this batch's rows again, K = row)
         // out of the ring buffer now, so that their latency hides under the epilogue instead of stalling the DMMAs.
-        if (!TMA && b + nwarps < nbatches) load_any(phys(b + nwarps) * 32);
+        if (!TMA && b + nwarps < nbatches) load_any((b + nwarps) * 32);
         double xbe[TMA ? 8 : 1][NTU];
         if (TMA) {
             const TX* ubs = stage_rows + (size_t)t * d + g * VU;
@@ -360,8 +355,8 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
                 const int st1 = (int)((it + 1) % (STAGES > 0 ? STAGES : 1));
                 s_mbar_wait(&full_bar[warp][st1], ((it + 1) / (STAGES > 0 ? STAGES : 1)) & 1u);
                 const TX* rows1 = ring_w + (size_t)st1 * 32 * d;
-                if (phys(b1) * 32 + 32 <= n) load_rows_smem(rows1, phys(b1) * 32, std::true_type{});
-                else load_rows_smem(rows1, phys(b1) * 32, std::false_type{});
+                if (b1 * 32 + 32 <= n) load_rows_smem(rows1, b1 * 32, std::true_type{});
+                else load_rows_smem(rows1, b1 * 32, std::false_type{});
             }
         }
     };
@@ -374,15 +369,15 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
             }
         if (wglobal < nbatches) {
             s_mbar_wait(&full_bar[warp][0], 0u);
-            if (phys(wglobal) * 32 + 32 <= n) load_rows_smem(ring_w, phys(wglobal) * 32, std::true_type{});
-            else load_rows_smem(ring_w, phys(wglobal) * 32, std::false_type{});
+            if (wglobal * 32 + 32 <= n) load_rows_smem(ring_w, wglobal * 32, std::true_type{});
+            else load_rows_smem(ring_w, wglobal * 32, std::false_type{});
         }
     } else if (wglobal < nbatches) {
-        load_any(phys(wglobal) * 32);
+        load_any(wglobal * 32);
     }
     uint32_t it = 0;
     for (uint64_t b = wglobal; b < nbatches; b += nwarps, it++) {
-        if (DFULL && phys(b) * 32 + 32 <= n) batch(b, it, std::true_type{});
+        if (DFULL && b * 32 + 32 <= n) batch(b, it, std::true_type{});
         else batch(b, it, std::false_type{});
     }
     // rows handed to refine_rows_kernel (rare); the reduction is unconditional: every lane must reach the shuffles
@@ -458,8 +453,7 @@ static int launch_stream_f(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* gr
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbatches + STREAM_WARPS - 1) / STREAM_WARPS,
                                                                               (uint64_t)ctx->num_sms * ctas_per_sm));
     kern<<<grid, STREAM_WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, d, ctx->d_centroids, ctx->d_cnorm, ctx->d_mu,
-                                                        (uint32_t)k, ds->labels, ctx->d_partials, pk, ctx->d_flags,
-                                                        (ctx->loop_it & 1u) && !getenv("SCKM_STREAM_NOZIGZAG") ? 1u : 0u, SCKM_LOOP_ARGS(ctx));
+                                                        (uint32_t)k, ds->labels, ctx->d_partials, pk, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK_S(ctx);
     *grid_out = grid;
     return SCKM_OK;
@@ -525,10 +519,7 @@ int launch_assign_stream(sckm_dataset* ds, uint64_t k) {
     // kernel just stored, or still-zero ones beyond them (kernel order on the stream makes that safe)
     const unsigned rgrid = (grid + STREAM_WARPS - 1) / STREAM_WARPS;
     ctx->partial_slots_used = std::max(grid, rgrid * STREAM_WARPS);
-    // Inside a single-GPU Lloyd loop the refine launch also folds the partial slots, finalises the centroids and
-    // applies the stop rule (its last CTA): the step is then TWO launches.  The payload here is tiny (k*d <= 480).
-    const bool tail = ctx->loop_it != 0 && ctx->nranks == 1 && !getenv("SCKM_NO_TAIL");
-    return launch_refine_rows(ds, k, pk, rgrid, tail ? ctx->partial_slots_used : 0u);
+    return launch_refine_rows(ds, k, pk, rgrid);
 }
 
 }  // namespace sckm

@@ -35,7 +35,7 @@ namespace sckm {
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
-int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas, uint32_t tail_slots = 0);   // sckm_dmma.cu
+int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas);   // sckm_dmma.cu
 int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center);                  // sckm_dmma.cu
 
 constexpr int TC_BM = 128;               // rows per MMA tile (TMEM lanes)

@@ -13,6 +13,6 @@ Layout
 There is no CPU fallback: importing cabi without the built CUDA library raises.
 """
 from .cabi import Context, Dataset, SckmError, F32, F64  # noqa: F401
-from .cluster import KMeans, KMeansParameters, KMeansSearchParameters, DenseMatrix, Failed  # noqa: F401
+from .cluster import KMeans, KMeansParameters, KMeansSearchParameters, DenseMatrix, Failed, set_std_rand, get_std_rand  # noqa: F401
 from .metrics import HCVScore, contingency_matrix, entropy, mutual_info_score  # noqa: F401
 from .neighbour import LinearKNNSearch  # noqa: F401

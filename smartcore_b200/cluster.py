@@ -32,6 +32,10 @@ _h.sch_kmeans_eq.argtypes = [_vp, _vp]
 _h.sch_search_parameters.argtypes = [_vp, C.c_size_t, _vp, C.c_size_t, _vp, _vp, C.c_size_t, _vp, _vp, _vp, _vp, C.c_size_t]
 _h.sch_search_parameters.restype = C.c_size_t
 _h.sch_kmeanspp_draws.argtypes = [C.c_int, C.c_uint64, C.c_uint64, C.c_size_t, _vp, _vp]; _h.sch_kmeanspp_draws.restype = None
+_h.sch_set_std_rand.argtypes = [C.c_int]; _h.sch_set_std_rand.restype = None
+_h.sch_get_std_rand.restype = C.c_int
+_h.sch_rng_next_u64.argtypes = [C.c_uint64, C.c_int, C.c_size_t, _vp]; _h.sch_rng_next_u64.restype = None
+_h.sch_chacha_block.argtypes = [_vp, C.c_uint64, C.c_int, _vp]; _h.sch_chacha_block.restype = None
 _h.sch_dense_get_f64.argtypes = [_vp, C.c_size_t, C.c_size_t, C.c_int, C.c_size_t, C.c_size_t]
 _h.sch_dense_get_f64.restype = C.c_double
 
@@ -113,6 +117,28 @@ class KMeansSearchParameters:
         n = _h.sch_search_parameters(_p(k), len(k), _p(m), len(m), _p(s), _p(hs), len(s), _p(ok), _p(om), _p(os_), _p(oh), cap)
         for i in range(n):
             yield KMeansParameters(int(ok[i]), int(om[i]), int(os_[i]) if oh[i] else None)
+
+
+def set_std_rand(on):
+    """Follow smartcore built with feature `std_rand` (RngImpl = StdRng = ChaCha12; forced by `datasets`) instead of the
+    default-feature build (SmallRng = xoshiro256++): src/rand_custom.rs:1-4."""
+    _h.sch_set_std_rand(1 if on else 0)
+
+
+def get_std_rand():
+    return bool(_h.sch_get_std_rand())
+
+
+def rng_next_u64(seed, count, std_rand=False):
+    out = np.zeros(count, dtype=np.uint64)
+    _h.sch_rng_next_u64(seed, 1 if std_rand else 0, count, _p(out))
+    return out
+
+
+def chacha_block(key_words, counter, rounds):
+    key = np.ascontiguousarray(key_words, dtype=np.uint32); out = np.zeros(16, dtype=np.uint32)
+    _h.sch_chacha_block(_p(key), counter, rounds, _p(out))
+    return out
 
 
 def kmeanspp_draws(seed, n, k):

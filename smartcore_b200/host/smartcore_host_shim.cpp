@@ -161,6 +161,21 @@ size_t sch_search_parameters(const size_t* k, size_t nk, const size_t* max_iter,
     return n;
 }
 
+// which smartcore build the host mirror follows: 0 = default features (SmallRng), 1 = `std_rand` (StdRng = ChaCha12)
+void sch_set_std_rand(int on) { rand_custom::set_std_rand(on != 0); }
+int sch_get_std_rand(void) { return rand_custom::std_rand_switch() ? 1 : 0; }
+// raw generator output (KATs): `count` next_u64 values after seed_from_u64(seed) of the selected RngImpl
+void sch_rng_next_u64(uint64_t seed, int std_rand, size_t count, uint64_t* out) {
+    auto r = rand_custom::RngImpl::seed_from_u64(seed, false, std_rand != 0);
+    for (size_t i = 0; i < count; i++) out[i] = r.next_u64();
+}
+void sch_chacha_block(const uint32_t* key8, uint64_t counter, int rounds, uint32_t* out16) {
+    uint32_t key[8], out[16];
+    for (int i = 0; i < 8; i++) key[i] = key8[i];
+    rand_custom::RngImpl::chacha_block(key, counter, rounds, out);
+    for (int i = 0; i < 16; i++) out16[i] = out[i];
+}
+
 // the host RNG draw sequence of kmeans_plus_plus for (seed, n, k): first index + k-1 uniforms
 void sch_kmeanspp_draws(int has_seed, uint64_t seed, uint64_t n, size_t k, uint64_t* first, double* uniforms) {
     auto rng = rand_custom::get_rng_impl(has_seed ? std::optional<uint64_t>(seed) : std::nullopt);

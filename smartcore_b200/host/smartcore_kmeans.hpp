@@ -20,6 +20,7 @@
 #include <cstddef>
 #include <cstdlib>
 #include <optional>
+#include <random>
 #include <string>
 #include <type_traits>
 #include <utility>
@@ -103,22 +104,45 @@ public:
 
 // ---------------------------------------------------------------------------------------------
 namespace rand_custom {
-// rand 0.8.5 SmallRng on 64-bit targets = xoshiro256++; seed_from_u64 = rand_core 0.6's default PCG32
-// fill of the 32-byte seed (SmallRng does not forward xoshiro's SplitMix override in 0.8.x).
-// set SplitMixSeeding to follow rand >= 0.9 instead.  (Published algorithm restated; see SURVEY App. B.)
+// smartcore's RngImpl (src/rand_custom.rs:1-4) is a compile-time choice:
+//   default features      -> rand 0.8.5 SmallRng = xoshiro256++ (64-bit targets)
+//   feature `std_rand`    -> rand 0.8.5 StdRng   = rand_chacha 0.3 ChaCha12Rng   (forced by `datasets`, Cargo.toml:39-40)
+// Both are mirrored here behind a process-wide switch (set_std_rand), so either smartcore build can be followed.
+// seed_from_u64 is rand_core 0.6's default for both (PCG32 fill of the 32-byte seed; SmallRng does not forward
+// xoshiro's SplitMix override in 0.8.x -- `splitmix = true` follows rand >= 0.9 instead).  gen::<f64>() and
+// gen_range(0..n) are generator-independent (Standard: 53 high bits; UniformInt<usize>::sample_single on next_u64).
+// (Published algorithms restated; rand is not part of the reference tree -- SURVEY App. B.  Pins: xoshiro256++ upstream
+// vector, ChaCha TC1 vectors for 8/12/20 rounds, PCG32 XSH-RR demo vector -- checked by the CPU test suite under tests/.)
+inline bool& std_rand_switch() { static bool on = false; return on; }
+inline void set_std_rand(bool on) { std_rand_switch() = on; }
+
+inline void pcg32_fill(uint64_t state, uint32_t (&w)[8]) {       // rand_core 0.6 SeedableRng::seed_from_u64
+    const uint64_t MUL = 6364136223846793005ULL, INC = 11634580027462260723ULL;
+    for (int i = 0; i < 8; i++) {
+        state = state * MUL + INC;
+        const uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27), rot = (uint32_t)(state >> 59);
+        w[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
+    }
+}
+
 class RngImpl {
 public:
-    static RngImpl seed_from_u64(uint64_t state, bool splitmix = false) {
+    // SmallRng (default) or StdRng (std_rand switch) seeded the way `RngImpl::seed_from_u64` does it
+    static RngImpl seed_from_u64(uint64_t state, bool splitmix = false) { return seed_from_u64(state, splitmix, std_rand_switch()); }
+    static RngImpl seed_from_u64(uint64_t state, bool splitmix, bool std_rand) {
         RngImpl r;
+        r.chacha = std_rand;
+        uint32_t w[8];
+        if (std_rand) {                                   // StdRng: the PCG32 words are the ChaCha key
+            pcg32_fill(state, w);
+            for (int i = 0; i < 8; i++) r.key[i] = w[i];
+            r.counter = 0; r.index = 16;
+            return r;
+        }
         if (!splitmix) {
-            const uint64_t MUL = 6364136223846793005ULL, INC = 11634580027462260723ULL;
-            uint32_t w[8]; bool all_zero = true;
-            for (int i = 0; i < 8; i++) {
-                state = state * MUL + INC;
-                uint32_t xs = (uint32_t)(((state >> 18) ^ state) >> 27), rot = (uint32_t)(state >> 59);
-                w[i] = (xs >> rot) | (xs << ((32 - rot) & 31));
-                all_zero = all_zero && w[i] == 0;
-            }
+            pcg32_fill(state, w);
+            bool all_zero = true;
+            for (int i = 0; i < 8; i++) all_zero = all_zero && w[i] == 0;
             if (!all_zero) { for (int i = 0; i < 4; i++) r.s[i] = ((uint64_t)w[2 * i + 1] << 32) | w[2 * i]; return r; }
             state = 0;
         }
@@ -132,6 +156,12 @@ public:
         return r;
     }
     uint64_t next_u64() {
+        if (chacha) {                                     // BlockRng: 16 words per block, two consecutive words, low first
+            if (index >= 16) { block(); index = 0; }
+            const uint64_t v = (uint64_t)buf[index] | ((uint64_t)buf[index + 1] << 32);
+            index += 2;
+            return v;
+        }
         auto rotl = [](uint64_t x, int k) { return (x << k) | (x >> (64 - k)); };
         uint64_t result = rotl(s[0] + s[3], 23) + s[0], t = s[1] << 17;
         s[2] ^= s[0]; s[3] ^= s[1]; s[1] ^= s[2]; s[0] ^= s[3]; s[2] ^= t; s[3] = rotl(s[3], 45);
@@ -146,10 +176,39 @@ public:
             if ((uint64_t)m <= zone) return (uint64_t)(m >> 64);
         }
     }
+    // ChaCha block function, `rounds` rounds, 64-bit block counter in words 12-13, stream id 0 (rand_chacha 0.3 layout)
+    static void chacha_block(const uint32_t (&key)[8], uint64_t counter, int rounds, uint32_t (&out)[16]) {
+        const uint32_t st[16] = {0x61707865u, 0x3320646eu, 0x79622d32u, 0x6b206574u, key[0], key[1], key[2], key[3],
+                                 key[4], key[5], key[6], key[7], (uint32_t)counter, (uint32_t)(counter >> 32), 0u, 0u};
+        uint32_t x[16];
+        for (int i = 0; i < 16; i++) x[i] = st[i];
+        auto rotl = [](uint32_t v, int k) { return (v << k) | (v >> (32 - k)); };
+        auto qr = [&](int a, int b, int c, int d) {
+            x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 16); x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 12);
+            x[a] += x[b]; x[d] = rotl(x[d] ^ x[a], 8);  x[c] += x[d]; x[b] = rotl(x[b] ^ x[c], 7);
+        };
+        for (int r = 0; r < rounds; r += 2) {
+            qr(0, 4, 8, 12); qr(1, 5, 9, 13); qr(2, 6, 10, 14); qr(3, 7, 11, 15);
+            qr(0, 5, 10, 15); qr(1, 6, 11, 12); qr(2, 7, 8, 13); qr(3, 4, 9, 14);
+        }
+        for (int i = 0; i < 16; i++) out[i] = x[i] + st[i];
+    }
     uint64_t s[4] = {0, 0, 0, 0};
+    bool chacha = false;
+    uint32_t key[8] = {0, 0, 0, 0, 0, 0, 0, 0}, buf[16] = {0};
+    uint64_t counter = 0;
+    int index = 16;
+private:
+    void block() { chacha_block(key, counter++, 12, buf); }
 };
-// default-feature build: None -> seed 0 (rand_custom.rs:24-28)
-inline RngImpl get_rng_impl(std::optional<uint64_t> seed) { return RngImpl::seed_from_u64(seed.value_or(0)); }
+// get_rng_impl (rand_custom.rs:8-33).  None: seed 0 in the default build (:24-28); in a std_rand build the reference
+// seeds from thread_rng (:13-16, unreproducible by design) -- mirrored with the system entropy source.
+inline RngImpl get_rng_impl(std::optional<uint64_t> seed) {
+    if (seed) return RngImpl::seed_from_u64(*seed);
+    if (!std_rand_switch()) return RngImpl::seed_from_u64(0);
+    std::random_device rd;
+    return RngImpl::seed_from_u64(((uint64_t)rd() << 32) | rd());
+}
 }  // namespace rand_custom
 
 // ---------------------------------------------------------------------------------------------

@@ -191,3 +191,94 @@ def test_knn_oracle_against_reference_kats():
     assert sorted(i for i, _ in K.find(data2, eu, [3., 3.], 3)) == [1, 2, 3]
     with pytest.raises(ValueError):
         K.find(data1, simple, 2, 11)
+
+
+# ---- RNG of the `std_rand` build and the seeding path: published known answers ----------------------------------------
+def _xsh_rr(state):
+    xs = (((state >> 18) ^ state) >> 27) & 0xFFFFFFFF
+    rot = state >> 59
+    return ((xs >> rot) | (xs << ((32 - rot) & 31))) & 0xFFFFFFFF
+
+
+PCG_MUL, MASK64 = 6364136223846793005, (1 << 64) - 1
+
+
+def test_pcg32_output_function_reproduces_the_pcg_reference_vector():
+    """PCG32 (XSH-RR 64/32) with the reference seeding (initstate 42, initseq 54) -- the demo vector of the PCG
+    distribution: pins the multiplier and the output permutation that rand_core's seed_from_u64 is built from."""
+    state, inc = 0, ((54 << 1) | 1)
+    out = []
+
+    def step():
+        nonlocal state
+        old = state
+        state = (old * PCG_MUL + inc) & MASK64
+        return _xsh_rr(old)
+    step(); state = (state + 42) & MASK64; step()
+    out = [step() for _ in range(6)]
+    assert out == [0xa15c02b7, 0x7b47f409, 0xba1d3330, 0x83d2f293, 0xbfa4784b, 0xcbed606e]
+
+
+def test_seed_from_u64_fill_matches_the_python_restatement(O):
+    """rand_core 0.6 SeedableRng::seed_from_u64: advance first (MUL, INC = 11634580027462260723), XSH-RR of the NEW state,
+    little-endian words -- restated here in Python on top of the output function pinned above, against the oracle (C++)
+    and the host mirror (C++), for both RngImpl kinds."""
+    import smartcore_b200.cluster as cl
+    for seed in (0, 1, 42, 2**63 + 12345, 2**64 - 1):
+        st, words = seed, []
+        for _ in range(8):
+            st = (st * PCG_MUL + 11634580027462260723) & MASK64
+            words.append(_xsh_rr(st))
+        assert O.pcg32_fill(seed).view("<u4").tolist() == words
+        # StdRng: the words are the ChaCha12 key; first outputs = block 0 of that key
+        blk = O.chacha_block(np.array(words, dtype=np.uint32), 0, 12)
+        want = [int(blk[2 * i]) | (int(blk[2 * i + 1]) << 32) for i in range(8)]
+        assert O.rand_next_u64(seed, O.SEED_MODE_STDRNG, 8).tolist() == want
+        assert cl.rng_next_u64(seed, 8, std_rand=True).tolist() == want
+        # SmallRng: the words are the xoshiro256++ state (LE u64s); mirror == oracle
+        assert cl.rng_next_u64(seed, 8, std_rand=False).tolist() == O.rand_next_u64(seed, O.SEED_MODE_PCG, 8).tolist()
+
+
+def test_chacha_block_published_vectors(O):
+    """ChaCha with an all-zero 256-bit key and IV, block 0 (TC1 of the published ChaCha test vectors): 8, 12 (StdRng's
+    variant in rand 0.8: ChaCha12Rng) and 20 rounds; oracle and host mirror."""
+    import smartcore_b200.cluster as cl
+    kat = {8: "3e00ef2f895f40d67f5bb8e81f09a5a12c840ec3ce9a7f3b181be188ef711a1e984ce172b9216f419f445367456d5619314a42a3da86b001387bfdb80e0cfe42",
+           12: "9bf49a6a0755f953811fce125f2683d50429c3bb49e074147e0089a52eae155f0564f879d27ae3c02ce82834acfa8c793a629f2ca0de6919610be82f411326be",
+           20: "76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7da41597c5157488d7724e03fb8d84a376a43b8f41518a11cc387b669b2ee6586"}
+    zero = np.zeros(8, dtype=np.uint32)
+    for rounds, hexv in kat.items():
+        assert O.chacha_block(zero, 0, rounds).astype("<u4").tobytes().hex() == hexv
+        assert cl.chacha_block(zero, 0, rounds).astype("<u4").tobytes().hex() == hexv
+    # the block counter occupies words 12-13 (64 bit): block 1 differs from block 0 and is what the 9th next_u64 reads
+    w = O.rand_next_u64(7, O.SEED_MODE_STDRNG, 9)
+    key = O.pcg32_fill(7).view("<u4")
+    b1 = O.chacha_block(key, 1, 12)
+    assert int(w[8]) == int(b1[0]) | (int(b1[1]) << 32)
+
+
+def test_std_rand_draw_sequence_host_mirror_equals_oracle(O):
+    import smartcore_b200 as sc
+    from smartcore_b200 import cluster as cl
+    try:
+        sc.set_std_rand(True)
+        assert sc.get_std_rand()
+        for seed, n, k in ((42, 150, 3), (0, 10_000_000, 256), (2**40 + 3, 77, 12)):
+            f, u = cl.kmeanspp_draws(seed, n, k)
+            fo, uo = O.draws(seed, n, k, O.SEED_MODE_STDRNG)
+            assert f == fo and np.array_equal(u, uo) and 0 <= f < n and np.all((u >= 0) & (u < 1))
+        sc.set_std_rand(False)
+        f, u = cl.kmeanspp_draws(42, 150, 3)
+        fo, uo = O.draws(42, 150, 3, O.SEED_MODE_PCG)
+        assert f == fo and np.array_equal(u, uo)
+        assert (f, u.tolist()) != tuple([O.draws(42, 150, 3, O.SEED_MODE_STDRNG)[0], O.draws(42, 150, 3, O.SEED_MODE_STDRNG)[1].tolist()])
+    finally:
+        sc.set_std_rand(False)
+
+
+def test_numpy_blob_generator_equals_the_host_twin():
+    """oracle/blobs_np.py (what the CPU arm of bench.py builds its input with) against sckm_blobs_fill_host, bit for bit."""
+    from oracle import blobs_np
+    from smartcore_b200 import cabi
+    for (row0, n, d, k, seed, dt) in ((0, 3000, 64, 256, 20260101, np.float64), ((1 << 33) + 5, 500, 7, 3, 99, np.float32), (123, 70000, 5, 8, 1, np.float64)):
+        assert np.array_equal(blobs_np.blobs(row0, n, d, k, seed, dtype=dt), cabi.blobs_host(row0, n, d, k, seed, dtype=dt))

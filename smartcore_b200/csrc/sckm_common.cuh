@@ -50,6 +50,8 @@ struct sckm_ctx {
     double* d_mu = nullptr;          // [d] centring shift of the GEMM-form kernels (see launch_cnorm); zeros = no shift
     size_t cap_mu = 0;
     bool mu_zero = true;             // d_mu currently holds zeros
+    bool mu_requested = false;       // what the last launch_cnorm was asked for (centred kernels vs raw norms)
+    bool center_on = false;          // ... and what it decided: the tile kernels subtract mu (CENTER instantiation)
     bool packed_centered = false;    // d_packed sums of the last step are sums of (x - mu), not of x
     double* d_packed = nullptr;      // [k*d sums | k counts | inertia]
     double* d_partials = nullptr;    // [P][k*d + k + 1] per-CTA/warp partial sums (deterministic)

@@ -20,7 +20,10 @@
 //     ||x - c||^2 does not change, but the cancellation error of the GEMM form now scales with the spread of the
 //     data around mu instead of its distance from the origin, and so do the near-tie threshold and the per-point
 //     distance.  The fused update accumulates the centred values; finalize_kernel adds mu back
-//     (centroid = sum(x - mu) / count + mu).
+//     (centroid = sum(x - mu) / count + mu).  The subtraction is not free on the FP64 datapath the DMMAs use (measured
+//     on B200: +2.8 % on the resident kernel at C3, +12 % on the streamed-centroid kernel at C4), so it is a template
+//     switch (CENTER) that launch_cnorm turns on only when the data sit further from the origin than they are wide
+//     (||mu||^2 > max_j ||c_j - mu||^2): centring then buys more than a factor 4 in precision; otherwise mu = 0.
 //   * Rows whose best/second gap is within 1e-10*(||x||^2 + max||c||^2) (>= 1e4 x the rounding
 //     error bound of the GEMM form) are marked and re-decided by refine_rows_kernel with the
 //     reference's exact arithmetic (euclidian.rs:56-63), so labels equal the exact direct-form argmin.
@@ -103,7 +106,7 @@ __device__ __forceinline__ void epilogue_all(const double (&acc)[MT][NT][2], uin
 // kernel: it is the headline path and its instruction schedule is tuned (87.8 % of the FP64 peak).
 // KSTEPS: d padded to 4*KSTEPS; MT: m-tiles (8 rows each) per warp slab; DMMA_NT: n-tiles (8 centroids each) per
 // accumulator sub-block; DMMA_WARPS: warps per CTA (one CTA per SM)
-template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool UPDATE, typename TX>
+template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool UPDATE, bool CENTER, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, const double* __restrict__ mu, uint32_t k, uint32_t bn, uint32_t* __restrict__ labels,
@@ -148,7 +151,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
             for (int ks = 0; ks < KSTEPS; ks++) {
                 const uint32_t col = ks * 4 + t;
                 double v = 0.0;
-                if (rok && col < d) v = (double)__ldg(xr + col) - mu_s[col];
+                if (rok && col < d) v = CENTER ? (double)__ldg(xr + col) - mu_s[col] : (double)__ldg(xr + col);
                 a[mt][ks] = v;
                 s = fma(v, v, s);
             }
@@ -169,7 +172,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
                 for (uint32_t e = threadIdx.x; e < bn * DP; e += blockDim.x) {
                     const uint32_t r = e / DP, c = e - r * DP;
                     double v = 0.0;
-                    if (c0 + r < k && c < d) v = centroids[(size_t)(c0 + r) * d + c] - mu_s[c];
+                    if (c0 + r < k && c < d) v = CENTER ? centroids[(size_t)(c0 + r) * d + c] - mu_s[c] : centroids[(size_t)(c0 + r) * d + c];
                     cbuf[(size_t)r * PITCH + c] = v;
                 }
                 for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
@@ -252,7 +255,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
 // (best, second, argbest) of every row in a small per-warp shared-memory table between blocks.  Rows are re-read per
 // block, but a round's working set (148 CTAs x warps x sl slabs) is L2-resident, so HBM still sees X once.
 // MULTI = false is the compile-time specialisation for a fully resident centroid set (one block, sl = 1, no state).
-template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool MULTI, bool UPDATE, typename TX>
+template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool MULTI, bool UPDATE, bool CENTER, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, const double* __restrict__ mu, uint32_t k, uint32_t bn, uint32_t sl_arg, uint32_t* __restrict__ labels,
@@ -295,7 +298,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                 for (uint32_t e = threadIdx.x; e < bn * DP; e += blockDim.x) {
                     const uint32_t r = e / DP, c = e - r * DP;
                     double v = 0.0;
-                    if (c0 + r < k && c < d) v = centroids[(size_t)(c0 + r) * d + c] - mu_s[c];
+                    if (c0 + r < k && c < d) v = CENTER ? centroids[(size_t)(c0 + r) * d + c] - mu_s[c] : centroids[(size_t)(c0 + r) * d + c];
                     cbuf[(size_t)r * PITCH + c] = v;
                 }
                 for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
@@ -324,7 +327,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                     for (int ks = 0; ks < KSTEPS; ks++) {
                         const uint32_t col = ks * 4 + t;
                         double v = 0.0;
-                        if (rok && col < d) v = (double)__ldg(xr + col) - mu_s[col];
+                        if (rok && col < d) v = CENTER ? (double)__ldg(xr + col) - mu_s[col] : (double)__ldg(xr + col);
                         a[mt][ks] = v;
                         s = fma(v, v, s);
                     }
@@ -562,13 +565,15 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     const size_t smem = (size_t)bn * row_bytes + (size_t)DP * 8 + (multi ? (size_t)WARPS * sl * ROWS * 3 * sizeof(long long) : 0);
     ctx->partial_slots_used = dmma_grid(ctx) * WARPS;
     if (!multi) {
-        auto kern = assign_dmma_resident_kernel<KSTEPS, MT, NT, WARPS, UPDATE, TX>;
+        auto kern = ctx->center_on ? assign_dmma_resident_kernel<KSTEPS, MT, NT, WARPS, UPDATE, true, TX>
+                                   : assign_dmma_resident_kernel<KSTEPS, MT, NT, WARPS, UPDATE, false, TX>;
         SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
                                                               ctx->d_cnorm, ctx->d_mu, (uint32_t)k, bn, ds->labels, ds->mind,
                                                               ctx->d_partials, pk, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     } else {
-        auto kern = assign_dmma_kernel<KSTEPS, MT, NT, WARPS, true, UPDATE, TX>;
+        auto kern = ctx->center_on ? assign_dmma_kernel<KSTEPS, MT, NT, WARPS, true, UPDATE, true, TX>
+                                   : assign_dmma_kernel<KSTEPS, MT, NT, WARPS, true, UPDATE, false, TX>;
         SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
                                                               ctx->d_cnorm, ctx->d_mu, (uint32_t)k, bn, sl, ds->labels, ds->mind,
@@ -590,17 +595,55 @@ static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     return launch_t<32, 1, 4, 12, UPDATE, TX>(ds, k, pk);
 }
 
+// [0] = ||mu||^2, [1] = max_j ||c_j - mu||^2 (NaN norms ignored): the two numbers the centring decision needs
+__global__ void center_stats_kernel(const double* __restrict__ mu, uint32_t d, const double* __restrict__ cnorm, uint32_t k,
+                                    double* __restrict__ out2) {
+    double s = 0.0;
+    for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) s = fma(mu[j], mu[j], s);
+    const double total = cta_max(cnorm, k);                 // (called by every thread)
+    __shared__ double s_sum[32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) s_sum[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+        for (uint32_t w = 0; w < (blockDim.x + 31) / 32; w++) t += s_sum[w];
+        out2[0] = t; out2[1] = total;
+    }
+}
+
 // Centring shift and ||c - mu||^2 of ctx->d_centroids -- only needed when the centroids came from the host (start of
 // a fit, sckm_lloyd_step, predict); inside the Lloyd loop mu stays what it was at the start of the fit and the
-// finalize kernel keeps the norms current (an unchanged centroid keeps its norm).  center = false (tcgen05 path, which
-// ranks raw f32 rows): mu = 0, i.e. the raw norms.
+// finalize kernel keeps the norms current (an unchanged centroid keeps its norm).
+// center = true (DMMA tile / streaming kernels): mu = mean of the finite centroids IF the data sit further from the
+// origin than they are wide (||mu||^2 > max_j ||c_j - mu||^2; one 16-byte read-back per fit decides), else mu = 0 and
+// the tile kernels run their subtraction-free instantiation.  Every rank of a multi-GPU fit holds the same centroids,
+// hence takes the same decision.  SCKM_CENTER=0/1 forces it (tests).
+// center = false (tcgen05 path, which ranks raw f32 rows): mu = 0, i.e. the raw norms.
 int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center) {
-    if (ctx->cnorm_valid && ctx->mu_zero == !center) return SCKM_OK;
-    if (center) { center_kernel<<<1, 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_mu); ctx->launches++; }
-    else SCKM_CUDA(ctx, cudaMemsetAsync(ctx->d_mu, 0, d * sizeof(double), ctx->stream));
-    ctx->mu_zero = !center;
-    cnorm_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_mu, ctx->d_cnorm);
+    if (ctx->cnorm_valid && ctx->mu_requested == center) return SCKM_OK;
+    bool on = false;
+    if (center) {
+        center_kernel<<<1, 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_mu);
+        cnorm_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_mu, ctx->d_cnorm);
+        center_stats_kernel<<<1, 256, 0, ctx->stream>>>(ctx->d_mu, (uint32_t)d, ctx->d_cnorm, (uint32_t)k, (double*)(ctx->d_flags + 2));
+        ctx->launches += 3;
+        SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->h_pinned + 8, ctx->d_flags + 2, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+        SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        on = ctx->h_pinned[8] > ctx->h_pinned[9];
+        if (const char* e = getenv("SCKM_CENTER")) on = atoi(e) != 0;
+    }
+    if (!on) {
+        SCKM_CUDA(ctx, cudaMemsetAsync(ctx->d_mu, 0, d * sizeof(double), ctx->stream));
+        cnorm_kernel<<<(unsigned)((k + 127) / 128), 128, 0, ctx->stream>>>(ctx->d_centroids, (uint32_t)k, (uint32_t)d, ctx->d_mu, ctx->d_cnorm);
+        ctx->launches++;
+    }
     LAUNCH_CHECK_D(ctx);
+    ctx->launches--;                                          // (LAUNCH_CHECK_D counted one that was already counted)
+    ctx->mu_requested = center;
+    ctx->center_on = on;
+    ctx->mu_zero = !on;
     ctx->cnorm_valid = true;
     return SCKM_OK;
 }
@@ -626,7 +669,7 @@ int launch_assign_dmma(sckm_dataset* ds, uint64_t k) {
     SCKM_TRY(ensure_workspace(ctx, k, ds->d, dmma_partial_slots(ctx)));
     if (ds->n == 0) return SCKM_OK;
     SCKM_TRY(launch_cnorm(ctx, k, ds->d, true));
-    ctx->packed_centered = true;                                   // the slots receive sums of x - mu
+    ctx->packed_centered = ctx->center_on;                         // the slots receive sums of x - mu
     return ds->dtype == SCKM_F32 ? launch_by_d<true, float>(ds, k, pk) : launch_by_d<true, double>(ds, k, pk);
 }
 

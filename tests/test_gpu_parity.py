@@ -405,6 +405,36 @@ def test_lloyd_step_far_from_origin(ctx, O, n, d, k, dtype, offset, scale):
         assert abs(out["distortion"] - dist_ref) <= rt * dist_ref + cond, (out["distortion"], dist_ref, cond)
 
 
+@pytest.mark.parametrize("force", ["1", "0"])
+def test_centring_switch_does_not_change_results(ctx, O, force, monkeypatch):
+    """The tile kernels have a centred (x - mu, c - mu) and a plain instantiation; launch_cnorm picks by where the data
+    sit.  Forced either way (SCKM_CENTER) on ordinary and on offset data, labels must equal the oracle's and sums /
+    inertia / centroids stay within the north-star tolerance; predict labels are bit-equal to the direct form."""
+    monkeypatch.setenv("SCKM_CENTER", force)
+    for (n, d, k, dtype, offset) in ((20000, 64, 256, np.float64, 0.0), (6001, 128, 300, np.float64, 0.0), (9000, 20, 33, np.float64, 50.0),
+                                     (12000, 48, 40, np.float32, 0.0), (8000, 64, 64, np.float64, 1e3)):
+        x = (blobs(n, d, k, n + d, np.float64, spread=1.5) + offset).astype(dtype)
+        cent = x[np.random.default_rng(1).choice(n, k, replace=False)].astype(np.float64) * 1.001
+        ctx.set_assign_kernel(cabi.ASSIGN_DMMA)
+        ds = ctx.upload(x)
+        inertia, sums, counts = ds.lloyd_step(cent)
+        ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+        d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+        assert np.array_equal(ds.labels().astype(np.int64), m_o)
+        assert counts.tolist() == c_o.tolist()
+        np.testing.assert_allclose(sums, s_o, rtol=RTOL, atol=1e-9)
+        assert abs(inertia - d_o) <= RTOL * d_o
+        out = ds.lloyd_fit(cent, 5)
+        ds.close()
+        c_ref = cent.copy()
+        for _ in range(out["iters"]):
+            dd, ss, cc, mm = O.brute_clustering(x, c_ref)
+            nz = cc > 0
+            c_ref[nz] = ss[nz] / cc[nz, None]
+        np.testing.assert_allclose(out["centroids"], c_ref, rtol=RTOL if dtype == np.float64 else 1e-6, atol=1e-12)
+        assert np.array_equal(ctx.predict(x, cent).astype(np.int64), O.predict(x, cent))
+
+
 def test_step_is_bit_reproducible_at_full_size(ctx):
     """The stop rule compares successive inertias exactly, so a step must be bit-reproducible run to run: config C3
     (10M x 64, k = 256), five repeats of the same step -- packed sums, counts, inertia and labels identical."""

@@ -1,6 +1,6 @@
 """Config C2 (1M x 16, k = 8, f64) tuning probe: per-step and assignment-kernel times of the streaming path under the
-run-time toggles (zig-zag traversal, fused refine/reduce/finalize tail), and the wall time of a whole lloyd_fit with the
-device-side stop rule at different enqueue batch sizes."""
+run-time toggles (one-launch reduce + finalize, bulk-copy ring) and library variants (SCKM_LIB_VARIANT), and the wall
+time of a whole lloyd_fit with the device-side stop rule at different enqueue batch sizes."""
 import os, sys, time, numpy as np
 sys.path.insert(0, ".")
 import smartcore_b200 as sc
@@ -15,7 +15,7 @@ cent0, _ = ds.init_centroids(k)
 hbm = n * (d * 8 + 4)
 
 def steps(label, env):
-    for key in ("SCKM_STREAM_NOZIGZAG", "SCKM_NO_TAIL", "SCKM_STREAM_TMA"):
+    for key in ("SCKM_NO_STEP_SMALL", "SCKM_STREAM_TMA"):
         os.environ.pop(key, None)
     os.environ.update(env)
     ds.lloyd_iterate(cent0, 5)
@@ -26,8 +26,27 @@ def steps(label, env):
         if best is None or ms < best[0]:
             best = (ms, ams, out)
     ms, ams, out = best
-    print("%-34s step %7.2f us  assign %7.2f us  -> %5.3f of 6551 GB/s per step, %5.3f kernel" %
-          (label, ms * 1e3, ams * 1e3, hbm / (ms * 1e-3) / 1e9 / 6551.4, hbm / (ams * 1e-3) / 1e9 / 6551.4), flush=True)
+    print("[%s] %-40s step %7.2f us  assign %7.2f us  -> %5.3f of 6551 GB/s per step, %5.3f kernel" %
+          (os.environ.get("SCKM_LIB_VARIANT", "default"), label, ms * 1e3, ams * 1e3, hbm / (ms * 1e-3) / 1e9 / 6551.4, hbm / (ams * 1e-3) / 1e9 / 6551.4), flush=True)
+    return out
+
+a = steps("default (one-launch reduce+finalize)", {})
+e = steps("three-launch post-step (round-1 shape)", {"SCKM_NO_STEP_SMALL": "1"})
+f = steps("TMA ring", {"SCKM_STREAM_TMA": "1"})
+print("same sizes:", np.array_equal(a["size"], e["size"]), "centroids bit-equal:", np.array_equal(a["centroids"], e["centroids"]))
+for key in ("SCKM_NO_STEP_SMALL", "SCKM_STREAM_TMA"):
+        os.environ.pop(key, None)
+    os.environ.update(env)
+    ds.lloyd_iterate(cent0, 5)
+    best = None
+    for _ in range(3):
+        out = ds.lloyd_iterate(cent0, 40)
+        ms, ams = float(np.mean(out["ms"][2:])), float(np.mean(out["assign_ms"][2:]))
+        if best is None or ms < best[0]:
+            best = (ms, ams, out)
+    ms, ams, out = best
+    print("[%s] %-40s step %7.2f us  assign %7.2f us  -> %5.3f of 6551 GB/s per step, %5.3f kernel" %
+          (os.environ.get("SCKM_LIB_VARIANT", "default"), label, ms * 1e3, ams * 1e3, hbm / (ms * 1e-3) / 1e9 / 6551.4, hbm / (ams * 1e-3) / 1e9 / 6551.4), flush=True)
     return out
 
 a = steps("zigzag + tail (default)", {})
@@ -37,7 +56,7 @@ e = steps("no zigzag, no tail (round-1 shape)", {"SCKM_STREAM_NOZIGZAG": "1", "S
 f = steps("TMA ring + zigzag + tail", {"SCKM_STREAM_TMA": "1"})
 print("same sizes:", np.array_equal(a["size"], e["size"]), "max rel centroid diff default vs round-1 shape:",
       float(np.max(np.abs(a["centroids"] - e["centroids"]) / np.abs(e["centroids"]))))
-for key in ("SCKM_STREAM_NOZIGZAG", "SCKM_NO_TAIL", "SCKM_STREAM_TMA"):
+for key in ("SCKM_NO_STEP_SMALL", "SCKM_STREAM_TMA"):
     os.environ.pop(key, None)
 for batch in ("1", "4", "8", ""):
     if batch: os.environ["SCKM_LLOYD_BATCH"] = batch

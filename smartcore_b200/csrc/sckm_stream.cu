@@ -33,6 +33,14 @@ namespace sckm {
     } while (0)
 
 constexpr int STREAM_WARPS = 8;
+// Update scheme of the registers-direct path.  1 (default): lanes regroup as (cluster, feature slice) and add the rows of
+// THEIR cluster with plain DADDs -- a 32-row batch costs ~max_c(rows of c) x (features per lane) adds instead of the
+// 8*KT*NTU DMMAs of the one-hot GEMM (C2: ~32 DADD issue slots instead of 16 DMMAs = 256 clocks of the same FP64
+// datapath) and the dependent chain per batch shrinks from 8 DMMA latencies to the adds of one cluster.
+// 0: the one-hot GEMM (kept for A/B builds, tools/build_variant.sh, and used by the bulk-copy ring variant).
+#ifndef SCKM_STREAM_GROUPED
+#define SCKM_STREAM_GROUPED 1
+#endif
 constexpr int STREAM_MAX_K = 15;
 constexpr double STREAM_TIE_REL = 1e-10;
 
@@ -103,6 +111,10 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
     if (loop_done(loop_st, loop_it)) return;             // the fit's stop rule already fired (kmeans.rs:305)
     constexpr int NTU = KS / 2 > 0 ? KS / 2 : 1;         // feature n-tiles of the update GEMM (8 features each)
     constexpr int VU = VW < NTU ? VW : NTU;              // features per update load
+    constexpr bool GROUPED = SCKM_STREAM_GROUPED != 0 && STAGES == 0;
+    constexpr int LPC = 32 / (8 * KT);                   // grouped update: lanes per cluster (4 for k <= 8, 2 for k <= 16)
+    constexpr int FPL = (4 * KS) / LPC;                  // ... and features per lane (the padded d split over them)
+    constexpr int VG = VW < FPL ? VW : FPL;              // ... loaded VG at a time
     const uint32_t d = DFULL ? (uint32_t)(4 * KS) : d_rt;
     extern __shared__ __align__(16) double smem_s[];     // [warps][k*d] sums | [warps][16] counts | [warps] inertia
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -144,6 +156,12 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
     uint32_t cnt[KT];
 #pragma unroll
     for (int ct = 0; ct < KT; ct++) cnt[ct] = 0;
+    // grouped update: this lane adds features [fs*FPL, fs*FPL + FPL) of the rows assigned to cluster cq
+    const uint32_t cq = (uint32_t)lane / LPC, fs = (uint32_t)lane % LPC;
+    double su[GROUPED ? FPL : 1];
+#pragma unroll
+    for (int j = 0; j < (GROUPED ? FPL : 1); j++) su[j] = 0.0;
+    uint32_t cnt_g = 0;
     double inertia = 0.0;                                // this lane's share (rows whose winning score it holds)
     uint32_t nties = 0;
 
@@ -309,6 +327,34 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         nties += (valid && !ok) ? 1u : 0u;
         const uint32_t lab = ok ? bi : 0xffffffffu;
         if (valid) labels[row0 + lane] = lab;
+        if (GROUPED) {
+            // ---- update, grouped: which rows of the batch went to MY cluster (marked / invalid rows carry 0xffffffff
+            // and match nothing), then add them in ascending row order -- a fixed order, no atomics.  The rows come out
+            // of L1 (this batch was just loaded through it). ----
+            unsigned mine = 0;
+#pragma unroll
+            for (uint32_t c = 0; c < 8u * KT; c++) {
+                const unsigned m = __ballot_sync(0xffffffffu, lab == c);
+                mine = c == cq ? m : mine;
+            }
+            cnt_g += __popc(mine);
+            const int rounds = __reduce_max_sync(0xffffffffu, __popc(mine));
+            const TX* gb = x + row0 * d + fs * FPL;
+            for (int r = 0; r < rounds; r++) {
+                const bool act = mine != 0u;
+                const int row = act ? __ffs(mine) - 1 : 0;
+                mine &= mine - 1u;
+#pragma unroll
+                for (int j = 0; j < FPL / VG; j++) {
+                    double v[VG];
+#pragma unroll
+                    for (int e = 0; e < VG; e++) v[e] = 0.0;
+                    if (act && (DFULL || fs * FPL + j * VG < d)) VecLoad<TX, VG>::ld(gb + (size_t)row * d + j * VG, v);
+#pragma unroll
+                    for (int e = 0; e < VG; e++) su[GROUPED ? j * VG + e : 0] = __dadd_rn(su[GROUPED ? j * VG + e : 0], v[e]);
+                }
+            }
+        } else {
         // ---- update: sums[cluster][feature] += onehot(label)^T . X as DMMAs accumulating in registers.
         // K dimension = the 32 rows (row 4*ks+t), A = one-hot of the labels, B = the rows again (L1 hits). ----
         const TX* ub = x + (row0 + t) * d + g * VU;
@@ -343,6 +389,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
 #pragma unroll
                 for (int nt = 0; nt < NTU; nt++) dmma884(cu[ct][nt][0], cu[ct][nt][1], oh, xb[nt]);
             }
+        }
         }
         if (TMA) {
             // every lane is done reading this buffer: hand it to the copy engine for the batch STAGES turns ahead
@@ -390,6 +437,14 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
     double* s_sum = smem_s + (size_t)warp * kd;
     uint32_t* s_cnt = reinterpret_cast<uint32_t*>(smem_s + (size_t)STREAM_WARPS * kd) + warp * 16;
     double* s_in = smem_s + (size_t)STREAM_WARPS * kd + STREAM_WARPS * 8;
+    if (GROUPED) {
+#pragma unroll
+        for (int j = 0; j < (GROUPED ? FPL : 1); j++) {
+            const uint32_t f = fs * FPL + j;
+            if (cq < k && f < d) s_sum[(size_t)cq * d + f] = su[j];
+        }
+        if (fs == 0 && cq < 16) s_cnt[cq] = cnt_g;
+    } else {
 #pragma unroll
     for (int ct = 0; ct < KT; ct++) {
         const uint32_t c = ct * 8 + g;
@@ -404,6 +459,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         cc += __shfl_xor_sync(0xffffffffu, cc, 1);
         cc += __shfl_xor_sync(0xffffffffu, cc, 2);
         if (t == 0 && c < 16) s_cnt[c] = cc;
+    }
     }
     double v = inertia;
 #pragma unroll

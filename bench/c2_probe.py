@@ -35,28 +35,6 @@ e = steps("three-launch post-step (round-1 shape)", {"SCKM_NO_STEP_SMALL": "1"})
 f = steps("TMA ring", {"SCKM_STREAM_TMA": "1"})
 print("same sizes:", np.array_equal(a["size"], e["size"]), "centroids bit-equal:", np.array_equal(a["centroids"], e["centroids"]))
 for key in ("SCKM_NO_STEP_SMALL", "SCKM_STREAM_TMA"):
-        os.environ.pop(key, None)
-    os.environ.update(env)
-    ds.lloyd_iterate(cent0, 5)
-    best = None
-    for _ in range(3):
-        out = ds.lloyd_iterate(cent0, 40)
-        ms, ams = float(np.mean(out["ms"][2:])), float(np.mean(out["assign_ms"][2:]))
-        if best is None or ms < best[0]:
-            best = (ms, ams, out)
-    ms, ams, out = best
-    print("[%s] %-40s step %7.2f us  assign %7.2f us  -> %5.3f of 6551 GB/s per step, %5.3f kernel" %
-          (os.environ.get("SCKM_LIB_VARIANT", "default"), label, ms * 1e3, ams * 1e3, hbm / (ms * 1e-3) / 1e9 / 6551.4, hbm / (ams * 1e-3) / 1e9 / 6551.4), flush=True)
-    return out
-
-a = steps("zigzag + tail (default)", {})
-b = steps("no zigzag, tail", {"SCKM_STREAM_NOZIGZAG": "1"})
-c = steps("zigzag, no tail", {"SCKM_NO_TAIL": "1"})
-e = steps("no zigzag, no tail (round-1 shape)", {"SCKM_STREAM_NOZIGZAG": "1", "SCKM_NO_TAIL": "1"})
-f = steps("TMA ring + zigzag + tail", {"SCKM_STREAM_TMA": "1"})
-print("same sizes:", np.array_equal(a["size"], e["size"]), "max rel centroid diff default vs round-1 shape:",
-      float(np.max(np.abs(a["centroids"] - e["centroids"]) / np.abs(e["centroids"]))))
-for key in ("SCKM_NO_STEP_SMALL", "SCKM_STREAM_TMA"):
     os.environ.pop(key, None)
 for batch in ("1", "4", "8", ""):
     if batch: os.environ["SCKM_LLOYD_BATCH"] = batch

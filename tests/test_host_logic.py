@@ -36,6 +36,21 @@ def test_no_cpu_fallback_when_device_missing():
     assert str(e2.value).startswith("Fit failed: CUDA backend unavailable")
 
 
+def test_rust_ffi_declares_every_header_symbol():
+    """rust/src/gpu/ffi.rs (uncompiled here: no rustc) must declare exactly the functions include/*.h exports, and the
+    wrapper must not need `'static` / TypeId on `Number` (it is not `'static`: src/numbers/basenum.rs:8-23)."""
+    header = open(os.path.join(ROOT, "include", "smartcore_kmeans_cuda.h")).read()
+    declared = set(re.findall(r"\b(sckm_[a-z0-9_]+)\s*\(", header))
+    ffi = open(os.path.join(ROOT, "rust", "src", "gpu", "ffi.rs")).read()
+    bound = set(re.findall(r"pub fn (sckm_[a-z0-9_]+)\s*\(", ffi))
+    assert declared == bound == set(cabi.SYMBOLS), (declared ^ bound, declared ^ set(cabi.SYMBOLS))
+    assert "SCKM_ABI_VERSION: c_int = %d" % cabi.lib.sckm_abi_version() in ffi
+    mod = open(os.path.join(ROOT, "rust", "src", "gpu", "mod.rs")).read()
+    code = "\n".join(l for l in mod.splitlines() if not l.lstrip().startswith("//"))      # comments may mention them
+    assert "TypeId" not in code and "'static" not in code
+    assert os.path.exists(os.path.join(ROOT, "rust", "build.rs"))
+
+
 def test_product_package_never_touches_the_oracle():
     for dirpath, _, files in os.walk(os.path.join(ROOT, "smartcore_b200")):
         for f in files:

@@ -30,10 +30,9 @@ def steps(label, env):
           (os.environ.get("SCKM_LIB_VARIANT", "default"), label, ms * 1e3, ams * 1e3, hbm / (ms * 1e-3) / 1e9 / 6551.4, hbm / (ams * 1e-3) / 1e9 / 6551.4), flush=True)
     return out
 
-a = steps("default (one-launch reduce+finalize)", {})
-e = steps("three-launch post-step (round-1 shape)", {"SCKM_NO_STEP_SMALL": "1"})
+a = steps("default", {})
 f = steps("TMA ring", {"SCKM_STREAM_TMA": "1"})
-print("same sizes:", np.array_equal(a["size"], e["size"]), "centroids bit-equal:", np.array_equal(a["centroids"], e["centroids"]))
+
 for key in ("SCKM_NO_STEP_SMALL", "SCKM_STREAM_TMA"):
     os.environ.pop(key, None)
 for batch in ("1", "4", "8", ""):

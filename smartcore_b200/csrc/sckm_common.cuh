@@ -52,7 +52,6 @@ struct sckm_ctx {
     bool mu_zero = true;             // d_mu currently holds zeros
     bool mu_requested = false;       // what the last launch_cnorm was asked for (centred kernels vs raw norms)
     bool center_on = false;          // ... and what it decided: the tile kernels subtract mu (CENTER instantiation)
-    bool step_finalized = false;     // the last clustering step already reduced, finalised and applied the stop rule
     bool packed_centered = false;    // d_packed sums of the last step are sums of (x - mu), not of x
     double* d_packed = nullptr;      // [k*d sums | k counts | inertia]
     double* d_partials = nullptr;    // [P][k*d + k + 1] per-CTA/warp partial sums (deterministic)
@@ -213,8 +212,6 @@ int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia);
 int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk);
 // centroids = sums / counts (guarded: keep old when count == 0; unguarded for the initial means)
 int launch_finalize(sckm_ctx* ctx, uint64_t k, uint64_t d, bool guarded);
-bool step_small_applicable(const sckm_ctx* ctx, size_t pk);
-int launch_step_small(sckm_ctx* ctx, uint32_t slots, uint64_t k, uint64_t d);
 int launch_loop_init(sckm_ctx* ctx, uint64_t max_iter, bool honor_stop);
 int launch_labels_widen(sckm_ctx* ctx, const uint32_t* in, uint64_t* out, uint64_t n);
 int measure_peaks(sckm_ctx* ctx, double* out3);

@@ -592,7 +592,11 @@ static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     if (d <= 16) return launch_t<4, 2, 4, 12, UPDATE, TX>(ds, k, pk);
     if (d <= 32) return launch_t<8, 2, 4, 12, UPDATE, TX>(ds, k, pk);
     if (d <= 64) return launch_t<16, 2, 4, 12, UPDATE, TX>(ds, k, pk);
+#ifdef SCKM_DMMA_D128_MT2
+    return launch_t<32, 2, 4, 8, UPDATE, TX>(ds, k, pk);      // A/B build: 16-row slabs, 8 warps (each B fragment feeds two DMMAs)
+#else
     return launch_t<32, 1, 4, 12, UPDATE, TX>(ds, k, pk);
+#endif
 }
 
 // [0] = ||mu||^2, [1] = max_j ||c_j - mu||^2 (NaN norms ignored): the two numbers the centring decision needs

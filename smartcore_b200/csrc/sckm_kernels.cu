@@ -818,77 +818,6 @@ __global__ void finalize_kernel(const double* __restrict__ packed, uint32_t k, u
     }
 }
 
-// Small payloads (k*d + k + 1 <= 512: config C2), one GPU, inside a Lloyd loop: reduce_partials_kernel<32> and
-// finalize_kernel as ONE single-CTA launch -- at 50 us per step every launch boundary counts.  The summation order is
-// exactly that of reduce_partials_kernel<32> (32 slot groups summed sequentially, then the group sums in order), so the
-// result is bit-identical to the two-launch path.
-__global__ void __launch_bounds__(1024)
-step_small_kernel(double* __restrict__ partials, uint32_t nslots, uint32_t pk, uint32_t pitch, double* __restrict__ packed,
-                  unsigned long long* __restrict__ nmarked, uint32_t k, uint32_t d, int centered, const double* __restrict__ mu,
-                  double* __restrict__ centroids, double* __restrict__ cnorm, long long* __restrict__ size,
-                  LoopState* __restrict__ loop_st, uint32_t loop_it, double* __restrict__ inertia_trace) {
-    if (loop_done(loop_st, loop_it)) return;
-    __shared__ double sh[32][33];
-    __shared__ double s_packed[512];
-    const uint32_t lane = threadIdx.x & 31, grp = threadIdx.x >> 5;
-    const uint32_t per = (nslots + 31) / 32;
-    const uint32_t p0 = min(nslots, grp * per), p1 = min(nslots, p0 + per);
-    for (uint32_t e0 = 0; e0 < pk; e0 += 32) {
-        const uint32_t e = e0 + lane;
-        double s = 0.0;
-        if (e < pk) {
-            double* q = partials + (size_t)p0 * pitch + e;
-            uint32_t p = p0;
-            for (; p + 8 <= p1; p += 8) {                 // 8 independent loads in flight, added in slot order
-                double v[8];
-#pragma unroll
-                for (int i = 0; i < 8; i++) v[i] = __ldcg(q + (size_t)i * pitch);
-#pragma unroll
-                for (int i = 0; i < 8; i++) { s = __dadd_rn(s, v[i]); __stcg(q + (size_t)i * pitch, 0.0); }
-                q += (size_t)8 * pitch;
-            }
-            for (; p < p1; p++, q += pitch) { s = __dadd_rn(s, __ldcg(q)); __stcg(q, 0.0); }
-        }
-        sh[grp][lane] = s;
-        __syncthreads();
-        if (grp == 0 && e < pk) {
-            double t = 0.0;
-#pragma unroll
-            for (int i = 0; i < 32; i++) t = __dadd_rn(t, sh[i][lane]);
-            s_packed[e] = t;
-            packed[e] = t;
-        }
-        __syncthreads();
-    }
-    // finalize (kmeans.rs:297-303 guarded) + norms + stop rule (kmeans.rs:305-309), as finalize_kernel does
-    const uint32_t kd = k * d;
-    for (uint32_t e = threadIdx.x; e < kd; e += blockDim.x) {
-        const uint32_t c = e / d, j = e - c * d;
-        const double cnt = s_packed[kd + c];
-        if (cnt > 0.0) {
-            const double mean = __ddiv_rn(s_packed[e], cnt);
-            centroids[e] = centered ? __dadd_rn(mean, mu[j]) : mean;
-        }
-    }
-    __syncthreads();
-    for (uint32_t c = threadIdx.x; c < k; c += blockDim.x) {
-        size[c] = (long long)s_packed[kd + c];
-        double s = 0.0;
-        for (uint32_t j = 0; j < d; j++) { const double v = centroids[(size_t)c * d + j] - mu[j]; s = fma(v, v, s); }
-        cnorm[c] = s;
-    }
-    if (threadIdx.x == 0) {
-        *nmarked = 0ull;                                   // consumed by the refine pass of this step
-        const double dist = s_packed[kd + k];
-        if (inertia_trace) inertia_trace[loop_it - 1] = dist;
-        loop_st->iters = loop_it;
-        if (loop_st->honor_stop) {
-            if (loop_st->distortion <= dist) loop_st->done_at = loop_it;
-            else loop_st->distortion = dist;
-        }
-    }
-}
-
 __global__ void loop_init_kernel(LoopState* st, int honor_stop) {
     st->distortion = DBL_MAX; st->done_at = 0ull; st->iters = 0ull; st->honor_stop = honor_stop ? 1ull : 0ull;
 }
@@ -1240,20 +1169,6 @@ int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk) {
     else
         reduce_partials_kernel<8><<<blocks, dim3(32, 8), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK(ctx);
-    return SCKM_OK;
-}
-
-// reduce + finalize + stop rule of one step in a single launch; only for small payloads on one GPU inside a Lloyd loop
-bool step_small_applicable(const sckm_ctx* ctx, size_t pk) {
-    return ctx->loop_it != 0 && ctx->nranks == 1 && pk <= 512 && !getenv("SCKM_NO_STEP_SMALL");
-}
-int launch_step_small(sckm_ctx* ctx, uint32_t slots, uint64_t k, uint64_t d) {
-    const size_t pk = (size_t)k * d + k + 1;
-    step_small_kernel<<<1, 1024, 0, ctx->stream>>>(ctx->d_partials, slots, (uint32_t)pk, (uint32_t)slot_pitch(pk), ctx->d_packed, ctx->d_flags,
-                                                   (uint32_t)k, (uint32_t)d, ctx->packed_centered ? 1 : 0, ctx->d_mu, ctx->d_centroids,
-                                                   ctx->d_cnorm, (long long*)ctx->d_size, ctx->d_loop, ctx->loop_it, ctx->d_inertia_trace);
-    LAUNCH_CHECK(ctx);
-    ctx->step_finalized = true;
     return SCKM_OK;
 }
 

@@ -16,6 +16,13 @@
 //            block tcgen05.ld the row's 128 scores and keep a running top-2 + argmax in registers; at the end the
 //            exact f64 distance, the near-tie mark, and the deterministic fused update (same scheme as sckm_dmma.cu:
 //            fire-and-forget RED.ADD.F64 into the warp's private partial, same-label rows serialised by rank).
+//            The top-2 tracking (five half-rate ALU instructions per score) is what bounds this kernel, so most of it
+//            is skipped: every row is PRIMED with the score of the centroid it was assigned to in the previous step
+//            (one 32-term dot product), and a 32-column chunk only goes through the tracking when, for some row of the
+//            warp, its maximum (one FADD + half an FMNMX3 per score) exceeds max(second best so far, primed score -
+//            2.5 tie margins) -- columns below that can neither win nor come within the tie margin of the winner.
+//            After a few Lloyd steps few rows change cluster: a warp then tracks little more than the chunks that hold
+//            its 32 rows' own centroids.
 // mbarrier rings: x_full/x_ready/x_empty (2 stages), c_full/c_empty (2 stages), t_full/t_empty (2 TMEM stages).
 #include "sckm_common.cuh"
 #include "sckm_tile.cuh"
@@ -125,7 +132,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1)
 assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapCh,
                   const __grid_constant__ CUtensorMap mapCl, const TXS* __restrict__ xsrc, uint64_t n, uint32_t d,
                   const double* __restrict__ centroids, const double* __restrict__ cnorm, const float* __restrict__ hcn,
-                  uint32_t k, uint32_t nblocks, uint32_t* __restrict__ labels, double* __restrict__ mind,
+                  const float* __restrict__ ch_g, const float* __restrict__ cl_g, const uint32_t* prev_labels,
+                  uint32_t k, uint32_t nblocks, uint32_t* labels, double* __restrict__ mind,
                   double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked,
                   const LoopState* __restrict__ loop_st, uint32_t loop_it) {
     if (loop_done(loop_st, loop_it)) return;                          // the fit's stop rule already fired (kmeans.rs:305)
@@ -261,6 +269,37 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             const uint64_t row = st * rows_per_super + (uint64_t)m * TC_BM + rloc;
             const bool valid = row < n;
             double xn = xn_next;
+            // ---- priming: a lower bound of this row's winning score from the centroid it had in the previous step ----
+            float prime = -FLT_MAX;
+            if (prev_labels != nullptr) {
+                prime = FLT_MAX;                                       // rows past the end never ask for a scan
+                if (valid) {
+                    prime = -FLT_MAX;
+                    const uint32_t pl = prev_labels[row];
+                    if (pl < k) {
+                        float dot = 0.f, xx = 0.f;
+#pragma unroll
+                        for (int a = 0; a < NK; a++) {
+                            const float4* c_h = reinterpret_cast<const float4*>(ch_g + (size_t)pl * (32 * NK) + 32 * a);
+                            const float4* c_l = reinterpret_cast<const float4*>(cl_g + (size_t)pl * (32 * NK) + 32 * a);
+#pragma unroll
+                            for (int c4 = 0; c4 < 8; c4++) {
+                                const float4 h = reinterpret_cast<const float4*>(S.xh[xs][m][a] + rloc * 32)[c4 ^ (rloc & 7)];
+                                const float4 l = reinterpret_cast<const float4*>(S.xl[xs][m][a] + rloc * 32)[c4 ^ (rloc & 7)];
+                                const float4 ph = __ldg(c_h + c4), pw = __ldg(c_l + c4);
+                                const float x0 = h.x + l.x, x1 = h.y + l.y, x2 = h.z + l.z, x3 = h.w + l.w;    // exact: x = hi + lo
+                                dot = fmaf(x0, ph.x + pw.x, dot); dot = fmaf(x1, ph.y + pw.y, dot);
+                                dot = fmaf(x2, ph.z + pw.z, dot); dot = fmaf(x3, ph.w + pw.w, dot);
+                                xx = fmaf(x0, x0, xx); xx = fmaf(x1, x1, xx); xx = fmaf(x2, x2, xx); xx = fmaf(x3, x3, xx);
+                            }
+                        }
+                        // 2.5 tie margins in score space (the tie test below works on 2 * (best - second)); the score the
+                        // tensor cores produce for that centroid differs from `dot` by ~1e-6 (xx + cmax), a tenth of one margin
+                        const float p = dot + __ldg(hcn + pl) - 2.5f * (float)(0.5 * TC_TIE_REL) * (xx + (float)cmax);
+                        prime = p == p ? p : -FLT_MAX;                 // NaN centroid: no priming
+                    }
+                }
+            }
             // ---- running top-2 over all centroid blocks (my columns only) ----
             float best = -FLT_MAX, second = -FLT_MAX; uint32_t bi = 0;
             for (uint32_t b = 0; b < nblocks; b++, j++) {
@@ -276,6 +315,16 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 // until tcgen05.wait::ld) while chunk c goes through the top-2 update
                 uint32_t va[32], vb[32];
                 auto consume = [&](const uint32_t (&v)[32], int c0) {
+                    {   // can this chunk change any row's best or second, or come within the tie margin of a winner?
+                        float mx = -FLT_MAX;
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const float4 hv = HCN_SMEM ? h4[(c0 >> 2) + u] : __ldg(h4 + (c0 >> 2) + u);
+                            mx = fmaxf(fmaxf(mx, __uint_as_float(v[u * 4 + 0]) + hv.x), __uint_as_float(v[u * 4 + 1]) + hv.y);
+                            mx = fmaxf(fmaxf(mx, __uint_as_float(v[u * 4 + 2]) + hv.z), __uint_as_float(v[u * 4 + 3]) + hv.w);
+                        }
+                        if (!__any_sync(0xffffffffu, mx > fmaxf(second, prime))) return;
+                    }
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         const float4 hv = HCN_SMEM ? h4[(c0 >> 2) + u] : __ldg(h4 + (c0 >> 2) + u);
@@ -318,7 +367,7 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 if (cp == 1) { S.m_best[mb][rloc] = best; S.m_second[mb][rloc] = second; S.m_idx[mb][rloc] = bi; S.m_xn[mb][rloc] = xn; }
                 asm volatile("bar.sync 1, 256;" ::: "memory");       // the 8 epilogue warps
                 if (cp == 0) {
-                    const float ob = S.m_best[mb][rloc], os = S.m_second[mb][rloc]; const uint32_t oi = S.m_idx[mb][rloc];
+                    const float ob = S.m_best[mb][rloc], os = S.m_second[mb][rloc]; const uint32_t oi = S.m_idx[mb][rloc];   // (both parts used the same `prime`)
                     xn += S.m_xn[mb][rloc];
                     const bool take = ob > best || (ob == best && oi < bi);
                     second = fmaxf(fmaxf(second, os), fminf(best, ob));
@@ -328,6 +377,8 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
             }
             if (cp == 0) {
                 // ---- decide: near-tie mark; exact f64 distance to the winner and the update, cooperatively per row ----
+                // columns of skipped chunks lie at or below max(second, prime): that is the runner-up the tie test must assume
+                second = fmaxf(second, prime);
                 const double gap = 2.0 * ((double)best - (double)second);
                 const bool tie = !(gap > TC_TIE_REL * (xn + cmax)) || bi >= k;
                 const bool part_ok = valid && !tie;
@@ -463,7 +514,8 @@ static int launch_tc5_t(sckm_dataset* ds, uint64_t k, size_t pk, const float* x3
     auto kern = hcn_smem ? assign_tc5_kernel<NK, TILES, BN, true, TXS> : assign_tc5_kernel<NK, TILES, BN, false, TXS>;
     SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     kern<<<grid, TC_THREADS, smem, ctx->stream>>>(mapX, mapCh, mapCl, (const TXS*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
-                                                  ctx->d_cnorm, hcn, (uint32_t)k, nblocks, ds->labels, ds->mind,
+                                                  ctx->d_cnorm, hcn, ch, cl, (ds->have_labels && !getenv("SCKM_TC5_NOPRIME")) ? ds->labels : nullptr,
+                                                  (uint32_t)k, nblocks, ds->labels, ds->mind,
                                                   ctx->d_partials, pk, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK_T(ctx);
     return SCKM_OK;

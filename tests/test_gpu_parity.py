@@ -230,6 +230,42 @@ def test_tc5_tile_kernel(ctx, O, n, d, k, dtype):
     ds.close()
 
 
+@pytest.mark.parametrize("n,d,k", [(40000, 32, 512), (30000, 16, 128), (20000, 64, 300)])
+def test_tc5_primed_steps_match_oracle(ctx, O, n, d, k, monkeypatch):
+    """From the second step on, the tcgen05 kernel primes every row with the score of its previous centroid and skips
+    32-column chunks that cannot matter.  The labels it starts from may be anything: stale ones from very different
+    centroids (most rows change cluster), or exactly right ones (nothing changes) -- labels, sums and inertia must equal
+    the oracle's either way, and equal the unprimed kernel's (SCKM_TC5_NOPRIME)."""
+    x = blobs(n, d, k, 3 * n + d, np.float32, spread=1.5)
+    rng = np.random.default_rng(4)
+    cent_a = x[rng.choice(n, k, replace=False)].astype(np.float64) + 0.01
+    cent_b = x[rng.choice(n, k, replace=False)].astype(np.float64) - 0.02          # unrelated centroids
+    ds = ctx.upload(x)
+    ds.lloyd_step(cent_a)                                                          # unprimed (no labels yet); leaves labels for cent_a
+    for cent in (cent_b, cent_b, cent_a):                                          # stale labels, exact labels, stale again
+        inertia, sums, counts = ds.lloyd_step(cent)
+        lab = ds.labels().astype(np.int64)
+        d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+        bad = np.nonzero(lab != m_o)[0]
+        assert np.all(gap[bad] < 1e-5), "%d labels differ beyond the f32 tolerance" % len(bad)
+        assert abs(inertia - d_o) <= 1e-4 * d_o
+        if len(bad) == 0:
+            assert counts.tolist() == c_o.tolist()
+            np.testing.assert_allclose(sums, s_o, rtol=1e-9, atol=1e-6)
+    # a labelling that points every row at a far-away centroid (worst case for the priming bound)
+    far = O.predict(x, -cent_b)
+    ds2 = ctx.upload(x)
+    ds2.lloyd_step(-cent_b)
+    inertia, sums, counts = ds2.lloyd_step(cent_b)
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent_b, want_gap=True)
+    bad = np.nonzero(ds2.labels().astype(np.int64) != m_o)[0]
+    assert np.all(gap[bad] < 1e-5) and abs(inertia - d_o) <= 1e-4 * d_o
+    monkeypatch.setenv("SCKM_TC5_NOPRIME", "1")
+    i2, s2, c2 = ds2.lloyd_step(cent_b)
+    assert i2 == inertia and np.array_equal(s2, sums) and np.array_equal(c2, counts)
+    ds.close(); ds2.close()
+
+
 def test_tc5_ties_and_duplicates(ctx, O):
     rng = np.random.default_rng(0)
     base = rng.normal(size=(16, 32)).astype(np.float32)

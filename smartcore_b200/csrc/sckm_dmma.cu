@@ -102,6 +102,59 @@ __device__ __forceinline__ void epilogue_all(const double (&acc)[MT][NT][2], uin
     for (int item = 0; item < MT * NT * 2; item++) epi_item<MT, NT>(acc, item, col_base, t, best, second, bidx);
 }
 
+// Centroid block [c0, c0 + bn) -> shared memory (row pitch PITCH doubles, zero rows past k), -||c - mu||^2 / 2 -> cn.
+// Whole rows (d == DP: no column padding) go as 16-byte cp.async copies, all of a thread's copies in flight at once and
+// no register round trip: the streamed-centroid kernel switches blocks ~500 times per launch at config C4, and the
+// first version of this loop (one dependent 8-byte load per iteration, ~50 L2 round trips in a row) cost ~35 us per
+// switch -- 16 % of the step (measured: the step time grew linearly with the number of switches).
+__device__ __forceinline__ void dmma_cp_async16(void* smem_dst, const void* gmem_src) {
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+template <int DP, int PITCH, bool CENTER>
+__device__ __forceinline__ void stage_centroid_block(double* __restrict__ cbuf, double* __restrict__ cn,
+                                                     const double* __restrict__ centroids, const double* __restrict__ cnorm,
+                                                     const double* __restrict__ mu_s, uint32_t c0, uint32_t bn, uint32_t k, uint32_t d) {
+    if (d == (uint32_t)DP) {
+        constexpr uint32_t CPR = DP / 2;                           // 16-byte chunks per row
+        const uint32_t total = bn * CPR;
+        for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
+            const uint32_t r = e / CPR, q = e - r * CPR;
+            double* dst = cbuf + (size_t)r * PITCH + 2 * q;
+            if (c0 + r < k) dmma_cp_async16(dst, centroids + (size_t)(c0 + r) * DP + 2 * q);
+            else *reinterpret_cast<double2*>(dst) = make_double2(0.0, 0.0);
+        }
+        asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+        if (CENTER) {                                              // (a thread sees its own copies after the wait)
+            for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
+                const uint32_t r = e / CPR, q = e - r * CPR;
+                if (c0 + r >= k) continue;
+                double2* p = reinterpret_cast<double2*>(cbuf + (size_t)r * PITCH + 2 * q);
+                double2 v = *p;
+                v.x -= mu_s[2 * q]; v.y -= mu_s[2 * q + 1];
+                *p = v;
+            }
+        }
+    } else {                                                       // ragged d: eight independent loads in flight per thread
+        const uint32_t total = bn * DP;
+        for (uint32_t e0 = threadIdx.x; e0 < total; e0 += 8 * blockDim.x) {
+            double v[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t e = e0 + i * blockDim.x, r = e / DP, c = e - r * DP;
+                v[i] = (e < total && c0 + r < k && c < d) ? centroids[(size_t)(c0 + r) * d + c] : 0.0;
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t e = e0 + i * blockDim.x, r = e / DP, c = e - r * DP;
+                if (e < total) cbuf[(size_t)r * PITCH + c] = (CENTER && c0 + r < k && c < d) ? v[i] - mu_s[c] : v[i];
+            }
+        }
+    }
+    for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
+        cn[r] = (c0 + r < k) ? -0.5 * cnorm[c0 + r] : -INFINITY;
+}
+
 // Resident-centroid specialisation (the whole centroid set fits in shared memory: config C3).  Kept as its own
 // kernel: it is the headline path and its instruction schedule is tuned (87.8 % of the FP64 peak).
 // KSTEPS: d padded to 4*KSTEPS; MT: m-tiles (8 rows each) per warp slab; DMMA_NT: n-tiles (8 centroids each) per
@@ -169,14 +222,7 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
             if (nchunks > 1 || rd == 0) {
                 // (re)load the centroid block; resident across rounds when it is the only one
                 if (nchunks > 1) __syncthreads();
-                for (uint32_t e = threadIdx.x; e < bn * DP; e += blockDim.x) {
-                    const uint32_t r = e / DP, c = e - r * DP;
-                    double v = 0.0;
-                    if (c0 + r < k && c < d) v = CENTER ? centroids[(size_t)(c0 + r) * d + c] - mu_s[c] : centroids[(size_t)(c0 + r) * d + c];
-                    cbuf[(size_t)r * PITCH + c] = v;
-                }
-                for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
-                    cn[r] = (c0 + r < k) ? -0.5 * cnorm[c0 + r] : -INFINITY;
+                stage_centroid_block<DP, PITCH, CENTER>(cbuf, cn, centroids, cnorm, mu_s, c0, bn, k, d);
                 __syncthreads();
             }
             const uint32_t cols = min(bn, k - c0);
@@ -295,14 +341,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
             if (nchunks > 1 || rd == 0) {
                 // (re)load the centroid block; resident for the whole launch when it is the only one
                 if (nchunks > 1) __syncthreads();
-                for (uint32_t e = threadIdx.x; e < bn * DP; e += blockDim.x) {
-                    const uint32_t r = e / DP, c = e - r * DP;
-                    double v = 0.0;
-                    if (c0 + r < k && c < d) v = CENTER ? centroids[(size_t)(c0 + r) * d + c] - mu_s[c] : centroids[(size_t)(c0 + r) * d + c];
-                    cbuf[(size_t)r * PITCH + c] = v;
-                }
-                for (uint32_t r = threadIdx.x; r < bn; r += blockDim.x)
-                    cn[r] = (c0 + r < k) ? -0.5 * cnorm[c0 + r] : -INFINITY;
+                stage_centroid_block<DP, PITCH, CENTER>(cbuf, cn, centroids, cnorm, mu_s, c0, bn, k, d);
                 __syncthreads();
             }
             const uint32_t cols = min(bn, k - c0);
@@ -592,11 +631,9 @@ static int launch_by_d(sckm_dataset* ds, uint64_t k, size_t pk) {
     if (d <= 16) return launch_t<4, 2, 4, 12, UPDATE, TX>(ds, k, pk);
     if (d <= 32) return launch_t<8, 2, 4, 12, UPDATE, TX>(ds, k, pk);
     if (d <= 64) return launch_t<16, 2, 4, 12, UPDATE, TX>(ds, k, pk);
-#ifdef SCKM_DMMA_D128_MT2
-    return launch_t<32, 2, 4, 8, UPDATE, TX>(ds, k, pk);      // A/B build: 16-row slabs, 8 warps (each B fragment feeds two DMMAs)
-#else
+    // (d > 64: 8-row slabs, 12 warps.  16-row slabs on 8 warps -- each B fragment feeding two DMMAs, 250 registers -- were
+    // measured at 0.57 of the FP64 peak on the C4 shard against 0.78 for this shape: too few warps to cover the row loads.)
     return launch_t<32, 1, 4, 12, UPDATE, TX>(ds, k, pk);
-#endif
 }
 
 // [0] = ||mu||^2, [1] = max_j ||c_j - mu||^2 (NaN norms ignored): the two numbers the centring decision needs

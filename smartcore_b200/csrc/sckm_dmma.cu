@@ -591,7 +591,11 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
         bn = kpad;                                                     // whole centroid set resident, no row state
     } else {
         multi = true;
-        sl = 12;                                                       // slabs per warp per resident centroid block
+        // slabs per warp per resident centroid block.  Every block switch costs two CTA barriers, a staging pass and a
+        // pipeline refill (fewer, longer phases win), but the rows of a round are re-read once per block and the round
+        // already overflows L2 (148 x 12 warps x sl x 8 KB): measured on the C4 shard, fraction of the FP64 peak for
+        // sl = 4 / 6 / 8 / 12 / 14 / 16: 0.775 / 0.79 / 0.80 / 0.86 / 0.81 / 0.81 -- a shallow optimum at 12
+        sl = 12;
         if (const char* e = getenv("SCKM_DMMA_SL")) sl = (uint32_t)std::max(1, std::min(16, atoi(e)));   // tuning knob
         const size_t state = (size_t)WARPS * sl * ROWS * 3 * sizeof(long long);
         bn = (uint32_t)(((size_t)ctx->smem_optin - fixed - state) / row_bytes);

@@ -102,6 +102,79 @@ __device__ __forceinline__ void epilogue_all(const double (&acc)[MT][NT][2], uin
     for (int item = 0; item < MT * NT * 2; item++) epi_item<MT, NT>(acc, item, col_base, t, best, second, bidx);
 }
 
+// The 4 lanes that share a row each hold the top-2 of their own columns: butterfly-merge them (lowest index wins ties)
+template <int MT>
+__device__ __forceinline__ void merge_row_lanes(key_t (&best)[MT], key_t (&second)[MT], uint32_t (&bidx)[MT]) {
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+#pragma unroll
+        for (int o = 1; o <= 2; o <<= 1) {
+            const key_t ob = __shfl_xor_sync(0xffffffffu, best[mt], o);
+            const key_t os = __shfl_xor_sync(0xffffffffu, second[mt], o);
+            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bidx[mt], o);
+            const bool take = ob > best[mt] || (ob == best[mt] && oi < bidx[mt]);
+            const key_t lo_best = ob < best[mt] ? ob : best[mt];
+            key_t s2 = os > second[mt] ? os : second[mt];
+            second[mt] = lo_best > s2 ? lo_best : s2;
+            bidx[mt] = take ? oi : bidx[mt];
+            best[mt] = ob > best[mt] ? ob : best[mt];
+        }
+    }
+}
+
+// End of a slab (all centroids seen, lanes merged): labels out, near-ties marked, and the fused update while the rows
+// are still in registers.  n_valid = number of rows that exist (0 for an inactive slab).
+template <int KSTEPS, int MT, bool UPDATE>
+__device__ __forceinline__ void finish_slab(const double (&a)[MT][KSTEPS], const double (&xn)[MT], const key_t (&best)[MT],
+                                            const key_t (&second)[MT], const uint32_t (&bidx)[MT], uint64_t r0, uint64_t n_valid,
+                                            uint32_t d, uint32_t k, double cmax, int g, int t, int lane, unsigned lanemask_lt,
+                                            uint32_t* __restrict__ labels, double* __restrict__ mind, double* __restrict__ part,
+                                            size_t pk, unsigned long long* __restrict__ nmarked) {
+    double slab_inertia = 0.0;
+#pragma unroll
+    for (int mt = 0; mt < MT; mt++) {
+        const uint64_t row = r0 + mt * 8 + g;
+        const bool valid = row < n_valid;
+        const double bestv = dunkey(best[mt]), secondv = dunkey(second[mt]);   // x.c - ||c||^2/2
+        const double dist = fmax(0.0, fma(-2.0, bestv, xn[mt]));
+        const double gap = 2.0 * (bestv - secondv);
+        const bool tie = !(gap > DMMA_TIE_REL * (xn[mt] + cmax));   // also catches NaN
+        if (valid && t == 0) {
+            labels[row] = tie ? 0xffffffffu : bidx[mt];             // ties are re-decided by refine_rows_kernel
+            if (UPDATE) mind[row] = dist;
+            if (tie) atomicAdd(nmarked, 1ull);
+        }
+        // Deterministic per-label accumulation (the update of bbd_tree.rs:151-155) into this warp's
+        // private partial: the 4 lanes of a row add their A-fragment elements.  Rows of this m-tile that
+        // share a label are serialised in ascending row order (rank), so the order of every f64 addition is
+        // fixed by (n, grid) alone.
+        const bool part_ok = UPDATE && valid && !tie;        // UPDATE = false: labels only (predict)
+        const uint32_t key = part_ok ? bidx[mt] : (0x80000000u | (uint32_t)g);
+        const unsigned peers = __match_any_sync(0xffffffffu, key);
+        const int rank = __popc(peers & lanemask_lt) >> 2;
+        const int maxrank = __reduce_max_sync(0xffffffffu, part_ok ? rank : 0);
+        for (int r = 0; r <= maxrank; r++) {
+            if (r) { __threadfence(); __syncwarp(); }     // order the (rare) same-label rows of this m-tile
+            if (part_ok && rank == r) {
+                // fire-and-forget RED.ADD.F64 into the warp-private partial: a given address only ever
+                // receives adds from this warp, same-thread adds stay in program order and cross-lane
+                // same-label adds are separated by the fence above => the summation order is fixed.
+                double* p = part + (size_t)bidx[mt] * d + t;
+#pragma unroll
+                for (int ks = 0; ks < KSTEPS; ks++)
+                    if (ks * 4 + t < d) atomicAdd(p + ks * 4, a[mt][ks]);
+                if (t == 0) atomicAdd(part + (size_t)k * d + bidx[mt], 1.0);
+            }
+        }
+        double v = (part_ok && t == 0) ? dist : 0.0;                 // fixed-order sum over the 8 rows
+        v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
+        v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 8));
+        v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
+        slab_inertia = __dadd_rn(slab_inertia, v);
+    }
+    if (UPDATE && lane == 0 && n_valid) atomicAdd(part + pk - 1, slab_inertia);
+}
+
 // Centroid block [c0, c0 + bn) -> shared memory (row pitch PITCH doubles, zero rows past k), -||c - mu||^2 / 2 -> cn.
 // Whole rows (d == DP: no column padding) go as 16-byte cp.async copies, all of a thread's copies in flight at once and
 // no register round trip: the streamed-centroid kernel switches blocks ~500 times per launch at config C4, and the
@@ -236,61 +309,9 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
             }
         }
         // ---- merge the 4 lanes that share a row, write out, mark near-ties, fused update ----
-        double slab_inertia = 0.0;
-#pragma unroll
-        for (int mt = 0; mt < MT; mt++) {
-#pragma unroll
-            for (int o = 1; o <= 2; o <<= 1) {
-                const key_t ob = __shfl_xor_sync(0xffffffffu, best[mt], o);
-                const key_t os = __shfl_xor_sync(0xffffffffu, second[mt], o);
-                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bidx[mt], o);
-                const bool take = ob > best[mt] || (ob == best[mt] && oi < bidx[mt]);
-                const key_t lo_best = ob < best[mt] ? ob : best[mt];
-                key_t s2 = os > second[mt] ? os : second[mt];
-                second[mt] = lo_best > s2 ? lo_best : s2;
-                bidx[mt] = take ? oi : bidx[mt];
-                best[mt] = ob > best[mt] ? ob : best[mt];
-            }
-            const uint64_t row = r0 + mt * 8 + g;
-            const bool valid = active && row < n;
-            const double bestv = dunkey(best[mt]), secondv = dunkey(second[mt]);   // x.c - ||c||^2/2
-            const double dist = fmax(0.0, fma(-2.0, bestv, xn[mt]));
-            const double gap = 2.0 * (bestv - secondv);
-            const bool tie = !(gap > DMMA_TIE_REL * (xn[mt] + cmax));   // also catches NaN
-            if (valid && t == 0) {
-                labels[row] = tie ? 0xffffffffu : bidx[mt];             // ties are re-decided by refine_rows_kernel
-                if (UPDATE) mind[row] = dist;
-                if (tie) atomicAdd(nmarked, 1ull);
-            }
-            // Deterministic per-label accumulation (the update of bbd_tree.rs:151-155) into this warp's
-            // private partial: the 4 lanes of a row add their A-fragment elements.  Rows of this m-tile that
-            // share a label are serialised in ascending row order (rank), so the order of every f64 addition is
-            // fixed by (n, grid) alone.
-            const bool part_ok = UPDATE && valid && !tie;        // UPDATE = false: labels only (predict)
-            const uint32_t key = part_ok ? bidx[mt] : (0x80000000u | (uint32_t)g);
-            const unsigned peers = __match_any_sync(0xffffffffu, key);
-            const int rank = __popc(peers & lanemask_lt) >> 2;
-            const int maxrank = __reduce_max_sync(0xffffffffu, part_ok ? rank : 0);
-            for (int r = 0; r <= maxrank; r++) {
-                if (r) { __threadfence(); __syncwarp(); }     // order the (rare) same-label rows of this m-tile
-                if (part_ok && rank == r) {
-                    // fire-and-forget RED.ADD.F64 into the warp-private partial: a given address only ever
-                    // receives adds from this warp, same-thread adds stay in program order and cross-lane
-                    // same-label adds are separated by the fence above => the summation order is fixed.
-                    double* p = part + (size_t)bidx[mt] * d + t;
-#pragma unroll
-                    for (int ks = 0; ks < KSTEPS; ks++)
-                        if (ks * 4 + t < d) atomicAdd(p + ks * 4, a[mt][ks]);
-                    if (t == 0) atomicAdd(part + (size_t)k * d + bidx[mt], 1.0);
-                }
-            }
-            double v = (part_ok && t == 0) ? dist : 0.0;                 // fixed-order sum over the 8 rows
-            v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
-            v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 8));
-            v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
-            slab_inertia = __dadd_rn(slab_inertia, v);
-        }
-        if (UPDATE && lane == 0 && active) atomicAdd(part + pk - 1, slab_inertia);
+        merge_row_lanes<MT>(best, second, bidx);
+        finish_slab<KSTEPS, MT, UPDATE>(a, xn, best, second, bidx, r0, active ? n : 0, d, k, cmax, g, t, lane, lanemask_lt,
+                                        labels, mind, part, pk, nmarked);
     }
 }
 
@@ -300,15 +321,15 @@ assign_dmma_resident_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, co
 // block load (and its two CTA barriers) a warp then runs `sl` slabs against the resident block, keeping the running
 // (best, second, argbest) of every row in a small per-warp shared-memory table between blocks.  Rows are re-read per
 // block, but a round's working set (148 CTAs x warps x sl slabs) is L2-resident, so HBM still sees X once.
-// MULTI = false is the compile-time specialisation for a fully resident centroid set (one block, sl = 1, no state).
-template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool MULTI, bool UPDATE, bool CENTER, typename TX>
+// (A fully resident centroid set takes assign_dmma_resident_kernel above.)
+template <int KSTEPS, int MT, int DMMA_NT, int DMMA_WARPS, bool UPDATE, bool CENTER, typename TX>
 __global__ void __launch_bounds__(DMMA_WARPS * 32, 1)
 assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids,
                    const double* __restrict__ cnorm, const double* __restrict__ mu, uint32_t k, uint32_t bn, uint32_t sl_arg, uint32_t* __restrict__ labels,
                    double* __restrict__ mind, double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked,
                    const LoopState* __restrict__ loop_st, uint32_t loop_it) {
     if (loop_done(loop_st, loop_it)) return;       // the fit's stop rule already fired (kmeans.rs:305)
-    const uint32_t sl = MULTI ? sl_arg : 1u;
+    const uint32_t sl = sl_arg;
     constexpr int DP = KSTEPS * 4;                 // padded feature count
     constexpr int PITCH = DP + 4;                  // doubles per staged centroid row (pitch = d*8+32 B)
     constexpr int ROWS = 8 * MT;
@@ -329,7 +350,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
     const uint64_t nslabs = (n + ROWS - 1) / ROWS;
     const uint64_t stride = (uint64_t)gridDim.x * DMMA_WARPS;
     const uint64_t rounds = (nslabs + stride * sl - 1) / (stride * sl);
-    const uint32_t nchunks = MULTI ? (k + bn - 1) / bn : 1u;
+    const uint32_t nchunks = (k + bn - 1) / bn;
     const double* bbase = cbuf + (size_t)g * PITCH + t;
     double* part = partials + ((size_t)blockIdx.x * DMMA_WARPS + warp) * ((pk + 15) / 16 * 16);   // this warp's private partial
     unsigned lanemask_lt;
@@ -380,7 +401,7 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
 #pragma unroll
                 for (int mt = 0; mt < MT; mt++) {
                     best[mt] = KEY_MIN; second[mt] = KEY_MIN; bidx[mt] = 0;
-                    if (MULTI && ch > 0 && t == 0) {
+                    if (ch > 0 && t == 0) {
                         const uint32_t o = si * ROWS + mt * 8 + g;
                         best[mt] = st_best[o]; second[mt] = st_second[o]; bidx[mt] = (uint32_t)st_idx[o];
                     }
@@ -391,23 +412,8 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                     kloop<KSTEPS, MT, DMMA_NT, PITCH>(acc, a, bbase + (size_t)sb * SUB * PITCH);
                     epilogue_all<MT, DMMA_NT>(acc, c0 + sb * SUB, t, best, second, bidx);
                 }
-                // ---- merge the 4 lanes that share a row ----
-#pragma unroll
-                for (int mt = 0; mt < MT; mt++) {
-#pragma unroll
-                    for (int o = 1; o <= 2; o <<= 1) {
-                        const key_t ob = __shfl_xor_sync(0xffffffffu, best[mt], o);
-                        const key_t os = __shfl_xor_sync(0xffffffffu, second[mt], o);
-                        const uint32_t oi = __shfl_xor_sync(0xffffffffu, bidx[mt], o);
-                        const bool take = ob > best[mt] || (ob == best[mt] && oi < bidx[mt]);
-                        const key_t lo_best = ob < best[mt] ? ob : best[mt];
-                        key_t s2 = os > second[mt] ? os : second[mt];
-                        second[mt] = lo_best > s2 ? lo_best : s2;
-                        bidx[mt] = take ? oi : bidx[mt];
-                        best[mt] = ob > best[mt] ? ob : best[mt];
-                    }
-                }
-                if (MULTI && !last) {                                     // park the row state until the next block
+                merge_row_lanes<MT>(best, second, bidx);
+                if (!last) {                                              // park the row state until the next block
                     if (t == 0) {
 #pragma unroll
                         for (int mt = 0; mt < MT; mt++) {
@@ -418,49 +424,8 @@ assign_dmma_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                     continue;
                 }
                 // ---- last block: write out, mark near-ties, fused update ----
-                double slab_inertia = 0.0;
-#pragma unroll
-                for (int mt = 0; mt < MT; mt++) {
-                    const uint64_t row = r0 + mt * 8 + g;
-                    const bool valid = row < n;
-                    const double bestv = dunkey(best[mt]), secondv = dunkey(second[mt]);   // x.c - ||c||^2/2
-                    const double dist = fmax(0.0, fma(-2.0, bestv, xn[mt]));
-                    const double gap = 2.0 * (bestv - secondv);
-                    const bool tie = !(gap > DMMA_TIE_REL * (xn[mt] + cmax));   // also catches NaN
-                    if (valid && t == 0) {
-                        labels[row] = tie ? 0xffffffffu : bidx[mt];             // ties are re-decided by refine_rows_kernel
-                        if (UPDATE) mind[row] = dist;
-                        if (tie) atomicAdd(nmarked, 1ull);
-                    }
-                    // Deterministic per-label accumulation (the update of bbd_tree.rs:151-155) into this warp's
-                    // private partial: the 4 lanes of a row add their A-fragment elements.  Rows of this m-tile that
-                    // share a label are serialised in ascending row order (rank), so the order of every f64 addition
-                    // is fixed by (n, grid) alone.
-                    const bool part_ok = UPDATE && valid && !tie;        // UPDATE = false: labels only (predict)
-                    const uint32_t key = part_ok ? bidx[mt] : (0x80000000u | (uint32_t)g);
-                    const unsigned peers = __match_any_sync(0xffffffffu, key);
-                    const int rank = __popc(peers & lanemask_lt) >> 2;
-                    const int maxrank = __reduce_max_sync(0xffffffffu, part_ok ? rank : 0);
-                    for (int r = 0; r <= maxrank; r++) {
-                        if (r) { __threadfence(); __syncwarp(); }     // order the (rare) same-label rows of this m-tile
-                        if (part_ok && rank == r) {
-                            // fire-and-forget RED.ADD.F64 into the warp-private partial: a given address only ever
-                            // receives adds from this warp, same-thread adds stay in program order and cross-lane
-                            // same-label adds are separated by the fence above => the summation order is fixed.
-                            double* p = part + (size_t)bidx[mt] * d + t;
-#pragma unroll
-                            for (int ks = 0; ks < KSTEPS; ks++)
-                                if (ks * 4 + t < d) atomicAdd(p + ks * 4, a[mt][ks]);
-                            if (t == 0) atomicAdd(part + (size_t)k * d + bidx[mt], 1.0);
-                        }
-                    }
-                    double v = (part_ok && t == 0) ? dist : 0.0;                 // fixed-order sum over the 8 rows
-                    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 4));
-                    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 8));
-                    v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, 16));
-                    slab_inertia = __dadd_rn(slab_inertia, v);
-                }
-                if (UPDATE && lane == 0) atomicAdd(part + pk - 1, slab_inertia);
+                finish_slab<KSTEPS, MT, UPDATE>(a, xn, best, second, bidx, r0, n, d, k, cmax, g, t, lane, lanemask_lt,
+                                                labels, mind, part, pk, nmarked);
             }
         }
     }
@@ -615,8 +580,8 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
                                                               ctx->d_cnorm, ctx->d_mu, (uint32_t)k, bn, ds->labels, ds->mind,
                                                               ctx->d_partials, pk, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
     } else {
-        auto kern = ctx->center_on ? assign_dmma_kernel<KSTEPS, MT, NT, WARPS, true, UPDATE, true, TX>
-                                   : assign_dmma_kernel<KSTEPS, MT, NT, WARPS, true, UPDATE, false, TX>;
+        auto kern = ctx->center_on ? assign_dmma_kernel<KSTEPS, MT, NT, WARPS, UPDATE, true, TX>
+                                   : assign_dmma_kernel<KSTEPS, MT, NT, WARPS, UPDATE, false, TX>;
         SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         kern<<<dmma_grid(ctx), WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids,
                                                               ctx->d_cnorm, ctx->d_mu, (uint32_t)k, bn, sl, ds->labels, ds->mind,

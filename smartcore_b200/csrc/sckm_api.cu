@@ -363,8 +363,8 @@ static int pick_assign(const sckm_dataset* ds, uint64_t k) {
     const sckm_ctx* ctx = ds->ctx;
     int which = ctx->assign_kernel;
     if (which == SCKM_ASSIGN_AUTO)
-        which = tc5_auto(ds, k) ? SCKM_ASSIGN_TC5 : dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA
-                : stream_supported(ds, k) ? SCKM_ASSIGN_STREAM : SCKM_ASSIGN_DIRECT;
+        which = tc5_auto(ds, k) ? SCKM_ASSIGN_TC5 : stream_supported(ds, k) ? SCKM_ASSIGN_STREAM
+                : dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA : SCKM_ASSIGN_DIRECT;
     if (which == SCKM_ASSIGN_TC5 && !tc5_supported(ds, k)) which = dmma_supported(ds, k) ? SCKM_ASSIGN_DMMA : SCKM_ASSIGN_DIRECT;
     if (which == SCKM_ASSIGN_DMMA && !dmma_supported(ds, k)) which = SCKM_ASSIGN_DIRECT;
     if (which == SCKM_ASSIGN_STREAM && !stream_supported(ds, k)) which = SCKM_ASSIGN_DIRECT;

@@ -532,8 +532,10 @@ __global__ void cnorm_kernel(const double* __restrict__ centroids, uint32_t k, u
     cnorm[c] = s;
 }
 
+// Any k >= 2: fewer than 32 centroids leave part of the one 32-column sub-block padded with -inf scores (wasted DMMAs,
+// still several times the direct form's rate -- the streaming kernel takes k <= 15 when d <= 32, this kernel when d > 32).
 bool dmma_supported(const sckm_dataset* ds, uint64_t k) {
-    return ds->d >= 4 && ds->d <= 128 && k >= 16 && k <= (1u << 24) && ds->n < 0xFFFFFFFFull;
+    return ds->d >= 4 && ds->d <= 128 && k >= 2 && k <= (1u << 24) && ds->n < 0xFFFFFFFFull;
 }
 
 static unsigned dmma_grid(const sckm_ctx* ctx) { return (unsigned)ctx->num_sms; }

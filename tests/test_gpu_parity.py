@@ -471,6 +471,27 @@ def test_centring_switch_does_not_change_results(ctx, O, force, monkeypatch):
         assert np.array_equal(ctx.predict(x, cent).astype(np.int64), O.predict(x, cent))
 
 
+@pytest.mark.parametrize("n,d,k,dtype", [(9000, 64, 2, np.float64), (12000, 48, 5, np.float64), (7000, 128, 8, np.float64),
+                                         (10000, 100, 15, np.float64), (8000, 40, 11, np.float32), (5000, 36, 3, np.float64)])
+def test_small_k_wide_rows_take_the_tile_kernel(ctx, O, n, d, k, dtype):
+    """k < 16 with d > 32 (outside the streaming kernel): the DMMA tile kernel with a partly padded sub-block instead
+    of the direct form.  Step and whole fit against the oracle."""
+    x = blobs(n, d, k, 2 * n + d + k, dtype, spread=1.0)
+    cent = x[np.random.default_rng(5).choice(n, k, replace=False)].astype(np.float64) + 0.01
+    ds = ctx.upload(x)
+    l0 = ctx.launch_count()
+    inertia, sums, counts = ds.lloyd_step(cent)
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+    assert_labels_match(ds.labels(), m_o, gap)
+    assert abs(inertia - d_o) <= RTOL * d_o
+    if np.array_equal(ds.labels().astype(np.int64), m_o):
+        assert counts.tolist() == c_o.tolist()
+        np.testing.assert_allclose(sums, s_o, rtol=RTOL, atol=1e-9)
+    ds.close()
+    got = fit_gpu(ctx, x, k, 3)
+    check_fit(O, x, k, 3, got)
+
+
 def test_step_is_bit_reproducible_at_full_size(ctx):
     """The stop rule compares successive inertias exactly, so a step must be bit-reproducible run to run: config C3
     (10M x 64, k = 256), five repeats of the same step -- packed sums, counts, inertia and labels identical."""

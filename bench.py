@@ -235,6 +235,9 @@ class Bench:
             self.tdist = tdist
             tdist.init_process_group("nccl", device_id=torch.device("cuda", self.local))
             self.cpu_group = tdist.new_group(backend="gloo")   # a barrier that parks a rank on the CPU, its GPU left alone
+        # N ranks share this host's cores: give each rank's pinned staging ring its share of them (the library alone sees
+        # one process and would start 8 memcpy threads per rank)
+        os.environ.setdefault("SCKM_INGEST_THREADS", str(max(2, min(8, (os.cpu_count() or 16) // max(self.world, 1)))))
         self.sampler = ClockSampler(self.local)
         self.sampler.start()                 # nvidia-smi takes seconds to start: begin now, select the timed windows later
         self.ctx = sc.Context(self.local)
@@ -409,7 +412,9 @@ class Bench:
                                    "loop (device-side stop rule, max_iter = steps) + labels (usize) / centroids download; bytes "
                                    "are per fit divided by the iterations executed" % ("sckm_kmeans_fit_shard" if self.distributed else "sckm_kmeans_fit"),
                            "iters": iters, "total_s": t_e2e, "upload_s": self.maxr(ph["upload_s"]), "kmeanspp_init_s": self.maxr(ph["kmeanspp_init_s"]),
-                           "lloyd_s": self.maxr(ph["lloyd_s"]), "download_s": self.maxr(ph["download_s"]), "distortion": fit["distortion"]}}
+                           "lloyd_s": self.maxr(ph["lloyd_s"]), "download_s": self.maxr(ph["download_s"]), "distortion": fit["distortion"],
+                           "upload_gbs_per_gpu": hx.nbytes / 1e9 / max(self.maxr(ph["upload_s"]), 1e-9),
+                           "host_cores": os.cpu_count(), "staging_threads_per_rank": int(os.environ["SCKM_INGEST_THREADS"])}}
 
     # -- strong scaling of C3 + the single-process drop-in call over the N devices -----------------------------------------------
     def strong(self, headline):
@@ -446,7 +451,8 @@ class Bench:
                 it = max(int(fit["iters"]), 1)
                 e["single_process_e2e"] = {
                     "what": "sckm_ctx_create_multi over the N devices, ONE sckm_kmeans_fit call from one pageable host buffer "
-                            "(what KMeans::fit gets through the Rust shim), rank 0 only",
+                            "(what KMeans::fit gets through the Rust shim), rank 0 only; measured INSIDE this torchrun job, whose other "
+                            "ranks stay resident on the devices (bench/multi_probe.py is the same call in a process of its own)",
                     "value": n * it / t, "unit": "point-iters/s", "iters": it, "total_s": t, "devices": ph["devices"],
                     "upload_s": ph["upload_s"], "kmeanspp_init_s": ph["kmeanspp_init_s"], "lloyd_s": ph["lloyd_s"], "download_s": ph["download_s"],
                     "h2d_bytes_per_step": int(hx.nbytes // it), "d2h_bytes_per_step": int((fit["labels"].nbytes + fit["centroids"].nbytes) // it),

@@ -317,7 +317,11 @@ def check_fit(O, x, k, seed, got):
     np.testing.assert_allclose(got["centroids"], want.centroids, rtol=RTOL, atol=1e-12)
     assert abs(got["distortion"] - want.distortion) <= RTOL * want.distortion
     assert got["size"].tolist() == want.size.tolist()
-    assert got["iters"] == want.iters
+    # The loop ends when the inertia stops DECREASING (kmeans.rs:305).  At the fixed point (labels unchanged) successive
+    # inertias are equal up to the rounding of two differently ordered sums, so `<=` can fire one step earlier or later
+    # in two correct implementations; the state it ends in is the same one (asserted above).  Anything else must agree.
+    assert got["iters"] == want.iters or (abs(got["iters"] - want.iters) == 1 and
+                                          np.array_equal(got["labels"].astype(np.int64), want.y)), (got["iters"], want.iters)
     return want
 
 

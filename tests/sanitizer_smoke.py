@@ -23,9 +23,15 @@ def main():
              (2000, 64, 48, np.float64, cabi.ASSIGN_DMMA), (1777, 20, 33, np.float32, cabi.ASSIGN_DMMA),
              (1200, 128, 300, np.float64, cabi.ASSIGN_DMMA),          # streamed centroid blocks
              (4096, 32, 64, np.float32, cabi.ASSIGN_TC5),              # tcgen05 / TMA / TMEM kernel
-             (900, 9, 4, np.float64, cabi.ASSIGN_DIRECT), (700, 40, 6, np.float64, cabi.ASSIGN_DIRECT)]
+             (900, 9, 4, np.float64, cabi.ASSIGN_DIRECT), (700, 40, 6, np.float64, cabi.ASSIGN_DIRECT),
+             (1300, 64, 5, np.float64, cabi.ASSIGN_AUTO),              # k < 16, d > 32: tile kernel, partly padded sub-block
+             (1500, 64, 40, np.float64, "center"), (1100, 128, 200, np.float64, "center"),   # centred instantiations
+             (1400, 12, 9, np.float64, "center")]                      # streaming kernel on offset data
     for n, d, k, dt, kern in cases:
         x = (rng.normal(size=(n, d)) + 3.0 * rng.integers(0, k, size=(n, 1))).astype(dt)
+        if kern == "center":                                           # data far from the origin: launch_cnorm centres
+            x = x + 1e4
+            kern = cabi.ASSIGN_AUTO
         first, u = cluster.kmeanspp_draws(3, n, k)
         ds = ctx.upload(x)
         seeds = ds.kmeanspp(k, first, u)
@@ -73,6 +79,17 @@ def main():
         assert set(np.nonzero(full <= 4.0 * (1 - 1e-9))[0].tolist()) <= set(res[qi][0].tolist()) <= set(np.nonzero(full <= 4.0 * (1 + 1e-9))[0].tolist())
     dk.close()
     print("ok knn / radius 3000x16 k=33", flush=True)
+    # rows that are not 16-byte multiples (element-wise staging) and k > 64 (passes of 64)
+    xo = rng.normal(size=(900, 3)).astype(np.float32); qo = xo[:4] + np.float32(0.1)
+    do = ctx.upload(xo)
+    idx, dist = do.knn(qo, 100)
+    for qi in range(4):
+        d2 = ((xo.astype(np.float64) - qo[qi].astype(np.float64)) ** 2).sum(axis=1)
+        assert set(idx[qi].tolist()) == set(np.argsort(d2, kind="stable")[:100].tolist()) and np.all(np.diff(dist[qi]) >= 0)
+    res = do.radius(qo, 0.8)
+    assert all(np.all(np.diff(i) > 0) and np.all(dv <= 0.8) for i, dv in res)
+    do.close()
+    print("ok knn / radius 900x3 f32 k=100", flush=True)
     g = ctx.generate_blobs(3000, 16, 8, 5)
     assert np.array_equal(g.download_rows(10, 20), cabi.blobs_host(10, 20, 16, 8, 5))
     g.close()

@@ -547,6 +547,22 @@ def test_multi_context_on_one_device_is_the_plain_context(O):
         sc.Context(devices=[0, 0])
 
 
+def test_fit_shard_on_one_rank_is_the_whole_fit(ctx, O):
+    """sckm_kmeans_fit_shard (the per-rank form for torchrun deployments) with one rank holding every row must be
+    sckm_kmeans_fit; the phase clock of the last fit is filled in."""
+    x = blobs(30000, 24, 12, 8, spread=2.0)
+    first, u = cluster.kmeanspp_draws(9, 30000, 12)
+    a = ctx.kmeans_fit(x, 12, 50, first, u)
+    b = ctx.kmeans_fit_shard(x, 0, 30000, 12, 50, first, u)
+    assert a["iters"] == b["iters"] and a["distortion"] == b["distortion"] and np.array_equal(a["labels"], b["labels"])
+    assert np.array_equal(a["centroids"], b["centroids"]) and np.array_equal(a["size"], b["size"])
+    t = ctx.last_fit_times()
+    assert t["devices"] == 1 and t["total_s"] >= t["lloyd_s"] > 0 and ctx.device_count() == 1
+    check_fit(O, x, 12, 9, b)
+    with pytest.raises(cabi.SckmError):
+        ctx.kmeans_fit_shard(x, 5, 30000, 12, 50, first, u)          # rows [5, 30005) exceed n_global
+
+
 @pytest.mark.parametrize("n,d,k,dtype", [(50_000, 32, 24, np.float64), (300_000, 64, 256, np.float64), (40_000, 16, 8, np.float64),
                                          (120_000, 32, 128, np.float32), (5_000, 3, 4, np.float64)])
 def test_multi_context_fit_and_predict_equal_single_device(ctx, O, n, d, k, dtype, monkeypatch):

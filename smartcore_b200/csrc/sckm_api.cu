@@ -739,6 +739,24 @@ int fit_upload(sckm_ctx* ctx, const void* x_host, uint64_t host_rows, uint64_t l
     *out = ds;
     return SCKM_OK;
 }
+// Every device allocation the compute phase will need (kmeans++ scratch, centroid workspaces, the partial slots of the
+// assignment kernel this shape selects), made up front: in a multi-GPU fit a rank that ran out of memory in the middle
+// of the loop would leave the others waiting in a collective, so all allocation failures must surface before the join.
+int fit_reserve(sckm_dataset* ds, uint64_t k) {
+    sckm_ctx* ctx = ds->ctx;
+    SCKM_CUDA(ctx, cudaSetDevice(ctx->device));
+    SCKM_TRY(check_k(ds, k));
+    SCKM_TRY(ensure_kpp(ds, k));
+    size_t slots = (size_t)ctx->num_sms * 16;                     // direct path: update_partial_kernel / update_given_kernel
+    switch (pick_assign(ds, k)) {
+        case SCKM_ASSIGN_DMMA: slots = dmma_partial_slots(ctx); break;
+        case SCKM_ASSIGN_TC5: slots = std::max<size_t>(slots, (size_t)ctx->num_sms * 8); break;
+        case SCKM_ASSIGN_STREAM: slots = std::max<size_t>(slots, (size_t)ctx->num_sms * 4 * 8); break;
+        default: break;
+    }
+    slots = std::max<size_t>(slots, dmma_partial_slots(ctx));      // the initial means of a large fit use the tile-layout update
+    return ensure_workspace(ctx, k, ds->d, slots);
+}
 int fit_compute(sckm_dataset* ds, uint64_t k, uint64_t max_iter, uint64_t first_index, const double* uniforms,
                 int64_t* size_out, double* centroids_out, double* distortion_out, int64_t* iters_out, double* phase_s) {
     sckm_ctx* ctx = ds->ctx;

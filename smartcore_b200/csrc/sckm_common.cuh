@@ -186,6 +186,7 @@ int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop,
                double* distortion_out, int64_t* iters_out, double* inertia_trace, float* ms_trace, float* assign_ms_trace);
 int fit_upload(sckm_ctx* ctx, const void* x_host, uint64_t host_rows, uint64_t lo, uint64_t n_local, uint64_t d, int dtype,
                int column_major, sckm_dataset** out);
+int fit_reserve(sckm_dataset* ds, uint64_t k);
 int fit_compute(sckm_dataset* ds, uint64_t k, uint64_t max_iter, uint64_t first_index, const double* uniforms,
                 int64_t* size_out, double* centroids_out, double* distortion_out, int64_t* iters_out, double* phase_s);
 int predict_rows(sckm_ctx* ctx, const void* x_host, uint64_t host_rows, uint64_t lo, uint64_t n, uint64_t d, int dtype,

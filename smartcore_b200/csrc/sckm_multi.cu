@@ -13,8 +13,9 @@
 //                     collectives per Lloyd step: one all-reduce of [k*d sums | k counts | inertia] (sckm_nccl.cu);
 //                     every rank evaluates the stop rule on the same all-reduced inertia, so all break together.
 //   sckm_predict    : per rank  its slice of the rows, no collective.
-// The upload phase ends with a join: if any rank failed to get its memory, every rank stops BEFORE the first
-// collective (a rank that never enqueues its all-reduce would hang the others).
+// The upload phase also reserves every workspace the compute phase needs and ends with a join: if any rank failed to
+// get its memory, every rank stops BEFORE the first collective (a rank that never enqueues its all-reduce would hang
+// the others).
 #include "sckm_common.cuh"
 #include <algorithm>
 #include <atomic>
@@ -99,7 +100,10 @@ int multi_kmeans_fit(sckm_ctx* ctx, const void* x_host, uint64_t n, uint64_t d, 
     std::vector<sckm_dataset*> ds(G, nullptr);
     const double t0 = now_s();
     // phase 1: every rank lands its rows (G staging rings work on disjoint slices of the caller's buffer)
-    int rc = on_all(m, [&](int r) { return fit_upload(m->dev[r], x_host, n, b[r], b[r + 1] - b[r], d, dtype, column_major, &ds[r]); });
+    int rc = on_all(m, [&](int r) {
+        const int rc_up = fit_upload(m->dev[r], x_host, n, b[r], b[r + 1] - b[r], d, dtype, column_major, &ds[r]);
+        return rc_up != SCKM_OK ? rc_up : fit_reserve(ds[r], k);      // every allocation of the compute phase, before the join
+    });
     const double t1 = now_s();
     // phase 2: the single-rank driver on every rank; collectives inside keep the ranks in lock step
     std::vector<double> ph(2 * G, 0.0);

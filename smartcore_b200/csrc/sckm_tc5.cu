@@ -310,7 +310,19 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TSTAGE + m * BN + cp * COLS);
                 const uint32_t col0 = b * BN + cp * COLS;
-                const float4* h4 = reinterpret_cast<const float4*>((HCN_SMEM ? s_hcn : hcn) + col0);
+                // -||c||^2/2 of this thread's columns, four at a time: an explicit ld.shared when the table is resident (the
+                // compiler cannot tell the address space of `HCN_SMEM ? s_hcn : hcn` and emitted generic LD.E.128, whose
+                // latency showed up as FADD stalls all over the chunk loops)
+                const uint32_t h_sm = smem_u32(s_hcn + col0);
+                const float4* h_gl = reinterpret_cast<const float4*>(hcn + col0);
+                auto hcn4 = [&](int i) -> float4 {
+                    if (HCN_SMEM) {
+                        float4 r;
+                        asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(h_sm + 16u * (uint32_t)i));
+                        return r;
+                    }
+                    return __ldg(h_gl + i);
+                };
                 // software pipeline over the 32-column chunks: chunk c+1 is in flight (tcgen05.ld is asynchronous
                 // until tcgen05.wait::ld) while chunk c goes through the top-2 update
                 uint32_t va[32], vb[32];
@@ -322,8 +334,7 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                         float m[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
 #pragma unroll
                         for (int u = 0; u < 8; u += 2) {
-                            const float4 ha = HCN_SMEM ? h4[(c0 >> 2) + u] : __ldg(h4 + (c0 >> 2) + u);
-                            const float4 hb = HCN_SMEM ? h4[(c0 >> 2) + u + 1] : __ldg(h4 + (c0 >> 2) + u + 1);
+                            const float4 ha = hcn4((c0 >> 2) + u), hb = hcn4((c0 >> 2) + u + 1);
                             m[0] = fmaxf(fmaxf(m[0], __uint_as_float(v[u * 4 + 0]) + ha.x), __uint_as_float(v[u * 4 + 4]) + hb.x);
                             m[1] = fmaxf(fmaxf(m[1], __uint_as_float(v[u * 4 + 1]) + ha.y), __uint_as_float(v[u * 4 + 5]) + hb.y);
                             m[2] = fmaxf(fmaxf(m[2], __uint_as_float(v[u * 4 + 2]) + ha.z), __uint_as_float(v[u * 4 + 6]) + hb.z);
@@ -336,7 +347,7 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                     uint32_t i4[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
-                        const float4 hv = HCN_SMEM ? h4[(c0 >> 2) + u] : __ldg(h4 + (c0 >> 2) + u);
+                        const float4 hv = hcn4((c0 >> 2) + u);
                         const float hh[4] = {hv.x, hv.y, hv.z, hv.w};
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
@@ -472,14 +483,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
+    // (function-local static: initialised once, thread-safe -- a multi-GPU context calls this from one thread per device)
+    static const EncodeTiledFn fn = []() -> EncodeTiledFn {
         void* p = nullptr; cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            fn = (EncodeTiledFn)p;
-    }
+            return (EncodeTiledFn)p;
+        cudaGetLastError();
+        return nullptr;
+    }();
     return fn;
 }
 

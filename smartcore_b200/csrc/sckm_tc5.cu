@@ -327,24 +327,17 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 // until tcgen05.wait::ld) while chunk c goes through the top-2 update
                 uint32_t va[32], vb[32];
                 auto consume = [&](const uint32_t (&v)[32], int c0) {
-                    // Every loop below keeps FOUR independent dependency chains (columns j, j+4, j+8, ... of the chunk):
-                    // with two epilogue warps per scheduler a single running max / top-2 chain is bound by the latency of
-                    // its own select / min-max instructions, not by any pipe.
                     {   // can this chunk change any row's best or second, or come within the tie margin of a winner?
-                        float m[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+                        float mx = -FLT_MAX;
 #pragma unroll
-                        for (int u = 0; u < 8; u += 2) {
-                            const float4 ha = hcn4((c0 >> 2) + u), hb = hcn4((c0 >> 2) + u + 1);
-                            m[0] = fmaxf(fmaxf(m[0], __uint_as_float(v[u * 4 + 0]) + ha.x), __uint_as_float(v[u * 4 + 4]) + hb.x);
-                            m[1] = fmaxf(fmaxf(m[1], __uint_as_float(v[u * 4 + 1]) + ha.y), __uint_as_float(v[u * 4 + 5]) + hb.y);
-                            m[2] = fmaxf(fmaxf(m[2], __uint_as_float(v[u * 4 + 2]) + ha.z), __uint_as_float(v[u * 4 + 6]) + hb.z);
-                            m[3] = fmaxf(fmaxf(m[3], __uint_as_float(v[u * 4 + 3]) + ha.w), __uint_as_float(v[u * 4 + 7]) + hb.w);
+                        for (int u = 0; u < 8; u++) {
+                            const float4 hv = hcn4((c0 >> 2) + u);
+                            mx = fmaxf(fmaxf(mx, __uint_as_float(v[u * 4 + 0]) + hv.x), __uint_as_float(v[u * 4 + 1]) + hv.y);
+                            mx = fmaxf(fmaxf(mx, __uint_as_float(v[u * 4 + 2]) + hv.z), __uint_as_float(v[u * 4 + 3]) + hv.w);
                         }
-                        const float mx = fmaxf(fmaxf(m[0], m[1]), fmaxf(m[2], m[3]));
                         if (!__any_sync(0xffffffffu, mx > fmaxf(second, prime))) return;
                     }
-                    float b4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX}, s4[4] = {-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
-                    uint32_t i4[4] = {0u, 0u, 0u, 0u};
+                    // (four independent top-2 chains per chunk were tried: no gain -- the warp is not bound by this chain)
 #pragma unroll
                     for (int u = 0; u < 8; u++) {
                         const float4 hv = hcn4((c0 >> 2) + u);
@@ -352,19 +345,11 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 #pragma unroll
                         for (int e = 0; e < 4; e++) {
                             const float sc = __uint_as_float(v[u * 4 + e]) + hh[e];
-                            const bool gt = sc > b4[e];
-                            s4[e] = fmaxf(s4[e], gt ? b4[e] : sc);
-                            i4[e] = gt ? (col0 + c0 + u * 4 + e) : i4[e];
-                            b4[e] = fmaxf(b4[e], sc);
+                            const bool gt = sc > best;
+                            second = fmaxf(second, gt ? best : sc);
+                            bi = gt ? (col0 + c0 + u * 4 + e) : bi;
+                            best = fmaxf(best, sc);
                         }
-                    }
-                    // fold the four column classes into the row's running top-2 (equal scores: such a row is a tie and is
-                    // re-decided exactly anyway, so which index survives here does not matter)
-#pragma unroll
-                    for (int e = 0; e < 4; e++) {
-                        second = fmaxf(fmaxf(second, s4[e]), fminf(best, b4[e]));
-                        bi = b4[e] > best ? i4[e] : bi;
-                        best = fmaxf(best, b4[e]);
                     }
                 };
                 auto release_stage = [&]() {                           // all of this stage's columns are in registers

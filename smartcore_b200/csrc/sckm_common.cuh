@@ -151,6 +151,25 @@ __device__ __forceinline__ bool loop_done(const LoopState* st, uint32_t it) {
 }
 #endif
 
+#ifdef __CUDACC__
+// Programmatic dependent launch (PDL): a kernel launched with launch_pdl() may be scheduled while its predecessor on the
+// stream is still draining; it must call pdl_wait() before touching anything the predecessor wrote (the wait returns
+// once that grid has completed and its writes are visible).  For the tiny kernels around a 40 us assignment launch
+// (refine, reduce, finalize: config C2) this hides most of the launch latency of each boundary.  A kernel launched the
+// ordinary way sees pdl_wait() as a no-op.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+#endif
+
 #define SCKM_CUDA(ctx, call)                                                               \
     do {                                                                                   \
         cudaError_t _e = (call);                                                           \

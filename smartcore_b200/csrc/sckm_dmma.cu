@@ -442,6 +442,7 @@ refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
                    uint32_t* __restrict__ labels, double* __restrict__ mind, double* __restrict__ partials, size_t pk,
                    const unsigned long long* __restrict__ nmarked, const double* __restrict__ mu,
                    const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    pdl_wait();
     if (*nmarked == 0ull || loop_done(loop_st, loop_it)) return; // nothing was marked in this step (the common case)
     const int lane = threadIdx.x & 31;
     const uint64_t w = (uint64_t)blockIdx.x * DMMA_WARPS + (threadIdx.x >> 5);
@@ -664,11 +665,13 @@ int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center) {
 int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas) {
     sckm_ctx* ctx = ds->ctx;
     if (ds->dtype == SCKM_F32)
-        refine_rows_kernel<float, 8><<<grid_ctas, 256, 0, ctx->stream>>>((const float*)ds->x, ds->n, (uint32_t)ds->d,
-            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, nullptr, SCKM_LOOP_ARGS(ctx));
+        SCKM_CUDA(ctx, launch_pdl(refine_rows_kernel<float, 8>, dim3(grid_ctas), dim3(256), 0, ctx->stream, (const float*)ds->x, ds->n, (uint32_t)ds->d,
+            (const double*)ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, (const unsigned long long*)ctx->d_flags,
+            (const double*)nullptr, SCKM_LOOP_ARGS(ctx)));
     else
-        refine_rows_kernel<double, 8><<<grid_ctas, 256, 0, ctx->stream>>>((const double*)ds->x, ds->n, (uint32_t)ds->d,
-            ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, nullptr, SCKM_LOOP_ARGS(ctx));
+        SCKM_CUDA(ctx, launch_pdl(refine_rows_kernel<double, 8>, dim3(grid_ctas), dim3(256), 0, ctx->stream, (const double*)ds->x, ds->n, (uint32_t)ds->d,
+            (const double*)ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, (const unsigned long long*)ctx->d_flags,
+            (const double*)nullptr, SCKM_LOOP_ARGS(ctx)));
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }

@@ -741,6 +741,7 @@ __global__ void __launch_bounds__(32 * GROUPS) reduce_partials_kernel(double* __
                                                                      size_t pitch, double* __restrict__ packed,
                                                                      unsigned long long* __restrict__ nmarked,
                                                                      const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    pdl_wait();
     if (loop_done(loop_st, loop_it)) return;
     __shared__ double2 sh[GROUPS][33];
     if (blockIdx.x == 0 && threadIdx.x == 0 && threadIdx.y == 0) *nmarked = 0ull;   // consumed by the refine pass of this step
@@ -792,6 +793,7 @@ __global__ void finalize_kernel(const double* __restrict__ packed, uint32_t k, u
                                 const double* __restrict__ mu, double* __restrict__ centroids, double* __restrict__ cnorm,
                                 long long* __restrict__ size, LoopState* __restrict__ loop_st, uint32_t loop_it,
                                 double* __restrict__ inertia_trace) {
+    pdl_wait();
     if (loop_done(loop_st, loop_it)) return;
     const uint32_t c = blockIdx.x;
     const double cnt = packed[(size_t)k * d + c];
@@ -1165,19 +1167,20 @@ int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk) {
     const unsigned blocks = (unsigned)((pitch / 2 + 31) / 32);
     // small payload, or many slots to walk: more slot groups per block so that enough loads are in flight
     if (blocks < (unsigned)ctx->num_sms || slots >= 256)
-        reduce_partials_kernel<32><<<blocks, dim3(32, 32), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
+        SCKM_CUDA(ctx, launch_pdl(reduce_partials_kernel<32>, dim3(blocks), dim3(32, 32), 0, ctx->stream, ctx->d_partials, slots, pk, pitch,
+                                  ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx)));
     else
-        reduce_partials_kernel<8><<<blocks, dim3(32, 8), 0, ctx->stream>>>(ctx->d_partials, slots, pk, pitch, ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
+        SCKM_CUDA(ctx, launch_pdl(reduce_partials_kernel<8>, dim3(blocks), dim3(32, 8), 0, ctx->stream, ctx->d_partials, slots, pk, pitch,
+                                  ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx)));
     LAUNCH_CHECK(ctx);
     return SCKM_OK;
 }
 
 int launch_finalize(sckm_ctx* ctx, uint64_t k, uint64_t d, bool guarded) {
     const unsigned threads = (unsigned)std::min<uint64_t>(256, (d + 31) / 32 * 32);
-    finalize_kernel<<<(unsigned)k, threads, 0, ctx->stream>>>(ctx->d_packed, (uint32_t)k, (uint32_t)d, guarded ? 1 : 0,
-                                                            ctx->packed_centered ? 1 : 0, ctx->d_mu,
-                                                            ctx->d_centroids, ctx->d_cnorm, (long long*)ctx->d_size,
-                                                            SCKM_LOOP_ARGS(ctx), ctx->loop_it ? ctx->d_inertia_trace : nullptr);
+    SCKM_CUDA(ctx, launch_pdl(finalize_kernel, dim3((unsigned)k), dim3(threads), 0, ctx->stream, (const double*)ctx->d_packed, (uint32_t)k,
+                              (uint32_t)d, guarded ? 1 : 0, ctx->packed_centered ? 1 : 0, (const double*)ctx->d_mu, ctx->d_centroids,
+                              ctx->d_cnorm, (long long*)ctx->d_size, SCKM_LOOP_ARGS(ctx), ctx->loop_it ? ctx->d_inertia_trace : (double*)nullptr));
     LAUNCH_CHECK(ctx);
     ctx->cnorm_valid = ctx->cnorm_valid || !guarded;   // a guarded update keeps stale norms of empty clusters stale
     return SCKM_OK;

@@ -108,6 +108,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
                      const double* __restrict__ cnorm, const double* __restrict__ mu, uint32_t k, uint32_t* __restrict__ labels,
                      double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked,
                      const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+    pdl_wait();                                          // (launched with launch_pdl: the previous step's finalize may still be draining)
     if (loop_done(loop_st, loop_it)) return;             // the fit's stop rule already fired (kmeans.rs:305)
     constexpr int NTU = KS / 2 > 0 ? KS / 2 : 1;         // feature n-tiles of the update GEMM (8 features each)
     constexpr int VU = VW < NTU ? VW : NTU;              // features per update load
@@ -119,7 +120,10 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
     extern __shared__ __align__(16) double smem_s[];     // [warps][k*d] sums | [warps][16] counts | [warps] inertia
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    const double cmax = cta_max(cnorm, k);
+    // max_j ||c_j - mu||^2 over the <= 15 centroids: every thread reads them itself (L1 broadcasts) -- no CTA barrier in
+    // the prologue of a kernel whose whole run is ~40 us at config C2
+    double cmax = 0.0;
+    for (uint32_t j = 0; j < k; j++) cmax = fmax(cmax, __ldg(cnorm + j));
     const double tie_half = 0.5 * STREAM_TIE_REL;
     constexpr bool TMA = STAGES > 0;
     static_assert(!TMA || DFULL, "the bulk-copy ring needs d == 4*KS");
@@ -508,8 +512,9 @@ static int launch_stream_f(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* gr
     const uint64_t nbatches = (ds->n + 31) / 32;
     const unsigned grid = (unsigned)std::max<uint64_t>(1, std::min<uint64_t>((nbatches + STREAM_WARPS - 1) / STREAM_WARPS,
                                                                               (uint64_t)ctx->num_sms * ctas_per_sm));
-    kern<<<grid, STREAM_WARPS * 32, smem, ctx->stream>>>((const TX*)ds->x, ds->n, d, ctx->d_centroids, ctx->d_cnorm, ctx->d_mu,
-                                                        (uint32_t)k, ds->labels, ctx->d_partials, pk, ctx->d_flags, SCKM_LOOP_ARGS(ctx));
+    SCKM_CUDA(ctx, launch_pdl(kern, dim3(grid), dim3(STREAM_WARPS * 32), smem, ctx->stream, (const TX*)ds->x, ds->n, d, (const double*)ctx->d_centroids,
+                              (const double*)ctx->d_cnorm, (const double*)ctx->d_mu, (uint32_t)k, ds->labels, ctx->d_partials, pk, ctx->d_flags,
+                              SCKM_LOOP_ARGS(ctx)));
     LAUNCH_CHECK_S(ctx);
     *grid_out = grid;
     return SCKM_OK;

@@ -9,7 +9,7 @@
 //     GEMM operands so a lane's elements are contiguous in memory) -- no staging, no shared memory in the loop;
 //   * scores  x.c_j - ||c_j||^2/2  as 8x8x4 DMMAs against centroid B-fragments that stay in registers for the
 //     whole launch; top-2 per row on integer keys; rows whose gap is within 1e-10*(||x||^2 + max||c||^2) are
-//     marked and re-decided exactly by refine_rows_kernel (same rule as the DMMA tile kernel), so labels equal
+//     re-decided exactly, in place, by the lane that owns the row (same rule as the DMMA tile kernel), so labels equal
 //     the exact direct-form argmin;
 //   * update: sums[cluster][feature] += onehot(label)^T . X, again as DMMAs whose accumulators live in registers
 //     for the whole launch (the FP64 tensor path used as a wide adder with a fixed, hardware-defined order: no
@@ -167,7 +167,6 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
     for (int j = 0; j < (GROUPED ? FPL : 1); j++) su[j] = 0.0;
     uint32_t cnt_g = 0;
     double inertia = 0.0;                                // this lane's share (rows whose winning score it holds)
-    uint32_t nties = 0;
 
     const uint64_t nbatches = (n + 31) / 32;
     const uint64_t wglobal = (uint64_t)blockIdx.x * STREAM_WARPS + warp;
@@ -311,7 +310,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         }
         __syncwarp();
         // ---- argmax of this lane's row (strict >: lowest index first); rows with another score within the tolerance
-        // of the winner (exact ties and NaN included) are marked and re-decided exactly by refine_rows_kernel ----
+        // of the winner (exact ties and NaN included) are re-decided exactly below ----
         double best = sc[0]; uint32_t bi = 0;
 #pragma unroll
         for (int j = 1; j < 8 * KT; j++) {
@@ -324,11 +323,32 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
 #pragma unroll
         for (int j = 0; j < 8 * KT; j++) nnear += (sc[j] >= thr) ? 1u : 0u;
         const bool valid = FULL || row0 + lane < n;
-        const bool ok = valid && nnear == 1u;                      // exactly the winner itself (NaN winner: 0)
+        bool ok = valid && nnear == 1u;                            // exactly the winner itself (NaN winner: 0)
         double dist = fma(-2.0, best, xn);
         dist = dist < 0.0 ? 0.0 : dist;
+        // Near-ties are re-decided right here, exactly, by the lane that owns the row: the reference's arithmetic (widen,
+        // diff, square, sequential sum, never fused; raw x and raw centroids), strict <, lowest index
+        // (kmeans.rs:334-347 / bbd_tree.rs:101-111).  With k <= 15 centroids that is a few hundred instructions for a
+        // rare row, and the step needs no separate refine launch (every launch boundary costs ~4 us of a ~45 us step).
+        if (__any_sync(0xffffffffu, valid && !ok)) {
+            if (valid && !ok) {
+                const TX* xr = x + (row0 + lane) * d;
+                double bestd = DBL_MAX; uint32_t bj = 0xffffffffu;
+                for (uint32_t c = 0; c < k; c++) {
+                    const double* cr = centroids + (size_t)c * d;
+                    double dd = 0.0;
+                    for (uint32_t j = 0; j < d; j++) {
+                        const double r = __dsub_rn((double)xr[j], cr[j]);
+                        dd = __dadd_rn(dd, __dmul_rn(r, r));
+                    }
+                    if (dd < bestd) { bestd = dd; bj = c; }
+                }
+                bi = bj == 0xffffffffu ? 0u : bj;                  // all distances NaN: the reference keeps cluster 0
+                dist = bestd;
+                ok = true;
+            }
+        }
         if (ok) inertia = __dadd_rn(inertia, dist);
-        nties += (valid && !ok) ? 1u : 0u;
         const uint32_t lab = ok ? bi : 0xffffffffu;
         if (valid) labels[row0 + lane] = lab;
         if (GROUPED) {
@@ -431,10 +451,6 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         if (DFULL && b * 32 + 32 <= n) batch(b, it, std::true_type{});
         else batch(b, it, std::false_type{});
     }
-    // rows handed to refine_rows_kernel (rare); the reduction is unconditional: every lane must reach the shuffles
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) nties += __shfl_xor_sync(0xffffffffu, nties, o);
-    if (lane == 0 && nties) atomicAdd(nmarked, (unsigned long long)nties);
     __syncthreads();                                      // the staging tiles are reused by the combine below
     // ---- per-warp results -> shared memory, CTA combine in warp order, store this CTA's partial slot ----
     const uint32_t kd = k * d;
@@ -576,11 +592,8 @@ int launch_assign_stream(sckm_dataset* ds, uint64_t k) {
     ctx->packed_centered = false;                                 // the update GEMM sums the rows as they are
     unsigned grid = 0;
     SCKM_TRY(ds->dtype == SCKM_F32 ? launch_stream_by_d<float>(ds, k, pk, &grid) : launch_stream_by_d<double>(ds, k, pk, &grid));
-    // exact re-decision of marked rows: (grid/8) CTAs x 8 warps, warp w adds into slot w -- the slots the streaming
-    // kernel just stored, or still-zero ones beyond them (kernel order on the stream makes that safe)
-    const unsigned rgrid = (grid + STREAM_WARPS - 1) / STREAM_WARPS;
-    ctx->partial_slots_used = std::max(grid, rgrid * STREAM_WARPS);
-    return launch_refine_rows(ds, k, pk, rgrid);
+    ctx->partial_slots_used = grid;          // one slot per CTA; near-ties were re-decided inside the kernel: no refine launch
+    return SCKM_OK;
 }
 
 }  // namespace sckm

@@ -375,14 +375,13 @@ static int pick_assign(const sckm_dataset* ds, uint64_t k) {
 static int clustering_step(sckm_dataset* ds, uint64_t k, cudaEvent_t ev_a0 = nullptr, cudaEvent_t ev_a1 = nullptr) {
     sckm_ctx* ctx = ds->ctx;
     const int which = pick_assign(ds, k);
-    ctx->step_finalized = false;
     if (ev_a0) SCKM_CUDA(ctx, cudaEventRecord(ev_a0, ctx->stream));
     if (which == SCKM_ASSIGN_DMMA || which == SCKM_ASSIGN_STREAM || which == SCKM_ASSIGN_TC5) {
         if (which == SCKM_ASSIGN_DMMA) SCKM_TRY(launch_assign_dmma(ds, k));   // assignment + fused partial sums
         else if (which == SCKM_ASSIGN_TC5) SCKM_TRY(launch_assign_tc5(ds, k));
         else SCKM_TRY(launch_assign_stream(ds, k));
         if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
-        SCKM_TRY(launch_reduce_partials(ctx, ctx->partial_slots_used, (size_t)k * ds->d + k + 1, k, ds->d));
+        SCKM_TRY(launch_reduce_partials(ctx, ctx->partial_slots_used, (size_t)k * ds->d + k + 1));
     } else {
         ctx->packed_centered = false;
         SCKM_TRY(launch_assign_direct(ds, k));
@@ -497,7 +496,7 @@ int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop,
             ctx->loop_it = (uint32_t)it;
             if (assign_ms_trace) rc = clustering_step(ds, k, evs_a[2 * (it - 1)], evs_a[2 * (it - 1) + 1]);
             else rc = clustering_step(ds, k);                                      // bbd.clustering(...)        kmeans.rs:296
-            if (rc == SCKM_OK && !ctx->step_finalized) rc = launch_finalize(ctx, k, ds->d, /*guarded=*/true);  // centroids = sums / size + stop rule  kmeans.rs:297-309
+            if (rc == SCKM_OK) rc = launch_finalize(ctx, k, ds->d, /*guarded=*/true);  // centroids = sums / size + stop rule  kmeans.rs:297-309
             if (rc == SCKM_OK && ms_trace && cudaEventRecord(evs[it], ctx->stream) != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "cudaEventRecord failed");
         }
         ctx->loop_it = 0;

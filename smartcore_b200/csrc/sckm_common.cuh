@@ -52,7 +52,6 @@ struct sckm_ctx {
     bool mu_zero = true;             // d_mu currently holds zeros
     bool mu_requested = false;       // what the last launch_cnorm was asked for (centred kernels vs raw norms)
     bool center_on = false;          // ... and what it decided: the tile kernels subtract mu (CENTER instantiation)
-    bool step_finalized = false;     // the reduce of the last clustering step also finalised it (centroids, sizes, stop rule)
     bool packed_centered = false;    // d_packed sums of the last step are sums of (x - mu), not of x
     double* d_packed = nullptr;      // [k*d sums | k counts | inertia]
     double* d_partials = nullptr;    // [P][k*d + k + 1] per-CTA/warp partial sums (deterministic)
@@ -230,8 +229,7 @@ int launch_assign_direct_raw(sckm_ctx* ctx, const void* x, int dtype, uint64_t n
                              uint32_t* labels, double* mind);
 // deterministic per-label sums/counts/inertia of the local rows into ctx->d_packed
 int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia);
-// tail_k != 0: the reduce may also finalise the step (one GPU, inside a loop, small k*d) -> ctx->step_finalized
-int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk, uint64_t tail_k = 0, uint64_t tail_d = 0);
+int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk);
 // centroids = sums / counts (guarded: keep old when count == 0; unguarded for the initial means)
 int launch_finalize(sckm_ctx* ctx, uint64_t k, uint64_t d, bool guarded);
 int launch_loop_init(sckm_ctx* ctx, uint64_t max_iter, bool honor_stop);

@@ -736,27 +736,11 @@ __global__ void update_partial_kernel(const T* __restrict__ x, uint64_t n, uint3
 // packed[e] = sum over the partial slots in a FIXED order (8 slot groups summed sequentially by 8 thread rows,
 // then the 8 group sums in order); the slots are zeroed for the next step.  blockDim = (32, 8); each thread owns
 // two adjacent elements (16-byte accesses; slot rows are 128-byte aligned).
-// tail.k != 0 (one GPU, inside a Lloyd loop, k*d small): the block that finishes LAST also does what finalize_kernel
-// does -- centroids = sums / counts (guarded, + mu for centred sums), sizes, norms, stop rule -- so a step needs one
-// launch less.  The reduction itself stays spread over all blocks (a lone CTA walking every slot was measured slower
-// than the launch it saves); only the k*d divisions ride on the last block.
-struct ReduceTail {
-    uint32_t k = 0, d = 0;
-    int centered = 0;
-    const double* mu = nullptr;
-    double* centroids = nullptr;
-    double* cnorm = nullptr;
-    long long* size = nullptr;
-    LoopState* state = nullptr;
-    double* inertia_trace = nullptr;
-    unsigned* ticket = nullptr;            // blocks finished so far (reset by the tail)
-};
-
 template <int GROUPS>
 __global__ void __launch_bounds__(32 * GROUPS) reduce_partials_kernel(double* __restrict__ partials, uint32_t nslots, size_t pk,
-                                                                     size_t pitch, double* packed,
+                                                                     size_t pitch, double* __restrict__ packed,
                                                                      unsigned long long* __restrict__ nmarked,
-                                                                     const LoopState* loop_st, uint32_t loop_it, ReduceTail tail) {
+                                                                     const LoopState* __restrict__ loop_st, uint32_t loop_it) {
     pdl_wait();
     if (loop_done(loop_st, loop_it)) return;
     __shared__ double2 sh[GROUPS][33];
@@ -795,42 +779,6 @@ __global__ void __launch_bounds__(32 * GROUPS) reduce_partials_kernel(double* __
         for (int i = 0; i < GROUPS; i++) { t.x = __dadd_rn(t.x, sh[i][threadIdx.x].x); t.y = __dadd_rn(t.y, sh[i][threadIdx.x].y); }
         if (e < pk) packed[e] = t.x;
         if (e + 1 < pk) packed[e + 1] = t.y;
-    }
-    if (tail.k == 0) return;
-    // ---- finalize + stop rule by the last block to get here ----
-    __shared__ bool s_last;
-    __threadfence();
-    __syncthreads();
-    const uint32_t tid = threadIdx.y * 32 + threadIdx.x, nthr = 32 * GROUPS;
-    if (tid == 0) s_last = atomicAdd(tail.ticket, 1u) == gridDim.x - 1;
-    __syncthreads();
-    if (!s_last) return;
-    __threadfence();
-    const uint32_t kd = tail.k * tail.d;
-    for (uint32_t i = tid; i < kd; i += nthr) {
-        const uint32_t c = i / tail.d, j = i - c * tail.d;
-        const double cnt = __ldcg(packed + kd + c);
-        if (cnt > 0.0) {                                               // kmeans.rs:298: an empty cluster keeps its centroid
-            const double mean = __ddiv_rn(__ldcg(packed + i), cnt);
-            tail.centroids[i] = tail.centered ? __dadd_rn(mean, tail.mu[j]) : mean;
-        }
-    }
-    __syncthreads();
-    for (uint32_t c = tid; c < tail.k; c += nthr) {
-        tail.size[c] = (long long)__ldcg(packed + kd + c);
-        double s2 = 0.0;
-        for (uint32_t j = 0; j < tail.d; j++) { const double v = tail.centroids[(size_t)c * tail.d + j] - tail.mu[j]; s2 = fma(v, v, s2); }
-        tail.cnorm[c] = s2;
-    }
-    if (tid == 0) {
-        *tail.ticket = 0u;
-        const double dist = __ldcg(packed + kd + tail.k);
-        if (tail.inertia_trace) tail.inertia_trace[loop_it - 1] = dist;
-        tail.state->iters = loop_it;
-        if (tail.state->honor_stop) {
-            if (tail.state->distortion <= dist) tail.state->done_at = loop_it;      // break (kmeans.rs:305-306)
-            else tail.state->distortion = dist;                                      // kmeans.rs:307-308
-        }
     }
 }
 
@@ -1214,24 +1162,16 @@ int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia) {
     return SCKM_OK;
 }
 
-int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk, uint64_t tail_k, uint64_t tail_d) {
-    ReduceTail tail;
-    ctx->step_finalized = false;
-    if (tail_k && ctx->loop_it != 0 && ctx->nranks == 1 && tail_k * tail_d <= 8192 && !getenv("SCKM_NO_TAIL")) {
-        tail.k = (uint32_t)tail_k; tail.d = (uint32_t)tail_d; tail.centered = ctx->packed_centered ? 1 : 0; tail.mu = ctx->d_mu;
-        tail.centroids = ctx->d_centroids; tail.cnorm = ctx->d_cnorm; tail.size = (long long*)ctx->d_size; tail.state = ctx->d_loop;
-        tail.inertia_trace = ctx->d_inertia_trace; tail.ticket = reinterpret_cast<unsigned*>(ctx->d_flags + 1);
-        ctx->step_finalized = true;
-    }
+int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk) {
     const size_t pitch = slot_pitch(pk);
     const unsigned blocks = (unsigned)((pitch / 2 + 31) / 32);
     // small payload, or many slots to walk: more slot groups per block so that enough loads are in flight
     if (blocks < (unsigned)ctx->num_sms || slots >= 256)
         SCKM_CUDA(ctx, launch_pdl(reduce_partials_kernel<32>, dim3(blocks), dim3(32, 32), 0, ctx->stream, ctx->d_partials, slots, pk, pitch,
-                                  ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx), tail));
+                                  ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx)));
     else
         SCKM_CUDA(ctx, launch_pdl(reduce_partials_kernel<8>, dim3(blocks), dim3(32, 8), 0, ctx->stream, ctx->d_partials, slots, pk, pitch,
-                                  ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx), tail));
+                                  ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx)));
     LAUNCH_CHECK(ctx);
     return SCKM_OK;
 }

@@ -138,7 +138,9 @@ int sckm_lloyd_fit(sckm_dataset* ds, uint64_t k, uint64_t max_iter, double* cent
 /* Same loop with the stop rule disabled (exactly n_iters steps) and device timing:
  * ms_per_iter_out[n_iters] (nullable) are CUDA-event times of each whole iteration on the context's
  * stream, assign_ms_out[n_iters] (nullable) those of the assignment kernel alone (the dominant
- * kernel, for the roofline).  inertia_out (nullable) gets n_iters values. */
+ * kernel, for the roofline).  With ms_per_iter_out but WITHOUT assign_ms_out the loop is timed as a whole --
+ * two events, none between the steps, which is how a fit runs -- and every slot carries the mean.
+ * inertia_out (nullable) gets n_iters values. */
 int sckm_lloyd_iterate(sckm_dataset* ds, uint64_t k, uint64_t n_iters, double* centroids_inout,
                        int64_t* size_out, double* inertia_out, float* ms_per_iter_out,
                        float* assign_ms_out);

@@ -272,10 +272,12 @@ class Dataset:
         self.ctx._check(lib.sckm_lloyd_fit(self.h, k, max_iter, _p(c), _p(size), C.addressof(dist), C.addressof(iters)))
         return dict(centroids=c, size=size, distortion=dist.value, iters=iters.value)
 
-    def lloyd_iterate(self, centroids, n_iters, want_inertia=False):
+    def lloyd_iterate(self, centroids, n_iters, want_inertia=False, per_step_events=True):
+        """per_step_events=False: time the n_iters steps as a whole (two events, as a fit runs); `ms` then carries the mean
+        in every slot and `assign_ms` is None."""
         c = np.array(centroids, dtype=np.float64, order="C"); k = c.shape[0]
         size = np.zeros(k, dtype=np.int64); ms = np.zeros(n_iters, dtype=np.float32)
-        ams = np.zeros(n_iters, dtype=np.float32)
+        ams = np.zeros(n_iters, dtype=np.float32) if per_step_events else None
         inertia = np.zeros(n_iters) if want_inertia else None
         self.ctx._check(lib.sckm_lloyd_iterate(self.h, k, n_iters, _p(c), _p(size), _p(inertia), _p(ms), _p(ams)))
         return dict(centroids=c, size=size, ms=ms, assign_ms=ams, inertia=inertia)

@@ -471,8 +471,12 @@ int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop,
         evs_a.resize(2 * max_iter);
         for (auto& e : evs_a) SCKM_CUDA(ctx, cudaEventCreate(&e));
     }
+    // ms_trace without assign_ms_trace: the loop is timed as a whole -- two events, none between the steps (an event record
+    // is a stream operation of its own: three per step cost ~8 us of a ~50 us step at config C2) -- and every slot of
+    // ms_trace carries the mean
+    const bool whole = ms_trace && !assign_ms_trace;
     if (ms_trace) {
-        evs.resize(max_iter + 1);
+        evs.resize(whole ? 2 : max_iter + 1);
         for (auto& e : evs) SCKM_CUDA(ctx, cudaEventCreate(&e));
         SCKM_CUDA(ctx, cudaEventRecord(evs[0], ctx->stream));
     }
@@ -497,10 +501,11 @@ int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop,
             if (assign_ms_trace) rc = clustering_step(ds, k, evs_a[2 * (it - 1)], evs_a[2 * (it - 1) + 1]);
             else rc = clustering_step(ds, k);                                      // bbd.clustering(...)        kmeans.rs:296
             if (rc == SCKM_OK) rc = launch_finalize(ctx, k, ds->d, /*guarded=*/true);  // centroids = sums / size + stop rule  kmeans.rs:297-309
-            if (rc == SCKM_OK && ms_trace && cudaEventRecord(evs[it], ctx->stream) != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "cudaEventRecord failed");
+            if (rc == SCKM_OK && ms_trace && !whole && cudaEventRecord(evs[it], ctx->stream) != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "cudaEventRecord failed");
         }
         ctx->loop_it = 0;
         if (rc != SCKM_OK) break;
+        if (whole && it >= max_iter && cudaEventRecord(evs[1], ctx->stream) != cudaSuccess) { rc = fail(ctx, SCKM_ERR_CUDA, "cudaEventRecord failed"); break; }
         if (cudaMemcpyAsync(h_state, ctx->d_loop, sizeof(LoopState), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
             cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
             rc = fail(ctx, SCKM_ERR_CUDA, "Lloyd loop failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -521,8 +526,13 @@ int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop,
     } else {
         cudaStreamSynchronize(ctx->stream);
     }
-    if (rc == SCKM_OK && ms_trace)
+    if (rc == SCKM_OK && ms_trace && !whole)
         for (int64_t i = 0; i < iters; i++) cudaEventElapsedTime(&ms_trace[i], evs[i], evs[i + 1]);
+    if (rc == SCKM_OK && whole && iters > 0) {
+        float total = 0.f;
+        cudaEventElapsedTime(&total, evs[0], evs[1]);
+        for (int64_t i = 0; i < iters; i++) ms_trace[i] = total / (float)iters;
+    }
     if (rc == SCKM_OK && assign_ms_trace)
         for (int64_t i = 0; i < iters; i++) cudaEventElapsedTime(&assign_ms_trace[i], evs_a[2 * i], evs_a[2 * i + 1]);
     for (auto& e : evs) cudaEventDestroy(e);

@@ -463,7 +463,7 @@ class Bench:
                     hx[q:q + m] = dsg.download_rows(q, m)
                 dsg.close(); gen.close()
                 first, u = self.cluster.kmeanspp_draws(KMEANS_SEED, n, K_CLUSTERS)
-                mc.kmeans_fit(hx[: 1 << 20], K_CLUSTERS, 2, first % (1 << 20), u)      # warm the staging rings / NCCL channels
+                mc.kmeans_fit(hx, K_CLUSTERS, 2, first, u)      # a first fit pins every device's staging lanes and warms NCCL
                 t0 = time.perf_counter()
                 fit = mc.kmeans_fit(hx, K_CLUSTERS, a.steps, first, u)
                 t = time.perf_counter() - t0

@@ -106,7 +106,7 @@ template <int KS, int KT, int VW, bool DFULL, int STAGES, typename TX>
 __global__ void __launch_bounds__(STREAM_WARPS * 32, (KS * KT <= 8) ? 2 : 1)
 assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const double* __restrict__ centroids,
                      const double* __restrict__ cnorm, const double* __restrict__ mu, uint32_t k, uint32_t* __restrict__ labels,
-                     double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked,
+                     double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked, uint32_t pf_ahead,
                      const LoopState* __restrict__ loop_st, uint32_t loop_it) {
     pdl_wait();                                          // (launched with launch_pdl: the previous step's finalize may still be draining)
     if (loop_done(loop_st, loop_it)) return;             // the fit's stop rule already fired (kmeans.rs:305)
@@ -197,6 +197,15 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
             }
         }
     };
+    // L2 prefetch of batch `b` (32 rows = 32 * d elements, contiguous): lane l touches the l-th 128-byte line (and the
+    // following ones when the batch is longer than 4 KB)
+    auto l2_prefetch_batch = [&](uint64_t b) {
+        if (pf_ahead == 0 || b >= nbatches) return;
+        const char* p0 = reinterpret_cast<const char*>(x + b * 32 * d);
+        const size_t bytes = (size_t)min((uint64_t)32, n - b * 32) * d * sizeof(TX);
+        for (size_t off = (size_t)lane * 128; off < bytes; off += 32 * 128)
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + off));
+    };
     auto load_any = [&](uint64_t row0) {
         if (DFULL && row0 + 32 <= n) load_rows(row0, std::true_type{});
         else load_rows(row0, std::false_type{});
@@ -280,6 +289,9 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         // hides under epilogue + update.  Ring mode: read the update's B fragments (this batch's rows again, K = row)
         // out of the ring buffer now, so that their latency hides under the epilogue instead of stalling the DMMAs.
         if (!TMA && b + nwarps < nbatches) load_any((b + nwarps) * 32);
+        // ... and pull the batches after that into L2 (one line per lane, no registers held): the kernel is latency-bound on
+        // its row loads at four warps per scheduler, and an L2 hit costs a third of an HBM access
+        if (!TMA) l2_prefetch_batch(b + (uint64_t)pf_ahead * nwarps);
         double xbe[TMA ? 8 : 1][NTU];
         if (TMA) {
             const TX* ubs = stage_rows + (size_t)t * d + g * VU;
@@ -445,6 +457,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         }
     } else if (wglobal < nbatches) {
         load_any(wglobal * 32);
+        for (uint32_t a = 1; a < pf_ahead; a++) l2_prefetch_batch(wglobal + (uint64_t)a * nwarps);
     }
     uint32_t it = 0;
     for (uint64_t b = wglobal; b < nbatches; b += nwarps, it++) {
@@ -521,6 +534,8 @@ static int launch_stream_f(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* gr
     const size_t ring = STAGES ? (size_t)STREAM_WARPS * STAGES * 32 * d * sizeof(TX) : 0;         // behind the tiles
     const size_t smem = std::max(combine, (tiles + 127) / 128 * 128 + ring);
     auto kern = assign_stream_kernel<KS, KT, VW, DFULL, STAGES, TX>;
+    uint32_t pf_ahead = 3;                                     // batches ahead of the register prefetch that are pulled into L2
+    if (const char* e = getenv("SCKM_STREAM_PF")) pf_ahead = (uint32_t)std::max(0, std::min(16, atoi(e)));
     if (smem > 48 * 1024) SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int ctas_per_sm = 0;
     SCKM_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, kern, STREAM_WARPS * 32, smem));
@@ -530,7 +545,7 @@ static int launch_stream_f(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* gr
                                                                               (uint64_t)ctx->num_sms * ctas_per_sm));
     SCKM_CUDA(ctx, launch_pdl(kern, dim3(grid), dim3(STREAM_WARPS * 32), smem, ctx->stream, (const TX*)ds->x, ds->n, d, (const double*)ctx->d_centroids,
                               (const double*)ctx->d_cnorm, (const double*)ctx->d_mu, (uint32_t)k, ds->labels, ctx->d_partials, pk, ctx->d_flags,
-                              SCKM_LOOP_ARGS(ctx)));
+                              pf_ahead, SCKM_LOOP_ARGS(ctx)));
     LAUNCH_CHECK_S(ctx);
     *grid_out = grid;
     return SCKM_OK;

@@ -440,7 +440,7 @@ template <typename TX, int DMMA_WARPS, bool UPDATE = true>
 __global__ void __launch_bounds__(DMMA_WARPS * 32)
 refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const double* __restrict__ centroids, uint32_t k,
                    uint32_t* __restrict__ labels, double* __restrict__ mind, double* __restrict__ partials, size_t pk,
-                   const unsigned long long* __restrict__ nmarked, const double* __restrict__ mu, uint32_t slot0,
+                   const unsigned long long* __restrict__ nmarked, const double* __restrict__ mu,
                    const LoopState* __restrict__ loop_st, uint32_t loop_it) {
     pdl_wait();
     if (*nmarked == 0ull || loop_done(loop_st, loop_it)) return; // nothing was marked in this step (the common case)
@@ -449,7 +449,7 @@ refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
     const uint64_t nw = (uint64_t)gridDim.x * DMMA_WARPS;
     const uint64_t per = ((n + nw - 1) / nw + 127) / 128 * 128;
     const uint64_t r_begin = min(n, w * per), r_end = min(n, r_begin + per);
-    double* part = partials + ((size_t)slot0 + w) * ((pk + 15) / 16 * 16);   // warp w of this launch owns slot slot0 + w
+    double* part = partials + w * ((pk + 15) / 16 * 16);
     double inertia = 0.0;
     bool any = false;
     for (uint64_t base4 = r_begin; base4 < r_end; base4 += 128) {
@@ -592,7 +592,7 @@ static int launch_t(sckm_dataset* ds, uint64_t k, size_t pk) {
     }
     LAUNCH_CHECK_D(ctx);
     refine_rows_kernel<TX, WARPS, UPDATE><<<dmma_grid(ctx), WARPS * 32, 0, ctx->stream>>>((const TX*)ds->x, ds->n, (uint32_t)ds->d,
-        ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, ctx->d_mu, 0u, SCKM_LOOP_ARGS(ctx));
+        ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags, ctx->d_mu, SCKM_LOOP_ARGS(ctx));
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }
@@ -662,16 +662,16 @@ int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center) {
 }
 
 // refine pass for the streaming kernel's launch geometry (8 warps per CTA)
-int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas, uint32_t slot0) {
+int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas) {
     sckm_ctx* ctx = ds->ctx;
     if (ds->dtype == SCKM_F32)
         SCKM_CUDA(ctx, launch_pdl(refine_rows_kernel<float, 8>, dim3(grid_ctas), dim3(256), 0, ctx->stream, (const float*)ds->x, ds->n, (uint32_t)ds->d,
             (const double*)ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, (const unsigned long long*)ctx->d_flags,
-            (const double*)nullptr, slot0, SCKM_LOOP_ARGS(ctx)));
+            (const double*)nullptr, SCKM_LOOP_ARGS(ctx)));
     else
         SCKM_CUDA(ctx, launch_pdl(refine_rows_kernel<double, 8>, dim3(grid_ctas), dim3(256), 0, ctx->stream, (const double*)ds->x, ds->n, (uint32_t)ds->d,
             (const double*)ctx->d_centroids, (uint32_t)k, ds->labels, ds->mind, ctx->d_partials, pk, (const unsigned long long*)ctx->d_flags,
-            (const double*)nullptr, slot0, SCKM_LOOP_ARGS(ctx)));
+            (const double*)nullptr, SCKM_LOOP_ARGS(ctx)));
     LAUNCH_CHECK_D(ctx);
     return SCKM_OK;
 }

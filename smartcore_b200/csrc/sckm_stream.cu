@@ -44,6 +44,7 @@ constexpr int STREAM_WARPS = 8;
 constexpr int STREAM_MAX_K = 15;
 constexpr double STREAM_TIE_REL = 1e-10;
 
+int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas);   // sckm_dmma.cu
 
 // Feature (k-dimension) permutation used by both operands of the scoring GEMM so that a lane's KS elements of a
 // row are VW-element vectors in memory (one 16-byte LDG per VW k-steps): the dot product does not care about the

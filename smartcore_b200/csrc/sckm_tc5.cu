@@ -14,11 +14,8 @@
 //            2 tiles x 3 products x 4 k-steps of 128x128x8, accumulators double-buffered in TMEM (2 x 256 columns)
 //   warps 2-9  one thread per row of the super-tile: split the landed X tile into hi/lo in place, then per centroid
 //            block tcgen05.ld the row's 128 scores and keep a running top-2 + argmax in registers; at the end the
-//            exact f64 distance and the near-tie mark; label and distance of every row are handed to
-//   warp 11  the UPDATE warp: it walks the super-tile's rows in order and adds each row (out of the staged tile) to the
-//            CTA's ONE partial slot with fire-and-forget RED.ADD.F64 -- a single warp in row order, hence a fixed
-//            summation order, and 148 slots instead of 148 x 8: at k*d = 131k the slots shrink from 1.28 GB to 160 MB
-//            and the slot reduce from 0.9 ms to ~0.2 ms per step (the update is ~2 % of one warp's time).
+//            exact f64 distance, the near-tie mark, and the deterministic fused update (same scheme as sckm_dmma.cu:
+//            fire-and-forget RED.ADD.F64 into the warp's private partial, same-label rows serialised by rank).
 //            The top-2 tracking (five half-rate ALU instructions per score) is what bounds this kernel, so most of it
 //            is skipped: every row is PRIMED with the score of the centroid it was assigned to in the previous step
 //            (one 32-term dot product), and a 32-column chunk only goes through the tracking when, for some row of the
@@ -45,13 +42,12 @@ namespace sckm {
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
-int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas, uint32_t slot0 = 0);   // sckm_dmma.cu
+int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas);   // sckm_dmma.cu
 int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center);                  // sckm_dmma.cu
 
 constexpr int TC_BM = 128;               // rows per MMA tile (TMEM lanes)
 constexpr int TC_EPI_WARPS = 8;
-constexpr int TC_THREADS = 12 * 32;      // warps: 0 X-producer, 1 MMA, 2..9 epilogue, 10 C-producer, 11 update
-constexpr unsigned TC_REFINE_CTAS = 16;  // refine_rows_kernel launch of this path: its 128 warps own the slots after the CTAs'
+constexpr int TC_THREADS = 11 * 32;      // warps: 0 X-producer, 1 MMA, 2..9 epilogue, 10 C-producer
 constexpr uint32_t TC_ATOM_FLOATS = TC_BM * 32;        // one 128-row x 128-byte swizzle atom of f32
 constexpr double TC_TIE_REL = 2e-5;      // >= 10x the 3xTF32 + FP32-accumulate error bound (bench/tc5_probe.cu: 1e-6)
 
@@ -102,9 +98,7 @@ struct alignas(16) TcSmemT {                  // dynamic shared memory image (ba
     float xl[2][TILES][NK][TC_ATOM_FLOATS];   // TF32 lo part
     float ch[2][NK][BN * 32];                 // centroid block, hi
     float cl[2][NK][BN * 32];                 // centroid block, lo
-    uint64_t x_full[2], x_ready[2], x_empty[2], c_full[2], c_empty[2], t_full[2], t_empty[2], u_full[2];
-    uint32_t u_lab[2][TILES * TC_BM];         // label of every row of the super-tile (0xffffffff: not to be added) ...
-    double u_dist[2][TILES * TC_BM];          // ... and its exact distance, for the update warp
+    uint64_t x_full[2], x_ready[2], x_empty[2], c_full[2], c_empty[2], t_full[2], t_empty[2];
     double m_xn[2][TC_BM];                    // column-part merge scratch (CP == 2), double-buffered by super-tile
     float m_best[2][TC_BM], m_second[2][TC_BM];
     uint32_t m_idx[2][TC_BM];
@@ -160,8 +154,7 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) {
-            mbar_init(&S.x_full[s], 1); mbar_init(&S.x_ready[s], TC_EPI_WARPS); mbar_init(&S.x_empty[s], 2 + TC_EPI_WARPS);
-            mbar_init(&S.u_full[s], TC_EPI_WARPS / CP);                      // the epilogue warps that finish rows (cp == 0)
+            mbar_init(&S.x_full[s], 1); mbar_init(&S.x_ready[s], TC_EPI_WARPS); mbar_init(&S.x_empty[s], 1 + TC_EPI_WARPS);
             mbar_init(&S.c_full[s], 1); mbar_init(&S.c_empty[s], 1);
             mbar_init(&S.t_full[s], 1); mbar_init(&S.t_empty[s], TC_EPI_WARPS);
         }
@@ -234,39 +227,6 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 umma_commit(&S.x_empty[xs]);                         // X stage: MMA side done (epilogue warps arrive too)
             }
         }
-    } else if (warp == 11) {
-        // ================= update warp: per-label sums, counts, inertia of the CTA's rows, in row order =================
-        double* part = partials + (size_t)blockIdx.x * ((pk + 15) / 16 * 16);      // this CTA's slot
-        uint32_t it = 0;
-        for (uint64_t st = blockIdx.x; st < nsuper; st += gridDim.x, it++) {
-            const int xs = it & 1; const uint32_t ph = (it >> 1) & 1;
-            mbar_wait(&S.u_full[xs], ph);
-            double dsum = 0.0;
-#pragma unroll 4
-            for (int r = 0; r < TILES * TC_BM; r++) {
-                const uint32_t lr = S.u_lab[xs][r];                    // same word for every lane
-                if (lr == 0xffffffffu) continue;
-                const int m = r / TC_BM, rt = r % TC_BM;
-                for (uint32_t f = lane; f < d; f += 32) {
-                    double xv;
-                    if (sizeof(TXS) == 8) {
-                        xv = (double)__ldg(xsrc + (st * rows_per_super + (uint64_t)r) * d + f);
-                    } else {
-                        const int a = f >> 5, fi = f & 31;
-                        const int phys = rt * 32 + ((((fi >> 2) ^ (rt & 7)) << 2) | (fi & 3));   // undo the 128-byte swizzle
-                        xv = (double)S.xh[xs][m][a][phys] + (double)S.xl[xs][m][a][phys];
-                    }
-                    atomicAdd(part + (size_t)lr * d + f, xv);
-                }
-                if (lane == 0) {
-                    atomicAdd(part + (size_t)k * d + lr, 1.0);
-                    dsum = __dadd_rn(dsum, S.u_dist[xs][r]);
-                }
-            }
-            if (lane == 0) atomicAdd(part + pk - 1, dsum);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&S.x_empty[xs]);               // done with the staged tile and with u_lab / u_dist
-        }
     } else {
         // ================= epilogue warps: one thread per (row, column part) =================
         const int ew = warp - 2;                                     // 0..7
@@ -274,6 +234,7 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         const int cp = TILES == 2 ? 0 : (ew >> 2);                   // column part
         const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
         const int rloc = q * 32 + lane;                              // row within the tile
+        double* part = partials + ((size_t)blockIdx.x * TC_EPI_WARPS + ew) * ((pk + 15) / 16 * 16);
         // split my share of X stage `xs` in place (a row is 128 bytes at rloc*128 inside each atom; the swizzle only
         // permutes 16-byte chunks inside it), return my part of ||x||^2, and tell the MMA warp the stage is ready
         auto split_stage = [&](int xs, uint32_t xph) -> double {
@@ -435,7 +396,27 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                 const bool tie = !(gap > TC_TIE_REL * (xn + cmax)) || bi >= k;
                 const bool part_ok = valid && !tie;
                 const uint32_t lab = part_ok ? bi : 0xffffffffu;
-                // exact f64 distance of my row to its winner: all loads independent (one memory round trip)
+                const uint64_t wrow0 = st * rows_per_super + (uint64_t)m * TC_BM + (uint64_t)q * 32;   // first row of this warp
+                // (a) update: the warp walks its 32 rows in order; lane f handles features f, f+32, ... and adds the
+                // row's value to the warp's private partial with a fire-and-forget RED (an address only ever receives
+                // adds from one thread, in program order => fixed summation order).  No dependent loads: nothing waits.
+#pragma unroll 4
+                for (int r = 0; r < 32; r++) {
+                    const uint32_t lr = __shfl_sync(0xffffffffu, lab, r);
+                    if (lr == 0xffffffffu) continue;                   // warp-uniform
+                    for (uint32_t f = lane; f < d; f += 32) {
+                        double xv;
+                        if (sizeof(TXS) == 8) {
+                            xv = (double)__ldg(xsrc + (wrow0 + r) * d + f);
+                        } else {
+                            const int a = f >> 5, fi = f & 31, rt = q * 32 + r;
+                            const int phys = rt * 32 + ((((fi >> 2) ^ (rt & 7)) << 2) | (fi & 3));   // undo the 128-byte swizzle
+                            xv = (double)S.xh[xs][m][a][phys] + (double)S.xl[xs][m][a][phys];
+                        }
+                        atomicAdd(part + (size_t)lr * d + f, xv);
+                    }
+                }
+                // (b) exact f64 distance of my row to its winner: all loads independent (one memory round trip)
                 double mydist = 0.0;
                 if (part_ok) {
                     const double* cr = centroids + (size_t)bi * d;
@@ -461,11 +442,15 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                     mydist = a0 + a1;
                 }
                 if (valid) { labels[row] = tie ? 0xffffffffu : bi; mind[row] = mydist; if (tie) atomicAdd(nmarked, 1ull); }
-                // hand the row to the update warp
-                S.u_lab[xs][m * TC_BM + rloc] = lab;
-                S.u_dist[xs][m * TC_BM + rloc] = part_ok ? mydist : 0.0;
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&S.u_full[xs]);              // (release: the stores above are visible to the waiter)
+                // counts: one add per distinct label of the warp (the lowest lane of each group adds the group size)
+                unsigned lanemask_lt;
+                asm("mov.u32 %0, %%lanemask_lt;" : "=r"(lanemask_lt));
+                const unsigned peers = __match_any_sync(0xffffffffu, part_ok ? bi : (0x80000000u | (uint32_t)lane));
+                if (part_ok && (peers & lanemask_lt) == 0) atomicAdd(part + (size_t)k * d + bi, (double)__popc(peers));
+                double v = part_ok ? mydist : 0.0;                    // fixed-order sum over the warp's 32 rows
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v = __dadd_rn(v, __shfl_xor_sync(0xffffffffu, v, o));
+                if (lane == 0) atomicAdd(part + pk - 1, v);
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.x_empty[xs]);
@@ -554,9 +539,8 @@ int launch_assign_tc5(sckm_dataset* ds, uint64_t k) {
     if (!tc5_supported(ds, k)) return fail(ctx, SCKM_ERR_INVALID, "shape not supported by the tcgen05 kernel");
     const size_t pk = (size_t)k * ds->d + k + 1;
     const unsigned grid = (unsigned)ctx->num_sms;
-    // one slot per CTA (its update warp) + one per warp of the refine launch that follows
-    SCKM_TRY(ensure_workspace(ctx, k, ds->d, (size_t)grid + TC_REFINE_CTAS * 8));
-    ctx->partial_slots_used = grid + TC_REFINE_CTAS * 8;
+    SCKM_TRY(ensure_workspace(ctx, k, ds->d, (size_t)grid * TC_EPI_WARPS));
+    ctx->partial_slots_used = grid * TC_EPI_WARPS;
     if (ds->n == 0) return SCKM_OK;
     SCKM_TRY(launch_cnorm(ctx, k, ds->d, false));                     // raw norms: this kernel ranks the raw f32 rows
     ctx->packed_centered = false;
@@ -573,7 +557,7 @@ int launch_assign_tc5(sckm_dataset* ds, uint64_t k) {
     if (ds->d <= 32) rc = ds->dtype == SCKM_F64 ? launch_tc5_t<1, 2, 128, double>(ds, k, pk, x32) : launch_tc5_t<1, 2, 128, float>(ds, k, pk, x32);
     else             rc = ds->dtype == SCKM_F64 ? launch_tc5_t<2, 1, 64, double>(ds, k, pk, x32) : launch_tc5_t<2, 1, 64, float>(ds, k, pk, x32);
     SCKM_TRY(rc);
-    return launch_refine_rows(ds, k, pk, TC_REFINE_CTAS, grid);   // its 8 warps per CTA own the slots behind the CTAs' own
+    return launch_refine_rows(ds, k, pk, grid);   // 8 warps per CTA: the same partial slots as the epilogue warps
 }
 
 }  // namespace sckm

@@ -308,6 +308,8 @@ class Bench:
              "ms_per_step": 1e3 * r["t_dev"] / r["steps"], "value": r["n_global"] * r["steps"] / r["t_dev"], "unit": "point-iters/s",
              "roofline": roof, "kmeanspp_init_s": r["t_init"], "gpu_launches": r["launches"],
              "inertia_non_increasing": r["inertia_non_increasing"], "clocks": self.sampler.window(r["w0"], r["w1"])}
+        if self.world > 1:
+            e["allreduce"] = self.ctx.allreduce_path()      # 'peer': summed over the ranks inside the finalize kernel; 'nccl'
         if extra:
             e.update(extra)
         return e
@@ -515,6 +517,7 @@ def main():
 
     # ---- headline: C3, weak ----
     head = B.run_steps(n_local, n_global, row0, d, k, args.dtype, args.steps, args.warmup, init=args.init, keep=want("parity"))
+    head_path = B.ctx.allreduce_path()
     value = n_global * args.steps / head["t_dev"]
     roof = shape_roofline(n_local, k, d, args.dtype, head["t_assign"], B.peaks, B.mp)
     traffic, traffic_src = ncu_traffic() if default_shape else (None, None)
@@ -567,7 +570,9 @@ def main():
             "config": {"workload": "C3 blobs 10M x 64 k=256 f64 per GPU (BASELINE.json configs[2])" if default_shape
                                    else "tuning shape %d x %d k=%d %s per GPU" % (n_local, d, k, args.dtype), "n_per_gpu": n_local,
                        "n_global": n_global, "d": d, "k": k, "l2": "inputs (5.12 GB/GPU) larger than L2; no flush",
-                       "parallelism": "rows sharded x%d, one NCCL all-reduce of k*d+k+1 f64 per step" % world,
+                       "parallelism": ("one GPU" if world == 1 else "rows sharded x%d; per step ONE sum of k*d+k+1 f64 over the ranks, %s"
+                                       % (world, "inside the finalize kernel over NVLink peer memory (csrc/sckm_peer.cu)"
+                                          if head_path == "peer" else "through ncclAllReduce")),
                        "kmeanspp_init_s": head["t_init"], "wall_s_timed_region": head["wall"],
                        "stop_rule": "evaluated on the device every step (finalize kernel); the timed steps include it"},
             "roofline": roof, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": head["launches"], "clocks": clocks,

@@ -83,6 +83,13 @@ int  sckm_ctx_device_count(const sckm_ctx* ctx);
 /* Wall-clock phases of the last sckm_kmeans_fit on this context, seconds: out6 = {upload, kmeans++ + initial means,
  * Lloyd loop, label download, total, devices used} (max over devices per phase). */
 int  sckm_ctx_last_fit_times(const sckm_ctx* ctx, double* out6);
+/* How the last Lloyd loop of this context summed its per-step vector over the ranks: SCKM_ALLREDUCE_NONE (one rank),
+ * SCKM_ALLREDUCE_NCCL, or SCKM_ALLREDUCE_PEER -- the one-shot sum over peer memory inside the finalize kernel
+ * (csrc/sckm_peer.cu; the default whenever every rank can map every other; SCKM_PEER_ALLREDUCE=0 turns it off). */
+#define SCKM_ALLREDUCE_NONE 0
+#define SCKM_ALLREDUCE_NCCL 1
+#define SCKM_ALLREDUCE_PEER 2
+int  sckm_ctx_allreduce_path(const sckm_ctx* ctx);
 /* Last error text of this context (or of the failed sckm_ctx_create when ctx == NULL). */
 const char* sckm_last_error(const sckm_ctx* ctx);
 /* Force an assignment kernel (SCKM_ASSIGN_*); default AUTO. */

@@ -29,6 +29,7 @@ extern "C" {
     pub fn sckm_ctx_create_multi(n_dev: c_int, dev_ids: *const c_int, out: *mut *mut sckm_ctx) -> c_int;
     pub fn sckm_ctx_device_count(ctx: *const sckm_ctx) -> c_int;
     pub fn sckm_ctx_last_fit_times(ctx: *const sckm_ctx, out6: *mut f64) -> c_int;
+    pub fn sckm_ctx_allreduce_path(ctx: *const sckm_ctx) -> c_int;
     pub fn sckm_ctx_destroy(ctx: *mut sckm_ctx);
     pub fn sckm_last_error(ctx: *const sckm_ctx) -> *const c_char;
     pub fn sckm_ctx_set_assign_kernel(ctx: *mut sckm_ctx, which: c_int) -> c_int;

@@ -25,7 +25,7 @@ SYMBOLS = [
     "sckm_labels_download", "sckm_mindist_download", "sckm_predict", "sckm_kmeans_fit", "sckm_device_peaks",
     "sckm_contingency", "sckm_contingency_host", "sckm_knn", "sckm_radius_count", "sckm_radius_fill",
     "sckm_flush_l2", "sckm_ctx_create_multi", "sckm_ctx_device_count", "sckm_ctx_last_fit_times",
-    "sckm_kmeans_fit_shard",
+    "sckm_kmeans_fit_shard", "sckm_ctx_allreduce_path",
 ]
 
 
@@ -48,6 +48,7 @@ def _load():
     L.sckm_ctx_create_multi.argtypes = [i32, vp, C.POINTER(vp)]
     L.sckm_ctx_device_count.argtypes = [vp]; L.sckm_ctx_device_count.restype = i32
     L.sckm_ctx_last_fit_times.argtypes = [vp, vp]
+    L.sckm_ctx_allreduce_path.argtypes = [vp]; L.sckm_ctx_allreduce_path.restype = i32
     L.sckm_ctx_destroy.argtypes = [vp]; L.sckm_ctx_destroy.restype = None
     L.sckm_last_error.argtypes = [vp]; L.sckm_last_error.restype = C.c_char_p
     L.sckm_ctx_set_assign_kernel.argtypes = [vp, i32]
@@ -124,6 +125,10 @@ class Context:
 
     def device_count(self):
         return int(lib.sckm_ctx_device_count(self.h))
+
+    def allreduce_path(self):
+        """How the last Lloyd loop summed over the ranks: 'none' (one rank), 'nccl' or 'peer' (inside the finalize kernel)."""
+        return ("none", "nccl", "peer")[int(lib.sckm_ctx_allreduce_path(self.h))]
 
     def last_fit_times(self):
         out = np.zeros(6)

@@ -90,6 +90,7 @@ void sckm_ctx_destroy(sckm_ctx* ctx) {
     multi_destroy(ctx);                       // the per-device contexts of a multi-GPU context, if any
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    peer_destroy(ctx);
     nccl_destroy(ctx);
     ingest_destroy(ctx);
     if (ctx->stream) dev_pool_trim(ctx);
@@ -388,7 +389,8 @@ static int clustering_step(sckm_dataset* ds, uint64_t k, cudaEvent_t ev_a0 = nul
         if (ev_a1) SCKM_CUDA(ctx, cudaEventRecord(ev_a1, ctx->stream));
         SCKM_TRY(launch_update(ds, k, true));
     }
-    SCKM_TRY(nccl_allreduce_f64(ctx, ctx->d_packed, (size_t)k * ds->d + k + 1));
+    // multi-GPU: the sum over the ranks -- inside the finalize launch that follows when the loop runs the peer exchange
+    if (!ctx->peer_step) SCKM_TRY(nccl_allreduce_f64(ctx, ctx->d_packed, (size_t)k * ds->d + k + 1));
     ds->have_labels = true;
     return SCKM_OK;
 }
@@ -465,6 +467,9 @@ int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop,
         SCKM_CUDA(ctx, cudaMemcpyAsync(ctx->d_centroids, centroids_inout, kd * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
         ctx->cnorm_valid = false;
     }
+    bool peers = false;
+    SCKM_TRY(peer_prepare(ctx, kd + k + 1, &peers));  // multi-GPU: map the ranks' exchange buffers (first loop / larger k*d)
+    ctx->allreduce_path = ctx->nranks <= 1 ? SCKM_ALLREDUCE_NONE : peers ? SCKM_ALLREDUCE_PEER : SCKM_ALLREDUCE_NCCL;
     SCKM_TRY(launch_loop_init(ctx, max_iter, honor_stop));
     std::vector<cudaEvent_t> evs, evs_a;
     if (assign_ms_trace) {
@@ -498,9 +503,11 @@ int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop,
         for (uint64_t b = 0; b < nb && rc == SCKM_OK; b++) {
             it++;
             ctx->loop_it = (uint32_t)it;
+            if (peers) { peer_next(ctx); ctx->peer_step = true; }
             if (assign_ms_trace) rc = clustering_step(ds, k, evs_a[2 * (it - 1)], evs_a[2 * (it - 1) + 1]);
             else rc = clustering_step(ds, k);                                      // bbd.clustering(...)        kmeans.rs:296
             if (rc == SCKM_OK) rc = launch_finalize(ctx, k, ds->d, /*guarded=*/true);  // centroids = sums / size + stop rule  kmeans.rs:297-309
+            ctx->peer_step = false;
             if (rc == SCKM_OK && ms_trace && !whole && cudaEventRecord(evs[it], ctx->stream) != cudaSuccess) rc = fail(ctx, SCKM_ERR_CUDA, "cudaEventRecord failed");
         }
         ctx->loop_it = 0;
@@ -523,6 +530,7 @@ int lloyd_loop(sckm_dataset* ds, uint64_t k, uint64_t max_iter, bool honor_stop,
             cudaMemcpyAsync(inertia_trace, ctx->d_inertia_trace, (size_t)iters * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess) rc = SCKM_ERR_CUDA;
         if (cudaStreamSynchronize(ctx->stream) != cudaSuccess) rc = SCKM_ERR_CUDA;
         if (rc != SCKM_OK) rc = fail(ctx, SCKM_ERR_CUDA, "Lloyd loop download failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (rc == SCKM_OK && peers) rc = peer_check(ctx);
     } else {
         cudaStreamSynchronize(ctx->stream);
     }

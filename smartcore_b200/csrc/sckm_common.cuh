@@ -18,6 +18,7 @@ constexpr int kKppBlockRows = 1024;   // fixed summation unit of the kmeans++ D^
 inline size_t slot_pitch(size_t pk) { return (pk + 15) / 16 * 16; }
 
 struct MultiExt;    // sckm_multi.cu
+struct PeerXchg;    // sckm_peer.cu
 struct StagePool;   // pinned staging ring of the host<->device transfer engine (sckm_ingest.cu)
 
 // Device-resident state of the loop of KMeans::fit (kmeans.rs:294-310).  The stop rule `if distortion <= dist { break }`
@@ -29,6 +30,21 @@ struct LoopState {
     unsigned long long done_at;    // iteration (1-based) whose stop test fired; 0 = still running
     unsigned long long iters;      // clustering steps executed so far
     unsigned long long honor_stop; // 0: fixed number of steps (sckm_lloyd_iterate)
+};
+
+// By-value argument of reduce_partials_kernel and finalize_kernel: the one-shot all-reduce of the step's packed vector
+// over peer memory (sckm_peer.cu).  G == 0: nothing to exchange, the kernels use `packed` as they always did.
+// A cell is 16 bytes {lo32(value), tag, hi32(value), tag}: each 8-byte half travels atomically, so a reader that finds
+// both tags equal to this exchange's tag holds the value -- no separate flag, no fence between data and flag.
+struct PeerArgs {
+    uint4* const* recv;                  // [G] every rank's receive area, mapped into this device:
+                                         //     recv[r][(half * G + src) * cap + e] = element e of rank src's vector, sent to rank r
+    unsigned int* err;                   // local: set when a wait ran into its time limit
+    double* packed_out;                  // local d_packed: receives the all-reduced vector
+    unsigned long long cap;              // cells per (half, source rank)
+    uint32_t tag;                        // tag of this exchange (never 0, the value of fresh memory)
+    uint32_t half;                       // exchange number & 1
+    uint32_t G, rank;
 };
 
 }  // namespace sckm
@@ -86,6 +102,9 @@ struct sckm_ctx {
     size_t flush_bytes = 0;
     double* h_pinned = nullptr;      // small pinned scratch (>= 64 doubles)
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    sckm::PeerXchg* peer = nullptr;          // peer-memory exchange buffers of the fused all-reduce (multi-rank only)
+    int allreduce_path = 0;                  // SCKM_ALLREDUCE_* of the last Lloyd loop
+    bool peer_step = false;                  // the step being enqueued sums over the ranks inside reduce_partials / finalize
     sckm::MultiExt* multi = nullptr;         // per-device contexts of a multi-GPU context (sckm_ctx_create_multi)
     int ingest_max_threads = 0;              // cap on the staging threads of this context (0 = default)
     double fit_times[6] = {0, 0, 0, 0, 0, 0}; // last sckm_kmeans_fit: upload, kmeans++ + means, loop, download, total [s], devices
@@ -191,6 +210,14 @@ void nccl_destroy(sckm_ctx* ctx);
 int nccl_allreduce_f64(sckm_ctx* ctx, double* buf, size_t count);
 int nccl_allreduce_u64(sckm_ctx* ctx, unsigned long long* buf, size_t count);
 int nccl_allgather_f64(sckm_ctx* ctx, const double* send1, double* recv);  // 1 double per rank
+int nccl_allgather_bytes(sckm_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank);
+
+// ---- fused one-shot all-reduce over peer memory (sckm_peer.cu) ----
+int peer_prepare(sckm_ctx* ctx, size_t pk, bool* use);   // collective: map every rank's exchange buffer; *use = false: stay on NCCL
+void peer_next(sckm_ctx* ctx);                // start the next exchange (once per step, before its reduce launch)
+PeerArgs peer_args(const sckm_ctx* ctx);      // kernel argument of the reduce and finalize launches of the current exchange
+int peer_check(sckm_ctx* ctx);                // after a stream synchronisation: did every wait of the loop come through
+void peer_destroy(sckm_ctx* ctx);
 
 // ---- host <-> device transfers (sckm_ingest.cu): blocking, pageable memory goes through a threaded pinned ring ----
 int copy_to_device(sckm_ctx* ctx, void* dst_dev, const void* src_host, size_t bytes, bool sync_first = true);

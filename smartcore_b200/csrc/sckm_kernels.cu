@@ -733,6 +733,51 @@ __global__ void update_partial_kernel(const T* __restrict__ x, uint64_t n, uint3
     if (threadIdx.x == 0) part[pk - 1] = inertia;
 }
 
+// ---- one-shot all-reduce over peer memory inside reduce_partials_kernel / finalize_kernel (protocol: sckm_peer.cu) ----
+__device__ __forceinline__ unsigned long long global_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ void st_cell(uint4* cell, double v, uint32_t tag) {      // two 8-byte halves {data32, tag}
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((uint32_t)__double2loint(v)), "r"(tag),
+                 "r"((uint32_t)__double2hiint(v)), "r"(tag) : "memory");
+}
+__device__ __forceinline__ uint4 ld_cell(const uint4* cell) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(cell) : "memory");
+    return v;
+}
+// this rank's element e of the current exchange -> every rank's receive area
+__device__ __forceinline__ void peer_send(const PeerArgs& pa, size_t e, double v) {
+    const size_t off = ((size_t)pa.half * pa.G + pa.rank) * pa.cap + e;
+    for (uint32_t r = 0; r < pa.G; r++) st_cell(pa.recv[r] + off, v, pa.tag);
+}
+// element e of the all-reduced vector: the G received copies added in rank order (identical on every rank)
+__device__ __forceinline__ double peer_sum(const PeerArgs& pa, size_t e) {
+    const uint4* mine = pa.recv[pa.rank] + (size_t)pa.half * pa.G * pa.cap + e;
+    double s = 0.0;
+    for (uint32_t r0 = 0; r0 < pa.G; r0 += 8) {
+        uint4 v[8];
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++) if (r0 + i < pa.G) v[i] = ld_cell(mine + (size_t)(r0 + i) * pa.cap);
+#pragma unroll
+        for (uint32_t i = 0; i < 8; i++) {
+            if (r0 + i >= pa.G) break;
+            if (v[i].y != pa.tag || v[i].w != pa.tag) {                   // still in flight: wait for it (30 s: the rank is gone)
+                const unsigned long long t0 = global_ns();
+                do {
+                    __nanosleep(20);
+                    v[i] = ld_cell(mine + (size_t)(r0 + i) * pa.cap);
+                    if (global_ns() - t0 > 30000000000ull) { atomicExch(pa.err, 1u); break; }
+                } while (v[i].y != pa.tag || v[i].w != pa.tag);
+            }
+            s = __dadd_rn(s, __hiloint2double((int)v[i].z, (int)v[i].x));
+        }
+    }
+    return s;
+}
+
 // packed[e] = sum over the partial slots in a FIXED order (8 slot groups summed sequentially by 8 thread rows,
 // then the 8 group sums in order); the slots are zeroed for the next step.  blockDim = (32, 8); each thread owns
 // two adjacent elements (16-byte accesses; slot rows are 128-byte aligned).
@@ -740,7 +785,7 @@ template <int GROUPS>
 __global__ void __launch_bounds__(32 * GROUPS) reduce_partials_kernel(double* __restrict__ partials, uint32_t nslots, size_t pk,
                                                                      size_t pitch, double* __restrict__ packed,
                                                                      unsigned long long* __restrict__ nmarked,
-                                                                     const LoopState* __restrict__ loop_st, uint32_t loop_it) {
+                                                                     const LoopState* __restrict__ loop_st, uint32_t loop_it, const PeerArgs pa) {
     pdl_wait();
     if (loop_done(loop_st, loop_it)) return;
     __shared__ double2 sh[GROUPS][33];
@@ -777,8 +822,13 @@ __global__ void __launch_bounds__(32 * GROUPS) reduce_partials_kernel(double* __
         double2 t = make_double2(0.0, 0.0);
 #pragma unroll
         for (int i = 0; i < GROUPS; i++) { t.x = __dadd_rn(t.x, sh[i][threadIdx.x].x); t.y = __dadd_rn(t.y, sh[i][threadIdx.x].y); }
-        if (e < pk) packed[e] = t.x;
-        if (e + 1 < pk) packed[e + 1] = t.y;
+        if (pa.G != 0) {                          // multi-GPU loop: straight into every rank's receive area (sckm_peer.cu)
+            if (e < pk) peer_send(pa, e, t.x);
+            if (e + 1 < pk) peer_send(pa, e + 1, t.y);
+        } else {
+            if (e < pk) packed[e] = t.x;
+            if (e + 1 < pk) packed[e + 1] = t.y;
+        }
     }
 }
 
@@ -789,20 +839,31 @@ __global__ void __launch_bounds__(32 * GROUPS) reduce_partials_kernel(double* __
 // the write cannot hide work of the iteration that sets it; every kernel of a later iteration returns at once.
 // centered != 0: the packed sums are sums of (x - mu) (tile kernel, see sckm_dmma.cu): centroid = sum / count + mu.
 // The norms are always ||c - mu||^2 for the shift currently in `mu` (zeros when nothing is centred).
+// pa.G != 0 (multi-GPU loop): `packed` is not read; the kernel first sums the ranks' vectors over peer memory
+// (peer_sum: the cells reduce_partials_kernel of every rank sent here) and leaves the all-reduced vector in pa.packed_out.
 __global__ void finalize_kernel(const double* __restrict__ packed, uint32_t k, uint32_t d, int guarded, int centered,
                                 const double* __restrict__ mu, double* __restrict__ centroids, double* __restrict__ cnorm,
                                 long long* __restrict__ size, LoopState* __restrict__ loop_st, uint32_t loop_it,
-                                double* __restrict__ inertia_trace) {
+                                double* __restrict__ inertia_trace, const PeerArgs pa) {
     pdl_wait();
     if (loop_done(loop_st, loop_it)) return;
     const uint32_t c = blockIdx.x;
-    const double cnt = packed[(size_t)k * d + c];
-    if (threadIdx.x == 0) size[c] = (long long)cnt;
-    if (!guarded || cnt > 0.0)
-        for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) {
-            const double mean = __ddiv_rn(packed[(size_t)c * d + j], cnt);
+    const bool peers = pa.G != 0;
+    const double cnt = peers ? peer_sum(pa, (size_t)k * d + c) : packed[(size_t)k * d + c];
+    if (threadIdx.x == 0) {
+        size[c] = (long long)cnt;
+        if (peers) pa.packed_out[(size_t)k * d + c] = cnt;
+    }
+    for (uint32_t j = threadIdx.x; j < d; j += blockDim.x) {
+        double sum;
+        if (peers) { sum = peer_sum(pa, (size_t)c * d + j); pa.packed_out[(size_t)c * d + j] = sum; }
+        else if (!guarded || cnt > 0.0) sum = packed[(size_t)c * d + j];
+        else continue;
+        if (!guarded || cnt > 0.0) {
+            const double mean = __ddiv_rn(sum, cnt);
             centroids[(size_t)c * d + j] = centered ? __dadd_rn(mean, mu[j]) : mean;
         }
+    }
     __syncthreads();
     if (threadIdx.x == 0 && cnorm) {
         double s = 0.0;
@@ -810,7 +871,8 @@ __global__ void finalize_kernel(const double* __restrict__ packed, uint32_t k, u
         cnorm[c] = s;
     }
     if (loop_st != nullptr && c == 0 && threadIdx.x == 0) {
-        const double dist = packed[(size_t)k * d + k];
+        const double dist = peers ? peer_sum(pa, (size_t)k * d + k) : packed[(size_t)k * d + k];
+        if (peers) pa.packed_out[(size_t)k * d + k] = dist;
         if (inertia_trace) inertia_trace[loop_it - 1] = dist;
         loop_st->iters = loop_it;
         if (loop_st->honor_stop) {
@@ -1165,22 +1227,28 @@ int launch_update(sckm_dataset* ds, uint64_t k, bool with_inertia) {
 int launch_reduce_partials(sckm_ctx* ctx, uint32_t slots, size_t pk) {
     const size_t pitch = slot_pitch(pk);
     const unsigned blocks = (unsigned)((pitch / 2 + 31) / 32);
+    PeerArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    if (ctx->peer_step) pa = peer_args(ctx);           // multi-GPU loop: the vector goes to every rank's receive area instead
     // small payload, or many slots to walk: more slot groups per block so that enough loads are in flight
     if (blocks < (unsigned)ctx->num_sms || slots >= 256)
         SCKM_CUDA(ctx, launch_pdl(reduce_partials_kernel<32>, dim3(blocks), dim3(32, 32), 0, ctx->stream, ctx->d_partials, slots, pk, pitch,
-                                  ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx)));
+                                  ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx), pa));
     else
         SCKM_CUDA(ctx, launch_pdl(reduce_partials_kernel<8>, dim3(blocks), dim3(32, 8), 0, ctx->stream, ctx->d_partials, slots, pk, pitch,
-                                  ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx)));
+                                  ctx->d_packed, ctx->d_flags, SCKM_LOOP_ARGS(ctx), pa));
     LAUNCH_CHECK(ctx);
     return SCKM_OK;
 }
 
 int launch_finalize(sckm_ctx* ctx, uint64_t k, uint64_t d, bool guarded) {
     const unsigned threads = (unsigned)std::min<uint64_t>(256, (d + 31) / 32 * 32);
+    PeerArgs pa;
+    memset(&pa, 0, sizeof(pa));
+    if (ctx->peer_step) pa = peer_args(ctx);           // the ranks' vectors sit in this rank's receive area: sum them here
     SCKM_CUDA(ctx, launch_pdl(finalize_kernel, dim3((unsigned)k), dim3(threads), 0, ctx->stream, (const double*)ctx->d_packed, (uint32_t)k,
                               (uint32_t)d, guarded ? 1 : 0, ctx->packed_centered ? 1 : 0, (const double*)ctx->d_mu, ctx->d_centroids,
-                              ctx->d_cnorm, (long long*)ctx->d_size, SCKM_LOOP_ARGS(ctx), ctx->loop_it ? ctx->d_inertia_trace : (double*)nullptr));
+                              ctx->d_cnorm, (long long*)ctx->d_size, SCKM_LOOP_ARGS(ctx), ctx->loop_it ? ctx->d_inertia_trace : (double*)nullptr, pa));
     LAUNCH_CHECK(ctx);
     ctx->cnorm_valid = ctx->cnorm_valid || !guarded;   // a guarded update keeps stale norms of empty clusters stale
     return SCKM_OK;

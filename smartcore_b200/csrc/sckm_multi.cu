@@ -204,6 +204,13 @@ int sckm_ctx_create_multi(int n_dev, const int* dev_ids, sckm_ctx** out) {
     return SCKM_OK;
 }
 
+int sckm_ctx_allreduce_path(const sckm_ctx* ctx) {
+    if (!ctx) return SCKM_ALLREDUCE_NONE;
+    // a multi-GPU context reports what its devices did in the last sharded fit (an unsharded one ran on the context itself)
+    if (ctx->multi && ctx->fit_times[5] > 1.0) return ctx->multi->dev[0]->allreduce_path;
+    return ctx->allreduce_path;
+}
+
 int sckm_ctx_device_count(const sckm_ctx* ctx) {
     if (!ctx) return 0;
     return ctx->multi ? (int)ctx->multi->dev.size() : 1;

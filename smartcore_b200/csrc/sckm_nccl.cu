@@ -16,7 +16,7 @@ namespace sckm {
 typedef struct { char internal[128]; } ncclUniqueId_t;
 typedef int ncclResult_t_;
 enum { ncclSum_ = 0 };
-enum { ncclUint64_ = 5, ncclFloat64_ = 8 };
+enum { ncclUint8_ = 1, ncclUint64_ = 5, ncclFloat64_ = 8 };
 
 struct NcclApi {
     void* handle = nullptr;
@@ -125,6 +125,13 @@ int nccl_allreduce_u64(sckm_ctx* ctx, unsigned long long* buf, size_t count) {
 int nccl_allgather_f64(sckm_ctx* ctx, const double* send1, double* recv) {
     if (ctx->nranks <= 1) return SCKM_OK;
     SCKM_NCCL(ctx, api()->AllGather(send1, recv, 1, ncclFloat64_, ctx->nccl_comm, ctx->stream));
+    ctx->launches++;
+    return SCKM_OK;
+}
+
+int nccl_allgather_bytes(sckm_ctx* ctx, const void* send, void* recv, size_t bytes_per_rank) {
+    if (ctx->nranks <= 1) return SCKM_OK;
+    SCKM_NCCL(ctx, api()->AllGather(send, recv, bytes_per_rank, ncclUint8_, ctx->nccl_comm, ctx->stream));
     ctx->launches++;
     return SCKM_OK;
 }

@@ -28,6 +28,17 @@ def main():
     seeds = ds.kmeanspp(k, first, u)
     cent, size = ds.init_centroids(k)
     fit = ds.lloyd_fit(cent, 50)
+    path = ctx.allreduce_path()                            # 'peer': the sum over the ranks ran inside the finalize kernel
+    # the same loop with the all-reduce through NCCL; every rank's result of the peer path gathered for a bitwise comparison
+    os.environ["SCKM_PEER_ALLREDUCE"] = "0"
+    fit_nccl = ds.lloyd_fit(cent, 50)
+    path_nccl = ctx.allreduce_path()
+    del os.environ["SCKM_PEER_ALLREDUCE"]
+    mine = torch.from_numpy(np.concatenate([fit["centroids"].ravel(), [fit["distortion"]]])).cuda()
+    everyone = [torch.empty_like(mine) for _ in range(world)]
+    tdist.all_gather(everyone, mine)
+    ranks_agree = all(torch.equal(e.view(torch.int64), mine.view(torch.int64)) for e in everyone)
+    fit = ds.lloyd_fit(cent, 50)                           # leaves the peer path's labels on the dataset
     truth = (np.arange(n) % k).astype(np.uint32)           # blobs_host: row i belongs to centre i % k
     table = ds.contingency(truth[lo:hi], k, k)             # summed over ranks inside the library (NCCL, u64)
     labels = torch.zeros(n, dtype=torch.int64, device="cuda")
@@ -46,7 +57,15 @@ def main():
               and fit["size"].tolist() == fit1["size"].tolist()
               and np.array_equal(labels.cpu().numpy(), ds1.labels().astype(np.int64))
               and np.array_equal(table, ds1.contingency(truth, k, k)) and int(table.sum()) == n)
-        print("MULTIRANK_RESULT " + json.dumps({"ok": bool(ok), "iters": int(fit["iters"]), "world": world}))
+        # NCCL vs peer: same iteration count; two ranks add the same two numbers (bit-equal), more ranks may differ in order
+        ok_paths = (path_nccl == "nccl" and path in ("peer", "nccl") and ranks_agree and fit_nccl["iters"] == fit["iters"]
+                    and fit_nccl["size"].tolist() == fit["size"].tolist()
+                    and np.allclose(fit_nccl["centroids"], fit["centroids"], rtol=1e-12, atol=0)
+                    and (world != 2 or np.array_equal(fit_nccl["centroids"], fit["centroids"])))
+        if os.environ.get("SCKM_EXPECT_PEER", "1") == "1" and torch.cuda.can_device_access_peer(0, 1):
+            ok_paths = ok_paths and path == "peer"
+        print("MULTIRANK_RESULT " + json.dumps({"ok": bool(ok and ok_paths), "fit_ok": bool(ok), "paths_ok": bool(ok_paths), "path": path,
+                                                "ranks_agree": bool(ranks_agree), "iters": int(fit["iters"]), "world": world}))
     ds.close(); ctx.close()
     tdist.destroy_process_group()
 

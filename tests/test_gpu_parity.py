@@ -583,6 +583,8 @@ def test_multi_context_fit_and_predict_equal_single_device(ctx, O, n, d, k, dtyp
     for cm in (False, True):
         many = fit_gpu(mc, x, k, 5, max_iter=40, column_major=cm)
         assert mc.last_fit_times()["devices"] == (ndev if sharded else 1)
+        if sharded and torch.cuda.can_device_access_peer(0, 1):
+            assert mc.allreduce_path() == "peer"                    # the sum over the devices ran inside the finalize kernel
         assert many["iters"] == one["iters"] and many["size"].tolist() == one["size"].tolist()
         assert np.array_equal(many["labels"], one["labels"])
         rt = RTOL if dtype == np.float64 else 1e-4
@@ -590,6 +592,14 @@ def test_multi_context_fit_and_predict_equal_single_device(ctx, O, n, d, k, dtyp
         assert abs(many["distortion"] - one["distortion"]) <= rt * one["distortion"]
     if n <= 60_000:
         check_fit(O, x, k, 5, fit_gpu(mc, x, k, 5))
+    if sharded:                                                      # the same fit with the all-reduce through NCCL
+        monkeypatch.setenv("SCKM_PEER_ALLREDUCE", "0")
+        nccl = fit_gpu(mc, x, k, 5, max_iter=40)
+        monkeypatch.delenv("SCKM_PEER_ALLREDUCE")
+        assert mc.allreduce_path() == "nccl" and nccl["iters"] == many["iters"] and np.array_equal(nccl["labels"], many["labels"])
+        np.testing.assert_allclose(nccl["centroids"], many["centroids"], rtol=1e-12, atol=0)
+        if ndev == 2:
+            assert np.array_equal(nccl["centroids"], many["centroids"])
     # predict: no collective, labels bit-equal to the single-device direct form
     assert np.array_equal(mc.predict(x, one["centroids"]), ctx.predict(x, one["centroids"]))
     assert np.array_equal(mc.predict(x, one["centroids"], column_major=True, width=4), ctx.predict(x, one["centroids"], width=4))

@@ -94,6 +94,21 @@ def main():
     assert np.array_equal(g.download_rows(10, 20), cabi.blobs_host(10, 20, 16, 8, 5))
     g.close()
     ctx.close()
+    # >= 2 GPUs: the sharded fit of a multi-GPU context -- its per-step sum over the devices runs inside the reduce /
+    # finalize kernels over peer memory (csrc/sckm_peer.cu)
+    os.environ["SCKM_MULTI_MIN_ROWS"] = "1"
+    mc = sc.Context(devices="all")
+    if mc.device_count() >= 2:
+        xm = (rng.normal(size=(6000, 16)) + 4.0 * rng.integers(0, 6, size=(6000, 1))).astype(np.float64)
+        first, u = cluster.kmeanspp_draws(11, 6000, 6)
+        one = sc.Context(0)
+        a = one.kmeans_fit(xm, 6, 30, first, u)
+        b = mc.kmeans_fit(xm, 6, 30, first, u)
+        assert mc.allreduce_path() in ("peer", "nccl") and b["iters"] == a["iters"] and np.array_equal(b["labels"], a["labels"])
+        assert np.allclose(b["centroids"], a["centroids"], rtol=1e-9, atol=1e-12)
+        one.close()
+        print("ok multi-GPU fit over %d devices, all-reduce path: %s" % (mc.device_count(), mc.allreduce_path()), flush=True)
+    mc.close()
     print("sanitizer smoke done")
 
 

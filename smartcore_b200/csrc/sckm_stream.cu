@@ -32,7 +32,10 @@ namespace sckm {
                         __FILE__, __LINE__);                                                       \
     } while (0)
 
-constexpr int STREAM_WARPS = 8;
+#ifndef SCKM_STREAM_WARPS
+#define SCKM_STREAM_WARPS 8
+#endif
+constexpr int STREAM_WARPS = SCKM_STREAM_WARPS;
 // Update scheme of the registers-direct path.  1 (default): lanes regroup as (cluster, feature slice) and add the rows of
 // THEIR cluster with plain DADDs -- a 32-row batch costs ~max_c(rows of c) x (features per lane) adds instead of the
 // 8*KT*NTU DMMAs of the one-hot GEMM (C2: ~32 DADD issue slots instead of 16 DMMAs = 256 clocks of the same FP64
@@ -40,6 +43,18 @@ constexpr int STREAM_WARPS = 8;
 // 0: the one-hot GEMM (kept for A/B builds, tools/build_variant.sh, and used by the bulk-copy ring variant).
 #ifndef SCKM_STREAM_GROUPED
 #define SCKM_STREAM_GROUPED 1
+#endif
+#ifdef SCKM_STREAM_TRACE
+// Diagnostic build only (tools/build_variant.sh trace "-DSCKM_STREAM_TRACE"): per-CTA timeline of the last launch --
+// [cta][0] entry, [1] after the dependency wait, [2] loop start, [3] loop end, [5] after the CTA barrier, [4] exit (ns, globaltimer)
+__device__ unsigned long long g_stream_trace[1024 * 8];
+__device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define STREAM_TRACE(slot) do { if (threadIdx.x == 0 && blockIdx.x < 1024) g_stream_trace[blockIdx.x * 8 + (slot)] = gtimer(); } while (0)
+#else
+#define STREAM_TRACE(slot) do { } while (0)
+#endif
+#ifndef SCKM_STREAM_UNROLL
+#define SCKM_STREAM_UNROLL 1
 #endif
 constexpr int STREAM_MAX_K = 15;
 constexpr double STREAM_TIE_REL = 1e-10;
@@ -75,6 +90,28 @@ template <> struct VecLoad<float, 4> {
         const float4 v = *reinterpret_cast<const float4*>(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
 };
 
+// 32-byte vectors: one LDG.256 per lane (sm_100 and later).  A warp request then covers FULL 128-byte lines (8 rows x 4
+// lanes x 32 B for the A fragments of a 16-double row) instead of half lines, which halves the L1 wavefronts of the row
+// loads -- the data stage of the L1 is the busiest unit of this kernel (ncu: 45 % of its peak, everything else < 35 %).
+template <> struct VecLoad<double, 4> {
+    static __device__ __forceinline__ void ld(const double* p, double (&o)[4]) {
+        asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p)); }
+    static __device__ __forceinline__ void lds(const double* p, double (&o)[4]) {
+        const double2 a = *reinterpret_cast<const double2*>(p), b = *reinterpret_cast<const double2*>(p + 2);
+        o[0] = a.x; o[1] = a.y; o[2] = b.x; o[3] = b.y; }
+};
+template <> struct VecLoad<float, 8> {
+    static __device__ __forceinline__ void ld(const float* p, double (&o)[8]) {
+        float f[8];
+        asm volatile("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]), "=f"(f[4]), "=f"(f[5]), "=f"(f[6]), "=f"(f[7]) : "l"(p));
+#pragma unroll
+        for (int i = 0; i < 8; i++) o[i] = f[i]; }
+    static __device__ __forceinline__ void lds(const float* p, double (&o)[8]) {
+        const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+        o[0] = a.x; o[1] = a.y; o[2] = a.z; o[3] = a.w; o[4] = b.x; o[5] = b.y; o[6] = b.z; o[7] = b.w; }
+};
+
 // ---- TMA ring (1-D bulk copies): PTX wrappers ----
 __device__ __forceinline__ uint32_t s_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void s_mbar_init(uint64_t* bar, int count) {
@@ -108,8 +145,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
                      const double* __restrict__ cnorm, const double* __restrict__ mu, uint32_t k, uint32_t* __restrict__ labels,
                      double* __restrict__ partials, size_t pk, unsigned long long* __restrict__ nmarked, uint32_t pf_ahead,
                      const LoopState* __restrict__ loop_st, uint32_t loop_it) {
-    pdl_wait();                                          // (launched with launch_pdl: the previous step's finalize may still be draining)
-    if (loop_done(loop_st, loop_it)) return;             // the fit's stop rule already fired (kmeans.rs:305)
+    STREAM_TRACE(0);
     constexpr int NTU = KS / 2 > 0 ? KS / 2 : 1;         // feature n-tiles of the update GEMM (8 features each)
     constexpr int VU = VW < NTU ? VW : NTU;              // features per update load
     constexpr bool GROUPED = SCKM_STREAM_GROUPED != 0 && STAGES == 0;
@@ -120,54 +156,8 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
     extern __shared__ __align__(16) double smem_s[];     // [warps][k*d] sums | [warps][16] counts | [warps] inertia
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int g = lane >> 2, t = lane & 3;
-    // max_j ||c_j - mu||^2 over the <= 15 centroids: every thread reads them itself (L1 broadcasts) -- no CTA barrier in
-    // the prologue of a kernel whose whole run is ~40 us at config C2
-    double cmax = 0.0;
-    for (uint32_t j = 0; j < k; j++) cmax = fmax(cmax, __ldg(cnorm + j));
-    const double tie_half = 0.5 * STREAM_TIE_REL;
     constexpr bool TMA = STAGES > 0;
     static_assert(!TMA || DFULL, "the bulk-copy ring needs d == 4*KS");
-    __shared__ __align__(8) uint64_t full_bar[TMA ? STREAM_WARPS : 1][TMA ? STAGES : 1];
-
-    // Both operands of the scoring GEMM are centred on the fit's shift mu (see sckm_dmma.cu / launch_cnorm): rows become
-    // x - mu as they arrive, the centroid fragments hold c - mu, cnorm holds ||c - mu||^2, so the cancellation error of
-    // ||x||^2 - 2 x.c + ||c||^2 follows the spread of the data, not its distance from the origin.  The update GEMM reads
-    // the rows again, uncentred: the sums this kernel stores are plain sums of x.
-    double mu_f[KS];
-#pragma unroll
-    for (int ks = 0; ks < KS; ks++) { const uint32_t col = kcol<VW>(t, ks); mu_f[ks] = col < d ? mu[col] : 0.0; }
-    // centroid B fragments and -||c - mu||^2/2, resident in registers for the whole launch
-    double bc[KT][KS], hc[KT][2];
-#pragma unroll
-    for (int nt = 0; nt < KT; nt++) {
-        const uint32_t c = nt * 8 + g;
-#pragma unroll
-        for (int ks = 0; ks < KS; ks++) {
-            const uint32_t col = kcol<VW>(t, ks);
-            bc[nt][ks] = (c < k && col < d) ? centroids[(size_t)c * d + col] - mu_f[ks] : 0.0;
-        }
-#pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const uint32_t ce = nt * 8 + 2 * t + e;
-            hc[nt][e] = ce < k ? -0.5 * cnorm[ce] : -INFINITY;
-        }
-    }
-    double cu[KT][NTU][2];                               // per-cluster sums: cluster ct*8+g, feature ucol(2t+e, nt)
-#pragma unroll
-    for (int ct = 0; ct < KT; ct++)
-#pragma unroll
-        for (int nt = 0; nt < NTU; nt++) { cu[ct][nt][0] = 0.0; cu[ct][nt][1] = 0.0; }
-    uint32_t cnt[KT];
-#pragma unroll
-    for (int ct = 0; ct < KT; ct++) cnt[ct] = 0;
-    // grouped update: this lane adds features [fs*FPL, fs*FPL + FPL) of the rows assigned to cluster cq
-    const uint32_t cq = (uint32_t)lane / LPC, fs = (uint32_t)lane % LPC;
-    double su[GROUPED ? FPL : 1];
-#pragma unroll
-    for (int j = 0; j < (GROUPED ? FPL : 1); j++) su[j] = 0.0;
-    uint32_t cnt_g = 0;
-    double inertia = 0.0;                                // this lane's share (rows whose winning score it holds)
-
     const uint64_t nbatches = (n + 31) / 32;
     const uint64_t wglobal = (uint64_t)blockIdx.x * STREAM_WARPS + warp;
     const uint64_t nwarps = (uint64_t)gridDim.x * STREAM_WARPS;
@@ -193,7 +183,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
                     if (have) VecLoad<TX, VW>::ld(base + (size_t)mt * 8 * d + i * 4 * VW, v);
                 }
 #pragma unroll
-                for (int e = 0; e < VW; e++) a[mt][i * VW + e] = have ? v[e] - mu_f[i * VW + e] : 0.0;
+                for (int e = 0; e < VW; e++) a[mt][i * VW + e] = have ? v[e] : 0.0;   // raw: batch() subtracts mu when it picks them up
             }
         }
     };
@@ -210,6 +200,65 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         if (DFULL && row0 + 32 <= n) load_rows(row0, std::true_type{});
         else load_rows(row0, std::false_type{});
     };
+    // X is an input of the whole fit, not a product of the kernel before this one on the stream: the first batch (and the
+    // L2 prefetches behind it) go out BEFORE the dependency wait and before the dependent loads of the prologue (stop
+    // flag, norms, shift, centroid fragments: three round trips that cost 3 us of a 35 us kernel when they came first)
+    if (!TMA && wglobal < nbatches) {
+        load_any(wglobal * 32);
+        for (uint32_t i = 1; i < pf_ahead; i++) l2_prefetch_batch(wglobal + (uint64_t)i * nwarps);
+    }
+    pdl_wait();                                          // (launched with launch_pdl: the previous step's finalize may still be draining)
+    STREAM_TRACE(1);
+    // the fit's stop rule may already have fired (kmeans.rs:305): the flag is read here and tested after the loads of the
+    // prologue have been issued, so that the whole prologue is one memory round trip, not one per dependent stage
+    const bool stop_fired = loop_done(loop_st, loop_it);
+    // max_j ||c_j - mu||^2 over the <= 15 centroids: every thread reads them itself (L1 broadcasts) -- no CTA barrier in
+    // the prologue of a kernel whose whole run is ~40 us at config C2
+    double cmax = 0.0;
+    for (uint32_t j = 0; j < k; j++) cmax = fmax(cmax, __ldg(cnorm + j));
+    const double tie_half = 0.5 * STREAM_TIE_REL;
+    __shared__ __align__(8) uint64_t full_bar[TMA ? STREAM_WARPS : 1][TMA ? STAGES : 1];
+
+    // Both operands of the scoring GEMM are centred on the fit's shift mu (see sckm_dmma.cu / launch_cnorm): rows become
+    // x - mu as they arrive, the centroid fragments hold c - mu, cnorm holds ||c - mu||^2, so the cancellation error of
+    // ||x||^2 - 2 x.c + ||c||^2 follows the spread of the data, not its distance from the origin.  The update GEMM reads
+    // the rows again, uncentred: the sums this kernel stores are plain sums of x.
+    double mu_f[KS];
+#pragma unroll
+    for (int ks = 0; ks < KS; ks++) { const uint32_t col = kcol<VW>(t, ks); mu_f[ks] = col < d ? mu[col] : 0.0; }
+    // centroid B fragments and -||c - mu||^2/2, resident in registers for the whole launch
+    double bc[KT][KS], hc[KT][2];
+#pragma unroll
+    for (int nt = 0; nt < KT; nt++) {
+        const uint32_t c = nt * 8 + g;
+#pragma unroll
+        for (int ks = 0; ks < KS; ks++) {
+            const uint32_t col = kcol<VW>(t, ks);
+            bc[nt][ks] = (c < k && col < d) ? centroids[(size_t)c * d + col] - mu_f[ks] : 0.0;
+        }
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const uint32_t ce = nt * 8 + 2 * t + e;
+            hc[nt][e] = ce < k ? -0.5 * cnorm[ce] : -INFINITY;
+        }
+    }
+    if (stop_fired) return;
+    double cu[KT][NTU][2];                               // per-cluster sums: cluster ct*8+g, feature ucol(2t+e, nt)
+#pragma unroll
+    for (int ct = 0; ct < KT; ct++)
+#pragma unroll
+        for (int nt = 0; nt < NTU; nt++) { cu[ct][nt][0] = 0.0; cu[ct][nt][1] = 0.0; }
+    uint32_t cnt[KT];
+#pragma unroll
+    for (int ct = 0; ct < KT; ct++) cnt[ct] = 0;
+    // grouped update: this lane adds features [fs*FPL, fs*FPL + FPL) of the rows assigned to cluster cq
+    const uint32_t cq = (uint32_t)lane / LPC, fs = (uint32_t)lane % LPC;
+    double su[GROUPED ? FPL : 1];
+#pragma unroll
+    for (int j = 0; j < (GROUPED ? FPL : 1); j++) su[j] = 0.0;
+    uint32_t cnt_g = 0;
+    double inertia = 0.0;                                // this lane's share (rows whose winning score it holds)
+
     // the same fragments out of a ring buffer (dense [32][d] image of the batch)
     auto load_rows_smem = [&](const TX* stage, uint64_t row0, auto full_tag) {
         constexpr bool FULL = decltype(full_tag)::value;
@@ -258,7 +307,13 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         const uint64_t row0 = b * 32;
         const int stage = TMA ? (int)(it % (STAGES > 0 ? STAGES : 1)) : 0;
         const TX* stage_rows = TMA ? ring_w + (size_t)stage * 32 * d : nullptr;
-        // (ring mode: the A fragments of this batch were read out of its ring buffer at the end of the previous turn)
+        // (ring mode: the A fragments of this batch were read out of its ring buffer, centred, at the end of the previous turn)
+        if (!TMA) {
+#pragma unroll
+            for (int mt = 0; mt < 4; mt++)
+#pragma unroll
+                for (int ks = 0; ks < KS; ks++) a[mt][ks] -= mu_f[ks];     // (rows past the end become -mu: their scores are never used)
+        }
         // ---- scores x.c - ||c||^2/2 on the FP64 tensor path ----
         double acc[4][KT][2];
 #pragma unroll
@@ -376,19 +431,31 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
             cnt_g += __popc(mine);
             const int rounds = __reduce_max_sync(0xffffffffu, __popc(mine));
             const TX* gb = x + row0 * d + fs * FPL;
-            for (int r = 0; r < rounds; r++) {
-                const bool act = mine != 0u;
-                const int row = act ? __ffs(mine) - 1 : 0;
-                mine &= mine - 1u;
+            // UR rounds per turn: their row loads are all issued before the first add, so a turn costs ONE L1 round trip
+            // instead of UR dependent ones (ncu, one round per turn: 31 % of the kernel's stall samples sat on the add
+            // that waits for its load).  Lanes that have run out of rows add 0.0.
+            constexpr int UR = SCKM_STREAM_UNROLL;
+            for (int r = 0; r < rounds; r += UR) {
+                double v[UR][GROUPED ? FPL : 1];
 #pragma unroll
-                for (int j = 0; j < FPL / VG; j++) {
-                    double v[VG];
+                for (int u = 0; u < UR; u++) {
+                    const bool act = mine != 0u;
+                    const int row = act ? __ffs(mine) - 1 : 0;
+                    mine &= mine - 1u;
 #pragma unroll
-                    for (int e = 0; e < VG; e++) v[e] = 0.0;
-                    if (act && (DFULL || fs * FPL + j * VG < d)) VecLoad<TX, VG>::ld(gb + (size_t)row * d + j * VG, v);
+                    for (int j = 0; j < FPL / VG; j++) {
+                        double w[VG];
 #pragma unroll
-                    for (int e = 0; e < VG; e++) su[GROUPED ? j * VG + e : 0] = __dadd_rn(su[GROUPED ? j * VG + e : 0], v[e]);
+                        for (int e = 0; e < VG; e++) w[e] = 0.0;
+                        if (act && (DFULL || fs * FPL + j * VG < d)) VecLoad<TX, VG>::ld(gb + (size_t)row * d + j * VG, w);
+#pragma unroll
+                        for (int e = 0; e < VG; e++) v[u][GROUPED ? j * VG + e : 0] = w[e];
+                    }
                 }
+#pragma unroll
+                for (int u = 0; u < UR; u++)
+#pragma unroll
+                    for (int e = 0; e < (GROUPED ? FPL : 1); e++) su[e] = __dadd_rn(su[e], v[u][e]);
             }
         } else {
         // ---- update: sums[cluster][feature] += onehot(label)^T . X as DMMAs accumulating in registers.
@@ -455,16 +522,16 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
             if (wglobal * 32 + 32 <= n) load_rows_smem(ring_w, wglobal * 32, std::true_type{});
             else load_rows_smem(ring_w, wglobal * 32, std::false_type{});
         }
-    } else if (wglobal < nbatches) {
-        load_any(wglobal * 32);
-        for (uint32_t a = 1; a < pf_ahead; a++) l2_prefetch_batch(wglobal + (uint64_t)a * nwarps);
     }
     uint32_t it = 0;
+    STREAM_TRACE(2);
     for (uint64_t b = wglobal; b < nbatches; b += nwarps, it++) {
         if (DFULL && b * 32 + 32 <= n) batch(b, it, std::true_type{});
         else batch(b, it, std::false_type{});
     }
+    STREAM_TRACE(3);
     __syncthreads();                                      // the staging tiles are reused by the combine below
+    STREAM_TRACE(5);
     // ---- per-warp results -> shared memory, CTA combine in warp order, store this CTA's partial slot ----
     const uint32_t kd = k * d;
     double* s_sum = smem_s + (size_t)warp * kd;
@@ -519,7 +586,14 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         for (int w = 0; w < STREAM_WARPS; w++) tsum = __dadd_rn(tsum, s_in[w]);
         part[pk - 1] = tsum;
     }
+    STREAM_TRACE(4);
 }
+
+#ifdef SCKM_STREAM_TRACE
+extern "C" int sckm_debug_stream_trace(unsigned long long* out, int n_ctas) {
+    return (int)cudaMemcpyFromSymbol(out, g_stream_trace, (size_t)n_ctas * 8 * sizeof(unsigned long long));
+}
+#endif
 
 bool stream_supported(const sckm_dataset* ds, uint64_t k) {
     return k >= 1 && k <= STREAM_MAX_K && ds->d >= 1 && ds->d <= 32 && ds->n < 0xFFFFFFFFull;
@@ -575,6 +649,9 @@ static int launch_stream_t(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* gr
 template <int KS, int KT, typename TX>
 static int launch_stream_vw(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* grid_out) {
     constexpr int VMAX = (16 / sizeof(TX)) < KS ? (16 / sizeof(TX)) : KS;     // widest 16-byte vector that fits KS
+    constexpr int V32 = 32 / sizeof(TX);                                       // 32-byte vectors (LDG.256) when they fit
+    if (V32 <= KS && ds->d % V32 == 0 && !getenv("SCKM_STREAM_NO256"))
+        return launch_stream_t<KS, KT, (V32 <= KS ? V32 : VMAX), TX>(ds, k, pk, grid_out);
     if (ds->d % VMAX == 0) return launch_stream_t<KS, KT, VMAX, TX>(ds, k, pk, grid_out);
     if (VMAX > 2 && ds->d % 2 == 0) return launch_stream_t<KS, KT, 2, TX>(ds, k, pk, grid_out);
     return launch_stream_t<KS, KT, 1, TX>(ds, k, pk, grid_out);

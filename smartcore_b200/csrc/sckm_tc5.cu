@@ -26,6 +26,7 @@
 // mbarrier rings: x_full/x_ready/x_empty (2 stages), c_full/c_empty (2 stages), t_full/t_empty (2 TMEM stages).
 #include "sckm_common.cuh"
 #include "sckm_tile.cuh"
+#include "sckm_umma.cuh"
 #include <cuda.h>
 #include <cfloat>
 #include <algorithm>
@@ -44,6 +45,8 @@ namespace sckm {
 
 int launch_refine_rows(sckm_dataset* ds, uint64_t k, size_t pk, unsigned grid_ctas);   // sckm_dmma.cu
 int launch_cnorm(sckm_ctx* ctx, uint64_t k, uint64_t d, bool center);                  // sckm_dmma.cu
+bool tc5h_supported(const sckm_dataset* ds, uint64_t k);                               // sckm_tc5h.cu
+int launch_tc5h(sckm_dataset* ds, uint64_t k, size_t pk, const float* x32);            // sckm_tc5h.cu
 
 constexpr int TC_BM = 128;               // rows per MMA tile (TMEM lanes)
 constexpr int TC_EPI_WARPS = 8;
@@ -51,44 +54,6 @@ constexpr int TC_THREADS = 11 * 32;      // warps: 0 X-producer, 1 MMA, 2..9 epi
 constexpr uint32_t TC_ATOM_FLOATS = TC_BM * 32;        // one 128-row x 128-byte swizzle atom of f32
 constexpr double TC_TIE_REL = 2e-5;      // >= 10x the 3xTF32 + FP32-accumulate error bound (bench/tc5_probe.cu: 1e-6)
 
-// ---- PTX wrappers -----------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    asm volatile("{\n .reg .pred p;\n WAIT_%=:\n mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n @p bra DONE_%=;\n bra WAIT_%=;\n DONE_%=:\n }"
-                 ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
-}
-// K-major SWIZZLE_128B operand descriptor (cute::UMMA::SmemDescriptor): start>>4 | LBO=1 | SBO=1024 B | version 1 | layout 2
-__device__ __forceinline__ uint64_t umma_desc_sw128(const void* smem) {
-    return (uint64_t)((smem_u32(smem) >> 4) & 0x3FFF) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
-}
-__device__ __forceinline__ void umma_tf32(uint32_t tmem_c, uint64_t da, uint64_t db, uint32_t idesc, uint32_t accumulate) {
-    asm volatile("{\n .reg .pred p;\n setp.ne.b32 p, %4, 0;\n tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n }"
-                 ::"r"(tmem_c), "l"(da), "l"(db), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tmem_ld32(uint32_t addr, uint32_t (&v)[32]) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-                 : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]),
-                   "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]),
-                   "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]),
-                   "=r"(v[30]), "=r"(v[31]) : "r"(addr));
-}
 
 // NK: 128-byte swizzle atoms along K (d <= 32*NK); TILES: 128-row tiles per super-tile; BN: centroids per block.
 // The 8 epilogue warps cover TILES tiles x 4 TMEM lane quadrants x CP column parts (CP = 2 / TILES).
@@ -462,22 +427,6 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
     if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(TMEM_COLS));
 }
 
-// ---- host side --------------------------------------------------------------------------------------------------
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-static EncodeTiledFn encode_fn() {
-    // (function-local static: initialised once, thread-safe -- a multi-GPU context calls this from one thread per device)
-    static const EncodeTiledFn fn = []() -> EncodeTiledFn {
-        void* p = nullptr; cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
-            return (EncodeTiledFn)p;
-        cudaGetLastError();
-        return nullptr;
-    }();
-    return fn;
-}
 
 static int make_map(sckm_ctx* ctx, CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     EncodeTiledFn enc = encode_fn();
@@ -554,7 +503,8 @@ int launch_assign_tc5(sckm_dataset* ds, uint64_t k) {
         x32 = ds->x32;
     }
     int rc;
-    if (ds->d <= 32) rc = ds->dtype == SCKM_F64 ? launch_tc5_t<1, 2, 128, double>(ds, k, pk, x32) : launch_tc5_t<1, 2, 128, float>(ds, k, pk, x32);
+    if (tc5h_supported(ds, k)) rc = launch_tc5h(ds, k, pk, x32);      // d <= 32: the 3xFP16 form (sckm_tc5h.cu); SCKM_TC5_TF32=1 keeps this file's
+    else if (ds->d <= 32) rc = ds->dtype == SCKM_F64 ? launch_tc5_t<1, 2, 128, double>(ds, k, pk, x32) : launch_tc5_t<1, 2, 128, float>(ds, k, pk, x32);
     else             rc = ds->dtype == SCKM_F64 ? launch_tc5_t<2, 1, 64, double>(ds, k, pk, x32) : launch_tc5_t<2, 1, 64, float>(ds, k, pk, x32);
     SCKM_TRY(rc);
     return launch_refine_rows(ds, k, pk, grid);   // 8 warps per CTA: the same partial slots as the epilogue warps

@@ -51,8 +51,9 @@ namespace sckm {
 constexpr int H_BM = 128;                // rows per MMA tile (TMEM lanes)
 constexpr int H_BN = 128;                // centroids per block
 constexpr int H_TILES = 2;               // tiles per super-tile
-constexpr int H_EPI_WARPS = 8;
-constexpr int H_THREADS = 11 * 32;       // warps: 0 X-producer, 1 MMA, 2..9 epilogue, 10 C-producer
+constexpr int H_SLOT_WARPS = 8;          // partial slots per CTA: one per (tile, TMEM lane quadrant)
+// EW epilogue warps (8 or 16): warps 0 X-producer, 1 MMA, 2..EW+1 epilogue, EW+2 C-producer.  With 16, a row's 128 columns
+// of a block are shared by two threads (column parts) that merge their top-2 at the end of the super-tile.
 constexpr double H_TIE_REL = 2e-5;       // as K2: >= 10x the error of (22-bit operands, FP32 accumulation)
 constexpr int H_XMAX_EXP = 13;           // scaled operands lie below 2^(13+1) (rows) / 2^13 (centroids)
 constexpr int H_ROW_FLOOR = 20;          // a row is never scaled as if it were smaller than 2^-20 of the centroids
@@ -64,9 +65,28 @@ struct alignas(1024) HSmem {             // dynamic shared memory image (base al
     __nv_bfloat16 xe[2][H_TILES][H_BM * 16];       // rank-one A operand: row r = {p, p, p, 0, ...}, p = 2^s_row (no swizzle)
     __nv_bfloat16 ce[2][H_BN * 16];                // rank-one B operand: centroid c = {h1, h2, h3, 0, ...} (no swizzle)
     uint64_t raw_full[2], raw_empty[2], x_ready[2], x_empty[2], c_full[2], c_empty[2];
-    uint64_t t_full[2][H_TILES], t_empty[2][H_TILES];   // one accumulator ring per tile: its four epilogue warps and the MMA warp
+    uint64_t t_full[2][H_TILES], t_empty[2][H_TILES];   // one accumulator ring per tile: its epilogue warps and the MMA warp
+    float m_best[2][H_TILES][H_BM], m_second[2][H_TILES][H_BM];   // column-part merge scratch (EW == 16), double-buffered by super-tile
+    uint32_t m_idx[2][H_TILES][H_BM];
     uint32_t tmem_base;
 };
+
+#ifdef SCKM_TC5H_TRACE
+// Diagnostic build only (tools/build_variant.sh h5trace "-DSCKM_TC5H_TRACE"): clocks spent by the MMA warp and by epilogue
+// warp 2 of every CTA in each of their waits, summed over the launch: [cta][0] MMA x_ready, [1] c_full, [2] t_empty,
+// [3] MMA total, [4] epilogue t_full, [5] split, [6] exact part, [7] epilogue total
+__device__ long long g_tc5h_trace[1024 * 8];
+#define H_T0() const long long _t0 = clock64()
+#define H_ACC(slot) do { if ((threadIdx.x & 31) == 0) g_tc5h_trace[blockIdx.x * 8 + (slot)] += clock64() - _t0; } while (0)
+extern "C" int sckm_debug_tc5h_trace(long long* out, int n_ctas, int reset) {
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_tc5h_trace, (size_t)n_ctas * 8 * sizeof(long long));
+    if (reset) { static long long z[1024 * 8]; cudaMemcpyToSymbol(g_tc5h_trace, z, sizeof(z)); }
+    return (int)e;
+}
+#else
+#define H_T0() do { } while (0)
+#define H_ACC(slot) do { } while (0)
+#endif
 
 // exponent m with 2^m >= sqrt(cmax) (cmax = max ||c||^2), clamped; 0 when there is nothing to scale by
 __host__ __device__ __forceinline__ int h_centroid_exp(double cmax) {
@@ -132,8 +152,11 @@ tc5h_prep_kernel(const double* __restrict__ centroids, const double* __restrict_
 
 // FOLD: the norm term rides in the GEMM (rank-one BF16 MMA); else it is added per score in the epilogue.
 // TXS: type of the rows used for the exact part (float = the data itself, double = f64 data ranked through an f32 shadow).
-template <bool FOLD, typename TXS>
-__global__ void __launch_bounds__(H_THREADS, 1)
+// KS: 16-column K-steps per product (1: d <= 16, 2: d <= 32) -- a template parameter so that the MMA warp's issue loop
+// unrolls completely: with run-time loops and per-MMA descriptor arithmetic that ONE thread needed ~1850 clocks per
+// centroid block for 14 MMAs the tensor pipe executes in ~900, and the whole CTA ran at its pace (bench/c5_trace_probe.py).
+template <bool FOLD, int EW, int KS, typename TXS>
+__global__ void __launch_bounds__((EW + 3) * 32, 1)
 assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapC,
                    const TXS* __restrict__ xsrc, uint64_t n, uint32_t d,
                    const double* __restrict__ centroids, const double* __restrict__ cnorm, const float* __restrict__ hcn_sc,
@@ -143,6 +166,9 @@ assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                    const LoopState* __restrict__ loop_st, uint32_t loop_it) {
     if (loop_done(loop_st, loop_it)) return;                          // the fit's stop rule already fired (kmeans.rs:305)
     constexpr int TSTAGE = H_TILES * H_BN;                            // TMEM columns per accumulator stage
+    constexpr int CP = EW / 8;                                        // column parts per row (threads sharing a row)
+    constexpr int COLS = H_BN / CP;                                   // columns per epilogue thread per block
+    static_assert(EW == 8 || EW == 16, "8 or 16 epilogue warps");
     constexpr uint32_t IDESC_F16 = (1u << 4) | ((uint32_t)(H_BN >> 3) << 17) | ((uint32_t)(H_BM >> 4) << 24);   // F16 x F16 -> F32
     constexpr uint32_t IDESC_BF16 = IDESC_F16 | (1u << 7) | (1u << 10);                                         // BF16 x BF16 -> F32
     extern __shared__ unsigned char smem_raw[];
@@ -153,14 +179,13 @@ assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
     const double cmax = cta_max(cnorm, k);                            // max_j ||c_j||^2 (all threads take part)
     const int m_c = h_centroid_exp(cmax);
     const int s_c = H_XMAX_EXP - m_c;
-    const uint32_t ksteps = d <= 16 ? 1u : 2u;                        // K = 16 per MMA; columns >= d are zero-filled
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; s++) {
-            mbar_init(&S.raw_full[s], 1); mbar_init(&S.raw_empty[s], H_EPI_WARPS);
-            mbar_init(&S.x_ready[s], H_EPI_WARPS); mbar_init(&S.x_empty[s], 1);
+            mbar_init(&S.raw_full[s], 1); mbar_init(&S.raw_empty[s], H_SLOT_WARPS);
+            mbar_init(&S.x_ready[s], EW); mbar_init(&S.x_empty[s], 1);
             mbar_init(&S.c_full[s], 1); mbar_init(&S.c_empty[s], 1);
-            for (int m = 0; m < H_TILES; m++) { mbar_init(&S.t_full[s][m], 1); mbar_init(&S.t_empty[s][m], H_EPI_WARPS / H_TILES); }
+            for (int m = 0; m < H_TILES; m++) { mbar_init(&S.t_full[s][m], 1); mbar_init(&S.t_empty[s][m], EW / H_TILES); }
         }
         asm volatile("fence.mbarrier_init.release.cluster;");
     }
@@ -191,7 +216,7 @@ assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                     tma_load_2d(S.xraw[rs][m], &mapX, 0, (int)(st * rows_per_super + (uint64_t)m * H_BM), &S.raw_full[rs]);
             }
         }
-    } else if (warp == 10) {
+    } else if (warp == EW + 2) {
         // ================= TMA producer: centroid blocks (FP16 image + the rank-one operand) =================
         if (lane == 0) {
             uint32_t j = 0;
@@ -206,43 +231,73 @@ assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The WHOLE warp walks the loops and waits on the barriers; one elected lane issues.  Everything the MMAs take
+        // (descriptor words, TMEM columns) is then warp-uniform and lives in uniform registers -- with `if (lane == 0)`
+        // around the loops the compiler moved each operand into a uniform register through a per-MMA election loop
+        // (~14 instructions and two branches per tcgen05.mma).
+        {
             uint32_t it = 0, j = 0;
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            // low / high words of the operand descriptors (see umma_desc_sw128 / umma_desc_nosw)
+            constexpr uint32_t SW128_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t NOSW_HI = (uint32_t)(256 >> 4) | (1u << 14);
+            const uint32_t x_lo0 = ((smem_u32(&S.xs[0][0][0]) >> 4) & 0x3FFF) | (1u << 16);
+            const uint32_t c_lo0 = ((smem_u32(&S.cs[0][0]) >> 4) & 0x3FFF) | (1u << 16);
+            const uint32_t xe_lo0 = ((smem_u32(&S.xe[0][0][0]) >> 4) & 0x3FFF) | ((uint32_t)(128 >> 4) << 16);
+            const uint32_t ce_lo0 = ((smem_u32(&S.ce[0][0]) >> 4) & 0x3FFF) | ((uint32_t)(128 >> 4) << 16);
+#ifdef SCKM_TC5H_TRACE
+            const long long tm0 = clock64();
+#endif
             for (uint64_t st = blockIdx.x; st < nsuper; st += gridDim.x, it++) {
                 const int xs = it & 1; const uint32_t xph = (it >> 1) & 1;
-                mbar_wait(&S.x_ready[xs], xph);                      // scaled hi | lo image written by the epilogue warps
+                { H_T0(); mbar_wait(&S.x_ready[xs], xph); H_ACC(0); }   // scaled hi | lo image written by the epilogue warps
                 asm volatile("tcgen05.fence::after_thread_sync;");
                 for (uint32_t b = 0; b < nblocks; b++, j++) {
                     const int cs = j & 1; const uint32_t ph = (j >> 1) & 1;   // centroid stage == TMEM stage index
-                    mbar_wait(&S.c_full[cs], ph);
-                    const uint64_t dC = umma_desc_sw128(S.cs[cs]);
+                    { H_T0(); mbar_wait(&S.c_full[cs], ph); H_ACC(1); }
+                    // descriptors differ from stage to stage only in the 14-bit address field of their low word, and the
+                    // K offsets (hi at byte 0 of the 128-byte row, lo at byte 64, 32 bytes per K-step; units of 16 B) never
+                    // carry out of it: tiles are 1024-byte aligned
+                    const uint32_t cLo = c_lo0 + (uint32_t)cs * (uint32_t)(sizeof(S.cs[0]) >> 4);
+                    const uint32_t ceLo = ce_lo0 + (uint32_t)cs * (uint32_t)(sizeof(S.ce[0]) >> 4);
+#pragma unroll
                     for (int m = 0; m < H_TILES; m++) {
-                        mbar_wait(&S.t_empty[cs][m], ph ^ 1);
+                        { H_T0(); mbar_wait(&S.t_empty[cs][m], ph ^ 1); H_ACC(2); }
                         asm volatile("tcgen05.fence::after_thread_sync;");
-                        const uint32_t tcol = tmem + (uint32_t)(cs * TSTAGE + m * H_BN);
-                        const uint64_t dX = umma_desc_sw128(S.xs[xs][m]);
-                        uint32_t acc = 0;
-                        // Xh.Ch + Xh.Cl + Xl.Ch: hi at byte 0 of the 128-byte row, lo at byte 64 (descriptor units of 16 B)
+                        const uint32_t tcol = tmem_u + (uint32_t)(cs * TSTAGE + m * H_BN);
+                        const uint32_t xLo = x_lo0 + (uint32_t)(xs * H_TILES + m) * (uint32_t)(sizeof(S.xs[0][0]) >> 4);
+                        if (elect_one()) {
+                        // Xh.Ch + Xh.Cl + Xl.Ch
+#pragma unroll
                         for (int prod = 0; prod < 3; prod++)
-                            for (uint32_t ks = 0; ks < ksteps; ks++) {
-                                umma_f16(tcol, dX + (prod == 2 ? 4 : 0) + 2 * ks, dC + (prod == 1 ? 4 : 0) + 2 * ks, IDESC_F16, acc);
-                                acc = 1;
-                            }
-                        if (FOLD) umma_f16(tcol, umma_desc_nosw(S.xe[xs][m], 128, 256), umma_desc_nosw(S.ce[cs], 128, 256), IDESC_BF16, 1);
+#pragma unroll
+                            for (int ks = 0; ks < KS; ks++)
+                                umma_f16_parts(tcol, xLo + (prod == 2 ? 4 : 0) + 2 * ks, SW128_HI, cLo + (prod == 1 ? 4 : 0) + 2 * ks, SW128_HI,
+                                               IDESC_F16, (prod | ks) != 0);
+                        if (FOLD) umma_f16_parts(tcol, xe_lo0 + (uint32_t)(xs * H_TILES + m) * (uint32_t)(sizeof(S.xe[0][0]) >> 4), NOSW_HI,
+                                                 ceLo, NOSW_HI, IDESC_BF16, 1);
                         umma_commit(&S.t_full[cs][m]);               // this tile's accumulators are ready for its four epilogue warps
+                        if (m == H_TILES - 1) {
+                            umma_commit(&S.c_empty[cs]);             // centroid stage free once these MMAs have read it
+                            if (b + 1 == nblocks) umma_commit(&S.x_empty[xs]);   // X stage free for the split of super-tile it + 2
+                        }
+                        }
+                        __syncwarp();
                     }
-                    umma_commit(&S.c_empty[cs]);                     // centroid stage free once these MMAs have read it
                 }
-                umma_commit(&S.x_empty[xs]);                         // X stage free for the split of super-tile it + 2
             }
+#ifdef SCKM_TC5H_TRACE
+            if (lane == 0) g_tc5h_trace[blockIdx.x * 8 + 3] += clock64() - tm0;
+#endif
         }
     } else {
         // ================= epilogue warps: one thread per row =================
-        const int ew = warp - 2;                                     // 0..7
-        const int m = ew >> 2;                                       // tile of the super-tile
+        const int ew = warp - 2;                                     // 0..EW-1
+        const int m = (ew >> 2) / CP;                                // tile of the super-tile
+        const int cp = (ew >> 2) % CP;                               // column part of the row this thread ranks
         const int q = warp & 3;                                      // TMEM lane quadrant this warp may access
         const int rloc = q * 32 + lane;                              // row within the tile
-        double* part = partials + ((size_t)blockIdx.x * H_EPI_WARPS + ew) * ((pk + 15) / 16 * 16);
+        double* part = partials + ((size_t)blockIdx.x * H_SLOT_WARPS + (m * 4 + (ew & 3))) * ((pk + 15) / 16 * 16);
         const float tie25 = 2.5f * (float)(0.5 * H_TIE_REL);
         const float cmax_f = (float)cmax, cscale = h_pow2f(s_c);
         // what the split leaves behind for the super-tile it prepared
@@ -304,12 +359,14 @@ assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                 const float2 f0 = __half22float2(h0), f1 = __half22float2(h1), f2 = __half22float2(h2), f3 = __half22float2(h3);
                 const __half2 l0 = __floats2half2_rn(a0 - f0.x, a1 - f0.y), l1 = __floats2half2_rn(a2 - f1.x, a3 - f1.y);
                 const __half2 l2 = __floats2half2_rn(a4 - f2.x, a5 - f2.y), l3 = __floats2half2_rn(a6 - f3.x, a7 - f3.y);
-                dst[c ^ (rloc & 7)] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
-                                                 *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
-                dst[(c + 4) ^ (rloc & 7)] = make_uint4(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1),
+                if (cp == 0)                                          // (two threads per row: one writes hi, the other lo)
+                    dst[c ^ (rloc & 7)] = make_uint4(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1),
+                                                     *reinterpret_cast<const uint32_t*>(&h2), *reinterpret_cast<const uint32_t*>(&h3));
+                if (cp == CP - 1)
+                    dst[(c + 4) ^ (rloc & 7)] = make_uint4(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1),
                                                        *reinterpret_cast<const uint32_t*>(&l2), *reinterpret_cast<const uint32_t*>(&l3));
             }
-            if (FOLD) {                                               // K-chunk 0 of my row: {p, p, p, 0, 0, 0, 0, 0}, p = 2^s_row in BF16
+            if (FOLD && cp == 0) {                                    // K-chunk 0 of my row: {p, p, p, 0, 0, 0, 0, 0}, p = 2^s_row in BF16
                 const uint32_t pb = (uint32_t)(s_row + 127) << 7;
                 reinterpret_cast<uint4*>(S.xe[xs][m])[(rloc >> 3) * 16 + (rloc & 7)] = make_uint4(pb | (pb << 16), pb, 0u, 0u);
             }
@@ -319,6 +376,9 @@ assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             xn_next = xn; prime_next = prime; sf_next = sf; srow_next = s_row; force_next = force;
         };
         uint32_t it = 0, j = 0;
+#ifdef SCKM_TC5H_TRACE
+        const long long tep0 = clock64();
+#endif
         if (blockIdx.x < nsuper) split_stage(0, blockIdx.x);
         const uint32_t split_at = nblocks > 4 ? 4u : nblocks - 1;    // late enough for the next raw tile to have landed
         for (uint64_t st = blockIdx.x; st < nsuper; st += gridDim.x, it++) {
@@ -331,11 +391,25 @@ assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             for (uint32_t b = 0; b < nblocks; b++, j++) {
                 const int ts = j & 1; const uint32_t ph = (j >> 1) & 1;
                 // split the NEXT super-tile as soon as this one is under way, so the MMA warp never waits for it
-                if (b == split_at && st + gridDim.x < nsuper) split_stage(it + 1, st + gridDim.x);
+                if (b == split_at && st + gridDim.x < nsuper) {
+#ifdef SCKM_TC5H_TRACE
+                    const long long ts0 = clock64();
+#endif
+                    split_stage(it + 1, st + gridDim.x);
+#ifdef SCKM_TC5H_TRACE
+                    if (threadIdx.x == 64) g_tc5h_trace[blockIdx.x * 8 + 5] += clock64() - ts0;
+#endif
+                }
+#ifdef SCKM_TC5H_TRACE
+                const long long tw0 = clock64();
+#endif
                 mbar_wait(&S.t_full[ts][m], ph);
+#ifdef SCKM_TC5H_TRACE
+                if (threadIdx.x == 64) g_tc5h_trace[blockIdx.x * 8 + 4] += clock64() - tw0;
+#endif
                 asm volatile("tcgen05.fence::after_thread_sync;");
-                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TSTAGE + m * H_BN);
-                const uint32_t col0 = b * H_BN;
+                const uint32_t taddr = tmem + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * TSTAGE + m * H_BN + cp * COLS);
+                const uint32_t col0 = b * H_BN + cp * COLS;
                 const float4* h_gl = reinterpret_cast<const float4*>(hcn_sc + col0);
                 uint32_t va[32], vb[32];
                 auto consume = [&](const uint32_t (&v)[32], int c0) {
@@ -351,23 +425,31 @@ assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                             s[4 * u + 2] = fmaf(hv.z, sf, __uint_as_float(v[4 * u + 2])); s[4 * u + 3] = fmaf(hv.w, sf, __uint_as_float(v[4 * u + 3]));
                         }
                     }
-                    {   // can this chunk change any row's best or second, or come within the tie margin of a winner?
-                        float m0 = -FLT_MAX, m1 = -FLT_MAX, m2 = -FLT_MAX, m3 = -FLT_MAX;   // four chains: the warp waits on latency here
+                    // Can this chunk change any row's best or second, or come within the tie margin of a winner?  The maxima
+                    // of its four 8-column groups (four independent chains: the warp waits on latency here) answer that for
+                    // the chunk, and then group by group: in the steady state ONE column of a chunk is above a row's bar
+                    // (the row's own centroid), so the five-instruction top-2 update runs over 8 columns, not 32.
+                    float mg[4];
 #pragma unroll
-                        for (int u = 0; u < 4; u++) {
-                            m0 = fmaxf(fmaxf(m0, s[8 * u + 0]), s[8 * u + 1]); m1 = fmaxf(fmaxf(m1, s[8 * u + 2]), s[8 * u + 3]);
-                            m2 = fmaxf(fmaxf(m2, s[8 * u + 4]), s[8 * u + 5]); m3 = fmaxf(fmaxf(m3, s[8 * u + 6]), s[8 * u + 7]);
-                        }
-                        const float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
-                        if (!__any_sync(0xffffffffu, mx > fmaxf(second, prime))) return;
+                    for (int g = 0; g < 4; g++) {
+                        mg[g] = fmaxf(fmaxf(s[8 * g], s[8 * g + 1]), s[8 * g + 2]);
+                        mg[g] = fmaxf(fmaxf(mg[g], s[8 * g + 3]), s[8 * g + 4]);
+                        mg[g] = fmaxf(fmaxf(mg[g], s[8 * g + 5]), s[8 * g + 6]);
+                        mg[g] = fmaxf(mg[g], s[8 * g + 7]);
                     }
+                    const float bar = fmaxf(second, prime);            // columns at or below it can neither win nor come within the margin
+                    if (!__any_sync(0xffffffffu, fmaxf(fmaxf(mg[0], mg[1]), fmaxf(mg[2], mg[3])) > bar)) return;
 #pragma unroll
-                    for (int e = 0; e < 32; e++) {
-                        const float sc = s[e];
-                        const bool gt = sc > best;
-                        second = fmaxf(second, gt ? best : sc);
-                        bi = gt ? (col0 + c0 + e) : bi;
-                        best = fmaxf(best, sc);
+                    for (int g = 0; g < 4; g++) {
+                        if (!__any_sync(0xffffffffu, mg[g] > bar)) continue;
+#pragma unroll
+                        for (int e = 8 * g; e < 8 * g + 8; e++) {
+                            const float sc = s[e];
+                            const bool gt = sc > best;
+                            second = fmaxf(second, gt ? best : sc);
+                            bi = gt ? (col0 + c0 + e) : bi;
+                            best = fmaxf(best, sc);
+                        }
                     }
                 };
                 auto release_stage = [&]() {                           // all of this stage's columns are in registers
@@ -375,19 +457,44 @@ assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&S.t_empty[ts][m]);
                 };
-                // software pipeline over the 32-column chunks: chunk c+1 is in flight while chunk c is ranked
-                tmem_ld32(taddr, va);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int c0 = 0; c0 < H_BN; c0 += 64) {
-                    tmem_ld32(taddr + c0 + 32, vb);
-                    consume(va, c0);
+                if (COLS == 64) {
+                    // both chunks of my part at once: the columns go back to the MMA warp before the first is ranked
+                    tmem_ld32(taddr, va);
+                    tmem_ld32(taddr + 32, vb);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    if (c0 + 64 < H_BN) tmem_ld32(taddr + c0 + 64, va); else release_stage();
-                    consume(vb, c0 + 32);
-                    if (c0 + 64 < H_BN) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    release_stage();
+                    consume(va, 0);
+                    consume(vb, 32);
+                } else {
+                    // software pipeline over the 32-column chunks: chunk c+1 is in flight while chunk c is ranked
+                    tmem_ld32(taddr, va);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+                    for (int c0 = 0; c0 < COLS; c0 += 64) {
+                        tmem_ld32(taddr + c0 + 32, vb);
+                        consume(va, c0);
+                        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                        if (c0 + 64 < COLS) tmem_ld32(taddr + c0 + 64, va); else release_stage();
+                        consume(vb, c0 + 32);
+                        if (c0 + 64 < COLS) asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    }
                 }
             }
+            // ---- two column parts per row: merge their top-2 through shared memory (one barrier per tile and super-tile) ----
+            if (CP == 2) {
+                const int mb = it & 1;
+                if (cp == 1) { S.m_best[mb][m][rloc] = best; S.m_second[mb][m][rloc] = second; S.m_idx[mb][m][rloc] = bi; }
+                asm volatile("bar.sync %0, 256;" ::"r"(1 + m) : "memory");   // the 8 epilogue warps of this tile
+                if (cp == 1) continue;                                 // the exact part belongs to part 0
+                const float ob = S.m_best[mb][m][rloc], os = S.m_second[mb][m][rloc]; const uint32_t oi = S.m_idx[mb][m][rloc];
+                const bool take = ob > best || (ob == best && oi < bi);
+                second = fmaxf(fmaxf(second, os), fminf(best, ob));
+                bi = take ? oi : bi;
+                best = fmaxf(best, ob);
+            }
+#ifdef SCKM_TC5H_TRACE
+            const long long te0 = clock64();
+#endif
             // ---- decide: near-tie mark; exact f64 distance to the winner and the update, cooperatively per row ----
             // columns of skipped chunks lie at or below max(second, prime): that is the runner-up the tie test must assume
             second = fmaxf(second, prime);
@@ -449,7 +556,13 @@ assign_tc5h_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_consta
             if (lane == 0) atomicAdd(part + pk - 1, vsum);
             __syncwarp();
             if (lane == 0) mbar_arrive(&S.raw_empty[xs]);            // the raw tile may be overwritten by super-tile it + 2
+#ifdef SCKM_TC5H_TRACE
+            if (threadIdx.x == 64) g_tc5h_trace[blockIdx.x * 8 + 6] += clock64() - te0;
+#endif
         }
+#ifdef SCKM_TC5H_TRACE
+        if (threadIdx.x == 64) g_tc5h_trace[blockIdx.x * 8 + 7] += clock64() - tep0;
+#endif
     }
     // ---- teardown ----
     asm volatile("tcgen05.fence::before_thread_sync;");
@@ -476,7 +589,7 @@ bool tc5h_supported(const sckm_dataset* ds, uint64_t k) {
            encode_fn() != nullptr && !getenv("SCKM_TC5_TF32");
 }
 
-template <bool FOLD, typename TXS>
+template <bool FOLD, int EW, int KS, typename TXS>
 static int launch_tc5h_t(sckm_dataset* ds, uint64_t k, size_t pk, const float* x32) {
     sckm_ctx* ctx = ds->ctx;
     const unsigned grid = (unsigned)ctx->num_sms;
@@ -498,9 +611,9 @@ static int launch_tc5h_t(sckm_dataset* ds, uint64_t k, size_t pk, const float* x
     SCKM_TRY(make_map_h(ctx, &mapX, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, x32, ds->n, ds->d, 32, H_BM));
     SCKM_TRY(make_map_h(ctx, &mapC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, chl, kpad, 64, 64, H_BN));
     const size_t smem = sizeof(HSmem) + 1024;
-    auto kern = assign_tc5h_kernel<FOLD, TXS>;
+    auto kern = assign_tc5h_kernel<FOLD, EW, KS, TXS>;
     SCKM_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<grid, H_THREADS, smem, ctx->stream>>>(mapX, mapC, (const TXS*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids, ctx->d_cnorm,
+    kern<<<grid, (EW + 3) * 32, smem, ctx->stream>>>(mapX, mapC, (const TXS*)ds->x, ds->n, (uint32_t)ds->d, ctx->d_centroids, ctx->d_cnorm,
                                                  hcn_sc, c32, ce_g, (ds->have_labels && !getenv("SCKM_TC5_NOPRIME")) ? ds->labels : nullptr,
                                                  (uint32_t)k, nblocks, ds->labels, ds->mind, ctx->d_partials, pk, ctx->d_flags,
                                                  SCKM_LOOP_ARGS(ctx));
@@ -511,8 +624,18 @@ static int launch_tc5h_t(sckm_dataset* ds, uint64_t k, size_t pk, const float* x
 // called by launch_assign_tc5 (sckm_tc5.cu) after the workspaces, norms and the f32 shadow are in place
 int launch_tc5h(sckm_dataset* ds, uint64_t k, size_t pk, const float* x32) {
     const bool fold = !getenv("SCKM_TC5H_NOFOLD");
-    if (ds->dtype == SCKM_F64) return fold ? launch_tc5h_t<true, double>(ds, k, pk, x32) : launch_tc5h_t<false, double>(ds, k, pk, x32);
-    return fold ? launch_tc5h_t<true, float>(ds, k, pk, x32) : launch_tc5h_t<false, float>(ds, k, pk, x32);
+    // 16 epilogue warps (two threads per row) measured SLOWER in a sustained run (17.7 vs 16.9 ms per 10M-row step: more
+    // instructions for the same work under the power cap), so one thread per row stays the default; SCKM_TC5H_EW16=1 for A/B
+    const bool ew8 = getenv("SCKM_TC5H_EW16") == nullptr;
+    const bool k1 = ds->d <= 16;                                      // one 16-column K-step per product
+    if (ds->dtype == SCKM_F64) {
+        if (!fold) return k1 ? launch_tc5h_t<false, 8, 1, double>(ds, k, pk, x32) : launch_tc5h_t<false, 8, 2, double>(ds, k, pk, x32);
+        if (!ew8) return k1 ? launch_tc5h_t<true, 16, 1, double>(ds, k, pk, x32) : launch_tc5h_t<true, 16, 2, double>(ds, k, pk, x32);
+        return k1 ? launch_tc5h_t<true, 8, 1, double>(ds, k, pk, x32) : launch_tc5h_t<true, 8, 2, double>(ds, k, pk, x32);
+    }
+    if (!fold) return k1 ? launch_tc5h_t<false, 8, 1, float>(ds, k, pk, x32) : launch_tc5h_t<false, 8, 2, float>(ds, k, pk, x32);
+    if (!ew8) return k1 ? launch_tc5h_t<true, 16, 1, float>(ds, k, pk, x32) : launch_tc5h_t<true, 16, 2, float>(ds, k, pk, x32);
+    return k1 ? launch_tc5h_t<true, 8, 1, float>(ds, k, pk, x32) : launch_tc5h_t<true, 8, 2, float>(ds, k, pk, x32);
 }
 
 }  // namespace sckm

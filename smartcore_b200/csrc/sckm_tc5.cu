@@ -165,8 +165,18 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         }
     } else if (warp == 1) {
         // ================= MMA issuer =================
-        if (lane == 0) {
+        // The whole warp walks the loops and waits on the barriers, one elected lane issues: the operands are then
+        // warp-uniform (uniform registers, no per-MMA election loop), and the loops over products / atoms / K-steps are
+        // unrolled with the descriptors as (low, high) words -- a stage or K-step change is one 32-bit add (see sckm_tc5h.cu)
+        {
             uint32_t it = 0, j = 0;
+            constexpr uint32_t SW128_HI = (uint32_t)(1024 >> 4) | (1u << 14) | (2u << 29);
+            constexpr uint32_t ATOM16 = (uint32_t)(TC_ATOM_FLOATS * 4) >> 4, CATOM16 = (uint32_t)(BN * 32 * 4) >> 4;   // tile sizes in 16-byte units
+            const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+            const uint32_t xh_lo0 = ((smem_u32(&S.xh[0][0][0][0]) >> 4) & 0x3FFF) | (1u << 16);
+            const uint32_t xl_lo0 = ((smem_u32(&S.xl[0][0][0][0]) >> 4) & 0x3FFF) | (1u << 16);
+            const uint32_t ch_lo0 = ((smem_u32(&S.ch[0][0][0]) >> 4) & 0x3FFF) | (1u << 16);
+            const uint32_t cl_lo0 = ((smem_u32(&S.cl[0][0][0]) >> 4) & 0x3FFF) | (1u << 16);
             for (uint64_t st = blockIdx.x; st < nsuper; st += gridDim.x, it++) {
                 const int xs = it & 1; const uint32_t xph = (it >> 1) & 1;
                 mbar_wait(&S.x_ready[xs], xph);                      // hi/lo split done by the epilogue warps
@@ -176,20 +186,27 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
                     mbar_wait(&S.c_full[cs], ph);
                     mbar_wait(&S.t_empty[cs], ph ^ 1);
                     asm volatile("tcgen05.fence::after_thread_sync;");
-                    for (int m = 0; m < TILES; m++) {
-                        const uint32_t tcol = tmem + (uint32_t)(cs * TSTAGE + m * BN);
-                        uint32_t acc = 0;
-                        for (int prod = 0; prod < 3; prod++)          // Xh.Ch + Xh.Cl + Xl.Ch
-                            for (int a = 0; a < NK; a++) {
-                                const uint64_t dX = umma_desc_sw128(prod == 2 ? S.xl[xs][m][a] : S.xh[xs][m][a]);
-                                const uint64_t dC = umma_desc_sw128(prod == 1 ? S.cl[cs][a] : S.ch[cs][a]);
-                                for (int ks = 0; ks < 4; ks++) { umma_tf32(tcol, dX + 2 * ks, dC + 2 * ks, IDESC, acc); acc = 1; }
-                            }
+                    if (elect_one()) {
+#pragma unroll
+                        for (int m = 0; m < TILES; m++) {
+                            const uint32_t tcol = tmem_u + (uint32_t)(cs * TSTAGE + m * BN);
+#pragma unroll
+                            for (int prod = 0; prod < 3; prod++)          // Xh.Ch + Xh.Cl + Xl.Ch
+#pragma unroll
+                                for (int a = 0; a < NK; a++) {
+                                    const uint32_t xlo = (prod == 2 ? xl_lo0 : xh_lo0) + (uint32_t)((xs * TILES + m) * NK + a) * ATOM16;
+                                    const uint32_t clo = (prod == 1 ? cl_lo0 : ch_lo0) + (uint32_t)(cs * NK + a) * CATOM16;
+#pragma unroll
+                                    for (int ks = 0; ks < 4; ks++)
+                                        umma_tf32_parts(tcol, xlo + 2 * ks, SW128_HI, clo + 2 * ks, SW128_HI, IDESC, (prod | a | ks) != 0);
+                                }
+                        }
+                        umma_commit(&S.c_empty[cs]);                 // centroid stage free once these MMAs have read it
+                        umma_commit(&S.t_full[cs]);                  // accumulators ready for the epilogue
+                        if (b + 1 == nblocks) umma_commit(&S.x_empty[xs]);   // X stage: MMA side done (epilogue warps arrive too)
                     }
-                    umma_commit(&S.c_empty[cs]);                     // centroid stage free once these MMAs have read it
-                    umma_commit(&S.t_full[cs]);                      // accumulators ready for the epilogue
+                    __syncwarp();
                 }
-                umma_commit(&S.x_empty[xs]);                         // X stage: MMA side done (epilogue warps arrive too)
             }
         }
     } else {

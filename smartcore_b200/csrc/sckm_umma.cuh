@@ -74,6 +74,12 @@ __device__ __forceinline__ void umma_f16_parts(uint32_t tmem_c, uint32_t a_lo, u
                  " tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n }"
                  ::"r"(tmem_c), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+__device__ __forceinline__ void umma_tf32_parts(uint32_t tmem_c, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                                uint32_t idesc, uint32_t accumulate) {
+    asm volatile("{\n .reg .pred p;\n .reg .b64 da, db;\n mov.b64 da, {%1, %2};\n mov.b64 db, {%3, %4};\n setp.ne.b32 p, %6, 0;\n"
+                 " tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n }"
+                 ::"r"(tmem_c), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
 
 // ---- host side: cuTensorMapEncodeTiled through the runtime's driver entry point (no -lcuda) ----
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,

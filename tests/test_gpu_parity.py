@@ -280,6 +280,76 @@ def test_tc5_ties_and_duplicates(ctx, O):
     ds.close()
 
 
+@pytest.mark.parametrize("case", ["row_scales", "tiny_rows", "huge_scale", "tiny_scale", "extreme_scale", "zero_rows", "one_k_step"])
+@pytest.mark.parametrize("fold", [True, False])
+def test_tc5h_scaling_edge_cases(ctx, O, case, fold, monkeypatch):
+    """The 3xFP16 kernel (d <= 32) scales every row and the centroids by powers of two to fit FP16's 5-bit exponent and
+    folds -||c||^2/2 into the GEMM as a rank-one BF16 term.  Whatever the magnitudes -- rows of very different size, rows
+    far below the centroids, data near either end of the f32 range, all-zero rows -- labels must equal the exact f64
+    argmin (rows the reduced-precision ranking cannot decide are re-decided exactly), sums and inertia stay f64."""
+    if not fold:
+        monkeypatch.setenv("SCKM_TC5H_NOFOLD", "1")
+    n, d, k = 20000, 32, 200
+    rng = np.random.default_rng(11)
+    x = blobs(n, d, k, 5, np.float32, spread=2.0).astype(np.float64)
+    if case == "row_scales":
+        x *= 10.0 ** rng.uniform(-3, 3, size=(n, 1))
+    elif case == "tiny_rows":
+        x[::2] *= 1e-12
+    elif case == "huge_scale":
+        x *= 1e15
+    elif case == "tiny_scale":
+        x *= 1e-18
+    elif case == "extreme_scale":
+        x *= 1e30
+    elif case == "zero_rows":
+        x[::7] = 0.0
+    elif case == "one_k_step":
+        d = 12
+        x = x[:, :d].copy()
+    x = np.ascontiguousarray(x.astype(np.float32))
+    cent = x[rng.choice(n, k, replace=False)].astype(np.float64)
+    if case == "zero_rows":
+        cent[0] = 0.0
+    cent = cent * (1.0 + 1e-3)
+    ctx.set_assign_kernel(cabi.ASSIGN_TC5)
+    ds = ctx.upload(x)
+    inertia, sums, counts = ds.lloyd_step(cent)
+    again = ds.lloyd_step(cent)                                    # primed by the labels of the first call
+    ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+    d_o, s_o, c_o, m_o, gap = O.brute_clustering(x, cent, want_gap=True)
+    assert np.array_equal(ds.labels().astype(np.int64), m_o)
+    assert counts.tolist() == c_o.tolist()
+    np.testing.assert_allclose(sums, s_o, rtol=RTOL, atol=1e-9 * float(np.abs(s_o).max()))
+    assert abs(inertia - d_o) <= RTOL * d_o
+    assert again[0] == inertia and np.array_equal(again[1], sums) and np.array_equal(again[2], counts)
+    ds.close()
+
+
+def test_tc5h_matches_the_tf32_kernel(ctx, O, monkeypatch):
+    """Both tcgen05 forms (3xFP16 with 8 or 16 epilogue warps, and 3xTF32) only rank; what they hand on is exact, so a few
+    Lloyd steps from the same start end in the same labels, sizes and bit-identical inertia trace sums."""
+    n, d, k = 60000, 32, 700
+    x = blobs(n, d, k, 9, np.float32, spread=1.5)
+    cent = x[np.random.default_rng(3).choice(n, k, replace=False)].astype(np.float64) + 0.01
+    res = {}
+    for name, env in (("f16", {}), ("f16_ew16", {"SCKM_TC5H_EW16": "1"}), ("tf32", {"SCKM_TC5_TF32": "1"})):
+        for key in ("SCKM_TC5H_EW16", "SCKM_TC5_TF32"):
+            monkeypatch.delenv(key, raising=False)
+        for key, v in env.items():
+            monkeypatch.setenv(key, v)
+        ctx.set_assign_kernel(cabi.ASSIGN_TC5)
+        ds = ctx.upload(x)
+        out = ds.lloyd_iterate(cent, 4, want_inertia=True)
+        ctx.set_assign_kernel(cabi.ASSIGN_AUTO)
+        res[name] = (ds.labels().copy(), out["size"].copy(), out["inertia"].copy(), out["centroids"].copy())
+        ds.close()
+    for name in ("f16_ew16", "tf32"):
+        assert np.array_equal(res[name][0], res["f16"][0]) and np.array_equal(res[name][1], res["f16"][1])
+        np.testing.assert_allclose(res[name][2], res["f16"][2], rtol=1e-12)
+        np.testing.assert_allclose(res[name][3], res["f16"][3], rtol=1e-12, atol=1e-12)
+
+
 def test_init_centroids_are_label_means(ctx, O):
     x = blobs(3000, 8, 6, 11)
     first, u = cluster.kmeanspp_draws(5, 3000, 6)

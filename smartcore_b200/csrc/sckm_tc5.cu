@@ -246,6 +246,9 @@ assign_tc5_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constan
         };
         uint32_t it = 0, j = 0;
         double xn_next = blockIdx.x < nsuper ? split_stage(0, 0) : 0.0;
+        // CP == 2: a row's two atoms are split by two different warps, and the priming below reads both.  From the second
+        // super-tile on the merge barrier at the end of the previous one orders that; the first needs its own (racecheck)
+        if (CP == 2 && blockIdx.x < nsuper) asm volatile("bar.sync 1, 256;" ::: "memory");
         for (uint64_t st = blockIdx.x; st < nsuper; st += gridDim.x, it++) {
             const int xs = it & 1;
             const uint64_t row = st * rows_per_super + (uint64_t)m * TC_BM + rloc;

@@ -22,7 +22,12 @@ def main():
     cases = [(1500, 16, 8, np.float64, cabi.ASSIGN_STREAM), (1111, 7, 5, np.float32, cabi.ASSIGN_STREAM),
              (2000, 64, 48, np.float64, cabi.ASSIGN_DMMA), (1777, 20, 33, np.float32, cabi.ASSIGN_DMMA),
              (1200, 128, 300, np.float64, cabi.ASSIGN_DMMA),          # streamed centroid blocks
-             (4096, 32, 64, np.float32, cabi.ASSIGN_TC5),              # tcgen05 / TMA / TMEM kernel
+             (4096, 32, 64, np.float32, cabi.ASSIGN_TC5),              # tcgen05 / TMA / TMEM kernel (3xFP16 form, d <= 32)
+             (3000, 12, 150, np.float32, cabi.ASSIGN_TC5),             # ... one K-step per product, padded centroid block
+             (3000, 32, 130, np.float32, "tc5_ew16"),                  # ... two epilogue threads per row
+             (3000, 32, 130, np.float32, "tc5_nofold"),                # ... norm term in the epilogue
+             (3000, 32, 130, np.float32, "tc5_tf32"),                  # 3xTF32 form (the only one for 32 < d <= 64)
+             (2500, 48, 70, np.float32, cabi.ASSIGN_TC5),
              (900, 9, 4, np.float64, cabi.ASSIGN_DIRECT), (700, 40, 6, np.float64, cabi.ASSIGN_DIRECT),
              (1300, 64, 5, np.float64, cabi.ASSIGN_AUTO),              # k < 16, d > 32: tile kernel, partly padded sub-block
              (1500, 64, 40, np.float64, "center"), (1100, 128, 200, np.float64, "center"),   # centred instantiations
@@ -32,6 +37,11 @@ def main():
         if kern == "center":                                           # data far from the origin: launch_cnorm centres
             x = x + 1e4
             kern = cabi.ASSIGN_AUTO
+        for key in ("SCKM_TC5H_EW16", "SCKM_TC5H_NOFOLD", "SCKM_TC5_TF32"):
+            os.environ.pop(key, None)
+        if isinstance(kern, str) and kern.startswith("tc5_"):
+            os.environ[{"tc5_ew16": "SCKM_TC5H_EW16", "tc5_nofold": "SCKM_TC5H_NOFOLD", "tc5_tf32": "SCKM_TC5_TF32"}[kern]] = "1"
+            kern = cabi.ASSIGN_TC5
         first, u = cluster.kmeanspp_draws(3, n, k)
         ds = ctx.upload(x)
         seeds = ds.kmeanspp(k, first, u)

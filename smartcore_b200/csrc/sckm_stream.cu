@@ -53,6 +53,9 @@ __device__ __forceinline__ unsigned long long gtimer() { unsigned long long t; a
 #else
 #define STREAM_TRACE(slot) do { } while (0)
 #endif
+#ifndef SCKM_STREAM_EARLY
+#define SCKM_STREAM_EARLY 1      // first row loads before the dependency wait (0: after the prologue, A/B builds)
+#endif
 #ifndef SCKM_STREAM_UNROLL
 #define SCKM_STREAM_UNROLL 1
 #endif
@@ -93,6 +96,7 @@ template <> struct VecLoad<float, 4> {
 // 32-byte vectors: one LDG.256 per lane (sm_100 and later).  A warp request then covers FULL 128-byte lines (8 rows x 4
 // lanes x 32 B for the A fragments of a 16-double row) instead of half lines, which halves the L1 wavefronts of the row
 // loads -- the data stage of the L1 is the busiest unit of this kernel (ncu: 45 % of its peak, everything else < 35 %).
+// It did not pay (see launch_stream_vw): kept as an opt-in instantiation.
 template <> struct VecLoad<double, 4> {
     static __device__ __forceinline__ void ld(const double* p, double (&o)[4]) {
         asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(o[0]), "=d"(o[1]), "=d"(o[2]), "=d"(o[3]) : "l"(p)); }
@@ -203,7 +207,7 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
     // X is an input of the whole fit, not a product of the kernel before this one on the stream: the first batch (and the
     // L2 prefetches behind it) go out BEFORE the dependency wait and before the dependent loads of the prologue (stop
     // flag, norms, shift, centroid fragments: three round trips that cost 3 us of a 35 us kernel when they came first)
-    if (!TMA && wglobal < nbatches) {
+    if (SCKM_STREAM_EARLY && !TMA && wglobal < nbatches) {
         load_any(wglobal * 32);
         for (uint32_t i = 1; i < pf_ahead; i++) l2_prefetch_batch(wglobal + (uint64_t)i * nwarps);
     }
@@ -511,6 +515,10 @@ assign_stream_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d_rt, const 
         }
     };
 
+    if (!SCKM_STREAM_EARLY && !TMA && wglobal < nbatches) {
+        load_any(wglobal * 32);
+        for (uint32_t i = 1; i < pf_ahead; i++) l2_prefetch_batch(wglobal + (uint64_t)i * nwarps);
+    }
     if (TMA) {
         if (lane == 0)
             for (int s = 0; s < (STAGES > 0 ? STAGES : 1); s++) {
@@ -650,7 +658,9 @@ template <int KS, int KT, typename TX>
 static int launch_stream_vw(sckm_dataset* ds, uint64_t k, size_t pk, unsigned* grid_out) {
     constexpr int VMAX = (16 / sizeof(TX)) < KS ? (16 / sizeof(TX)) : KS;     // widest 16-byte vector that fits KS
     constexpr int V32 = 32 / sizeof(TX);                                       // 32-byte vectors (LDG.256) when they fit
-    if (V32 <= KS && ds->d % V32 == 0 && !getenv("SCKM_STREAM_NO256"))
+    // Measured at C2 (bench.py, 1M x 16): 40.8 us with 16-byte loads, 51.6 us with 32-byte loads when the update takes one
+    // round per turn (39.1 us when it takes four, SCKM_STREAM_UNROLL=4: no better than the 16-byte form) -- opt-in only
+    if (V32 <= KS && ds->d % V32 == 0 && getenv("SCKM_STREAM_256"))
         return launch_stream_t<KS, KT, (V32 <= KS ? V32 : VMAX), TX>(ds, k, pk, grid_out);
     if (ds->d % VMAX == 0) return launch_stream_t<KS, KT, VMAX, TX>(ds, k, pk, grid_out);
     if (VMAX > 2 && ds->d % 2 == 0) return launch_stream_t<KS, KT, 2, TX>(ds, k, pk, grid_out);

@@ -142,14 +142,17 @@ def test_dmma_ties_duplicates_and_exact_refine(ctx, O):
     ds.close()
 
 
-@pytest.mark.parametrize("tma_ring", [False, True])
+@pytest.mark.parametrize("tma_ring", [False, True, "ldg256"])
 def test_stream_kernel_ties_and_shapes(ctx, O, tma_ring, monkeypatch):
     """Small-k streaming kernel (k < 16): exact ties, odd d (scalar staging path), f32, ragged n; with the rows
-    loaded straight into registers (default) and through the cp.async.bulk ring (SCKM_STREAM_TMA)."""
-    if tma_ring:
+    loaded straight into registers (default), through the cp.async.bulk ring (SCKM_STREAM_TMA), and with 32-byte loads
+    (SCKM_STREAM_256: the opt-in LDG.256 instantiation)."""
+    monkeypatch.delenv("SCKM_STREAM_TMA", raising=False)
+    monkeypatch.delenv("SCKM_STREAM_256", raising=False)
+    if tma_ring == "ldg256":
+        monkeypatch.setenv("SCKM_STREAM_256", "1")
+    elif tma_ring:
         monkeypatch.setenv("SCKM_STREAM_TMA", "1")
-    else:
-        monkeypatch.delenv("SCKM_STREAM_TMA", raising=False)
     rng = np.random.default_rng(2)
     base = rng.normal(size=(6, 16))
     x = base[rng.integers(0, 6, size=3001)]

@@ -62,7 +62,7 @@ enum {
     SCKM_ASSIGN_DIRECT = 1, /* direct-difference form, bit-exact distances (euclidian.rs:56-63) */
     SCKM_ASSIGN_DMMA = 2,   /* ||x||^2 - 2 X.C^T + ||c||^2 on FP64 DMMA tiles + exact near-tie refine */
     SCKM_ASSIGN_STREAM = 3, /* small k (<16), d <= 32: one HBM pass does assignment and update */
-    SCKM_ASSIGN_TC5 = 4     /* f32 data, d <= 32: 3xTF32 on tcgen05 (TMA + TMEM) + exact f64 decision */
+    SCKM_ASSIGN_TC5 = 4     /* f32 data: tcgen05 (TMA + TMEM) ranking, 3xFP16 for d <= 32, 3xTF32 for d <= 64, + exact f64 decision */
 };
 
 int sckm_abi_version(void);

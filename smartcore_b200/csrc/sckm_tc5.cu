@@ -527,6 +527,12 @@ int launch_assign_tc5(sckm_dataset* ds, uint64_t k) {
     else if (ds->d <= 32) rc = ds->dtype == SCKM_F64 ? launch_tc5_t<1, 2, 128, double>(ds, k, pk, x32) : launch_tc5_t<1, 2, 128, float>(ds, k, pk, x32);
     else             rc = ds->dtype == SCKM_F64 ? launch_tc5_t<2, 1, 64, double>(ds, k, pk, x32) : launch_tc5_t<2, 1, 64, float>(ds, k, pk, x32);
     SCKM_TRY(rc);
+    if (getenv("SCKM_TRACE_MARKED")) {                              // diagnostic: rows this step hands to the exact re-decision
+        unsigned long long m = 0;
+        SCKM_CUDA(ctx, cudaMemcpyAsync(&m, ctx->d_flags, sizeof(m), cudaMemcpyDeviceToHost, ctx->stream));
+        SCKM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        fprintf(stderr, "[sckm] tcgen05 step: %llu of %llu rows marked as near-ties (%.4f %%)\n", m, (unsigned long long)ds->n, 100.0 * (double)m / (double)ds->n);
+    }
     return launch_refine_rows(ds, k, pk, grid);   // 8 warps per CTA: the same partial slots as the epilogue warps
 }
 

@@ -476,20 +476,39 @@ refine_rows_kernel(const TX* __restrict__ x, uint64_t n, uint32_t d, const doubl
             const uint64_t row = base + src;
             const TX* xr = x + row * d;
             double best = DBL_MAX; uint32_t bi = 0xffffffffu;
+            double xv[32];                                           // the row's features of the current 32-feature chunk
+            auto load_x = [&](uint32_t j0) {
+#pragma unroll
+                for (int jj = 0; jj < 32; jj++) xv[jj] = j0 + jj < d ? (double)xr[j0 + jj] : 0.0;
+            };
+            const bool one_chunk = d <= 32;
+            if (one_chunk) load_x(0);
+            const uint32_t tile_s = (uint32_t)__cvta_generic_to_shared(tile);
             for (uint32_t c0 = 0; c0 < k; c0 += 32) {                // 32 centroids at a time: lane l takes centroid c0 + l
                 double dist = 0.0;
                 for (uint32_t j0 = 0; j0 < d; j0 += 32) {            // ... 32 features at a time, in order
                     __syncwarp();
-                    const uint32_t nc = min(32u, k - c0), nj = min(32u, d - j0);
-                    for (uint32_t cl = 0; cl < nc; cl++)             // centroid row cl: one coalesced request, lane = feature
-                        if ((uint32_t)lane < nj) tile[cl * 33 + lane] = centroids[(size_t)(c0 + cl) * d + j0 + lane];
+                    // centroid row cl: one coalesced request (lane = feature), straight into the tile; all 32 rows in
+                    // flight at once -- a loop of dependent load/store pairs here cost one L2 round trip per ROW
+                    if (j0 + lane < d) {
+#pragma unroll
+                        for (int cl = 0; cl < 32; cl++)
+                            if (c0 + cl < k)
+                                asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(tile_s + (uint32_t)(cl * 33 + lane) * 8u),
+                                             "l"(centroids + (size_t)(c0 + cl) * d + j0 + lane) : "memory");
+                    }
+                    asm volatile("cp.async.commit_group;" ::: "memory");
+                    if (!one_chunk) load_x(j0);
+                    asm volatile("cp.async.wait_group 0;" ::: "memory");
                     __syncwarp();
-                    if ((uint32_t)lane < nc) {
+                    if (c0 + lane < k) {
                         const double* tr = tile + lane * 33;
-                        for (uint32_t jj = 0; jj < nj; jj++) {
-                            const double r = __dsub_rn((double)xr[j0 + jj], tr[jj]);
-                            dist = __dadd_rn(dist, __dmul_rn(r, r));
-                        }
+#pragma unroll
+                        for (int jj = 0; jj < 32; jj++)
+                            if (j0 + jj < d) {
+                                const double r = __dsub_rn(xv[jj], tr[jj]);
+                                dist = __dadd_rn(dist, __dmul_rn(r, r));
+                            }
                     }
                 }
                 if (c0 + lane < k && dist < best) { best = dist; bi = c0 + lane; }

@@ -189,3 +189,21 @@ def test_model_bincode_layout():
     for bad in (want[:-1], want + b"\\0", struct.pack("<Q", 2) + struct.pack("<Q", 1 << 60)):
         with pytest.raises(sc.Failed):
             sc.KMeans.from_bincode(bad)
+
+
+def test_every_environment_switch_is_documented():
+    """INTEGRATION.md lists the SCKM_* environment switches the library reads (tests and experiments only): a switch added
+    to the sources without a line there fails here."""
+    import glob
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    found = set()
+    for path in glob.glob(os.path.join(root, "smartcore_b200", "csrc", "*.cu*")) + glob.glob(os.path.join(root, "smartcore_b200", "host", "*")) \
+            + glob.glob(os.path.join(root, "smartcore_b200", "*.py")):
+        text = open(path, errors="ignore").read()
+        found.update(re.findall(r'getenv\("(SCKM_[A-Z0-9_]+)"\)', text))
+        found.update(re.findall(r'environ[^\n]*?"(SCKM_[A-Z0-9_]+)"', text))
+    assert found, "no switches found: the scan is broken"
+    missing = sorted(v for v in found if v not in doc)
+    assert not missing, "undocumented environment switches: %s" % missing

@@ -22,12 +22,14 @@
 //     FMNMX3 per score.  (SCKM_TC5H_NOFOLD=1 keeps the norm in the epilogue instead, one FFMA per score: A/B + a
 //     fallback for the tests.)
 //
-// Shared memory per CTA (184 KB): raw f32 super-tile as TMA delivers it (two stages: the exact part at the end of a
-// super-tile reads its rows again from there),
-// FP16 image [row][hi 32 | lo 32] (128-byte rows, SWIZZLE_128B: hi and lo are K-offsets 0 / 64 B of ONE atom; two
-// stages), centroid block in the same form (two stages), and the two small BF16 operands of the rank-one MMA.
-// The accumulators of the two tiles of a super-tile are separate rings (their own full / empty barriers): a tile's four
+// Shared memory per CTA (190 KB): raw f32 super-tile as TMA delivers it (two stages: the exact part at the end of a
+// super-tile reads its rows again from there), FP16 image [row][hi 32 | lo 32] (128-byte rows, SWIZZLE_128B: hi and lo
+// are K-offsets 0 / 64 B of ONE atom; two stages), centroid block in the same form (two stages), the two small BF16
+// operands of the rank-one MMA, and the merge scratch of the two-threads-per-row variant.
+// The accumulators of the two tiles of a super-tile are separate rings (their own full / empty barriers): a tile's
 // epilogue warps start as soon as ITS seven MMAs are done and hand the columns back without waiting for the other tile.
+// The MMA warp walks its loops as a whole warp with ONE elected lane issuing, loops unrolled, descriptors as (low, high)
+// words: see the comment at the issuer.  How each of these steps was measured: DESIGN.md, K2h row; profiles/README.md.
 #include "sckm_common.cuh"
 #include "sckm_tile.cuh"
 #include "sckm_umma.cuh"
